@@ -1,0 +1,173 @@
+/* libscregclust_b200 -- C ABI of the B200-native scregclust hot path.
+ *
+ * Drop-in boundary for the `.Call` routines of the reference R package
+ * (R/RcppExports.R:4-117 <-> src/RcppExports.cpp:14-117) plus the three pure-R
+ * numeric helpers the hot path uses (R/utils.R:13-57, 533-541), and the batched
+ * session API that runs Step 1 / Step 2a / Step 2b of R/scregclust.R:1222-1803
+ * for every module and penalization value of a cycle in one call.
+ *
+ * Conventions (identical to what R passes):
+ *   - all matrices are FP64, column-major, tightly packed (leading dimension =
+ *     number of rows); the library never retains or frees caller pointers;
+ *   - module ids are 1-based, -1 = noise module; `update_order` and
+ *     `prior_idx` are 0-based (src/allocation.cpp:4-6);
+ *   - every function returns 0 on success or a negative status; the message of
+ *     the last failure on the calling thread is available from scrc_last_error().
+ *     Nothing throws across the ABI and nothing calls exit().
+ *   - there is no CPU fallback: without a usable CUDA device every compute
+ *     entry point fails with SCRC_ERR_CUDA.
+ */
+#ifndef SCREGCLUST_B200_H
+#define SCREGCLUST_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* status codes; the bridge maps them to the reference's Rcpp::stop() texts */
+#define SCRC_OK 0
+#define SCRC_ERR_COOP_DIMS (-1)      /* "COOP LASSO: Matrix dimensions of y and x need to be positive." optim.cpp:77 */
+#define SCRC_ERR_COOP_ROWS (-2)      /* "y and x need to have the same number of rows."                optim.cpp:81 */
+#define SCRC_ERR_COOP_BETA0 (-3)     /* "beta_0 needs to be of size p x m"                             optim.cpp:88 */
+#define SCRC_ERR_COOP_RHO (-4)       /* "rho_0 > 0 needs to hold"                                      optim.cpp:116 */
+#define SCRC_ERR_COOP_ALPHA (-5)     /* "0 < alpha_0 < 2 needs to hold"                                optim.cpp:121 */
+#define SCRC_ERR_NNLS_DIMS (-6)      /* "NNLS: Matrix dimensions of y and x need to be positive."      optim.cpp:409 */
+#define SCRC_ERR_ALLOC_TOO_LARGE (-7)/* "alloc_array: requested allocation too large"                  utils.cpp:20 */
+#define SCRC_ERR_RESET_DIMS (-8)     /* "reset_array: input has wrong dimensions"                      utils.cpp:52 */
+#define SCRC_ERR_ARG (-20)           /* any other invalid argument */
+#define SCRC_ERR_UNSUPPORTED (-21)
+#define SCRC_ERR_INTERNAL (-50)
+#define SCRC_ERR_CUDA (-100)         /* CUDA failures: -100 - cudaError_t */
+
+int scrc_version(void);
+const char* scrc_last_error(void);
+/* number of kernels of this library launched so far by the process */
+unsigned long long scrc_launch_count(void);
+/* selects the CUDA device used by the drop-in entry points (sessions carry their own) */
+int scrc_set_device(int device);
+
+/* ------------------------------------------------------------------ drop-ins */
+
+/* coop_lasso(y, x, lambda, weights, beta_0, rho_0, alpha_0, n_update, eps_corr, max_iter,
+ *            eps_rel, eps_abs, verbose) -> list(beta, iterations)
+ * R/RcppExports.R:66-68, src/optim.cpp:63-320.
+ * y: n x m, x: n_x x p, weights: p, beta0: p x m or NULL; beta_out: p x m; iterations_out: 1 int
+ * (max_iter + 1 when the iteration limit was hit, optim.cpp:295-305). */
+int scrc_coop_lasso(const double* y, int64_t n, int64_t m, const double* x, int64_t n_x, int64_t p,
+                    double lambda, const double* weights, const double* beta0, int64_t beta0_rows,
+                    int64_t beta0_cols, double rho0, double alpha0, int n_update, double eps_corr,
+                    int max_iter, double eps_rel, double eps_abs, double* beta_out, int* iterations_out);
+
+/* coef_nnls(x, y, eps, max_iter) -> list(beta, iterations)
+ * R/RcppExports.R:93-95, src/optim.cpp:403-549.
+ * x: nobs x nvar, y: nobs_y x m; beta_out: nvar x m; iterations_out: m ints
+ * (max_iter, and a zero column, for columns that never converged). */
+int scrc_coef_nnls(const double* x, int64_t nobs, int64_t nvar, const double* y, int64_t nobs_y, int64_t m,
+                   double eps, int max_iter, double* beta_out, int* iterations_out);
+
+/* allocate_into_modules(resid_array, resid_var, prior_indicator, k_, update_order,
+ *                       prior_baseline, prior_weight) -> integer[T]
+ * R/RcppExports.R:4-6, src/allocation.cpp:8-100.
+ * sq_resid: K x n2 x T squared residuals; resid_var: T x K; prior_indicator as CSR
+ * (prior_off: T+1 offsets into prior_idx, both may be NULL when there is no prior);
+ * k_in / k_out: T (1-based, -1 noise); update_order: T (0-based permutation).
+ * votes_out (T x K, row-major by gene: votes_out[t*K + k]) may be NULL. */
+int scrc_allocate_into_modules(const double* sq_resid, int K, int64_t n2, int64_t T, const double* resid_var,
+                               const int* prior_off, const int* prior_idx, const int* k_in,
+                               const int* update_order, double prior_baseline, double prior_weight,
+                               int* k_out, int* votes_out);
+
+/* alloc_array(input, n_cl) / reset_array(arr, input): src/utils.cpp:12-34, 43-63.
+ * Host-side broadcasts kept for API completeness -- the session API never
+ * materialises the K x n_obs x n_genes array. */
+int scrc_alloc_array(const double* input, int64_t n_obs, int64_t n_genes, int64_t n_cl, double* out);
+int scrc_reset_array(double* arr, int64_t n_cl, int64_t n_obs, int64_t n_genes, const double* input,
+                     int64_t in_rows, int64_t in_cols);
+
+/* fast_cor(x, y): R/utils.R:533-541.  x: n x px, y: n x py, out: px x py. */
+int scrc_fast_cor(const double* x, const double* y, int64_t n, int64_t px, int64_t py, double* out);
+/* coef_ols(y, x): R/utils.R:13-37.  y: n x m, x: n x p, beta_out: p x m. */
+int scrc_coef_ols(const double* y, const double* x, int64_t n, int64_t p, int64_t m, double* beta_out);
+/* coef_ridge(y, x, lambda): R/utils.R:49-57. */
+int scrc_coef_ridge(const double* y, const double* x, int64_t n, int64_t p, int64_t m, double lambda,
+                    double* beta_out);
+/* crossprod(x, y) = x'y on the FP64 tensor pipe (compute_xtx, src/optim.cpp:17-27, when y == x). */
+int scrc_crossprod(const double* x, const double* y, int64_t n, int64_t px, int64_t py, double* out);
+
+/* Measurement hook: times `reps` launches of the TN GEMM kernel C = A'B (A: k x m, B: k x n,
+ * device-resident pseudo-random data) with CUDA events on the launching stream and returns
+ * the average milliseconds per launch.  symmetric != 0 uses the SYRK-style mirrored epilogue. */
+int scrc_bench_gemm(int64_t k, int64_t m, int64_t n, int symmetric, int reps, double* ms_per_launch);
+
+/* ------------------------------------------------------------------ session API */
+
+typedef struct scrc_ctx scrc_ctx;
+
+/* Solver knobs surfaced by scregclust() (R/scregclust.R:193-196) and the ADMM
+ * internals that stay at coop_lasso's defaults (src/optim.cpp:67-69). */
+typedef struct scrc_options {
+    int max_optim_iter;      /* 10000 */
+    double tol_coop_rel;     /* 1e-8  */
+    double tol_coop_abs;     /* 1e-12 */
+    double tol_nnls;         /* 1e-4  */
+    double rho0;             /* 0.2   */
+    double alpha0;           /* 1.5   */
+    int n_update;            /* 2     */
+    double eps_corr;         /* 0.2   */
+} scrc_options;
+void scrc_default_options(scrc_options* o);
+
+/* Uploads the four scaled data splits (R/scregclust.R:998-1009: z1_reg_scaled n1 x P,
+ * z2_reg_scaled n2 x P, z1_target_centered n1 x T, z2_target_centered n2 x T) and
+ * z1_target_sds (T) once, then builds on the device: the Gram matrices X'X, X'Y
+ * (optim.cpp:17-27,99,414,421), their eigenbasis, the OLS / ridge initial fit,
+ * res_sds and beta_adapt_sq (R/scregclust.R:1049-1113). */
+int scrc_ctx_create(scrc_ctx** out, int device, const double* z1_reg, const double* z2_reg,
+                    const double* z1_target, const double* z2_target, const double* z1_target_sds,
+                    int64_t n1, int64_t n2, int64_t P, int64_t T, int K);
+void scrc_ctx_destroy(scrc_ctx* ctx);
+
+/* res_sds (T), init_df (1), beta_init (P x T) -- any pointer may be NULL. */
+int scrc_ctx_get_init(scrc_ctx* ctx, double* res_sds, double* init_df, double* beta_init);
+/* cross_corr1 = fast_cor(z1_target_centered, z1_reg_scaled), T x P (R/scregclust.R:1116). */
+int scrc_ctx_cross_corr(scrc_ctx* ctx, double* out);
+/* G_rr (P x P) and G_rt (P x T), any may be NULL. */
+int scrc_ctx_get_gram(scrc_ctx* ctx, double* g_rr, double* g_rt);
+
+/* Outputs of one batched cycle.  Every pointer may be NULL.  Layouts per fit f:
+ * [f][k][p] / [f][k][t] are exactly R's P x K / T x K column-major matrices. */
+typedef struct scrc_cycle_out {
+    int* k_new;                /* F x T   first argmax of the votes, 1-based (allocation.cpp:88-94) */
+    int* votes;                /* F x T x K ([f][t][k]) */
+    unsigned char* models;     /* F x K x P  selected regulators (R/scregclust.R:1384) */
+    double* weights;           /* F x K x P  (R/scregclust.R:1385) */
+    double* signs;             /* F x K x P  NaN where unselected (R/scregclust.R:1386) */
+    double* r2_test;           /* F x K x T  (R/scregclust.R:1629-1631) */
+    double* resid_var;         /* F x K x T  (R/scregclust.R:1636-1638) */
+    double* best_r2;           /* F x T      (R/scregclust.R:1632) */
+    int* best_r2_idx;          /* F x T      1-based which.max (R/scregclust.R:1646) */
+    int* admm_iterations;      /* F x K      0 = empty module (R/scregclust.R:1345) */
+    int* nnls_iterations;      /* F x K x T  0 = module without regulators */
+    int* n_selected;           /* F x K      regulators per module */
+    long long* admm_sweeps;    /* 1          batched ADMM sweeps executed */
+} scrc_cycle_out;
+
+/* One cycle (Step 1, Step 2a and -- unless `skip_allocation` -- Step 2b of
+ * R/scregclust.R:1303-1739) for F independent fits at once.  Fit f uses penalty
+ * lambda[f] and the module assignment k_in[f*T .. f*T+T) (1-based, -1 noise).
+ * Fits are typically the penalization grid (R/scregclust.R:1223) but any mix of
+ * (lambda, configuration) pairs is allowed, e.g. the final configurations of a
+ * limit cycle (R/scregclust.R:1307-1311). */
+int scrc_fit_cycle(scrc_ctx* ctx, int F, const double* lambda, const int* k_in, const scrc_options* opt,
+                   int skip_allocation, scrc_cycle_out* out);
+
+/* NNLS coefficients of module k (0-based) of fit f from the last scrc_fit_cycle call:
+ * n_selected x T (R/scregclust.R:1588); sel_out receives the 0-based regulator indices. */
+int scrc_ctx_get_coeffs(scrc_ctx* ctx, int f, int k, double* coeffs_out, int* sel_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCREGCLUST_B200_H */

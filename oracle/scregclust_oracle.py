@@ -563,6 +563,19 @@ class FitResult:
     importance: list = field(default_factory=list)
 
 
+def _recycle(v, shape):
+    """R recycling of a length-T vector over an s x T matrix (column-major flat index).
+
+    ``coef_nnls(...)$beta * signs_cl * z1_target_sds_tmp`` (R/scregclust.R:1580-1588)
+    multiplies element (a, t) by ``sds[(a + t*s) mod T]`` -- NOT ``sds[t]`` -- because R
+    recycles the vector down the columns of the s x T matrix.  Observable in every
+    output downstream of Step 2a, hence reproduced here and on the GPU.
+    """
+    s_, t_ = shape
+    flat = np.arange(s_)[:, None] + np.arange(t_)[None, :] * s_
+    return np.asarray(v)[flat % len(v)]
+
+
 def _step1(pre, z1r_x, G_scaled, xty_scaled_all, k, lam, n_modules, tol_rel, tol_abs,
            max_iter, admm_it):
     """Step 1 for one configuration (R/scregclust.R:1313-1388)."""
@@ -670,7 +683,7 @@ def scregclust_fit(z1_reg_scaled, z2_reg_scaled, z1_target_centered, z2_target_c
                     xty_j = G_rt_nnls[reg_cl, :] * sg[:, None]
                     b_nn, its = coef_nnls(eps=tol_nnls, max_iter=max_optim_iter, xtx=xtx_j, xty=xty_j)
                     nn_it[j] = its
-                    beta_hat = b_nn * sg[:, None] * z1_target_sds[None, :]
+                    beta_hat = b_nn * sg[:, None] * _recycle(z1_target_sds, b_nn.shape)
                     betas[j] = beta_hat
                     r_train = z1t - z1r[:, reg_cl] @ beta_hat
                     r_test = z2t - z2r[:, reg_cl] @ beta_hat
@@ -772,7 +785,7 @@ def _importance(fr, z1r, z2r, z1t, z2t, z1_target_sds, G_rr, G_rt_nnls, n_module
                     xtx_j = G_rr[np.ix_(reg_mod, reg_mod)] * np.outer(sg, sg)
                     xty_j = G_rt_nnls[np.ix_(reg_mod, target_cl)] * sg[:, None]
                     b, _ = coef_nnls(eps=tol_nnls, max_iter=max_iter, xtx=xtx_j, xty=xty_j)
-                    bh = b * sg[:, None] * z1_target_sds[target_cl][None, :]
+                    bh = b * sg[:, None] * _recycle(z1_target_sds[target_cl], b.shape)
                     rt = z2t[:, target_cl] - z2r[:, reg_mod] @ bh
                     ssq[:, r] = np.sum(rt * rt, axis=0)
                 zc = z2t[:, target_cl] - z2t[:, target_cl].mean(axis=0)

@@ -1,0 +1,111 @@
+"""ctypes binding of libscregclust_b200.so (include/scregclust_b200.h).
+
+This is the Python stand-in for the thin Rcpp bridge: it passes
+the same column-major FP64 buffers and 1-based module ids R would pass.  There
+is no fallback: if the shared library is missing or no CUDA device is usable,
+every compute entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libscregclust_b200.so")
+
+c_double_p = C.POINTER(C.c_double)
+c_int_p = C.POINTER(C.c_int)
+c_ubyte_p = C.POINTER(C.c_ubyte)
+
+
+class ScrcError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"[scrc {code}] {msg}")
+        self.code = code
+        self.message = msg
+
+
+class Options(C.Structure):
+    _fields_ = [("max_optim_iter", C.c_int), ("tol_coop_rel", C.c_double), ("tol_coop_abs", C.c_double),
+                ("tol_nnls", C.c_double), ("rho0", C.c_double), ("alpha0", C.c_double),
+                ("n_update", C.c_int), ("eps_corr", C.c_double)]
+
+
+class CycleOut(C.Structure):
+    _fields_ = [("k_new", c_int_p), ("votes", c_int_p), ("models", c_ubyte_p), ("weights", c_double_p),
+                ("signs", c_double_p), ("r2_test", c_double_p), ("resid_var", c_double_p),
+                ("best_r2", c_double_p), ("best_r2_idx", c_int_p), ("admm_iterations", c_int_p),
+                ("nnls_iterations", c_int_p), ("n_selected", c_int_p), ("admm_sweeps", C.POINTER(C.c_longlong))]
+
+
+# name -> (restype, argtypes); also the list of symbols the header declares
+SIGNATURES = {
+    "scrc_version": (C.c_int, []),
+    "scrc_last_error": (C.c_char_p, []),
+    "scrc_launch_count": (C.c_ulonglong, []),
+    "scrc_set_device": (C.c_int, [C.c_int]),
+    "scrc_default_options": (None, [C.POINTER(Options)]),
+    "scrc_coop_lasso": (C.c_int, [c_double_p, C.c_int64, C.c_int64, c_double_p, C.c_int64, C.c_int64, C.c_double,
+                                  c_double_p, c_double_p, C.c_int64, C.c_int64, C.c_double, C.c_double, C.c_int,
+                                  C.c_double, C.c_int, C.c_double, C.c_double, c_double_p, c_int_p]),
+    "scrc_coef_nnls": (C.c_int, [c_double_p, C.c_int64, C.c_int64, c_double_p, C.c_int64, C.c_int64, C.c_double,
+                                 C.c_int, c_double_p, c_int_p]),
+    "scrc_allocate_into_modules": (C.c_int, [c_double_p, C.c_int, C.c_int64, C.c_int64, c_double_p, c_int_p, c_int_p,
+                                             c_int_p, c_int_p, C.c_double, C.c_double, c_int_p, c_int_p]),
+    "scrc_alloc_array": (C.c_int, [c_double_p, C.c_int64, C.c_int64, C.c_int64, c_double_p]),
+    "scrc_reset_array": (C.c_int, [c_double_p, C.c_int64, C.c_int64, C.c_int64, c_double_p, C.c_int64, C.c_int64]),
+    "scrc_fast_cor": (C.c_int, [c_double_p, c_double_p, C.c_int64, C.c_int64, C.c_int64, c_double_p]),
+    "scrc_coef_ols": (C.c_int, [c_double_p, c_double_p, C.c_int64, C.c_int64, C.c_int64, c_double_p]),
+    "scrc_coef_ridge": (C.c_int, [c_double_p, c_double_p, C.c_int64, C.c_int64, C.c_int64, C.c_double, c_double_p]),
+    "scrc_crossprod": (C.c_int, [c_double_p, c_double_p, C.c_int64, C.c_int64, C.c_int64, c_double_p]),
+    "scrc_bench_gemm": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int, c_double_p]),
+    "scrc_ctx_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, c_double_p, c_double_p, c_double_p, c_double_p,
+                                  c_double_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int]),
+    "scrc_ctx_destroy": (None, [C.c_void_p]),
+    "scrc_ctx_get_init": (C.c_int, [C.c_void_p, c_double_p, c_double_p, c_double_p]),
+    "scrc_ctx_cross_corr": (C.c_int, [C.c_void_p, c_double_p]),
+    "scrc_ctx_get_gram": (C.c_int, [C.c_void_p, c_double_p, c_double_p]),
+    "scrc_fit_cycle": (C.c_int, [C.c_void_p, C.c_int, c_double_p, c_int_p, C.POINTER(Options), C.c_int,
+                                 C.POINTER(CycleOut)]),
+    "scrc_ctx_get_coeffs": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_double_p, c_int_p]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the CUDA library; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ScrcError(-1000, f"{LIB_PATH} is missing: build it with `make -C scregclust_b200/csrc` "
+                               "(python -c 'import __graft_entry__ as g; g.build()'). There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(code):
+    if code != 0:
+        raise ScrcError(code, load().scrc_last_error().decode("utf-8", "replace"))
+
+
+def f64(a, order="F"):
+    """Column-major float64 view/copy, the layout R hands to .Call."""
+    return np.require(np.asarray(a, dtype=np.float64), requirements=["F_CONTIGUOUS", "ALIGNED"]) if order == "F" \
+        else np.ascontiguousarray(a, dtype=np.float64)
+
+
+def dptr(a):
+    return a.ctypes.data_as(c_double_p) if a is not None else None
+
+
+def iptr(a):
+    return a.ctypes.data_as(c_int_p) if a is not None else None

@@ -1,0 +1,351 @@
+// Batched cooperative-lasso ADMM kernels.  Operation order per problem follows
+// src/optim.cpp:134-308 step by step; only the linear
+// solve is restructured (eigenbasis GEMMs, admm.cuh).
+#include "admm.cuh"
+
+#include <algorithm>
+
+namespace scrc {
+
+struct AdmmDev {
+    int P, C, nprob, nslab;
+    int64_t ld, ldw;
+    const int* col_prob;
+    const int* c0;
+    const int* c1;
+    const double* lambda;
+    double* rho;
+    double* alpha;
+    int* active;
+    int* iters;
+    int* n_active;
+    const double* w;
+    const double* xty;
+    double *R, *W, *beta, *zeta, *mult, *beta_old, *zeta_old, *mult_old, *mult_hat_old;
+    double* partial;
+};
+
+void AdmmBatch::resize(int P_, int C_, int nprob_) {
+    P = P_; C = C_; nprob = nprob_;
+    nslab = (int)ceil_div(P, ADMM_SLAB);
+    col_prob.ensure(C); prob_c0.ensure(nprob); prob_c1.ensure(nprob);
+    prob_lambda.ensure(nprob); prob_rho.ensure(nprob); prob_alpha.ensure(nprob);
+    prob_active.ensure(nprob); prob_iters.ensure(nprob);
+    n_active.ensure(1);
+    w.reshape(P, nprob);
+    DMat* mats[] = {&xty, &R, &W, &beta, &zeta, &mult, &beta_old, &zeta_old, &mult_old, &mult_hat_old};
+    for (DMat* m : mats) m->reshape(P, C);
+    partial.ensure((size_t)nprob * nslab * ADMM_NSUM);
+}
+
+static AdmmDev make_dev(AdmmBatch& b) {
+    AdmmDev d;
+    d.P = b.P; d.C = b.C; d.nprob = b.nprob; d.nslab = b.nslab;
+    d.ld = b.xty.ld; d.ldw = b.w.ld;
+    d.col_prob = b.col_prob.p; d.c0 = b.prob_c0.p; d.c1 = b.prob_c1.p;
+    d.lambda = b.prob_lambda.p; d.rho = b.prob_rho.p; d.alpha = b.prob_alpha.p;
+    d.active = b.prob_active.p; d.iters = b.prob_iters.p; d.n_active = b.n_active.p;
+    d.w = b.w.data(); d.xty = b.xty.data();
+    d.R = b.R.data(); d.W = b.W.data(); d.beta = b.beta.data(); d.zeta = b.zeta.data();
+    d.mult = b.mult.data(); d.beta_old = b.beta_old.data(); d.zeta_old = b.zeta_old.data();
+    d.mult_old = b.mult_old.data(); d.mult_hat_old = b.mult_hat_old.data();
+    d.partial = b.partial.p;
+    return d;
+}
+
+// ------------------------------------------------------------------ init state
+__global__ void admm_init_prob_kernel(AdmmDev d, double rho0, double alpha0) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < d.nprob) {
+        d.rho[p] = rho0; d.alpha[p] = alpha0;
+        d.active[p] = (d.c1[p] > d.c0[p]) ? 1 : 0;
+        d.iters[p] = 0;
+    }
+    if (p == 0) *d.n_active = d.nprob;
+}
+
+// ------------------------------------------------------------------ rhs = xty + rho*zeta + mult   (optim.cpp:143)
+__global__ void __launch_bounds__(256) admm_rhs_kernel(AdmmDev d) {
+    const int c = blockIdx.x;
+    const int p = d.col_prob[c];
+    if (!d.active[p]) return;
+    const double rho = d.rho[p];
+    const int64_t base = (int64_t)c * d.ld;
+    for (int i = threadIdx.x; i < d.P; i += blockDim.x) {
+        const int64_t idx = base + i;
+        d.R[idx] = (d.xty[idx] + rho * d.zeta[idx]) + d.mult[idx];
+    }
+}
+
+// ------------------------------------------------------------------ GEMM policies
+// STEP 1: W = diag(1/(lam + rho_col)) V' R        STEP 2: beta = V W
+template <int BM_, int BN_, int STAGES_, int STEP>
+struct AdmmGemmPolicy {
+    static constexpr int BM = BM_, BN = BN_, STAGES = STAGES_;
+    struct Params {
+        CUtensorMap ta, tb;
+        double* out;
+        int64_t ld;
+        int P, C;
+        const int* col_prob;
+        const int* active;
+        const double* rho;
+        const double* lam;
+    };
+    __device__ static int tiles_m(const Params& p) { return (p.P + BM - 1) / BM; }
+    __device__ static int num_tiles(const Params& p) { return tiles_m(p) * ((p.C + BN - 1) / BN); }
+    __device__ static bool tile(const Params& p, int t, TileInfo& ti) {
+        const int tm = t % tiles_m(p), tn = t / tiles_m(p);
+        const int n0 = tn * BN;
+        const int last = min(n0 + BN, p.C) - 1;
+        const int pf = p.col_prob[n0], pl = p.col_prob[last];
+        int any = 0;
+        for (int q = pf; q <= pl; ++q) any |= p.active[q];
+        if (!any) return false;
+        ti.ta = &p.ta; ti.tb = &p.tb;
+        ti.m0 = tm * BM; ti.n0 = n0; ti.k0 = 0; ti.k1 = p.P;
+        return true;
+    }
+    template <int MT, int NT>
+    __device__ static void epilogue(const Params& p, const TileInfo& ti, double (&acc)[MT][NT][2],
+                                    int warp_m, int warp_n, int lane) {
+        for_each_acc<MT, NT>(acc, warp_m, warp_n, lane, [&](int rr, int cc, double v0, double v1) {
+            const int row = ti.m0 + rr;
+            if (row >= p.P) return;
+            const double lam = (STEP == 1) ? p.lam[row] : 0.0;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int col = ti.n0 + cc + e;
+                if (col >= p.C) continue;
+                const int q = p.col_prob[col];
+                if (!p.active[q]) continue;
+                double v = e ? v1 : v0;
+                if (STEP == 1) v = v / (lam + p.rho[q]);
+                p.out[row + (int64_t)col * p.ld] = v;
+            }
+        });
+    }
+};
+
+template <int BM, int BN, int STAGES, int STEP>
+static void launch_admm_gemm(const AdmmDev& d, const DMat& A, const double* Bm, double* out,
+                             int num_sms, const double* lam, cudaStream_t stream) {
+    using Pol = AdmmGemmPolicy<BM, BN, STAGES, STEP>;
+    typename Pol::Params p;
+    p.ta = make_tmap_f64(A.data(), d.P, d.P, A.ld, BM);
+    p.tb = make_tmap_f64(Bm, d.P, d.C, d.ld, BN);
+    p.out = out; p.ld = d.ld; p.P = d.P; p.C = d.C;
+    p.col_prob = d.col_prob; p.active = d.active; p.rho = d.rho; p.lam = lam;
+    constexpr int smem = GemmSmem<BM, BN, STAGES>::TOTAL;
+    static bool configured = false;
+    if (!configured) {
+        SCRC_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<Pol>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    const int64_t tiles = ceil_div(d.P, BM) * ceil_div(d.C, BN);
+    const int grid = (int)std::min<int64_t>(tiles, num_sms);
+    gemm_tn_kernel<Pol><<<grid, GEMM_THREADS, smem, stream>>>(p);
+    SCRC_CUDA(cudaGetLastError());
+    SCRC_LAUNCHED();
+}
+
+// ------------------------------------------------------------------ relax / shrink / dual update / reductions
+// One CTA per (32-row slab, problem).  Lane = regulator row, warps interleave the
+// problem's columns.  optim.cpp:146-176 and the sums needed by :192-254.
+template <bool UPDATE_ITER>
+__global__ void __launch_bounds__(ADMM_UPD_WARPS * 32) admm_update_kernel(AdmmDev d) {
+    const int p = blockIdx.y;
+    if (!d.active[p]) return;
+    const int slab = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int row = slab * ADMM_SLAB + lane;
+    const bool rv = row < d.P;
+    const int c0 = d.c0[p], c1 = d.c1[p];
+    const double rho = d.rho[p], alpha = d.alpha[p], lam = d.lambda[p];
+
+    __shared__ double s_norm[ADMM_UPD_WARPS][32][2];
+    __shared__ double s_sum[ADMM_UPD_WARPS][ADMM_NSUM];
+
+    double np2 = 0.0, nn2 = 0.0;
+    if (rv) {
+        for (int c = c0 + warp; c < c1; c += ADMM_UPD_WARPS) {
+            const int64_t idx = row + (int64_t)c * d.ld;
+            const double b = d.beta[idx], z = d.zeta[idx], m = d.mult[idx];
+            const double br = alpha * b + (1.0 - alpha) * z;
+            const double zn = br - m / rho;
+            const double pos = fmax(zn, 0.0), neg = fmin(zn, 0.0);
+            np2 += pos * pos;
+            nn2 += neg * neg;
+        }
+    }
+    s_norm[warp][lane][0] = np2;
+    s_norm[warp][lane][1] = nn2;
+    __syncthreads();
+    double tp = 0.0, tn = 0.0;
+#pragma unroll
+    for (int w = 0; w < ADMM_UPD_WARPS; ++w) { tp += s_norm[w][lane][0]; tn += s_norm[w][lane][1]; }
+    const double wi = rv ? d.w[row + (int64_t)p * d.ldw] : 0.0;
+    // optim.cpp:151-158 (a zero norm gives 1 - inf -> 0)
+    const double sp = fmax(1.0 - lam * wi / (rho * sqrt(tp)), 0.0);
+    const double sn = fmax(1.0 - lam * wi / (rho * sqrt(tn)), 0.0);
+
+    double s[ADMM_NSUM];
+#pragma unroll
+    for (int k = 0; k < ADMM_NSUM; ++k) s[k] = 0.0;
+    if (rv) {
+        for (int c = c0 + warp; c < c1; c += ADMM_UPD_WARPS) {
+            const int64_t idx = row + (int64_t)c * d.ld;
+            const double b = d.beta[idx], z = d.zeta[idx], m = d.mult[idx];
+            const double br = alpha * b + (1.0 - alpha) * z;
+            double zn = br - m / rho;
+            zn = (zn >= 0.0) ? zn * sp : zn * sn;                       // optim.cpp:160-168
+            const double mn = m + rho * (-br + zn);                     // optim.cpp:171
+            const double pr = -b + zn;                                  // optim.cpp:175
+            const double du = rho * (z - zn);                           // optim.cpp:176
+            s[0] += pr * pr; s[1] += du * du; s[2] += b * b; s[3] += zn * zn; s[4] += mn * mn;
+            if (UPDATE_ITER) {
+                const double mh = mn + rho * (-b + z);                  // optim.cpp:203
+                const double dmh = mh - d.mult_hat_old[idx];
+                const double dh = b - d.beta_old[idx];
+                const double dm = mn - d.mult_old[idx];
+                const double dg = d.zeta_old[idx] - z;
+                s[5] += dmh * dmh; s[6] += dh * dh; s[7] += dh * dmh;
+                s[8] += dm * dm; s[9] += dg * dg; s[10] += dg * dm;
+                d.beta_old[idx] = b; d.zeta_old[idx] = zn;              // optim.cpp:282-285
+                d.mult_old[idx] = mn; d.mult_hat_old[idx] = mh;
+            }
+            d.zeta[idx] = zn;                                           // optim.cpp:292
+            d.mult[idx] = mn;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < ADMM_NSUM; ++k) {
+        const double v = warp_sum(s[k]);
+        if (lane == 0) s_sum[warp][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < ADMM_NSUM) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < ADMM_UPD_WARPS; ++w) v += s_sum[w][threadIdx.x];
+        d.partial[((int64_t)p * d.nslab + slab) * ADMM_NSUM + threadIdx.x] = v;
+    }
+}
+
+// ------------------------------------------------------------------ stop test + adaptive rho / alpha
+// optim.cpp:192-196 (stop), :199-289 (spectral step-size / relaxation update), :295-305.
+__global__ void __launch_bounds__(256) admm_finalize_kernel(AdmmDev d, AdmmOpts o, int it, int is_update) {
+    __shared__ int s_cnt;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    for (int p = threadIdx.x; p < d.nprob; p += blockDim.x) {
+        if (!d.active[p]) continue;
+        double s[ADMM_NSUM];
+#pragma unroll
+        for (int k = 0; k < ADMM_NSUM; ++k) s[k] = 0.0;
+        for (int sl = 0; sl < d.nslab; ++sl) {
+            const double* q = d.partial + ((int64_t)p * d.nslab + sl) * ADMM_NSUM;
+#pragma unroll
+            for (int k = 0; k < ADMM_NSUM; ++k) s[k] += q[k];
+        }
+        const double n_primal = sqrt(s[0]), n_dual = sqrt(s[1]);
+        const double n_beta = sqrt(s[2]), n_zeta = sqrt(s[3]), n_mult = sqrt(s[4]);
+        const bool conv = (n_primal <= fmax(o.eps_rel * fmax(n_beta, n_zeta), o.eps_abs)) &&
+                          (n_dual <= fmax(o.eps_rel * n_mult, o.eps_abs));
+        if (conv) {
+            d.active[p] = 0;
+            d.iters[p] = it;
+            continue;
+        }
+        if (is_update) {
+            double rho = d.rho[p], alpha;
+            const double n_dmh = sqrt(s[5]), n_dh = sqrt(s[6]), n_dm = sqrt(s[8]), n_dg = sqrt(s[9]);
+            double a = 0.0, a_corr = 0.0;
+            if (n_dmh > 0.0 && n_dh > 0.0) {
+                const double hm = s[7];
+                const double a_sd = s[5] / hm;
+                const double a_mg = hm / s[6];
+                a = (2.0 * a_mg > a_sd) ? a_mg : a_sd - a_mg / 2.0;
+                a_corr = hm / (n_dh * n_dmh);
+            }
+            double b = 0.0, b_corr = 0.0;
+            if (n_dm > 0.0 && n_dg > 0.0) {
+                const double gm = s[10];
+                const double b_sd = s[8] / gm;
+                const double b_mg = gm / s[9];
+                b = (2.0 * b_mg > b_sd) ? b_mg : b_sd - b_mg / 2.0;
+                b_corr = gm / (n_dg * n_dm);
+            }
+            const bool ga = a_corr > o.eps_corr, gb = b_corr > o.eps_corr;
+            if (ga && gb) {
+                rho = sqrt(a * b);
+                alpha = 1.0 + 2.0 / (sqrt(a * b) * (1.0 / a + 1.0 / b));
+            } else if (ga && !gb) {
+                rho = a; alpha = 1.9;
+            } else if (!ga && gb) {
+                rho = b; alpha = 1.1;
+            } else {
+                alpha = 1.5;
+            }
+            d.rho[p] = rho;
+            d.alpha[p] = alpha;
+        }
+        if (it + 1 > o.max_iter) {
+            d.active[p] = 0;
+            d.iters[p] = it + 1;
+            continue;
+        }
+        atomicAdd(&s_cnt, 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *d.n_active = s_cnt;
+}
+
+// ------------------------------------------------------------------ driver
+int admm_solve(AdmmBatch& b, const EigBasis& eig, const AdmmOpts& o, bool cold, int num_sms,
+               cudaStream_t stream, int* h_scratch) {
+    if (b.nprob == 0 || b.C == 0) return 0;
+    AdmmDev d = make_dev(b);
+    if (cold) {
+        DMat* z[] = {&b.beta, &b.zeta, &b.beta_old, &b.zeta_old};
+        for (DMat* m : z) SCRC_CUDA(cudaMemsetAsync(m->data(), 0, m->bytes(), stream));
+    }
+    DMat* z2[] = {&b.mult, &b.mult_old, &b.mult_hat_old};
+    for (DMat* m : z2) SCRC_CUDA(cudaMemsetAsync(m->data(), 0, m->bytes(), stream));
+    admm_init_prob_kernel<<<(b.nprob + 127) / 128, 128, 0, stream>>>(d, o.rho0, o.alpha0);
+    SCRC_LAUNCHED();
+
+    const bool big = ceil_div(b.P, 128) * ceil_div(b.C, 128) >= num_sms;
+    const dim3 ugrid(b.nslab, b.nprob);
+    int it = 1;
+    int sweeps = 0;
+    while (true) {
+        admm_rhs_kernel<<<b.C, 256, 0, stream>>>(d);
+        SCRC_LAUNCHED();
+        if (big) {
+            launch_admm_gemm<128, 128, 6, 1>(d, eig.V, d.R, d.W, num_sms, eig.lam.p, stream);
+            launch_admm_gemm<128, 128, 6, 2>(d, eig.Vt, d.W, d.beta, num_sms, eig.lam.p, stream);
+        } else {
+            launch_admm_gemm<64, 64, 8, 1>(d, eig.V, d.R, d.W, num_sms, eig.lam.p, stream);
+            launch_admm_gemm<64, 64, 8, 2>(d, eig.Vt, d.W, d.beta, num_sms, eig.lam.p, stream);
+        }
+        const int is_update = (it % o.n_update == 0) ? 1 : 0;
+        if (is_update) admm_update_kernel<true><<<ugrid, ADMM_UPD_WARPS * 32, 0, stream>>>(d);
+        else admm_update_kernel<false><<<ugrid, ADMM_UPD_WARPS * 32, 0, stream>>>(d);
+        SCRC_LAUNCHED();
+        admm_finalize_kernel<<<1, 256, 0, stream>>>(d, o, it, is_update);
+        SCRC_LAUNCHED();
+        SCRC_CUDA(cudaGetLastError());
+        ++sweeps;
+        if ((it >= 4 && it % 2 == 0) || it >= o.max_iter) {
+            SCRC_CUDA(cudaMemcpyAsync(h_scratch, d.n_active, sizeof(int), cudaMemcpyDeviceToHost, stream));
+            SCRC_CUDA(cudaStreamSynchronize(stream));
+            if (*h_scratch == 0) break;
+        }
+        ++it;
+        if (it > o.max_iter + 1) break;  // safety net; finalize retires every problem at max_iter
+    }
+    return sweeps;
+}
+
+}  // namespace scrc

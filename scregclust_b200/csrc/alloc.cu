@@ -1,0 +1,339 @@
+#include "alloc.cuh"
+
+#include <algorithm>
+#include <cmath>
+
+namespace scrc {
+
+struct RvParams {
+    CUtensorMap ta, tb;
+    const double* Z; int64_t ldz;
+    int ncells, T, K, L;
+    const int* row_off;
+    const int* kpad;
+    const double* two_var;
+    const double* half_log;
+    double* partial;
+    int* votes;
+    int CR, tiles_n, ctiles;
+};
+
+constexpr int RV_A_BYTES = RV_BM * GEMM_BK * 8;
+constexpr int RV_B_BYTES = RV_BN * GEMM_BK * 8;
+constexpr int RV_STAGE_BYTES = RV_A_BYTES + RV_B_BYTES;
+
+__device__ __forceinline__ void consumer_bar() {   // the 8 consumer warps only
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+}
+
+template <bool VOTE>
+__global__ void __launch_bounds__(GEMM_THREADS, 1) resid_vote_kernel(const __grid_constant__ RvParams p) {
+    constexpr int MT = RV_BM / (GEMM_WARPS_M * 8);   // 4
+    constexpr int NT = RV_BN / (GEMM_WARPS_N * 8);   // 2
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + RV_STAGES * RV_STAGE_BYTES);
+    uint64_t* empty = full + RV_STAGES;
+    const int K1 = p.K + 1;
+    double* sse_s = reinterpret_cast<double*>(smem + RV_STAGES * RV_STAGE_BYTES + 2 * RV_STAGES * 8);  // [2][K1][64]
+    int* votes_s = reinterpret_cast<int*>(sse_s + 2 * K1 * RV_BN);                                     // [64][K]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < RV_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], GEMM_CONSUMER_WARPS); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const int nwork = p.L * p.CR * p.tiles_n;
+    const int ct_per = (p.ctiles + p.CR - 1) / p.CR;
+    PipeState ps;
+
+    if (warp < GEMM_PRODUCER_WARPS) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+        if (warp == 0 && lane == 0) {
+            for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
+                const int tn = w % p.tiles_n, cr = (w / p.tiles_n) % p.CR, l = w / (p.tiles_n * p.CR);
+                const int ct0 = cr * ct_per, ct1 = min(ct0 + ct_per, p.ctiles);
+                for (int ct = ct0; ct < ct1; ++ct) {
+                    for (int j = 0; j < p.K; ++j) {
+                        const int kp = p.kpad[l * p.K + j];
+                        const int ro = p.row_off[l * p.K + j];
+                        for (int kk = 0; kk < kp; kk += GEMM_BK) {
+                            mbar_wait(&empty[ps.stage], ps.phase ^ 1);
+                            uint8_t* sa = smem + ps.stage * RV_STAGE_BYTES;
+                            mbar_expect_tx(&full[ps.stage], RV_STAGE_BYTES);
+                            tma_load_2d(sa, &p.ta, ro + kk, ct * RV_BM, &full[ps.stage]);
+                            tma_load_2d(sa + RV_A_BYTES, &p.tb, ro + kk, tn * RV_BN, &full[ps.stage]);
+                            ps.advance<RV_STAGES>();
+                        }
+                    }
+                }
+            }
+        }
+        return;
+    }
+
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    const int cw = warp - GEMM_PRODUCER_WARPS;
+    const int ctid = threadIdx.x - GEMM_PRODUCER_WARPS * 32;
+    const int warp_m = cw / GEMM_WARPS_N, warp_n = cw % GEMM_WARPS_N;
+    const int a_row0 = warp_m * (MT * 8), b_col0 = warp_n * (NT * 8);
+    const int r = lane >> 2, q = lane & 3;
+
+    for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
+        const int tn = w % p.tiles_n, cr = (w / p.tiles_n) % p.CR, l = w / (p.tiles_n * p.CR);
+        const int ct0 = cr * ct_per, ct1 = min(ct0 + ct_per, p.ctiles);
+        const int t0 = tn * RV_BN;
+        // zero the per-work-item accumulators (each SSE entry is owned by exactly one thread)
+        if (r == 0) {
+            for (int j = 0; j < K1; ++j)
+#pragma unroll
+                for (int jj = 0; jj < NT; ++jj)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e)
+                        sse_s[(warp_m * K1 + j) * RV_BN + b_col0 + jj * 8 + q * 2 + e] = 0.0;
+        }
+        if (VOTE) {
+            for (int i = ctid; i < RV_BN * p.K; i += 256) votes_s[i] = 0;
+            consumer_bar();
+        }
+        for (int ct = ct0; ct < ct1; ++ct) {
+            const int c0 = ct * RV_BM;
+            double z[MT][NT][2], best[MT][NT][2];
+            int bidx[MT][NT][2];
+#pragma unroll
+            for (int i = 0; i < MT; ++i)
+#pragma unroll
+                for (int jj = 0; jj < NT; ++jj)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int row = c0 + a_row0 + i * 8 + r;
+                        const int col = t0 + b_col0 + jj * 8 + q * 2 + e;
+                        z[i][jj][e] = (row < p.ncells && col < p.T) ? p.Z[row + (int64_t)col * p.ldz] : 0.0;
+                        best[i][jj][e] = -INFINITY;
+                        bidx[i][jj][e] = 0;
+                    }
+            for (int j = 0; j <= p.K; ++j) {
+                double acc[MT][NT][2];
+#pragma unroll
+                for (int i = 0; i < MT; ++i)
+#pragma unroll
+                    for (int jj = 0; jj < NT; ++jj) acc[i][jj][0] = acc[i][jj][1] = 0.0;
+                if (j < p.K) {
+                    const int kp = p.kpad[l * p.K + j];
+                    for (int kk = 0; kk < kp; kk += GEMM_BK) {
+                        mbar_wait(&full[ps.stage], ps.phase);
+                        const double* As = reinterpret_cast<const double*>(smem + ps.stage * RV_STAGE_BYTES);
+                        const double* Bs = reinterpret_cast<const double*>(smem + ps.stage * RV_STAGE_BYTES + RV_A_BYTES);
+                        mma_kslice<MT, NT>(As, Bs, a_row0, b_col0, lane, acc);
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&empty[ps.stage]);
+                        ps.advance<RV_STAGES>();
+                    }
+                }
+                // residual, squared residual, column sums, per-cell score
+#pragma unroll
+                for (int jj = 0; jj < NT; ++jj)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int lc = b_col0 + jj * 8 + q * 2 + e;
+                        const int col = t0 + lc;
+                        double tv = 1.0, hl = 0.0;
+                        if (VOTE && j < p.K && col < p.T) {
+                            const int64_t vi = ((int64_t)l * p.K + j) * p.T + col;
+                            tv = p.two_var[vi];
+                            hl = p.half_log[vi];
+                        }
+                        double csum = 0.0;
+#pragma unroll
+                        for (int i = 0; i < MT; ++i) {
+                            const double res = z[i][jj][e] - acc[i][jj][e];   // scregclust.R:1593-1595
+                            const double sq = res * res;
+                            csum += sq;
+                            if (VOTE && j < p.K) {
+                                const double sc = (-sq) / tv - hl;            // allocation.cpp:59-62
+                                if (sc > best[i][jj][e]) { best[i][jj][e] = sc; bidx[i][jj][e] = j; }
+                            }
+                        }
+                        csum += __shfl_xor_sync(0xffffffffu, csum, 4);
+                        csum += __shfl_xor_sync(0xffffffffu, csum, 8);
+                        csum += __shfl_xor_sync(0xffffffffu, csum, 16);
+                        if (r == 0) sse_s[(warp_m * K1 + j) * RV_BN + lc] += csum;
+                    }
+            }
+            if (VOTE) {
+#pragma unroll
+                for (int i = 0; i < MT; ++i)
+#pragma unroll
+                    for (int jj = 0; jj < NT; ++jj)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int row = c0 + a_row0 + i * 8 + r;
+                            const int lc = b_col0 + jj * 8 + q * 2 + e;
+                            if (row < p.ncells && t0 + lc < p.T) atomicAdd(&votes_s[lc * p.K + bidx[i][jj][e]], 1);
+                        }
+            }
+        }
+        // flush
+        if (r == 0) {
+            for (int j = 0; j < K1; ++j)
+#pragma unroll
+                for (int jj = 0; jj < NT; ++jj)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int lc = b_col0 + jj * 8 + q * 2 + e;
+                        if (t0 + lc < p.T)
+                            p.partial[((((int64_t)l * p.CR + cr) * 2 + warp_m) * K1 + j) * p.T + t0 + lc] =
+                                sse_s[(warp_m * K1 + j) * RV_BN + lc];
+                    }
+        }
+        if (VOTE) {
+            consumer_bar();
+            for (int i = ctid; i < RV_BN * p.K; i += 256) {
+                const int lc = i / p.K, j = i % p.K;
+                const int v = votes_s[i];
+                if (v != 0 && t0 + lc < p.T) atomicAdd(&p.votes[((int64_t)l * p.T + t0 + lc) * p.K + j], v);
+            }
+            consumer_bar();
+        }
+    }
+}
+
+int resid_vote_pick_cr(int ncells, int T, int L, int num_sms) {
+    const int ctiles = (int)ceil_div(ncells, RV_BM);
+    const int64_t base = (int64_t)L * ceil_div(T, RV_BN);
+    int cr = (int)ceil_div((int64_t)num_sms * 4, base);
+    cr = std::max(1, std::min(cr, ctiles));
+    return cr;
+}
+size_t resid_vote_partial_elems(int T, int K, int L, int CR) {
+    return (size_t)L * CR * 2 * (K + 1) * T;
+}
+
+void resid_vote(const ResidVoteArgs& a, bool vote, int num_sms, cudaStream_t st) {
+    if (a.K + 1 > RV_MAX_K + 1) throw Error(-60, "resid_vote: at most 64 modules are supported");
+    RvParams p;
+    // operands are allocated with at least one 16-row block so that the maps are never empty
+    p.ta = make_tmap_f64(a.ZselT, std::max<int64_t>(a.rows_total, 16), a.ncells, a.ldzs, RV_BM);
+    p.tb = make_tmap_f64(a.beta, std::max<int64_t>(a.rows_total, 16), a.T, a.ldb, RV_BN);
+    p.Z = a.Z; p.ldz = a.ldz; p.ncells = a.ncells; p.T = a.T; p.K = a.K; p.L = a.L;
+    p.row_off = a.row_off; p.kpad = a.kpad; p.two_var = a.two_var; p.half_log = a.half_log;
+    p.partial = a.partial; p.votes = a.votes; p.CR = a.CR;
+    p.tiles_n = (int)ceil_div(a.T, RV_BN); p.ctiles = (int)ceil_div(a.ncells, RV_BM);
+    const int smem = RV_STAGES * RV_STAGE_BYTES + 2 * RV_STAGES * 8 + 2 * (a.K + 1) * RV_BN * 8 +
+                     RV_BN * a.K * 4 + 1024;
+    static int conf[2] = {0, 0};
+    if (smem > conf[vote ? 1 : 0]) {
+        if (vote) SCRC_CUDA(cudaFuncSetAttribute(resid_vote_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        else SCRC_CUDA(cudaFuncSetAttribute(resid_vote_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        conf[vote ? 1 : 0] = smem;
+    }
+    const int64_t nwork = (int64_t)a.L * a.CR * p.tiles_n;
+    const int grid = (int)std::min<int64_t>(nwork, num_sms);
+    if (vote) resid_vote_kernel<true><<<grid, GEMM_THREADS, smem, st>>>(p);
+    else resid_vote_kernel<false><<<grid, GEMM_THREADS, smem, st>>>(p);
+    SCRC_CUDA(cudaGetLastError());
+    SCRC_LAUNCHED();
+}
+
+// ---------------------------------------------------------------- reductions / finishing kernels
+__global__ void reduce_sse_kernel(const double* __restrict__ partial, int T, int K1, int L, int CR, double* sse) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // over L*K1*T
+    if (i >= (int64_t)L * K1 * T) return;
+    const int t = (int)(i % T);
+    const int j = (int)((i / T) % K1);
+    const int l = (int)(i / ((int64_t)T * K1));
+    double s = 0.0;
+    for (int c = 0; c < CR * 2; ++c) s += partial[(((int64_t)l * CR * 2 + c) * K1 + j) * T + t];
+    sse[i] = s;
+}
+void reduce_sse(const double* partial, int T, int K, int L, int CR, double* sse, cudaStream_t st) {
+    const int64_t n = (int64_t)L * (K + 1) * T;
+    reduce_sse_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(partial, T, K + 1, L, CR, sse);
+    SCRC_CUDA(cudaGetLastError());
+    SCRC_LAUNCHED();
+}
+
+__global__ void resid_var_kernel(const double* __restrict__ sse_train, const int* __restrict__ nsel, int n1, int T,
+                                 int K, int L, double* var, double* two_var, double* half_log) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // over L*K*T
+    if (i >= (int64_t)L * K * T) return;
+    const int t = (int)(i % T);
+    const int j = (int)((i / T) % K);
+    const int l = (int)(i / ((int64_t)T * K));
+    const double sse = sse_train[((int64_t)l * (K + 1) + j) * T + t];
+    const double v = sse / (double)(n1 - nsel[l * K + j]);             // scregclust.R:1636-1638
+    var[i] = v;
+    two_var[i] = 2.0 * v;                                               // allocation.cpp:60
+    half_log[i] = 0.5 * log((2.0 * M_PI) * v);                          // allocation.cpp:62
+}
+void make_resid_var(const double* sse_train, const int* nsel, int n1, int T, int K, int L, double* var,
+                    double* two_var, double* half_log, cudaStream_t st) {
+    const int64_t n = (int64_t)L * K * T;
+    resid_var_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(sse_train, nsel, n1, T, K, L, var, two_var, half_log);
+    SCRC_CUDA(cudaGetLastError());
+    SCRC_LAUNCHED();
+}
+
+__global__ void finish_alloc_kernel(const double* __restrict__ sse_test, const int* __restrict__ votes, int T, int K,
+                                    int L, double* r2, double* best_r2, int* best_idx, int* k_new) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // over L*T
+    if (i >= (int64_t)L * T) return;
+    const int t = (int)(i % T), l = (int)(i / T);
+    const double ss0 = sse_test[((int64_t)l * (K + 1) + K) * T + t];
+    double br = -INFINITY; int bi = 0;
+    int bv = -1, bk = 0;
+    for (int j = 0; j < K; ++j) {
+        const double v = 1.0 - sse_test[((int64_t)l * (K + 1) + j) * T + t] / ss0;   // scregclust.R:1629-1631
+        r2[((int64_t)l * K + j) * T + t] = v;
+        if (v > br) { br = v; bi = j; }
+        if (votes) {
+            const int vt = votes[((int64_t)l * T + t) * K + j];
+            if (vt > bv) { bv = vt; bk = j; }                                         // allocation.cpp:88-89
+        }
+    }
+    best_r2[i] = br;
+    best_idx[i] = bi + 1;
+    if (votes) k_new[i] = bk + 1;
+}
+void finish_alloc(const double* sse_test, const int* votes, int T, int K, int L, double* r2, double* best_r2,
+                  int* best_idx, int* k_new, cudaStream_t st) {
+    const int64_t n = (int64_t)L * T;
+    finish_alloc_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(sse_test, votes, T, K, L, r2, best_r2, best_idx, k_new);
+    SCRC_CUDA(cudaGetLastError());
+    SCRC_LAUNCHED();
+}
+
+// ---------------------------------------------------------------- gather + transpose of selected regulators
+__global__ void gather_transpose_kernel(const double* __restrict__ Zr, int64_t ldz, int ncells,
+                                        const int* __restrict__ row_src, int64_t rows, double* __restrict__ out,
+                                        int64_t ldo) {
+    __shared__ double tile[32][33];
+    const int64_t r0 = (int64_t)blockIdx.x * 32;   // stacked rows
+    const int64_t c0 = (int64_t)blockIdx.y * 32;   // cells
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int64_t rr = r0 + j, c = c0 + threadIdx.x;
+        double v = 0.0;
+        if (rr < rows && c < ncells) {
+            const int src = row_src[rr];
+            if (src >= 0) v = Zr[c + (int64_t)src * ldz];
+        }
+        tile[j][threadIdx.x] = v;
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int64_t rr = r0 + threadIdx.x, c = c0 + j;
+        if (rr < rows && c < ncells) out[rr + c * ldo] = tile[threadIdx.x][j];
+    }
+}
+void gather_transpose(const double* Zr, int64_t ldz, int ncells, const int* row_src, int64_t rows, double* out,
+                      int64_t ldo, cudaStream_t st) {
+    if (rows == 0 || ncells == 0) return;
+    dim3 grid((unsigned)ceil_div(rows, 32), (unsigned)ceil_div(ncells, 32));
+    gather_transpose_kernel<<<grid, dim3(32, 8), 0, st>>>(Zr, ldz, ncells, row_src, rows, out, ldo);
+    SCRC_CUDA(cudaGetLastError());
+    SCRC_LAUNCHED();
+}
+
+}  // namespace scrc

@@ -1,0 +1,51 @@
+// Fused predict -> residual -> SSE -> Gaussian log-lik -> per-cell argmax -> vote kernel
+// (replaces R/scregclust.R:1590-1602,1628-1638 + src/utils.cpp:12-63 +
+// src/allocation.cpp:59-94 without ever materialising the K x n2 x T array).
+#pragma once
+#include "dmat.cuh"
+#include "gemm_tn.cuh"
+
+namespace scrc {
+
+constexpr int RV_BM = 64;   // cells per tile
+constexpr int RV_BN = 64;   // targets per tile
+constexpr int RV_STAGES = 8;
+constexpr int RV_MAX_K = 64;  // modules (+1 pseudo module) kept in shared memory
+
+struct ResidVoteArgs {
+    // stacked, 16-row padded selections for all (penalty, module) pairs
+    const double* ZselT; int64_t ldzs;   // rows_total x ncells  (k contiguous)
+    const double* beta; int64_t ldb;     // rows_total x T
+    int64_t rows_total;
+    const double* Z; int64_t ldz;        // ncells x T targets (centred)
+    int ncells, T, K, L;
+    const int* row_off;                  // device [L*K]
+    const int* kpad;                     // device [L*K]  (0 = module without a model)
+    const double* two_var;               // device [L][K][T]   (vote mode)
+    const double* half_log;              // device [L][K][T]   (vote mode)
+    double* partial;                     // device [L][CR][2][K+1][T]
+    int* votes;                          // device [L][T][K]   (vote mode, pre-zeroed)
+    int CR;                              // cell ranges per (penalty, target tile)
+};
+int resid_vote_pick_cr(int ncells, int T, int L, int num_sms);
+size_t resid_vote_partial_elems(int T, int K, int L, int CR);
+void resid_vote(const ResidVoteArgs& a, bool vote, int num_sms, cudaStream_t s);
+
+// sse[l][j][t] (j = 0..K, the last one is the "no model" pseudo module) = fixed-order sum of partials
+void reduce_sse(const double* partial, int T, int K, int L, int CR, double* sse, cudaStream_t s);
+
+// resid_var = SSE_train / (n1 - s_j); two_var = 2 var; half_log = 0.5 log(2 pi var)
+// (R/scregclust.R:1635-1638, allocation.cpp:59-62).  nsel: device [L*K].
+void make_resid_var(const double* sse_train, const int* nsel, int n1, int T, int K, int L, double* var,
+                    double* two_var, double* half_log, cudaStream_t s);
+
+// r2[l][t][j] = 1 - SSE_test / SS0 ; best_r2 = row max ; best_idx = first argmax (1-based)
+// (R/scregclust.R:1628-1632, 1646).  k_new = first argmax of votes (1-based, allocation.cpp:88-94).
+void finish_alloc(const double* sse_test, const int* votes, int T, int K, int L, double* r2, double* best_r2,
+                  int* best_idx, int* k_new, cudaStream_t s);
+
+// out[r, c] = row_src[r] >= 0 ? Zr[c, row_src[r]] : 0   (out: rows x ncells, k contiguous)
+void gather_transpose(const double* Zr, int64_t ldz, int ncells, const int* row_src, int64_t rows,
+                      double* out, int64_t ldo, cudaStream_t s);
+
+}  // namespace scrc

@@ -1,0 +1,266 @@
+// extern "C" boundary of libscregclust_b200 (see include/scregclust_b200.h).
+#include <memory>
+#include <mutex>
+
+#include "session.cuh"
+
+using namespace scrc;
+
+struct scrc_ctx {
+    Ctx impl;
+};
+
+namespace {
+thread_local std::string g_err;
+std::mutex g_dev_mutex;
+std::unique_ptr<Device> g_dev;     // device used by the drop-in entry points
+int g_dev_id = 0;
+
+Device& dropin_device() {
+    std::lock_guard<std::mutex> lk(g_dev_mutex);
+    if (!g_dev || g_dev->id != g_dev_id) {
+        if (g_dev) g_dev->destroy();
+        g_dev.reset(new Device());
+        g_dev->init(g_dev_id);
+    }
+    SCRC_CUDA(cudaSetDevice(g_dev->id));
+    return *g_dev;
+}
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+template <class F>
+int guarded(F&& f) {
+    try {
+        f();
+        return SCRC_OK;
+    } catch (const Error& e) {
+        return fail(e.code, e.what());
+    } catch (const std::bad_alloc&) {
+        return fail(SCRC_ERR_INTERNAL, "host allocation failed");
+    } catch (const std::exception& e) {
+        return fail(SCRC_ERR_INTERNAL, e.what());
+    } catch (...) {
+        return fail(SCRC_ERR_INTERNAL, "unknown failure");
+    }
+}
+}  // namespace
+
+extern "C" {
+
+int scrc_version(void) { return 100; }
+const char* scrc_last_error(void) { return g_err.c_str(); }
+unsigned long long scrc_launch_count(void) { return scrc::g_launch_count; }
+int scrc_set_device(int device) {
+    if (device < 0) return fail(SCRC_ERR_ARG, "scrc_set_device: negative device index");
+    g_dev_id = device;
+    return SCRC_OK;
+}
+
+void scrc_default_options(scrc_options* o) {
+    if (!o) return;
+    o->max_optim_iter = 10000; o->tol_coop_rel = 1e-8; o->tol_coop_abs = 1e-12; o->tol_nnls = 1e-4;
+    o->rho0 = 0.2; o->alpha0 = 1.5; o->n_update = 2; o->eps_corr = 0.2;
+}
+
+int scrc_coop_lasso(const double* y, int64_t n, int64_t m, const double* x, int64_t n_x, int64_t p, double lambda,
+                    const double* weights, const double* beta0, int64_t beta0_rows, int64_t beta0_cols, double rho0,
+                    double alpha0, int n_update, double eps_corr, int max_iter, double eps_rel, double eps_abs,
+                    double* beta_out, int* iterations_out) {
+    // argument checks in the reference's order (optim.cpp:76-122)
+    if (n <= 0 || m <= 0 || p <= 0 || n_x <= 0)
+        return fail(SCRC_ERR_COOP_DIMS, "COOP LASSO: Matrix dimensions of y and x need to be positive.");
+    if (n_x != n) return fail(SCRC_ERR_COOP_ROWS, "y and x need to have the same number of rows.");
+    if (beta0 && (beta0_rows != p || beta0_cols != m))
+        return fail(SCRC_ERR_COOP_BETA0, "beta_0 needs to be of size p x m");
+    if (!(rho0 > 0.0)) return fail(SCRC_ERR_COOP_RHO, "rho_0 > 0 needs to hold");
+    if (alpha0 <= 0.0 || alpha0 > 2.0) return fail(SCRC_ERR_COOP_ALPHA, "0 < alpha_0 < 2 needs to hold");
+    if (!y || !x || !weights || !beta_out || !iterations_out || n_update <= 0)
+        return fail(SCRC_ERR_ARG, "scrc_coop_lasso: null pointer or n_update <= 0");
+    return guarded([&] {
+        AdmmOpts o;
+        o.rho0 = rho0; o.alpha0 = alpha0; o.n_update = n_update; o.eps_corr = eps_corr; o.max_iter = max_iter;
+        o.eps_rel = eps_rel; o.eps_abs = eps_abs;
+        dropin_coop_lasso(dropin_device(), y, n, m, x, p, lambda, weights, beta0, o, beta_out, iterations_out);
+    });
+}
+
+int scrc_coef_nnls(const double* x, int64_t nobs, int64_t nvar, const double* y, int64_t nobs_y, int64_t m, double eps,
+                   int max_iter, double* beta_out, int* iterations_out) {
+    if (nvar <= 0 || m <= 0 || nobs <= 0 || nobs_y <= 0)
+        return fail(SCRC_ERR_NNLS_DIMS, "NNLS: Matrix dimensions of y and x need to be positive.");
+    if (nobs != nobs_y) return fail(SCRC_ERR_ARG, "scrc_coef_nnls: x and y need the same number of rows");
+    if (!x || !y || !beta_out || !iterations_out) return fail(SCRC_ERR_ARG, "scrc_coef_nnls: null pointer");
+    return guarded([&] { dropin_nnls(dropin_device(), x, nobs, nvar, y, m, eps, max_iter, beta_out, iterations_out); });
+}
+
+int scrc_allocate_into_modules(const double* sq_resid, int K, int64_t n2, int64_t T, const double* resid_var,
+                               const int* prior_off, const int* prior_idx, const int* k_in, const int* update_order,
+                               double prior_baseline, double prior_weight, int* k_out, int* votes_out) {
+    if (!sq_resid || !resid_var || !k_in || !update_order || !k_out || K <= 0 || n2 <= 0 || T <= 0)
+        return fail(SCRC_ERR_ARG, "scrc_allocate_into_modules: invalid argument");
+    return guarded([&] {
+        dropin_allocate(dropin_device(), sq_resid, K, n2, T, resid_var, prior_off, prior_idx, k_in, update_order,
+                        prior_baseline, prior_weight, k_out, votes_out);
+    });
+}
+
+int scrc_alloc_array(const double* input, int64_t n_obs, int64_t n_genes, int64_t n_cl, double* out) {
+    if (!input || !out || n_obs < 0 || n_genes < 0 || n_cl < 0) return fail(SCRC_ERR_ARG, "scrc_alloc_array: invalid argument");
+    const long double total = (long double)n_cl * (long double)n_obs * (long double)n_genes;
+    if (total > 4503599627370496.0L)   // R_XLEN_T_MAX = 2^52 (utils.cpp:19-21)
+        return fail(SCRC_ERR_ALLOC_TOO_LARGE, "alloc_array: requested allocation too large");
+    for (int64_t i = 0, ub = n_obs * n_genes; i < ub; ++i)
+        for (int64_t j = 0; j < n_cl; ++j) out[i * n_cl + j] = input[i];
+    return SCRC_OK;
+}
+
+int scrc_reset_array(double* arr, int64_t n_cl, int64_t n_obs, int64_t n_genes, const double* input, int64_t in_rows,
+                     int64_t in_cols) {
+    if (!arr || !input) return fail(SCRC_ERR_ARG, "scrc_reset_array: null pointer");
+    if (in_rows != n_obs || in_cols != n_genes) return fail(SCRC_ERR_RESET_DIMS, "reset_array: input has wrong dimensions");
+    for (int64_t i = 0, ub = n_obs * n_genes; i < ub; ++i)
+        for (int64_t j = 0; j < n_cl; ++j) arr[i * n_cl + j] = input[i];
+    return SCRC_OK;
+}
+
+int scrc_fast_cor(const double* x, const double* y, int64_t n, int64_t px, int64_t py, double* out) {
+    if (!x || !y || !out || n <= 0 || px <= 0 || py <= 0) return fail(SCRC_ERR_ARG, "scrc_fast_cor: invalid argument");
+    return guarded([&] { dropin_fast_cor(dropin_device(), x, y, n, px, py, out); });
+}
+int scrc_coef_ols(const double* y, const double* x, int64_t n, int64_t p, int64_t m, double* beta_out) {
+    if (!x || !y || !beta_out || n <= 0 || p <= 0 || m <= 0) return fail(SCRC_ERR_ARG, "scrc_coef_ols: invalid argument");
+    return guarded([&] { dropin_ols(dropin_device(), y, x, n, p, m, 0.0, false, beta_out); });
+}
+int scrc_coef_ridge(const double* y, const double* x, int64_t n, int64_t p, int64_t m, double lambda, double* beta_out) {
+    if (!x || !y || !beta_out || n <= 0 || p <= 0 || m <= 0) return fail(SCRC_ERR_ARG, "scrc_coef_ridge: invalid argument");
+    return guarded([&] { dropin_ols(dropin_device(), y, x, n, p, m, lambda, true, beta_out); });
+}
+int scrc_crossprod(const double* x, const double* y, int64_t n, int64_t px, int64_t py, double* out) {
+    if (!x || !y || !out || n <= 0 || px <= 0 || py <= 0) return fail(SCRC_ERR_ARG, "scrc_crossprod: invalid argument");
+    return guarded([&] { dropin_crossprod(dropin_device(), x, y, n, px, py, out); });
+}
+
+__global__ void fill_pseudo_kernel(double* x, int64_t n, unsigned seed) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned h = (unsigned)i * 2654435761u ^ seed;
+    h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+    x[i] = ((double)(h & 0xffff) - 32768.0) / 32768.0;
+}
+
+int scrc_bench_gemm(int64_t k, int64_t m, int64_t n, int symmetric, int reps, double* ms_per_launch) {
+    if (k <= 0 || m <= 0 || n <= 0 || reps <= 0 || !ms_per_launch) return fail(SCRC_ERR_ARG, "scrc_bench_gemm: invalid argument");
+    return guarded([&] {
+        Device& dev = dropin_device();
+        cudaStream_t st = dev.stream;
+        DMat A(k, m), B(k, symmetric ? m : n), Cm(m, symmetric ? m : n);
+        fill_pseudo_kernel<<<(unsigned)ceil_div((int64_t)A.buf.n, 256), 256, 0, st>>>(A.data(), (int64_t)A.buf.n, 1u);
+        fill_pseudo_kernel<<<(unsigned)ceil_div((int64_t)B.buf.n, 256), 256, 0, st>>>(B.data(), (int64_t)B.buf.n, 2u);
+        DenseArgs a{A.data(), A.ld, symmetric ? A.data() : B.data(), symmetric ? A.ld : B.ld, Cm.data(), Cm.ld,
+                    (int)m, (int)(symmetric ? m : n), (int)k};
+        const int mode = symmetric ? EPI_SYM_LOWER : EPI_PLAIN;
+        for (int i = 0; i < 2; ++i) gemm_tn_dense(mode, a, dev.num_sms, st);
+        cudaEvent_t e0, e1;
+        SCRC_CUDA(cudaEventCreate(&e0)); SCRC_CUDA(cudaEventCreate(&e1));
+        SCRC_CUDA(cudaEventRecord(e0, st));
+        for (int i = 0; i < reps; ++i) gemm_tn_dense(mode, a, dev.num_sms, st);
+        SCRC_CUDA(cudaEventRecord(e1, st));
+        SCRC_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        SCRC_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        *ms_per_launch = (double)ms / reps;
+    });
+}
+
+int scrc_ctx_create(scrc_ctx** out, int device, const double* z1_reg, const double* z2_reg, const double* z1_target,
+                    const double* z2_target, const double* z1_target_sds, int64_t n1, int64_t n2, int64_t P, int64_t T,
+                    int K) {
+    if (!out || !z1_reg || !z2_reg || !z1_target || !z2_target || !z1_target_sds)
+        return fail(SCRC_ERR_ARG, "scrc_ctx_create: null pointer");
+    *out = nullptr;
+    return guarded([&] {
+        std::unique_ptr<scrc_ctx> c(new scrc_ctx());
+        c->impl.create(device, z1_reg, z2_reg, z1_target, z2_target, z1_target_sds, n1, n2, P, T, K);
+        *out = c.release();
+    });
+}
+void scrc_ctx_destroy(scrc_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->impl.dev.id);
+    delete ctx;
+}
+
+int scrc_ctx_get_init(scrc_ctx* ctx, double* res_sds, double* init_df, double* beta_init) {
+    if (!ctx) return fail(SCRC_ERR_ARG, "null context");
+    return guarded([&] {
+        Ctx& c = ctx->impl;
+        SCRC_CUDA(cudaSetDevice(c.dev.id));
+        if (res_sds) SCRC_CUDA(cudaMemcpyAsync(res_sds, c.res_sds.p, c.T * 8, cudaMemcpyDeviceToHost, c.dev.stream));
+        if (init_df) *init_df = c.init_df;
+        if (beta_init) c.beta_init.download(beta_init, c.P, c.dev.stream);
+        SCRC_CUDA(cudaStreamSynchronize(c.dev.stream));
+    });
+}
+int scrc_ctx_get_gram(scrc_ctx* ctx, double* g_rr, double* g_rt) {
+    if (!ctx) return fail(SCRC_ERR_ARG, "null context");
+    return guarded([&] {
+        Ctx& c = ctx->impl;
+        SCRC_CUDA(cudaSetDevice(c.dev.id));
+        if (g_rr) c.G_rr.download(g_rr, c.P, c.dev.stream);
+        if (g_rt) c.G_rt.download(g_rt, c.P, c.dev.stream);
+        SCRC_CUDA(cudaStreamSynchronize(c.dev.stream));
+    });
+}
+int scrc_ctx_cross_corr(scrc_ctx* ctx, double* out) {
+    if (!ctx || !out) return fail(SCRC_ERR_ARG, "null pointer");
+    return guarded([&] {
+        Ctx& c = ctx->impl;
+        SCRC_CUDA(cudaSetDevice(c.dev.id));
+        cudaStream_t st = c.dev.stream;
+        // fast_cor(z1_target_centered, z1_reg_scaled) on device copies (R/scregclust.R:1116)
+        DMat X(c.n1, c.T), Y(c.n1, c.P), C(c.T, c.P);
+        SCRC_CUDA(cudaMemcpyAsync(X.data(), c.Z1t.data(), c.Z1t.bytes(), cudaMemcpyDeviceToDevice, st));
+        SCRC_CUDA(cudaMemcpyAsync(Y.data(), c.Z1r.data(), c.Z1r.bytes(), cudaMemcpyDeviceToDevice, st));
+        DevBuf<double> xss(c.T), yss(c.P);
+        col_center_ss(X.data(), X.ld, c.n1, c.T, xss.p, st);
+        col_center_ss(Y.data(), Y.ld, c.n1, c.P, yss.p, st);
+        DenseArgs a{X.data(), X.ld, Y.data(), Y.ld, C.data(), C.ld, (int)c.T, (int)c.P, (int)c.n1};
+        a.rvec = xss.p; a.cvec = yss.p;
+        gemm_tn_dense(EPI_COR, a, c.dev.num_sms, st);
+        C.download(out, c.T, st);
+        SCRC_CUDA(cudaStreamSynchronize(st));
+    });
+}
+
+int scrc_fit_cycle(scrc_ctx* ctx, int F, const double* lambda, const int* k_in, const scrc_options* opt,
+                   int skip_allocation, scrc_cycle_out* out) {
+    if (!ctx || !lambda || !k_in) return fail(SCRC_ERR_ARG, "scrc_fit_cycle: null pointer");
+    scrc_options o;
+    if (opt) o = *opt; else scrc_default_options(&o);
+    if (o.max_optim_iter <= 0 || o.n_update <= 0 || !(o.rho0 > 0.0) || o.alpha0 <= 0.0 || o.alpha0 > 2.0)
+        return fail(SCRC_ERR_ARG, "scrc_fit_cycle: invalid options");
+    return guarded([&] { ctx->impl.fit_cycle(F, lambda, k_in, o, skip_allocation != 0, out); });
+}
+
+int scrc_ctx_get_coeffs(scrc_ctx* ctx, int f, int k, double* coeffs_out, int* sel_out) {
+    if (!ctx) return fail(SCRC_ERR_ARG, "null context");
+    return guarded([&] {
+        Ctx& c = ctx->impl;
+        if (f < 0 || f >= c.last_F || k < 0 || k >= c.K) throw Error(SCRC_ERR_ARG, "scrc_ctx_get_coeffs: index out of range");
+        SCRC_CUDA(cudaSetDevice(c.dev.id));
+        const FitSlot& sl = c.slots[(size_t)f * c.K + k];
+        if (sel_out) for (int a = 0; a < sl.s; ++a) sel_out[a] = sl.sel[a];
+        if (coeffs_out && sl.s > 0) {
+            SCRC_CUDA(cudaMemcpy2DAsync(coeffs_out, (size_t)sl.s * 8, c.nnls.beta.data() + sl.row_off, c.nnls.beta.ld * 8,
+                                        (size_t)sl.s * 8, c.T, cudaMemcpyDeviceToHost, c.dev.stream));
+            SCRC_CUDA(cudaStreamSynchronize(c.dev.stream));
+        }
+    });
+}
+
+}  // extern "C"

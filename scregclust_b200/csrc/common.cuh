@@ -1,0 +1,138 @@
+// Shared device/host helpers for libscregclust_b200 (sm_100a only).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <stdexcept>
+
+namespace scrc {
+
+// ----------------------------------------------------------------------------
+// Error plumbing: internal code throws, the extern "C" layer converts to codes.
+// ----------------------------------------------------------------------------
+struct Error : public std::runtime_error {
+    int code;
+    Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define SCRC_CUDA(expr)                                                                   \
+    do {                                                                                  \
+        cudaError_t _e = (expr);                                                          \
+        if (_e != cudaSuccess) {                                                          \
+            throw ::scrc::Error(-100 - (int)_e, std::string("CUDA error ") +              \
+                                cudaGetErrorName(_e) + " (" + cudaGetErrorString(_e) +    \
+                                ") at " + __FILE__ + ":" + std::to_string(__LINE__));     \
+        }                                                                                 \
+    } while (0)
+
+inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// Count of kernels of this library launched by the calling thread's process
+// (reported as `gpu_launches` by bench.py).
+extern unsigned long long g_launch_count;
+#define SCRC_LAUNCHED() (++::scrc::g_launch_count)
+
+// ----------------------------------------------------------------------------
+// Device buffer (RAII)
+// ----------------------------------------------------------------------------
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    DevBuf() = default;
+    explicit DevBuf(size_t n_) { alloc(n_); }
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept {
+        if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+        return *this;
+    }
+    ~DevBuf() { release(); }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void alloc(size_t n_) {
+        release();
+        n = n_;
+        if (n) SCRC_CUDA(cudaMalloc(&p, n * sizeof(T)));
+    }
+    void ensure(size_t n_) { if (n_ > n) alloc(n_); }
+    void zero(cudaStream_t s) { if (n) SCRC_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
+};
+
+#ifdef __CUDACC__
+// ----------------------------------------------------------------------------
+// PTX wrappers: mbarrier, TMA (cp.async.bulk.tensor), FP64 mma (DMMA)
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t addr, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    return ok;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    while (!mbar_try_wait(addr, parity)) {
+    }
+}
+// 2-D tiled TMA load: coordinates are (c0 = contiguous dim, c1 = strided dim).
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1,
+                                            uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, "
+        "{%2, %3}], [%4];" ::"r"(smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+// D(8x8) += A(8x4, row) * B(4x8, col), all FP64 -> SASS DMMA.8x8x4
+__device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+#endif  // __CUDACC__
+
+// ----------------------------------------------------------------------------
+// Host: TMA descriptor for a column-major FP64 matrix with `rows` contiguous.
+// Tensor dims = (rows, cols); box = (16, box_cols); 128-byte swizzle.
+// ----------------------------------------------------------------------------
+CUtensorMap make_tmap_f64(const double* base, int64_t rows, int64_t cols, int64_t ld,
+                          int box_cols);
+
+}  // namespace scrc

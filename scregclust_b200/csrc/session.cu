@@ -1,0 +1,666 @@
+#include "session.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <numeric>
+
+namespace scrc {
+
+// ============================================================================ device / helpers
+void Device::init(int device) {
+    id = device;
+    SCRC_CUDA(cudaSetDevice(id));
+    cudaDeviceProp prop;
+    SCRC_CUDA(cudaGetDeviceProperties(&prop, id));
+    if (prop.major < 10)
+        throw Error(SCRC_ERR_UNSUPPORTED, "libscregclust_b200 requires an sm_100a (Blackwell B200) device");
+    num_sms = prop.multiProcessorCount;
+    if (!stream) SCRC_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    if (!h_pinned) SCRC_CUDA(cudaMallocHost(&h_pinned, 64 * sizeof(int)));
+}
+void Device::destroy() {
+    if (stream) { cudaStreamDestroy(stream); stream = nullptr; }
+    if (h_pinned) { cudaFreeHost(h_pinned); h_pinned = nullptr; }
+}
+
+__global__ void scale_copy_kernel(const double* in, int64_t ldi, double* out, int64_t ldo, int64_t rows, int64_t cols,
+                                  double scale) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * cols) return;
+    const int64_t r = i % rows, c = i / rows;
+    out[r + c * ldo] = in[r + c * ldi] * scale;
+}
+
+void build_eig(const DMat& G, double scale, EigBasis& eig, Device& dev) {
+    const int P = (int)G.rows;
+    eig.P = P;
+    eig.V.alloc(P, P);
+    eig.Vt.alloc(P, P);
+    eig.lam.alloc(P);
+    SCRC_CUDA(cudaMemsetAsync(eig.V.data(), 0, eig.V.bytes(), dev.stream));
+    const int64_t n = (int64_t)P * P;
+    scale_copy_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, dev.stream>>>(G.data(), G.ld, eig.V.data(), eig.V.ld, P, P, scale);
+    SCRC_LAUNCHED();
+    sym_eig(eig.V.data(), eig.V.ld, P, eig.lam.p, dev.stream);
+    SCRC_CUDA(cudaMemsetAsync(eig.Vt.data(), 0, eig.Vt.bytes(), dev.stream));
+    transpose(eig.V.data(), eig.V.ld, P, P, eig.Vt.data(), eig.Vt.ld, dev.stream);
+}
+
+void eig_solve(const EigBasis& eig, double mult, double shift, double cut, const DMat& B, DMat& out, DMat& tmp,
+               Device& dev) {
+    const int P = eig.P;
+    tmp.reshape(P, B.cols);
+    out.reshape(P, B.cols);
+    if (tmp.ld != P) SCRC_CUDA(cudaMemsetAsync(tmp.data(), 0, tmp.bytes(), dev.stream));
+    DenseArgs a1{eig.V.data(), eig.V.ld, B.data(), B.ld, tmp.data(), tmp.ld, P, (int)B.cols, P};
+    a1.alpha = mult; a1.rvec = eig.lam.p; a1.shift = shift; a1.cut = cut;
+    gemm_tn_dense(EPI_ROWDIV, a1, dev.num_sms, dev.stream);
+    DenseArgs a2{eig.Vt.data(), eig.Vt.ld, tmp.data(), tmp.ld, out.data(), out.ld, P, (int)B.cols, P};
+    gemm_tn_dense(EPI_PLAIN, a2, dev.num_sms, dev.stream);
+}
+
+static void gram(const DMat& X, const DMat& Y, DMat& out, bool symmetric, Device& dev) {
+    out.alloc(X.cols, Y.cols);
+    SCRC_CUDA(cudaMemsetAsync(out.data(), 0, out.bytes(), dev.stream));
+    DenseArgs a{X.data(), X.ld, Y.data(), Y.ld, out.data(), out.ld, (int)X.cols, (int)Y.cols, (int)X.rows};
+    gemm_tn_dense(symmetric ? EPI_SYM_LOWER : EPI_PLAIN, a, dev.num_sms, dev.stream);
+}
+
+__global__ void vec_recip_kernel(const double* in, double* out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = 1.0 / in[i];
+}
+__global__ void res_sds_kernel(const double* ss, double denom, double* out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = sqrt(ss[i] / denom);                       // scregclust.R:1104-1107
+}
+__global__ void bas_kernel(const double* beta, int64_t ldb, const double* res_sds, double* bas, int64_t ldo, int64_t P,
+                           int64_t T) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P * T) return;
+    const int64_t r = i % P, c = i / P;
+    const double v = beta[r + c * ldb] * (1.0 / res_sds[c]);        // scregclust.R:1109-1113
+    bas[r + c * ldo] = v * v;
+}
+
+// ============================================================================ session creation
+void Ctx::create(int device, const double* z1r, const double* z2r, const double* z1t, const double* z2t,
+                 const double* sds, int64_t n1_, int64_t n2_, int64_t P_, int64_t T_, int K_) {
+    if (n1_ <= 1 || n2_ <= 0 || P_ <= 0 || T_ <= 0 || K_ <= 0) throw Error(SCRC_ERR_ARG, "scrc_ctx_create: non-positive dimension");
+    if (K_ > RV_MAX_K) throw Error(SCRC_ERR_UNSUPPORTED, "scrc_ctx_create: at most 64 modules are supported");
+    dev.init(device);
+    n1 = n1_; n2 = n2_; P = P_; T = T_; K = K_;
+    cudaStream_t st = dev.stream;
+    Z1r.alloc(n1, P); Z2r.alloc(n2, P); Z1t.alloc(n1, T); Z2t.alloc(n2, T);
+    Z1r.upload(z1r, n1, st); Z2r.upload(z2r, n2, st); Z1t.upload(z1t, n1, st); Z2t.upload(z2t, n2, st);
+    sds_t.alloc(T); inv_sds_t.alloc(T);
+    SCRC_CUDA(cudaMemcpyAsync(sds_t.p, sds, T * 8, cudaMemcpyHostToDevice, st));
+    vec_recip_kernel<<<(unsigned)ceil_div(T, 256), 256, 0, st>>>(sds_t.p, inv_sds_t.p, (int)T);
+    SCRC_LAUNCHED();
+
+    // Gram matrices (optim.cpp:17-27,99,414,421) -- computed once, the reference redoes them per call
+    gram(Z1r, Z1r, G_rr, true, dev);
+    gram(Z1r, Z1t, G_rt, false, dev);
+    build_eig(G_rr, 1.0 / (double)n1, eig, dev);   // eigenbasis of X'X with X = Z1r / sqrt(n1)
+
+    // Initial fit (scregclust.R:1049-1101): OLS when n1 >= P, ridge with the df search otherwise.
+    DMat tmp;
+    std::vector<double> lam(P);
+    SCRC_CUDA(cudaMemcpyAsync(lam.data(), eig.lam.p, P * 8, cudaMemcpyDeviceToHost, st));
+    SCRC_CUDA(cudaStreamSynchronize(st));
+    double ridge = 0.0;
+    if (n1 >= P) {
+        init_df = (double)P;
+    } else {
+        // es = eigenvalues of Z'Z, decreasing; lambda_minimal = es[n1 - 1] + 1e-4 (1-based)
+        std::vector<double> es(P);
+        for (int64_t i = 0; i < P; ++i) es[i] = lam[P - 1 - i] * (double)n1;
+        ridge = es[n1 - 2] + 1e-4;
+        auto df = [&](double l) { double s = 0.0; for (double e : es) s += e / (e + l); return s; };
+        init_df = df(ridge);
+        while (init_df >= (double)n1) { ridge *= 2.0; init_df = df(ridge); }
+    }
+    eig_solve(eig, (double)n1, ridge, 0.0, G_rt, beta_init, tmp, dev);
+
+    // res_sds = sqrt(colSums((Y - X beta)^2) / (n1 - df))  -- explicit residuals (scregclust.R:1104-1107)
+    {
+        DMat Z1rT(P, n1), resid(n1, T);
+        if (Z1rT.ld != P) SCRC_CUDA(cudaMemsetAsync(Z1rT.data(), 0, Z1rT.bytes(), st));
+        transpose(Z1r.data(), Z1r.ld, n1, P, Z1rT.data(), Z1rT.ld, st);
+        DenseArgs a{Z1rT.data(), Z1rT.ld, beta_init.data(), beta_init.ld, resid.data(), resid.ld, (int)n1, (int)T, (int)P};
+        a.D = Z1t.data(); a.ldd = Z1t.ld;
+        gemm_tn_dense(EPI_SUBFROM, a, dev.num_sms, st);
+        DevBuf<double> ss(T);
+        col_sumsq(resid.data(), resid.ld, n1, T, ss.p, st);
+        res_sds.alloc(T);
+        res_sds_kernel<<<(unsigned)ceil_div(T, 256), 256, 0, st>>>(ss.p, (double)n1 - init_df, res_sds.p, (int)T);
+        SCRC_LAUNCHED();
+        SCRC_CUDA(cudaStreamSynchronize(st));
+    }
+    bas.alloc(P, T);
+    bas_kernel<<<(unsigned)ceil_div(P * T, 256), 256, 0, st>>>(beta_init.data(), beta_init.ld, res_sds.p, bas.data(), bas.ld, P, T);
+    SCRC_LAUNCHED();
+    SCRC_CUDA(cudaStreamSynchronize(st));
+}
+
+// ============================================================================ Step 1 helper kernels
+// xty column c = X'y for target t(c):  G_rt[:, t] / res_sds[t] / n1   (scregclust.R:1353-1364, optim.cpp:99)
+__global__ void __launch_bounds__(256) admm_xty_kernel(const double* __restrict__ G_rt, int64_t ldg,
+                                                       const int* __restrict__ col_target,
+                                                       const double* __restrict__ res_sds, double n1, double* xty,
+                                                       int64_t ld, int P) {
+    const int c = blockIdx.x;
+    const int t = col_target[c];
+    const double sd = res_sds[t];
+    for (int i = threadIdx.x; i < P; i += blockDim.x) xty[i + (int64_t)c * ld] = G_rt[i + (int64_t)t * ldg] / sd / n1;
+}
+// ws = sqrt(m_j) / rowSums(beta_adapt_sq[, k == j])^(1/4)   (scregclust.R:1348-1351)
+__global__ void __launch_bounds__(256) admm_weights_kernel(const double* __restrict__ bas, int64_t ldb,
+                                                           const int* __restrict__ col_target, const int* c0s,
+                                                           const int* c1s, double* w, int64_t ldw, int P) {
+    const int p = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const int c0 = c0s[p], c1 = c1s[p];
+    double s = 0.0;
+    for (int c = c0; c < c1; ++c) s += bas[i + (int64_t)col_target[c] * ldb];
+    w[i + (int64_t)p * ldw] = sqrt((double)(c1 - c0)) / sqrt(sqrt(s));
+}
+// beta * res_sds, threshold 1e-6, models / weights / signs   (scregclust.R:1372-1386)
+__global__ void __launch_bounds__(256) admm_extract_kernel(const double* __restrict__ beta, int64_t ld,
+                                                           const int* __restrict__ col_target,
+                                                           const double* __restrict__ res_sds, const int* c0s,
+                                                           const int* c1s, const int* prob_fit, const int* prob_mod,
+                                                           int P, int K, unsigned char* models, double* weights,
+                                                           double* signs) {
+    __shared__ double s_sum[8][32];
+    __shared__ int s_any[8][32];
+    const int p = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int row = blockIdx.x * 32 + lane;
+    const int c0 = c0s[p], c1 = c1s[p];
+    double sum = 0.0;
+    int any = 0;
+    if (row < P) {
+        for (int c = c0 + warp; c < c1; c += 8) {
+            double v = beta[row + (int64_t)c * ld] * res_sds[col_target[c]];
+            if (fabs(v) < 1e-6) v = 0.0;
+            if (fabs(v) > 0.0) any = 1;
+            sum += v;
+        }
+    }
+    s_sum[warp][lane] = sum;
+    s_any[warp][lane] = any;
+    __syncthreads();
+    if (warp == 0 && row < P) {
+        double t = 0.0; int a = 0;
+        for (int w = 0; w < 8; ++w) { t += s_sum[w][lane]; a |= s_any[w][lane]; }
+        const double wt = t / (double)(c1 - c0);
+        const int64_t o = ((int64_t)prob_fit[p] * K + prob_mod[p]) * P + row;
+        models[o] = (unsigned char)a;
+        weights[o] = wt;
+        signs[o] = a ? (double)((wt > 0.0) - (wt < 0.0)) : nan("");
+    }
+}
+__global__ void fill_nan_kernel(double* x, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[i] = nan("");
+}
+
+// ============================================================================ one batched cycle
+void Ctx::fit_cycle(int F, const double* lambda, const int* k_in, const scrc_options& opt, bool skip_alloc,
+                    scrc_cycle_out* out) {
+    if (F <= 0) throw Error(SCRC_ERR_ARG, "scrc_fit_cycle: F must be positive");
+    SCRC_CUDA(cudaSetDevice(dev.id));
+    cudaStream_t st = dev.stream;
+    const int64_t FK = (int64_t)F * K;
+
+    // ---------------- Step 1: problem table (one problem per non-empty (fit, module)) ----------------
+    std::vector<int> h_col_target, h_col_prob, h_c0, h_c1, h_fit, h_mod;
+    std::vector<double> h_lambda;
+    for (int f = 0; f < F; ++f) {
+        const int* k = k_in + (int64_t)f * T;
+        for (int j = 1; j <= K; ++j) {
+            const int c0 = (int)h_col_target.size();
+            for (int64_t t = 0; t < T; ++t)
+                if (k[t] == j) { h_col_target.push_back((int)t); h_col_prob.push_back((int)h_c0.size()); }
+            const int c1 = (int)h_col_target.size();
+            if (c1 > c0) { h_c0.push_back(c0); h_c1.push_back(c1); h_fit.push_back(f); h_mod.push_back(j - 1); h_lambda.push_back(lambda[f]); }
+        }
+    }
+    const int C = (int)h_col_target.size(), nprob = (int)h_c0.size();
+
+    models_d.ensure(FK * P); weights_d.ensure(FK * P); signs_d.ensure(FK * P);
+    SCRC_CUDA(cudaMemsetAsync(models_d.p, 0, FK * P, st));
+    SCRC_CUDA(cudaMemsetAsync(weights_d.p, 0, FK * P * 8, st));
+    fill_nan_kernel<<<(unsigned)ceil_div(FK * P, 256), 256, 0, st>>>(signs_d.p, FK * P);
+    SCRC_LAUNCHED();
+
+    std::vector<int> h_admm_it(FK, 0);
+    long long sweeps = 0;
+    if (nprob > 0) {
+        admm.resize((int)P, C, nprob);
+        col_target.ensure(C); prob_fit.ensure(nprob); prob_mod.ensure(nprob);
+        SCRC_CUDA(cudaMemcpyAsync(col_target.p, h_col_target.data(), C * 4, cudaMemcpyHostToDevice, st));
+        SCRC_CUDA(cudaMemcpyAsync(admm.col_prob.p, h_col_prob.data(), C * 4, cudaMemcpyHostToDevice, st));
+        SCRC_CUDA(cudaMemcpyAsync(admm.prob_c0.p, h_c0.data(), nprob * 4, cudaMemcpyHostToDevice, st));
+        SCRC_CUDA(cudaMemcpyAsync(admm.prob_c1.p, h_c1.data(), nprob * 4, cudaMemcpyHostToDevice, st));
+        SCRC_CUDA(cudaMemcpyAsync(admm.prob_lambda.p, h_lambda.data(), nprob * 8, cudaMemcpyHostToDevice, st));
+        SCRC_CUDA(cudaMemcpyAsync(prob_fit.p, h_fit.data(), nprob * 4, cudaMemcpyHostToDevice, st));
+        SCRC_CUDA(cudaMemcpyAsync(prob_mod.p, h_mod.data(), nprob * 4, cudaMemcpyHostToDevice, st));
+        admm_xty_kernel<<<C, 256, 0, st>>>(G_rt.data(), G_rt.ld, col_target.p, res_sds.p, (double)n1, admm.xty.data(), admm.xty.ld, (int)P);
+        SCRC_LAUNCHED();
+        admm_weights_kernel<<<dim3((unsigned)ceil_div(P, 256), nprob), 256, 0, st>>>(bas.data(), bas.ld, col_target.p, admm.prob_c0.p, admm.prob_c1.p, admm.w.data(), admm.w.ld, (int)P);
+        SCRC_LAUNCHED();
+        AdmmOpts ao;
+        ao.rho0 = opt.rho0; ao.alpha0 = opt.alpha0; ao.eps_corr = opt.eps_corr; ao.n_update = opt.n_update;
+        ao.max_iter = opt.max_optim_iter; ao.eps_rel = opt.tol_coop_rel; ao.eps_abs = opt.tol_coop_abs;
+        sweeps = admm_solve(admm, eig, ao, true, dev.num_sms, st, dev.h_pinned);
+        admm_extract_kernel<<<dim3((unsigned)ceil_div(P, 32), nprob), 256, 0, st>>>(
+            admm.beta.data(), admm.beta.ld, col_target.p, res_sds.p, admm.prob_c0.p, admm.prob_c1.p, prob_fit.p,
+            prob_mod.p, (int)P, K, models_d.p, weights_d.p, signs_d.p);
+        SCRC_LAUNCHED();
+        std::vector<int> h_it(nprob);
+        SCRC_CUDA(cudaMemcpyAsync(h_it.data(), admm.prob_iters.p, nprob * 4, cudaMemcpyDeviceToHost, st));
+        SCRC_CUDA(cudaStreamSynchronize(st));
+        for (int p = 0; p < nprob; ++p) h_admm_it[(int64_t)h_fit[p] * K + h_mod[p]] = h_it[p];
+    }
+    std::vector<unsigned char> h_models(FK * P);
+    std::vector<double> h_signs(FK * P);
+    SCRC_CUDA(cudaMemcpyAsync(h_models.data(), models_d.p, FK * P, cudaMemcpyDeviceToHost, st));
+    SCRC_CUDA(cudaMemcpyAsync(h_signs.data(), signs_d.p, FK * P * 8, cudaMemcpyDeviceToHost, st));
+    SCRC_CUDA(cudaStreamSynchronize(st));
+
+    // ---------------- Step 2a: NNLS problem table ----------------
+    slots.assign(FK, FitSlot());
+    last_F = F;
+    std::vector<NnlsProblem> h_np;
+    std::vector<int> h_np_slot;
+    std::vector<int> h_sel, h_row_src, h_row_off(FK, 0), h_kpad(FK, 0), h_nsel(FK, 0);
+    std::vector<double> h_sign;
+    int64_t rows_total = 0, q_total = 0;
+    for (int64_t fk = 0; fk < FK; ++fk) {
+        FitSlot& sl = slots[fk];
+        const unsigned char* mk = h_models.data() + fk * P;
+        for (int64_t i = 0; i < P; ++i) if (mk[i]) sl.sel.push_back((int)i);
+        sl.s = (int)sl.sel.size();
+        h_nsel[fk] = sl.s;
+        if (sl.s == 0) continue;
+        const int kp = (int)round_up(sl.s, 16);
+        sl.row_off = (int)rows_total;
+        h_row_off[fk] = sl.row_off; h_kpad[fk] = kp;
+        NnlsProblem np;
+        np.s = sl.s; np.sel_off = (int)h_sel.size(); np.q_off = q_total; np.row_off = rows_total;
+        for (int a = 0; a < sl.s; ++a) { h_sel.push_back(sl.sel[a]); h_sign.push_back(h_signs[fk * P + sl.sel[a]]); h_row_src.push_back(sl.sel[a]); }
+        for (int a = sl.s; a < kp; ++a) h_row_src.push_back(-1);
+        h_np.push_back(np); h_np_slot.push_back((int)fk);
+        rows_total += kp; q_total += (int64_t)sl.s * sl.s;
+    }
+    if (rows_total > 0x7fffff00LL) throw Error(SCRC_ERR_UNSUPPORTED, "scrc_fit_cycle: too many selected regulators in one batch");
+    const int nnp = (int)h_np.size();
+    const int64_t rows_alloc = std::max<int64_t>(rows_total, 16);
+    nnls.nprob = nnp; nnls.m = (int)T; nnls.rows = rows_total;
+    nnls.prob.ensure(std::max(nnp, 1)); nnls.sel.ensure(std::max<size_t>(h_sel.size(), 1)); nnls.sign.ensure(std::max<size_t>(h_sign.size(), 1));
+    nnls.Q.ensure(std::max<int64_t>(q_total, 1)); nnls.dvec.ensure(rows_alloc);
+    nnls.grad0.reshape(rows_alloc, T); nnls.beta.reshape(rows_alloc, T);
+    nnls.iters.ensure(std::max<int64_t>((int64_t)nnp * T, 1));
+    row_src.ensure(rows_alloc); row_off_d.ensure(FK); kpad_d.ensure(FK); nsel_d.ensure(FK);
+    if (nnp > 0) {
+        SCRC_CUDA(cudaMemcpyAsync(nnls.prob.p, h_np.data(), nnp * sizeof(NnlsProblem), cudaMemcpyHostToDevice, st));
+        SCRC_CUDA(cudaMemcpyAsync(nnls.sel.p, h_sel.data(), h_sel.size() * 4, cudaMemcpyHostToDevice, st));
+        SCRC_CUDA(cudaMemcpyAsync(nnls.sign.p, h_sign.data(), h_sign.size() * 8, cudaMemcpyHostToDevice, st));
+        SCRC_CUDA(cudaMemcpyAsync(row_src.p, h_row_src.data(), h_row_src.size() * 4, cudaMemcpyHostToDevice, st));
+    }
+    SCRC_CUDA(cudaMemcpyAsync(row_off_d.p, h_row_off.data(), FK * 4, cudaMemcpyHostToDevice, st));
+    SCRC_CUDA(cudaMemcpyAsync(kpad_d.p, h_kpad.data(), FK * 4, cudaMemcpyHostToDevice, st));
+    SCRC_CUDA(cudaMemcpyAsync(nsel_d.p, h_nsel.data(), FK * 4, cudaMemcpyHostToDevice, st));
+    SCRC_CUDA(cudaMemsetAsync(nnls.beta.data(), 0, nnls.beta.bytes(), st));
+    if (nnp > 0) {
+        nnls_setup(nnls, G_rr.data(), G_rr.ld, G_rt.data(), G_rt.ld, inv_sds_t.p, st);
+        nnls_solve(nnls, opt.tol_nnls, opt.max_optim_iter, sds_t.p, (int)T, dev.num_sms, st);
+    }
+
+    // ---------------- Step 2a/2b: residuals, SSE, variances, votes ----------------
+    const int CRtr = resid_vote_pick_cr((int)n1, (int)T, F, dev.num_sms);
+    const int CRte = resid_vote_pick_cr((int)n2, (int)T, F, dev.num_sms);
+    partial.ensure(std::max(resid_vote_partial_elems((int)T, K, F, CRtr), resid_vote_partial_elems((int)T, K, F, CRte)));
+    const size_t fkt = (size_t)F * K * T, fk1t = (size_t)F * (K + 1) * T;
+    sse_train.ensure(fk1t); sse_test.ensure(fk1t); var.ensure(fkt); two_var.ensure(fkt); half_log.ensure(fkt);
+    r2.ensure(fkt); best_r2.ensure((size_t)F * T); best_idx.ensure((size_t)F * T); k_new.ensure((size_t)F * T);
+    votes.ensure(fkt);
+    ZselT.reshape(rows_alloc, std::max(n1, n2));
+
+    ResidVoteArgs ra;
+    ra.beta = nnls.beta.data(); ra.ldb = nnls.beta.ld; ra.rows_total = rows_total;
+    ra.T = (int)T; ra.K = K; ra.L = F; ra.row_off = row_off_d.p; ra.kpad = kpad_d.p;
+    ra.two_var = two_var.p; ra.half_log = half_log.p; ra.partial = partial.p; ra.votes = votes.p;
+    // train split
+    ZselT.reshape(rows_alloc, n1);
+    if (rows_total == 0) SCRC_CUDA(cudaMemsetAsync(ZselT.data(), 0, ZselT.bytes(), st));
+    gather_transpose(Z1r.data(), Z1r.ld, (int)n1, row_src.p, rows_total, ZselT.data(), ZselT.ld, st);
+    ra.ZselT = ZselT.data(); ra.ldzs = ZselT.ld; ra.Z = Z1t.data(); ra.ldz = Z1t.ld; ra.ncells = (int)n1; ra.CR = CRtr;
+    resid_vote(ra, false, dev.num_sms, st);
+    reduce_sse(partial.p, (int)T, K, F, CRtr, sse_train.p, st);
+    make_resid_var(sse_train.p, nsel_d.p, (int)n1, (int)T, K, F, var.p, two_var.p, half_log.p, st);
+    // test split
+    ZselT.reshape(rows_alloc, n2);
+    if (rows_total == 0) SCRC_CUDA(cudaMemsetAsync(ZselT.data(), 0, ZselT.bytes(), st));
+    gather_transpose(Z2r.data(), Z2r.ld, (int)n2, row_src.p, rows_total, ZselT.data(), ZselT.ld, st);
+    ra.ZselT = ZselT.data(); ra.ldzs = ZselT.ld; ra.Z = Z2t.data(); ra.ldz = Z2t.ld; ra.ncells = (int)n2; ra.CR = CRte;
+    const bool vote = !skip_alloc;
+    if (vote) SCRC_CUDA(cudaMemsetAsync(votes.p, 0, fkt * 4, st));
+    resid_vote(ra, vote, dev.num_sms, st);
+    reduce_sse(partial.p, (int)T, K, F, CRte, sse_test.p, st);
+    finish_alloc(sse_test.p, vote ? votes.p : nullptr, (int)T, K, F, r2.p, best_r2.p, best_idx.p, k_new.p, st);
+
+    // ---------------- outputs ----------------
+    if (out) {
+        auto d2h = [&](void* dst, const void* src, size_t bytes) {
+            if (dst && bytes) SCRC_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));
+        };
+        if (vote) { d2h(out->k_new, k_new.p, (size_t)F * T * 4); d2h(out->votes, votes.p, fkt * 4); }
+        d2h(out->weights, weights_d.p, FK * P * 8);
+        d2h(out->r2_test, r2.p, fkt * 8);
+        d2h(out->resid_var, var.p, fkt * 8);
+        d2h(out->best_r2, best_r2.p, (size_t)F * T * 8);
+        d2h(out->best_r2_idx, best_idx.p, (size_t)F * T * 4);
+        if (out->models) std::memcpy(out->models, h_models.data(), FK * P);
+        if (out->signs) std::memcpy(out->signs, h_signs.data(), FK * P * 8);
+        if (out->admm_iterations) std::memcpy(out->admm_iterations, h_admm_it.data(), FK * 4);
+        if (out->n_selected) std::memcpy(out->n_selected, h_nsel.data(), FK * 4);
+        if (out->admm_sweeps) *out->admm_sweeps = sweeps;
+        if (out->nnls_iterations) {
+            std::memset(out->nnls_iterations, 0, fkt * 4);
+            for (int q = 0; q < nnp; ++q)
+                d2h(out->nnls_iterations + (size_t)h_np_slot[q] * T, nnls.iters.p + (size_t)q * T, (size_t)T * 4);
+        }
+    }
+    SCRC_CUDA(cudaStreamSynchronize(st));
+}
+
+// ============================================================================ drop-ins
+void dropin_crossprod(Device& dev, const double* x, const double* y, int64_t n, int64_t px, int64_t py, double* out) {
+    cudaStream_t st = dev.stream;
+    DMat X(n, px), C;
+    X.upload(x, n, st);
+    if (y == x && px == py) {
+        gram(X, X, C, true, dev);
+    } else {
+        DMat Y(n, py);
+        Y.upload(y, n, st);
+        gram(X, Y, C, false, dev);
+        C.download(out, px, st);
+        SCRC_CUDA(cudaStreamSynchronize(st));
+        return;
+    }
+    C.download(out, px, st);
+    SCRC_CUDA(cudaStreamSynchronize(st));
+}
+
+void dropin_fast_cor(Device& dev, const double* x, const double* y, int64_t n, int64_t px, int64_t py, double* out) {
+    cudaStream_t st = dev.stream;
+    DMat X(n, px), Y(n, py), C(px, py);
+    X.upload(x, n, st); Y.upload(y, n, st);
+    DevBuf<double> xss(px), yss(py);
+    col_center_ss(X.data(), X.ld, n, px, xss.p, st);    // utils.R:534-537
+    col_center_ss(Y.data(), Y.ld, n, py, yss.p, st);
+    DenseArgs a{X.data(), X.ld, Y.data(), Y.ld, C.data(), C.ld, (int)px, (int)py, (int)n};
+    a.rvec = xss.p; a.cvec = yss.p;
+    gemm_tn_dense(EPI_COR, a, dev.num_sms, st);          // utils.R:538-540
+    C.download(out, px, st);
+    SCRC_CUDA(cudaStreamSynchronize(st));
+}
+
+void dropin_ols(Device& dev, const double* y, const double* x, int64_t n, int64_t p, int64_t m, double lambda, bool ridge,
+                double* beta_out) {
+    cudaStream_t st = dev.stream;
+    DMat X(n, p), Y(n, m), G, Gy, B, tmp;
+    X.upload(x, n, st); Y.upload(y, n, st);
+    gram(X, X, G, true, dev);
+    gram(X, Y, Gy, false, dev);
+    EigBasis eig;
+    build_eig(G, 1.0, eig, dev);
+    double shift = 0.0, cut = 0.0;
+    if (ridge) {
+        shift = lambda;
+    } else if (n < p) {
+        // Moore-Penrose inverse of X'X: drop eigenvalues <= eps * p * max(d)   (utils.R:20-30)
+        double lmax = 0.0;
+        SCRC_CUDA(cudaMemcpyAsync(&lmax, eig.lam.p + (p - 1), 8, cudaMemcpyDeviceToHost, st));
+        SCRC_CUDA(cudaStreamSynchronize(st));
+        cut = 2.220446049250313e-16 * (double)p * lmax;
+    }
+    eig_solve(eig, 1.0, shift, cut, Gy, B, tmp, dev);
+    B.download(beta_out, p, st);
+    SCRC_CUDA(cudaStreamSynchronize(st));
+}
+
+__global__ void set_warm_start_kernel(const double* b0, int64_t ld0, double* beta, double* zeta, double* beta_old,
+                                      double* zeta_old, int64_t ld, int64_t P, int64_t m) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P * m) return;
+    const int64_t r = i % P, c = i / P;
+    const double v = b0[r + c * ld0];
+    const int64_t o = r + c * ld;
+    beta[o] = v; zeta[o] = v; beta_old[o] = v; zeta_old[o] = v;      // optim.cpp:84-112
+}
+
+void dropin_coop_lasso(Device& dev, const double* y, int64_t n, int64_t m, const double* x, int64_t p, double lambda,
+                       const double* weights, const double* beta0, const AdmmOpts& o, double* beta_out, int* iters) {
+    cudaStream_t st = dev.stream;
+    DMat X(n, p), Y(n, m), G, Gy;
+    X.upload(x, n, st); Y.upload(y, n, st);
+    gram(X, X, G, true, dev);       // optim.cpp:97
+    gram(X, Y, Gy, false, dev);     // optim.cpp:99
+    EigBasis eig;
+    build_eig(G, 1.0, eig, dev);
+    AdmmBatch b;
+    b.resize((int)p, (int)m, 1);
+    std::vector<int> cp(m, 0);
+    const int c0 = 0, c1 = (int)m;
+    SCRC_CUDA(cudaMemcpyAsync(b.col_prob.p, cp.data(), m * 4, cudaMemcpyHostToDevice, st));
+    SCRC_CUDA(cudaMemcpyAsync(b.prob_c0.p, &c0, 4, cudaMemcpyHostToDevice, st));
+    SCRC_CUDA(cudaMemcpyAsync(b.prob_c1.p, &c1, 4, cudaMemcpyHostToDevice, st));
+    SCRC_CUDA(cudaMemcpyAsync(b.prob_lambda.p, &lambda, 8, cudaMemcpyHostToDevice, st));
+    SCRC_CUDA(cudaMemcpy2DAsync(b.w.data(), b.w.ld * 8, weights, p * 8, p * 8, 1, cudaMemcpyHostToDevice, st));
+    SCRC_CUDA(cudaMemcpy2DAsync(b.xty.data(), b.xty.ld * 8, Gy.data(), Gy.ld * 8, p * 8, m, cudaMemcpyDeviceToDevice, st));
+    bool cold = true;
+    DMat B0;
+    if (beta0) {
+        cold = false;
+        B0.alloc(p, m);
+        B0.upload(beta0, p, st);
+        set_warm_start_kernel<<<(unsigned)ceil_div(p * m, 256), 256, 0, st>>>(B0.data(), B0.ld, b.beta.data(), b.zeta.data(), b.beta_old.data(), b.zeta_old.data(), b.beta.ld, p, m);
+        SCRC_LAUNCHED();
+    }
+    SCRC_CUDA(cudaStreamSynchronize(st));   // host temporaries above must outlive the copies
+    admm_solve(b, eig, o, cold, dev.num_sms, st, dev.h_pinned);
+    b.beta.download(beta_out, p, st);
+    SCRC_CUDA(cudaMemcpyAsync(iters, b.prob_iters.p, 4, cudaMemcpyDeviceToHost, st));
+    SCRC_CUDA(cudaStreamSynchronize(st));
+}
+
+void dropin_nnls(Device& dev, const double* x, int64_t nobs, int64_t nvar, const double* y, int64_t m, double eps,
+                 int max_iter, double* beta_out, int* iters) {
+    cudaStream_t st = dev.stream;
+    DMat X(nobs, nvar), Y(nobs, m), G, Gy;
+    X.upload(x, nobs, st); Y.upload(y, nobs, st);
+    gram(X, X, G, true, dev);       // optim.cpp:414
+    gram(X, Y, Gy, false, dev);     // optim.cpp:421
+    NnlsBatch b;
+    b.nprob = 1; b.m = (int)m;
+    const int64_t rows = round_up(nvar, 16);
+    b.rows = rows;
+    NnlsProblem np{(int)nvar, 0, 0, 0};
+    std::vector<int> sel(nvar);
+    std::iota(sel.begin(), sel.end(), 0);
+    std::vector<double> sg(nvar, 1.0);
+    b.prob.alloc(1); b.sel.alloc(nvar); b.sign.alloc(nvar); b.Q.alloc((size_t)nvar * nvar); b.dvec.alloc(rows);
+    b.grad0.alloc(rows, m); b.beta.alloc(rows, m); b.iters.alloc(m);
+    SCRC_CUDA(cudaMemcpyAsync(b.prob.p, &np, sizeof(np), cudaMemcpyHostToDevice, st));
+    SCRC_CUDA(cudaMemcpyAsync(b.sel.p, sel.data(), nvar * 4, cudaMemcpyHostToDevice, st));
+    SCRC_CUDA(cudaMemcpyAsync(b.sign.p, sg.data(), nvar * 8, cudaMemcpyHostToDevice, st));
+    SCRC_CUDA(cudaStreamSynchronize(st));
+    nnls_setup(b, G.data(), G.ld, Gy.data(), Gy.ld, nullptr, st);
+    nnls_solve(b, eps, max_iter, nullptr, 1, dev.num_sms, st);
+    SCRC_CUDA(cudaMemcpy2DAsync(beta_out, nvar * 8, b.beta.data(), b.beta.ld * 8, nvar * 8, m, cudaMemcpyDeviceToHost, st));
+    SCRC_CUDA(cudaMemcpyAsync(iters, b.iters.p, m * 4, cudaMemcpyDeviceToHost, st));
+    SCRC_CUDA(cudaStreamSynchronize(st));
+}
+
+// ---------------------------------------------------------------- allocate_into_modules on a materialised array
+// One CTA per gene: per-cell Gaussian log-likelihood per module, first-max argmax, vote histogram
+// (allocation.cpp:59-94).  plp (K values, may be nullptr) is added with weight w.
+__device__ void gene_votes(const double* __restrict__ resid, int K, int64_t n_obs, const double* __restrict__ var_row,
+                           int64_t var_ld, double w, const double* plp, int* s_votes) {
+    for (int64_t c = threadIdx.x; c < n_obs; c += blockDim.x) {
+        const double* rc = resid + c * K;
+        double best = -INFINITY;
+        int bi = 0;
+        for (int k = 0; k < K; ++k) {
+            const double v = var_row[(int64_t)k * var_ld];
+            double sc = (-rc[k]) / (2.0 * v) - 0.5 * log((2.0 * M_PI) * v);
+            if (plp) sc = (1.0 - w) * sc + w * plp[k];                     // allocation.cpp:74-77
+            if (sc > best) { best = sc; bi = k; }
+        }
+        atomicAdd(&s_votes[bi], 1);
+    }
+}
+
+__global__ void __launch_bounds__(256) alloc_parallel_kernel(const double* __restrict__ arr, int K, int64_t n_obs,
+                                                             int64_t g0, int64_t ng, const double* __restrict__ resid_var,
+                                                             int64_t T, int* k_out, int* votes_out) {
+    __shared__ int s_votes[RV_MAX_K];
+    const int64_t g = blockIdx.x;
+    if (g >= ng) return;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) s_votes[k] = 0;
+    __syncthreads();
+    gene_votes(arr + g * K * n_obs, K, n_obs, resid_var + (g0 + g), T, 0.0, nullptr, s_votes);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int bv = -1, bk = 0;
+        for (int k = 0; k < K; ++k) {
+            if (s_votes[k] > bv) { bv = s_votes[k]; bk = k; }
+            if (votes_out) votes_out[(g0 + g) * K + k] = s_votes[k];
+        }
+        k_out[g0 + g] = bk + 1;
+    }
+}
+
+// Sequential Gauss-Seidel sweep with the network prior (allocation.cpp:33-97): one CTA walks
+// the genes in `order`; the module totals and k live in shared / global memory.
+__global__ void __launch_bounds__(1024) alloc_sequential_kernel(const double* __restrict__ arr, int K, int64_t n_obs,
+                                                                int64_t T, const double* __restrict__ resid_var,
+                                                                const int* __restrict__ prior_off,
+                                                                const int* __restrict__ prior_idx, int* k /* 0-based, -2 noise */,
+                                                                const int* __restrict__ order, double baseline, double w,
+                                                                int* votes_out) {
+    __shared__ int s_votes[RV_MAX_K];
+    __shared__ double s_tot[RV_MAX_K], s_plp[RV_MAX_K];
+    if (threadIdx.x < K) s_tot[threadIdx.x] = 0.0;
+    __syncthreads();
+    if (threadIdx.x == 0)
+        for (int64_t t = 0; t < T; ++t) if (k[t] != -2) s_tot[k[t]] += 1.0;   // allocation.cpp:25-30
+    __syncthreads();
+    for (int64_t oi = 0; oi < T; ++oi) {
+        const int64_t j = order[oi];
+        if (threadIdx.x < K) s_votes[threadIdx.x] = 0;
+        if (threadIdx.x == 0) {
+            double frac[RV_MAX_K];
+            for (int q = 0; q < K; ++q) frac[q] = 0.0;
+            if (prior_off)
+                for (int e = prior_off[j]; e < prior_off[j + 1]; ++e) {
+                    const int kk = k[prior_idx[e]];
+                    if (kk != -2) frac[kk] += 1.0;                            // allocation.cpp:41-46
+                }
+            double sum = 0.0;
+            for (int q = 0; q < K; ++q) {
+                if (s_tot[q] > 0.0) frac[q] /= s_tot[q];
+                frac[q] += baseline;
+                sum += frac[q];
+            }
+            const double ls = log(sum);
+            for (int q = 0; q < K; ++q) s_plp[q] = log(frac[q]) - ls;        // allocation.cpp:56
+        }
+        __syncthreads();
+        gene_votes(arr + j * K * n_obs, K, n_obs, resid_var + j, T, w, s_plp, s_votes);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int bv = -1, bk = 0;
+            for (int q = 0; q < K; ++q) {
+                if (s_votes[q] > bv) { bv = s_votes[q]; bk = q; }
+                if (votes_out) votes_out[j * K + q] = s_votes[q];
+            }
+            if (k[j] != -2) s_tot[k[j]] -= 1.0;
+            s_tot[bk] += 1.0;
+            k[j] = bk;                                                        // allocation.cpp:90-94
+        }
+        __syncthreads();
+    }
+}
+
+void dropin_allocate(Device& dev, const double* sq_resid, int K, int64_t n2, int64_t T, const double* resid_var,
+                     const int* prior_off, const int* prior_idx, const int* k_in, const int* order, double baseline,
+                     double weight, int* k_out, int* votes_out) {
+    cudaStream_t st = dev.stream;
+    if (K > RV_MAX_K) throw Error(SCRC_ERR_UNSUPPORTED, "allocate_into_modules: at most 64 modules are supported");
+    DevBuf<double> d_var((size_t)T * K);
+    SCRC_CUDA(cudaMemcpyAsync(d_var.p, resid_var, (size_t)T * K * 8, cudaMemcpyHostToDevice, st));
+    DevBuf<int> d_k(T), d_votes(votes_out ? (size_t)T * K : 0);
+    const int64_t per_gene = (int64_t)K * n2;
+    const bool has_prior = (weight != 0.0);
+    if (!has_prior) {
+        // genes are independent (allocation.cpp:39-56 contributes nothing): stream the array in chunks
+        const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(T, (int64_t)(1ull << 28) / std::max<int64_t>(per_gene, 1)));
+        DevBuf<double> d_arr[2];
+        d_arr[0].alloc((size_t)chunk * per_gene);
+        d_arr[1].alloc((size_t)chunk * per_gene);
+        cudaEvent_t done[2];
+        SCRC_CUDA(cudaEventCreateWithFlags(&done[0], cudaEventDisableTiming));
+        SCRC_CUDA(cudaEventCreateWithFlags(&done[1], cudaEventDisableTiming));
+        int buf = 0;
+        for (int64_t g0 = 0; g0 < T; g0 += chunk, buf ^= 1) {
+            const int64_t ng = std::min(chunk, T - g0);
+            SCRC_CUDA(cudaEventSynchronize(done[buf]));
+            SCRC_CUDA(cudaMemcpyAsync(d_arr[buf].p, sq_resid + g0 * per_gene, (size_t)ng * per_gene * 8, cudaMemcpyHostToDevice, st));
+            alloc_parallel_kernel<<<(unsigned)ng, 256, 0, st>>>(d_arr[buf].p, K, n2, g0, ng, d_var.p, T, d_k.p, d_votes.p);
+            SCRC_LAUNCHED();
+            SCRC_CUDA(cudaEventRecord(done[buf], st));
+        }
+        SCRC_CUDA(cudaGetLastError());
+        SCRC_CUDA(cudaStreamSynchronize(st));
+        cudaEventDestroy(done[0]); cudaEventDestroy(done[1]);
+    } else {
+        size_t free_b = 0, total_b = 0;
+        SCRC_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        const size_t need = (size_t)T * per_gene * 8;
+        if (need + (1ull << 30) > free_b)
+            throw Error(SCRC_ERR_UNSUPPORTED, "allocate_into_modules with a prior needs the K x n2 x T array resident on the device; use the session API");
+        DevBuf<double> d_arr((size_t)T * per_gene);
+        SCRC_CUDA(cudaMemcpyAsync(d_arr.p, sq_resid, need, cudaMemcpyHostToDevice, st));
+        std::vector<int> k0(T);
+        for (int64_t t = 0; t < T; ++t) k0[t] = k_in[t] - 1;                 // allocation.cpp:23
+        SCRC_CUDA(cudaMemcpyAsync(d_k.p, k0.data(), T * 4, cudaMemcpyHostToDevice, st));
+        DevBuf<int> d_order(T), d_off, d_idx;
+        SCRC_CUDA(cudaMemcpyAsync(d_order.p, order, T * 4, cudaMemcpyHostToDevice, st));
+        if (prior_off) {
+            d_off.alloc(T + 1);
+            SCRC_CUDA(cudaMemcpyAsync(d_off.p, prior_off, (T + 1) * 4, cudaMemcpyHostToDevice, st));
+            const int nidx = prior_off[T];
+            d_idx.alloc(std::max(nidx, 1));
+            if (nidx > 0) SCRC_CUDA(cudaMemcpyAsync(d_idx.p, prior_idx, (size_t)nidx * 4, cudaMemcpyHostToDevice, st));
+        }
+        alloc_sequential_kernel<<<1, 1024, 0, st>>>(d_arr.p, K, n2, T, d_var.p, prior_off ? d_off.p : nullptr,
+                                                    prior_off ? d_idx.p : nullptr, d_k.p, d_order.p, baseline, weight,
+                                                    d_votes.p);
+        SCRC_LAUNCHED();
+        SCRC_CUDA(cudaGetLastError());
+        SCRC_CUDA(cudaStreamSynchronize(st));
+    }
+    SCRC_CUDA(cudaMemcpyAsync(k_out, d_k.p, T * 4, cudaMemcpyDeviceToHost, st));
+    if (votes_out) SCRC_CUDA(cudaMemcpyAsync(votes_out, d_votes.p, (size_t)T * K * 4, cudaMemcpyDeviceToHost, st));
+    SCRC_CUDA(cudaStreamSynchronize(st));
+    if (has_prior) for (int64_t t = 0; t < T; ++t) k_out[t] += 1;             // allocation.cpp:99
+}
+
+}  // namespace scrc

@@ -1,0 +1,84 @@
+// Device-resident scregclust session: data splits, Gram matrices, eigenbasis,
+// initial fit and the per-cycle batched pipeline.
+#pragma once
+#include <vector>
+
+#include "../../include/scregclust_b200.h"
+#include "admm.cuh"
+#include "alloc.cuh"
+#include "misc.cuh"
+#include "nnls.cuh"
+
+namespace scrc {
+
+struct Device {
+    int id = 0;
+    int num_sms = 148;
+    cudaStream_t stream = nullptr;
+    int* h_pinned = nullptr;   // small pinned scratch (16 ints)
+    void init(int device);
+    void destroy();
+};
+
+// Builds eig (V, Vt, lam) of the symmetric matrix G * scale (G: P x P device matrix).
+void build_eig(const DMat& G, double scale, EigBasis& eig, Device& dev);
+
+// out = V diag(1 / (mult * lam + shift)) V' * B     (normal-equation solves, R/utils.R:13-57)
+void eig_solve(const EigBasis& eig, double mult, double shift, double cut, const DMat& B, DMat& out, DMat& tmp,
+               Device& dev);
+
+struct FitSlot {        // bookkeeping of one (fit, module) after Step 1
+    int s = 0;          // selected regulators
+    int row_off = 0;    // first stacked row
+    std::vector<int> sel;
+};
+
+struct Ctx {
+    Device dev;
+    int64_t n1 = 0, n2 = 0, P = 0, T = 0;
+    int K = 0;
+    DMat Z1r, Z2r, Z1t, Z2t;
+    DevBuf<double> sds_t;        // z1_target_sds
+    DevBuf<double> inv_sds_t;    // 1 / z1_target_sds
+    DMat G_rr, G_rt;             // Z1r'Z1r, Z1r'Z1t
+    EigBasis eig;                // of G_rr / n1
+    DMat beta_init;              // P x T
+    DevBuf<double> res_sds;      // T
+    DMat bas;                    // beta_adapt_sq, P x T
+    double init_df = 0.0;
+
+    // per-cycle state
+    AdmmBatch admm;
+    DevBuf<int> col_target;
+    DevBuf<int> prob_fit, prob_mod;
+    NnlsBatch nnls;
+    DevBuf<int> row_src, row_off_d, kpad_d, nsel_d;
+    DMat ZselT;
+    DevBuf<double> partial, sse_train, sse_test, var, two_var, half_log, r2, best_r2;
+    DevBuf<int> votes, best_idx, k_new;
+    DevBuf<unsigned char> models_d;
+    DevBuf<double> weights_d, signs_d;
+    std::vector<FitSlot> slots;  // F*K, from the last cycle
+    int last_F = 0;
+
+    void create(int device, const double* z1r, const double* z2r, const double* z1t, const double* z2t,
+                const double* sds, int64_t n1, int64_t n2, int64_t P, int64_t T, int K);
+    void fit_cycle(int F, const double* lambda, const int* k_in, const scrc_options& opt, bool skip_alloc,
+                   scrc_cycle_out* out);
+    ~Ctx() { dev.destroy(); }
+};
+
+// drop-in helpers (session.cu)
+void dropin_coop_lasso(Device& dev, const double* y, int64_t n, int64_t m, const double* x, int64_t p, double lambda,
+                       const double* weights, const double* beta0, const AdmmOpts& o, double* beta_out, int* iters);
+void dropin_nnls(Device& dev, const double* x, int64_t nobs, int64_t nvar, const double* y, int64_t m, double eps,
+                 int max_iter, double* beta_out, int* iters);
+void dropin_fast_cor(Device& dev, const double* x, const double* y, int64_t n, int64_t px, int64_t py, double* out);
+void dropin_ols(Device& dev, const double* y, const double* x, int64_t n, int64_t p, int64_t m, double lambda,
+                bool ridge, double* beta_out);
+void dropin_crossprod(Device& dev, const double* x, const double* y, int64_t n, int64_t px, int64_t py, double* out);
+void dropin_allocate(Device& dev, const double* sq_resid, int K, int64_t n2, int64_t T, const double* resid_var,
+                     const int* prior_off, const int* prior_idx, const int* k_in, const int* order, double baseline,
+                     double weight, int* k_out, int* votes_out);
+
+}  // namespace scrc

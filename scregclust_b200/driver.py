@@ -1,0 +1,279 @@
+"""Host driver of the alternating fit / reallocate loop on top of the session API.
+
+Mirrors the control flow of ``scregclust()`` (R/scregclust.R:1222-1803) for
+``allocate_per_obs = TRUE``, ``quick_mode = FALSE`` and no network prior: module
+history, noise threshold, minimum module size, convergence / limit-cycle
+detection and the final re-fit of every configuration of a limit cycle.  All
+numerics run in ``libscregclust_b200.so``; every penalization value that is still
+iterating is advanced by the same batched device call (the fits are independent,
+R/scregclust.R:1223,1245).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _capi
+from ._capi import CycleOut, Options, check, dptr, f64, iptr
+
+
+@dataclass
+class FitResult:
+    """Per-penalty outcome (subset of the list built in R/scregclust.R:2002-2088)."""
+    penalization: float
+    converged: bool = False
+    n_cycles_run: int = 0
+    k_history: list = field(default_factory=list)
+    final_cycle_length: int = 1
+    k_final: list = field(default_factory=list)
+    models: list = field(default_factory=list)        # P x K bool
+    signs: list = field(default_factory=list)         # P x K (nan where unselected)
+    weights: list = field(default_factory=list)       # P x K
+    coeffs: list = field(default_factory=list)        # per module: s_j x T or None
+    sigmas: list = field(default_factory=list)        # T x K
+    r2: list = field(default_factory=list)            # T x K
+    best_r2: list = field(default_factory=list)
+    best_r2_idx: list = field(default_factory=list)
+    admm_iterations: list = field(default_factory=list)
+    nnls_iterations: list = field(default_factory=list)
+    votes: list = field(default_factory=list)
+    models_history: list = field(default_factory=list)
+
+
+class Session:
+    """Owns a ``scrc_ctx``: data splits, Gram matrices, eigenbasis and initial fit on one GPU."""
+
+    def __init__(self, z1_reg_scaled, z2_reg_scaled, z1_target_centered, z2_target_centered, z1_target_sds,
+                 n_modules, device=0):
+        self._lib = _capi.load()
+        z1r, z2r = f64(z1_reg_scaled), f64(z2_reg_scaled)
+        z1t, z2t = f64(z1_target_centered), f64(z2_target_centered)
+        sds = np.ascontiguousarray(z1_target_sds, dtype=np.float64)
+        self.n1, self.P = z1r.shape
+        self.n2 = z2r.shape[0]
+        self.T = z1t.shape[1]
+        self.K = int(n_modules)
+        if z2r.shape[1] != self.P or z2t.shape != (self.n2, self.T) or z1t.shape[0] != self.n1 or sds.size != self.T:
+            raise ValueError("inconsistent split dimensions")
+        self._h = C.c_void_p()
+        check(self._lib.scrc_ctx_create(C.byref(self._h), int(device), dptr(z1r), dptr(z2r), dptr(z1t), dptr(z2t),
+                                        dptr(sds), self.n1, self.n2, self.P, self.T, self.K))
+        self.h2d_bytes = z1r.nbytes + z2r.nbytes + z1t.nbytes + z2t.nbytes + sds.nbytes
+        self.d2h_bytes = 0
+        self.admm_sweeps = 0
+        self.admm_problem_iterations = 0
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.scrc_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # ------------------------------------------------------------------ accessors
+    def initial_fit(self):
+        res_sds = np.zeros(self.T)
+        df = C.c_double(0.0)
+        beta = np.zeros((self.P, self.T), order="F")
+        check(self._lib.scrc_ctx_get_init(self._h, dptr(res_sds), C.byref(df), dptr(beta)))
+        return {"res_sds": res_sds, "init_df": df.value, "beta_init": beta}
+
+    def gram(self):
+        g_rr = np.zeros((self.P, self.P), order="F")
+        g_rt = np.zeros((self.P, self.T), order="F")
+        check(self._lib.scrc_ctx_get_gram(self._h, dptr(g_rr), dptr(g_rt)))
+        return g_rr, g_rt
+
+    def cross_corr(self):
+        out = np.zeros((self.T, self.P), order="F")
+        check(self._lib.scrc_ctx_cross_corr(self._h, dptr(out)))
+        return out
+
+    # ------------------------------------------------------------------ one batched cycle
+    def fit_cycle(self, lambdas, ks, options=None, skip_allocation=False, want_votes=False, want_nnls_iters=False):
+        """Step 1 + 2a (+ 2b) for ``F`` (lambda, k) pairs; returns a dict of arrays in R's layouts."""
+        lam = np.ascontiguousarray(lambdas, dtype=np.float64)
+        F = lam.size
+        k = np.ascontiguousarray(ks, dtype=np.int32).reshape(F, self.T)
+        opt = options if options is not None else default_options()
+        K, P, T = self.K, self.P, self.T
+        res = {
+            "k_new": None if skip_allocation else np.zeros((F, T), dtype=np.int32),
+            "votes": np.zeros((F, T, K), dtype=np.int32) if (want_votes and not skip_allocation) else None,
+            "models": np.zeros((F, K, P), dtype=np.uint8),
+            "weights": np.zeros((F, K, P)),
+            "signs": np.zeros((F, K, P)),
+            "r2_test": np.zeros((F, K, T)),
+            "resid_var": np.zeros((F, K, T)),
+            "best_r2": np.zeros((F, T)),
+            "best_r2_idx": np.zeros((F, T), dtype=np.int32),
+            "admm_iterations": np.zeros((F, K), dtype=np.int32),
+            "nnls_iterations": np.zeros((F, K, T), dtype=np.int32) if want_nnls_iters else None,
+            "n_selected": np.zeros((F, K), dtype=np.int32),
+        }
+        sweeps = C.c_longlong(0)
+        out = CycleOut()
+        out.k_new = iptr(res["k_new"]); out.votes = iptr(res["votes"])
+        out.models = res["models"].ctypes.data_as(_capi.c_ubyte_p)
+        out.weights = dptr(res["weights"]); out.signs = dptr(res["signs"])
+        out.r2_test = dptr(res["r2_test"]); out.resid_var = dptr(res["resid_var"])
+        out.best_r2 = dptr(res["best_r2"]); out.best_r2_idx = iptr(res["best_r2_idx"])
+        out.admm_iterations = iptr(res["admm_iterations"]); out.nnls_iterations = iptr(res["nnls_iterations"])
+        out.n_selected = iptr(res["n_selected"])
+        out.admm_sweeps = C.pointer(sweeps)
+        check(self._lib.scrc_fit_cycle(self._h, F, dptr(lam), iptr(k), C.byref(opt), 1 if skip_allocation else 0,
+                                       C.byref(out)))
+        self.h2d_bytes += lam.nbytes + k.nbytes
+        self.d2h_bytes += sum(v.nbytes for v in res.values() if v is not None)
+        self.admm_sweeps += int(sweeps.value)
+        self.admm_problem_iterations += int(res["admm_iterations"].sum())
+        return res
+
+    def coeffs(self, f, module):
+        """NNLS coefficients (s x T) and 0-based regulator indices of ``module`` (0-based) of fit ``f``."""
+        s = self._last_nsel[f, module]
+        if s == 0:
+            return None, np.zeros(0, dtype=np.int32)
+        co = np.zeros((s, self.T), order="F")
+        sel = np.zeros(s, dtype=np.int32)
+        check(self._lib.scrc_ctx_get_coeffs(self._h, int(f), int(module), dptr(co), iptr(sel)))
+        self.d2h_bytes += co.nbytes + sel.nbytes
+        return co, sel
+
+
+def default_options(**kw) -> Options:
+    o = Options()
+    _capi.load().scrc_default_options(C.byref(o))
+    for k_, v in kw.items():
+        setattr(o, k_, v)
+    return o
+
+
+@dataclass
+class _PenState:
+    k: np.ndarray
+    k_history: list
+    n_k: int = 2
+    last_cycle: bool = False
+    final_cycle_length: int = 1
+    converged: bool = False
+    cycle: int = 0
+    done: bool = False
+
+
+def _unpack(fr, res, f, K, keep_diag):
+    fr.admm_iterations.append(res["admm_iterations"][f].copy())
+    fr.models_history.append(res["models"][f].T.astype(bool))
+    if keep_diag and res["nnls_iterations"] is not None:
+        fr.nnls_iterations.append(res["nnls_iterations"][f].copy())
+
+
+def scregclust_fit(z1_reg_scaled=None, z2_reg_scaled=None, z1_target_centered=None, z2_target_centered=None,
+                   z1_target_sds=None, penalization=(), n_modules=1, initial_target_modules=None,
+                   min_module_size=0, noise_threshold=0.025, n_cycles=50, max_optim_iter=10000,
+                   tol_coop_rel=1e-8, tol_coop_abs=1e-12, tol_nnls=1e-4, device=0, session=None,
+                   keep_diagnostics=False, return_coeffs=True):
+    """The alternating loop of ``scregclust()`` (R/scregclust.R:1222-1803) for all penalization values.
+
+    Returns one :class:`FitResult` per penalization value, in order.  ``session`` may be passed to
+    reuse the device-resident precompute (R/scregclust.R:996-1183) across calls.
+    """
+    own = session is None
+    ses = session or Session(z1_reg_scaled, z2_reg_scaled, z1_target_centered, z2_target_centered, z1_target_sds,
+                             n_modules, device=device)
+    try:
+        K, T = ses.K, ses.T
+        opt = default_options(max_optim_iter=int(max_optim_iter), tol_coop_rel=float(tol_coop_rel),
+                              tol_coop_abs=float(tol_coop_abs), tol_nnls=float(tol_nnls))
+        pens = [float(p) for p in penalization]
+        k_start = np.asarray(initial_target_modules, dtype=np.int32)
+        if k_start.size != T:
+            raise ValueError("initial_target_modules needs one entry per target gene")
+        states = [_PenState(k=k_start.copy(), k_history=[k_start.copy()]) for _ in pens]
+        results = [FitResult(penalization=p) for p in pens]
+        for fr, stt in zip(results, states):
+            fr.k_history = stt.k_history
+
+        while not all(s.done for s in states):
+            # R/scregclust.R:1269-1284: cycle counter, forced last cycle after n_cycles
+            for s in states:
+                if not s.done:
+                    s.cycle += 1
+                    if s.cycle == n_cycles + 1:
+                        s.last_cycle = True
+            run = [i for i, s in enumerate(states) if not s.done and not s.last_cycle]
+            fin = [i for i, s in enumerate(states) if not s.done and s.last_cycle]
+
+            if run:
+                res = ses.fit_cycle([pens[i] for i in run], np.stack([states[i].k for i in run]), opt,
+                                    skip_allocation=False, want_votes=keep_diagnostics,
+                                    want_nnls_iters=keep_diagnostics)
+                for f, i in enumerate(run):
+                    s, fr = states[i], results[i]
+                    _unpack(fr, res, f, K, keep_diagnostics)
+                    if keep_diagnostics:
+                        fr.votes.append(res["votes"][f].copy())
+                    idx = res["k_new"][f].copy()
+                    # noise module and minimum module size (R/scregclust.R:1731-1739)
+                    idx[res["best_r2"][f] < noise_threshold] = -1
+                    sizes = np.bincount(idx[idx > 0], minlength=K + 1)[1:]
+                    small = np.flatnonzero(sizes < min_module_size) + 1
+                    if small.size:
+                        idx[np.isin(idx, small)] = -1
+                    k = idx.astype(np.int32)
+                    # convergence / limit cycle (R/scregclust.R:1763-1802)
+                    matching = [j for j, kh in enumerate(s.k_history, start=1) if np.array_equal(kh, k)]
+                    s.k_history.append(k.copy())
+                    if matching:
+                        s.converged = True
+                        if s.n_k - matching[0] != 1:
+                            s.final_cycle_length = s.n_k - matching[0]
+                        s.last_cycle = True
+                    s.n_k += 1
+                    s.k = k
+                    fr.n_cycles_run = s.cycle
+
+            if fin:
+                lam_f, k_f, owner = [], [], []
+                for i in fin:
+                    s = states[i]
+                    for m in range(1, s.final_cycle_length + 1):     # R/scregclust.R:1307-1311
+                        lam_f.append(pens[i]); k_f.append(s.k_history[len(s.k_history) - m]); owner.append(i)
+                res = ses.fit_cycle(lam_f, np.stack(k_f), opt, skip_allocation=True,
+                                    want_nnls_iters=keep_diagnostics)
+                ses._last_nsel = res["n_selected"]
+                for f, i in enumerate(owner):
+                    s, fr = states[i], results[i]
+                    _unpack(fr, res, f, K, keep_diagnostics)
+                    fr.k_final.append(np.asarray(k_f[f]).copy())
+                    fr.models.append(res["models"][f].T.astype(bool))
+                    fr.signs.append(res["signs"][f].T.copy())
+                    fr.weights.append(res["weights"][f].T.copy())
+                    fr.sigmas.append(np.sqrt(res["resid_var"][f].T))
+                    fr.r2.append(res["r2_test"][f].T.copy())
+                    fr.best_r2.append(res["best_r2"][f].copy())
+                    fr.best_r2_idx.append(res["best_r2_idx"][f].copy())
+                    if return_coeffs:
+                        fr.coeffs.append([ses.coeffs(f, j)[0] for j in range(K)])
+                for i in fin:
+                    s, fr = states[i], results[i]
+                    s.done = True
+                    fr.converged = s.converged
+                    fr.final_cycle_length = s.final_cycle_length
+                    fr.n_cycles_run = s.cycle
+        return results
+    finally:
+        if own:
+            ses.close()

@@ -1,0 +1,160 @@
+"""Parity of the CUDA kernels (through the C ABI) against the CPU oracle.
+
+Tolerances: discrete outputs (iteration counts, module ids, votes, selected
+regulators) bit-exact; floating point 1e-8 relative (BASELINE.json north_star),
+Gram / correlation 1e-12 relative.
+"""
+import numpy as np
+import pytest
+
+from conftest import rel_err
+from oracle import scregclust_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def api():
+    from scregclust_b200 import api as a
+    return a
+
+
+@pytest.mark.parametrize("n,px,py", [(64, 8, 8), (200, 50, 10), (1000, 130, 257), (2500, 500, 300), (333, 77, 1),
+                                     (17, 3, 5), (4096, 256, 1024)])
+def test_crossprod(api, rng, n, px, py):
+    x = rng.standard_normal((n, px)); y = rng.standard_normal((n, py))
+    got = api.crossprod(x, y)
+    assert rel_err(got, x.T @ y) < 1e-12
+    g = api.crossprod(x)
+    assert rel_err(g, x.T @ x) < 1e-12
+    assert np.array_equal(g, g.T)          # mirrored like optim.cpp:22-23
+
+
+def test_crossprod_linearity(api, rng):
+    # size-independent property at a BASELINE-scale contraction length
+    n, p = 10000, 192
+    x = rng.standard_normal((n, p)); y1 = rng.standard_normal((n, 64)); y2 = rng.standard_normal((n, 64))
+    a = api.crossprod(x, y1 + 2.0 * y2)
+    b = api.crossprod(x, y1) + 2.0 * api.crossprod(x, y2)
+    assert rel_err(a, b) < 1e-12
+
+
+@pytest.mark.parametrize("n,px,py", [(200, 50, 10), (1001, 33, 129)])
+def test_fast_cor(api, rng, n, px, py):
+    # tests/testthat/test-fast-cor.R: fast_cor == stats::cor
+    zt = rng.standard_normal((n, px)) + 3.0; zr = rng.standard_normal((n, py)) - 1.0
+    ref = np.corrcoef(zt.T, zr.T)[:px, px:]
+    got = api.fast_cor(zt, zr)
+    assert rel_err(got, ref) < 1e-12
+    assert rel_err(got, orc.fast_cor(zt, zr)) < 1e-12
+    assert np.all(np.abs(got) <= 1.0)
+
+
+def test_fast_cor_self_is_one(api, rng):
+    z = rng.standard_normal((500, 20))
+    got = api.fast_cor(z, z)
+    assert np.allclose(np.diag(got), 1.0, atol=1e-14)
+    assert np.all(got <= 1.0)
+
+
+def test_coef_ols_ridge(api, rng):
+    n, p, m = 600, 40, 25
+    x = rng.standard_normal((n, p)); y = x @ rng.standard_normal((p, m)) + rng.standard_normal((n, m))
+    assert rel_err(api.coef_ols(y, x), orc.coef_ols(y, x)) < 1e-9
+    assert rel_err(api.coef_ridge(y, x, 3.5), orc.coef_ridge(y, x, 3.5)) < 1e-9
+    # n < p: Moore-Penrose branch (R/utils.R:20-30)
+    x2 = rng.standard_normal((30, 50)); y2 = rng.standard_normal((30, 4))
+    assert rel_err(api.coef_ols(y2, x2), orc.coef_ols(y2, x2)) < 1e-7
+
+
+def _coop_case(rng, n, p, m, lam):
+    x = rng.standard_normal((n, p)) / np.sqrt(n)
+    b = np.zeros((p, m)); b[: max(2, p // 5)] = rng.standard_normal((max(2, p // 5), 1)) + 0.2 * rng.standard_normal((max(2, p // 5), m))
+    y = (x * np.sqrt(n)) @ b / np.sqrt(n) + rng.standard_normal((n, m)) / np.sqrt(n)
+    w = np.full(p, np.sqrt(m)) * (0.5 + rng.random(p))
+    return x, y, w, lam
+
+
+@pytest.mark.parametrize("n,p,m,lam", [(200, 10, 5, 0.1), (1000, 100, 80, 0.2), (2500, 300, 200, 0.05), (300, 20, 1, 0.3)])
+def test_coop_lasso(api, rng, n, p, m, lam):
+    x, y, w, lam = _coop_case(rng, n, p, m, lam)
+    ref_b, ref_it = orc.coop_lasso(y, x, lam, w, max_iter=10000)
+    got = api.coop_lasso(y, x, lam, w, max_iter=10000)
+    assert got["iterations"] == ref_it
+    assert rel_err(got["beta"], ref_b) < 1e-8
+    # selected set through the driver's 1e-6 threshold (R/scregclust.R:1382)
+    assert np.array_equal(np.abs(got["beta"]) >= 1e-6, np.abs(ref_b) >= 1e-6)
+
+
+def test_coop_lasso_warm_start_and_maxiter(api, rng):
+    x, y, w, lam = _coop_case(rng, 400, 30, 12, 0.15)
+    ref_b, ref_it = orc.coop_lasso(y, x, lam, w, max_iter=10000)
+    b0 = ref_b + 1e-3 * rng.standard_normal(ref_b.shape)
+    r2_b, r2_it = orc.coop_lasso(y, x, lam, w, beta_0=b0, max_iter=10000)
+    got = api.coop_lasso(y, x, lam, w, beta_0=b0, max_iter=10000)
+    assert got["iterations"] == r2_it and rel_err(got["beta"], r2_b) < 1e-8
+    r3_b, r3_it = orc.coop_lasso(y, x, lam, w, max_iter=5)
+    got = api.coop_lasso(y, x, lam, w, max_iter=5)
+    assert r3_it == 6 and got["iterations"] == 6          # optim.cpp:295-305
+    assert rel_err(got["beta"], r3_b) < 1e-8
+
+
+def test_coop_lasso_errors(api):
+    from scregclust_b200._capi import ScrcError
+    y = np.zeros((4, 2)); x = np.zeros((5, 3)); w = np.ones(3)
+    with pytest.raises(ScrcError, match="same number of rows"):
+        api.coop_lasso(y, x, 0.1, w)
+    x = np.ones((4, 3))
+    with pytest.raises(ScrcError, match="rho_0 > 0"):
+        api.coop_lasso(y, x, 0.1, w, rho_0=0.0)
+    with pytest.raises(ScrcError, match="alpha_0"):
+        api.coop_lasso(y, x, 0.1, w, alpha_0=2.5)
+    with pytest.raises(ScrcError, match="beta_0 needs"):
+        api.coop_lasso(y, x, 0.1, w, beta_0=np.zeros((2, 2)))
+
+
+@pytest.mark.parametrize("n,s,m", [(300, 1, 7), (500, 4, 33), (800, 13, 100), (1200, 64, 150), (900, 130, 40)])
+def test_coef_nnls(api, rng, n, s, m):
+    x = rng.standard_normal((n, s))
+    b = np.maximum(rng.standard_normal((s, m)), 0.0)
+    y = x @ b + 0.5 * rng.standard_normal((n, m))
+    for eps in (1e-4, 1e-10):
+        ref_b, ref_it = orc.coef_nnls(x, y, eps=eps, max_iter=10000)
+        got = api.coef_nnls(x, y, eps=eps, max_iter=10000)
+        assert np.array_equal(got["iterations"], ref_it)
+        assert rel_err(got["beta"], ref_b) < 1e-8
+        assert np.all(got["beta"] >= 0.0)
+        assert np.array_equal(got["beta"] == 0.0, ref_b == 0.0)
+
+
+def test_coef_nnls_unconverged_gives_zero(api, rng):
+    x = rng.standard_normal((200, 12)); x[:, 1] = x[:, 0] + 1e-3 * rng.standard_normal(200)
+    y = x @ np.abs(rng.standard_normal((12, 9))) + rng.standard_normal((200, 9))
+    ref_b, ref_it = orc.coef_nnls(x, y, eps=1e-13, max_iter=1)
+    got = api.coef_nnls(x, y, eps=1e-13, max_iter=1)
+    assert np.array_equal(got["iterations"], ref_it)
+    assert np.array_equal(got["beta"] == 0.0, ref_b == 0.0)      # optim.cpp:423,502
+    assert rel_err(got["beta"], ref_b) < 1e-8 or np.all(ref_b == 0)
+
+
+@pytest.mark.parametrize("K,n2,T,weight", [(3, 50, 20, 0.0), (5, 333, 64, 0.0), (10, 1000, 40, 0.0), (4, 120, 30, 0.5)])
+def test_allocate_into_modules(api, rng, K, n2, T, weight):
+    z2 = rng.standard_normal((n2, T))
+    arr = orc.alloc_array(z2 * z2, K)
+    got_arr = api.alloc_array(z2 * z2, K)
+    assert np.array_equal(arr, got_arr)
+    arr *= rng.random((K, 1, T)) + 0.5
+    arr[1] = arr[0]                                  # exact tie between module 1 and 2 -> first wins
+    resid_var = np.asfortranarray(rng.random((T, K)) + 0.5)
+    resid_var[:, 1] = resid_var[:, 0]
+    k = rng.integers(1, K + 1, size=T).astype(np.int32); k[::7] = -1
+    order = rng.permutation(T).astype(np.int32)
+    prior = [list(rng.choice(T, size=rng.integers(0, 5), replace=False)) for _ in range(T)] if weight > 0 else []
+    ref, ref_votes = orc.allocate_into_modules(arr, resid_var, prior, k, order, 1e-6, weight, return_votes=True)
+    got, votes = api.allocate_into_modules(arr, resid_var, prior, k, order, 1e-6, weight, return_votes=True)
+    assert np.array_equal(votes, ref_votes)
+    assert np.array_equal(got, ref)
+    if weight == 0.0:
+        assert not np.any(got == 2)
+    api.reset_array(got_arr, z2 * z2)
+    assert np.array_equal(got_arr, orc.alloc_array(z2 * z2, K))
