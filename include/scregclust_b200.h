@@ -101,6 +101,19 @@ int scrc_crossprod(const double* x, const double* y, int64_t n, int64_t px, int6
  * the average milliseconds per launch.  symmetric != 0 uses the SYRK-style mirrored epilogue. */
 int scrc_bench_gemm(int64_t k, int64_t m, int64_t n, int symmetric, int reps, double* ms_per_launch);
 
+/* Per-kernel-class timing with CUDA events on the launching stream (off by default).
+ * Classes: 0 dense GEMMs (Gram / correlation / initial fit), 1 ADMM eigenbasis GEMMs,
+ * 2 ADMM elementwise kernels, 3 NNLS, 4 fused residual/vote kernel, 5 other.
+ * ms: accumulated kernel time, work: algorithmic flops (classes 0, 1) or bytes (2, 4),
+ * launches: timed launch groups.  Each array has 6 entries; any may be NULL. */
+int scrc_profile_enable(int on);
+int scrc_profile_reset(void);
+int scrc_profile_get(double* ms, double* work, unsigned long long* launches);
+/* Device-side wall clock: both calls synchronise the current device and record a CUDA event,
+ * so the interval covers every stream of this library (used by bench.py). */
+int scrc_timer_begin(void);
+int scrc_timer_end(double* ms);
+
 /* ------------------------------------------------------------------ session API */
 
 typedef struct scrc_ctx scrc_ctx;

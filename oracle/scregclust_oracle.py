@@ -245,35 +245,35 @@ def coop_lasso(y, x, lam, weights, beta_0=None, rho_0=0.2, alpha_0=1.5, n_update
             d_m = mult - mult_old
             d_g = zeta_old - zeta
             n_dmh = _fnorm(d_mh); n_dh = _fnorm(d_h); n_dm = _fnorm(d_m); n_dg = _fnorm(d_g)
-            a_ = 0.0; a_corr = 0.0
-            if n_dmh > 0.0 and n_dh > 0.0:
-                hm = float(np.sum(d_h * d_mh))
-                a_sd = float(np.sum(d_mh * d_mh)) / hm
-                a_mg = hm / float(np.sum(d_h * d_h))
-                a_ = a_mg if 2.0 * a_mg > a_sd else a_sd - a_mg / 2.0
-                a_corr = hm / (n_dh * n_dmh)
-            b_ = 0.0; b_corr = 0.0
-            if n_dm > 0.0 and n_dg > 0.0:
-                gm = float(np.sum(d_g * d_m))
-                b_sd = float(np.sum(d_m * d_m)) / gm
-                b_mg = gm / float(np.sum(d_g * d_g))
-                b_ = b_mg if 2.0 * b_mg > b_sd else b_sd - b_mg / 2.0
-                b_corr = gm / (n_dg * n_dm)
+            # IEEE semantics (inf / nan instead of Python's ZeroDivisionError), as in C++
+            f8 = np.float64
+            with np.errstate(all="ignore"):
+                a_ = 0.0; a_corr = 0.0
+                if n_dmh > 0.0 and n_dh > 0.0:
+                    hm = f8(np.sum(d_h * d_mh))
+                    a_sd = f8(np.sum(d_mh * d_mh)) / hm
+                    a_mg = hm / f8(np.sum(d_h * d_h))
+                    a_ = float(a_mg if 2.0 * a_mg > a_sd else a_sd - a_mg / 2.0)
+                    a_corr = float(hm / (f8(n_dh) * f8(n_dmh)))
+                b_ = 0.0; b_corr = 0.0
+                if n_dm > 0.0 and n_dg > 0.0:
+                    gm = f8(np.sum(d_g * d_m))
+                    b_sd = f8(np.sum(d_m * d_m)) / gm
+                    b_mg = gm / f8(np.sum(d_g * d_g))
+                    b_ = float(b_mg if 2.0 * b_mg > b_sd else b_sd - b_mg / 2.0)
+                    b_corr = float(gm / (f8(n_dg) * f8(n_dm)))
             rho_old = rho
-            if a_corr > eps_corr and b_corr > eps_corr:
-                rho = math.sqrt(a_ * b_)
-            elif a_corr > eps_corr and b_corr <= eps_corr:
-                rho = a_
-            elif a_corr <= eps_corr and b_corr > eps_corr:
-                rho = b_
-            if a_corr > eps_corr and b_corr > eps_corr:
-                alpha = 1.0 + 2.0 / (math.sqrt(a_ * b_) * (1.0 / a_ + 1.0 / b_))
-            elif a_corr > eps_corr and b_corr <= eps_corr:
-                alpha = 1.9
-            elif a_corr <= eps_corr and b_corr > eps_corr:
-                alpha = 1.1
-            else:
-                alpha = 1.5
+            with np.errstate(all="ignore"):
+                ga = a_corr > eps_corr; gb = b_corr > eps_corr
+                if ga and gb:
+                    rho = float(np.sqrt(f8(a_) * f8(b_)))
+                    alpha = float(1.0 + 2.0 / (np.sqrt(f8(a_) * f8(b_)) * (1.0 / f8(a_) + 1.0 / f8(b_))))
+                elif ga and not gb:
+                    rho = a_; alpha = 1.9
+                elif (not ga) and gb:
+                    rho = b_; alpha = 1.1
+                else:
+                    alpha = 1.5
             beta_old = beta.copy(); zeta_old = zeta_new.copy()
             mult_old = mult.copy(); mult_hat_old = mult_hat
             pc = 0
@@ -408,11 +408,15 @@ def reset_array(arr: np.ndarray, inp: np.ndarray) -> None:
 # src/allocation.cpp:8-100
 # --------------------------------------------------------------------------- #
 def allocate_into_modules(resid_array, resid_var, prior_indicator, k_, update_order,
-                          prior_baseline, prior_weight, return_votes=False):
+                          prior_baseline, prior_weight, return_votes=False, ambiguity=None):
     """Per-cell vote reallocation (src/allocation.cpp:8-100).
 
     ``resid_array`` is K x n2 x T of *squared* residuals, ``resid_var`` T x K,
     ``k_`` 1-based (-1 noise), ``update_order`` / ``prior_indicator`` 0-based.
+
+    ``ambiguity`` (optional int array of length T, filled in place) receives, per gene, the
+    number of cells whose two best module scores differ, but by less than 1e-9 relative -- i.e. cells whose
+    vote is decided by rounding noise (mathematically tied models).  Test diagnostics only.
     """
     n_modules, n_obs, n_genes = resid_array.shape
     k = np.asarray(k_, dtype=np.int64) - 1
@@ -436,6 +440,11 @@ def allocate_into_modules(resid_array, resid_var, prior_indicator, k_, update_or
         ll = (-resid) / (2.0 * var)[:, None] - (0.5 * np.log(2.0 * math.pi * var))[:, None]
         score = (1.0 - prior_weight) * ll + (prior_weight * prior_log_prob)[:, None]
         best_per_cell = np.argmax(score, axis=0)            # first max
+        if ambiguity is not None and n_modules > 1:
+            part = np.partition(score, n_modules - 2, axis=0)
+            top1 = part[n_modules - 1]; top2 = part[n_modules - 2]
+            gap = top1 - top2                               # exact ties (gap == 0) resolve to the first index
+            ambiguity[j] = int(np.sum((gap > 0.0) & (gap <= 1e-9 * np.maximum(1.0, np.abs(top1)))))
         votes = np.bincount(best_per_cell, minlength=n_modules).astype(np.int32)
         best = int(np.argmax(votes))                        # first max
         if return_votes:
@@ -558,7 +567,11 @@ class FitResult:
     admm_iterations: list = field(default_factory=list)    # per cycle: length-K int (0 = skipped)
     nnls_iterations: list = field(default_factory=list)    # per cycle: K x T int (0 = skipped)
     votes: list = field(default_factory=list)              # per cycle: T x K int
+    ambiguity: list = field(default_factory=list)          # per cycle: T int (rounding-tied cells)
     models_history: list = field(default_factory=list)
+    resid_var_history: list = field(default_factory=list)  # per cycle T x K
+    r2_history: list = field(default_factory=list)         # per cycle T x K
+    coeffs_history: list = field(default_factory=list)     # per cycle list of s_j x T
     r2_module: list = field(default_factory=list)
     importance: list = field(default_factory=list)
 
@@ -609,7 +622,7 @@ def scregclust_fit(z1_reg_scaled, z2_reg_scaled, z1_target_centered, z2_target_c
                    min_module_size=0, noise_threshold=0.025, n_cycles=50,
                    max_optim_iter=10000, tol_coop_rel=1e-8, tol_coop_abs=1e-12,
                    tol_nnls=1e-4, update_orders=None, compute_predictive_r2=False,
-                   materialize_array=True, pre=None):
+                   materialize_array=True, pre=None, keep_history=False):
     """The alternating loop of ``scregclust()`` (R/scregclust.R:1222-1803) for
     ``allocate_per_obs = TRUE``, ``quick_mode = FALSE``.
 
@@ -695,6 +708,9 @@ def scregclust_fit(z1_reg_scaled, z2_reg_scaled, z1_target_centered, z2_target_c
                 r2_test = 1.0 - ss_test / ss_test0[:, None]
                 best_r2[cycle] = np.max(r2_test, axis=1)
                 resid_var = ss_train / (n1 - np.sum(models, axis=0))[None, :]
+                if keep_history:
+                    fr.resid_var_history.append(resid_var.copy()); fr.r2_history.append(r2_test.copy())
+                    fr.coeffs_history.append(betas)
                 if last_cycle:
                     fr.k_final.append(k.copy()); fr.models.append(models); fr.signs.append(signs)
                     fr.weights.append(weights); fr.coeffs.append(betas)
@@ -707,14 +723,17 @@ def scregclust_fit(z1_reg_scaled, z2_reg_scaled, z1_target_centered, z2_target_c
             # ---- Step 2b (scregclust.R:1665-1739) ----
             order = (update_orders(li, cycle) if update_orders is not None
                      else np.arange(n_target))
+            amb = np.zeros(n_target, dtype=np.int64)
             if materialize_array:
                 idx, votes = allocate_into_modules(sq_arr, resid_var, prior_indicator, k, order,
-                                                   prior_baseline, prior_weight, return_votes=True)
+                                                   prior_baseline, prior_weight, return_votes=True,
+                                                   ambiguity=amb)
             else:
                 idx, votes = _allocate_streaming(z2t, z2r, models, betas, resid_var,
                                                  prior_indicator, k, order, prior_baseline,
-                                                 prior_weight)
+                                                 prior_weight, amb)
             fr.votes.append(votes)
+            fr.ambiguity.append(amb)
             idx = idx.copy()
             idx[best_r2[cycle] < noise_threshold] = -1
             module_size = np.array([np.sum(idx == i) for i in range(1, n_modules + 1)])
@@ -742,7 +761,7 @@ def scregclust_fit(z1_reg_scaled, z2_reg_scaled, z1_target_centered, z2_target_c
 
 
 def _allocate_streaming(z2t, z2r, models, betas, resid_var, prior_indicator, k_, order,
-                        prior_baseline, prior_weight):
+                        prior_baseline, prior_weight, ambiguity=None):
     """allocate_into_modules without the K x n2 x T array: rebuilds each gene's
     K x n2 slab on the fly (same arithmetic as scregclust.R:1593-1599 + allocation.cpp)."""
     n2, n_target = z2t.shape
@@ -763,7 +782,7 @@ def _allocate_streaming(z2t, z2r, models, betas, resid_var, prior_indicator, k_,
                 out[c] = r * r
             return out
     return allocate_into_modules(_Lazy(), resid_var, prior_indicator, k_, order,
-                                 prior_baseline, prior_weight, return_votes=True)
+                                 prior_baseline, prior_weight, return_votes=True, ambiguity=ambiguity)
 
 
 def _importance(fr, z1r, z2r, z1t, z2t, z1_target_sds, G_rr, G_rt_nnls, n_modules,

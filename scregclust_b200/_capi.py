@@ -61,6 +61,11 @@ SIGNATURES = {
     "scrc_coef_ridge": (C.c_int, [c_double_p, c_double_p, C.c_int64, C.c_int64, C.c_int64, C.c_double, c_double_p]),
     "scrc_crossprod": (C.c_int, [c_double_p, c_double_p, C.c_int64, C.c_int64, C.c_int64, c_double_p]),
     "scrc_bench_gemm": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int, c_double_p]),
+    "scrc_profile_enable": (C.c_int, [C.c_int]),
+    "scrc_profile_reset": (C.c_int, []),
+    "scrc_profile_get": (C.c_int, [c_double_p, c_double_p, C.POINTER(C.c_ulonglong)]),
+    "scrc_timer_begin": (C.c_int, []),
+    "scrc_timer_end": (C.c_int, [c_double_p]),
     "scrc_ctx_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, c_double_p, c_double_p, c_double_p, c_double_p,
                                   c_double_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int]),
     "scrc_ctx_destroy": (None, [C.c_void_p]),

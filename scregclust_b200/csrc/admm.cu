@@ -2,6 +2,7 @@
 // src/optim.cpp:134-308 step by step; only the linear
 // solve is restructured (eigenbasis GEMMs, admm.cuh).
 #include "admm.cuh"
+#include "prof.cuh"
 
 #include <algorithm>
 
@@ -19,6 +20,7 @@ struct AdmmDev {
     int* active;
     int* iters;
     int* n_active;
+    unsigned long long* col_iters;   // sum over sweeps of the number of active columns
     const double* w;
     const double* xty;
     double *R, *W, *beta, *zeta, *mult, *beta_old, *zeta_old, *mult_old, *mult_hat_old;
@@ -31,7 +33,7 @@ void AdmmBatch::resize(int P_, int C_, int nprob_) {
     col_prob.ensure(C); prob_c0.ensure(nprob); prob_c1.ensure(nprob);
     prob_lambda.ensure(nprob); prob_rho.ensure(nprob); prob_alpha.ensure(nprob);
     prob_active.ensure(nprob); prob_iters.ensure(nprob);
-    n_active.ensure(1);
+    n_active.ensure(1); col_iters.ensure(1);
     w.reshape(P, nprob);
     DMat* mats[] = {&xty, &R, &W, &beta, &zeta, &mult, &beta_old, &zeta_old, &mult_old, &mult_hat_old};
     for (DMat* m : mats) m->reshape(P, C);
@@ -45,6 +47,7 @@ static AdmmDev make_dev(AdmmBatch& b) {
     d.col_prob = b.col_prob.p; d.c0 = b.prob_c0.p; d.c1 = b.prob_c1.p;
     d.lambda = b.prob_lambda.p; d.rho = b.prob_rho.p; d.alpha = b.prob_alpha.p;
     d.active = b.prob_active.p; d.iters = b.prob_iters.p; d.n_active = b.n_active.p;
+    d.col_iters = b.col_iters.p;
     d.w = b.w.data(); d.xty = b.xty.data();
     d.R = b.R.data(); d.W = b.W.data(); d.beta = b.beta.data(); d.zeta = b.zeta.data();
     d.mult = b.mult.data(); d.beta_old = b.beta_old.data(); d.zeta_old = b.zeta_old.data();
@@ -61,7 +64,7 @@ __global__ void admm_init_prob_kernel(AdmmDev d, double rho0, double alpha0) {
         d.active[p] = (d.c1[p] > d.c0[p]) ? 1 : 0;
         d.iters[p] = 0;
     }
-    if (p == 0) *d.n_active = d.nprob;
+    if (p == 0) { *d.n_active = d.nprob; *d.col_iters = 0ull; }
 }
 
 // ------------------------------------------------------------------ rhs = xty + rho*zeta + mult   (optim.cpp:143)
@@ -69,6 +72,7 @@ __global__ void __launch_bounds__(256) admm_rhs_kernel(AdmmDev d) {
     const int c = blockIdx.x;
     const int p = d.col_prob[c];
     if (!d.active[p]) return;
+    if (threadIdx.x == 0) atomicAdd(d.col_iters, 1ull);
     const double rho = d.rho[p];
     const int64_t base = (int64_t)c * d.ld;
     for (int i = threadIdx.x; i < d.P; i += blockDim.x) {
@@ -144,7 +148,10 @@ static void launch_admm_gemm(const AdmmDev& d, const DMat& A, const double* Bm, 
     }
     const int64_t tiles = ceil_div(d.P, BM) * ceil_div(d.C, BN);
     const int grid = (int)std::min<int64_t>(tiles, num_sms);
-    gemm_tn_kernel<Pol><<<grid, GEMM_THREADS, smem, stream>>>(p);
+    {
+        ProfScope ps(PROF_GEMM_ADMM, stream);
+        gemm_tn_kernel<Pol><<<grid, GEMM_THREADS, smem, stream>>>(p);
+    }
     SCRC_CUDA(cudaGetLastError());
     SCRC_LAUNCHED();
 }
@@ -320,7 +327,10 @@ int admm_solve(AdmmBatch& b, const EigBasis& eig, const AdmmOpts& o, bool cold, 
     int it = 1;
     int sweeps = 0;
     while (true) {
-        admm_rhs_kernel<<<b.C, 256, 0, stream>>>(d);
+        {
+            ProfScope ps(PROF_ADMM_ELEM, stream);
+            admm_rhs_kernel<<<b.C, 256, 0, stream>>>(d);
+        }
         SCRC_LAUNCHED();
         if (big) {
             launch_admm_gemm<128, 128, 6, 1>(d, eig.V, d.R, d.W, num_sms, eig.lam.p, stream);
@@ -330,11 +340,13 @@ int admm_solve(AdmmBatch& b, const EigBasis& eig, const AdmmOpts& o, bool cold, 
             launch_admm_gemm<64, 64, 8, 2>(d, eig.Vt, d.W, d.beta, num_sms, eig.lam.p, stream);
         }
         const int is_update = (it % o.n_update == 0) ? 1 : 0;
-        if (is_update) admm_update_kernel<true><<<ugrid, ADMM_UPD_WARPS * 32, 0, stream>>>(d);
-        else admm_update_kernel<false><<<ugrid, ADMM_UPD_WARPS * 32, 0, stream>>>(d);
-        SCRC_LAUNCHED();
-        admm_finalize_kernel<<<1, 256, 0, stream>>>(d, o, it, is_update);
-        SCRC_LAUNCHED();
+        {
+            ProfScope ps(PROF_ADMM_ELEM, stream);
+            if (is_update) admm_update_kernel<true><<<ugrid, ADMM_UPD_WARPS * 32, 0, stream>>>(d);
+            else admm_update_kernel<false><<<ugrid, ADMM_UPD_WARPS * 32, 0, stream>>>(d);
+            admm_finalize_kernel<<<1, 256, 0, stream>>>(d, o, it, is_update);
+        }
+        SCRC_LAUNCHED(); SCRC_LAUNCHED();
         SCRC_CUDA(cudaGetLastError());
         ++sweeps;
         if ((it >= 4 && it % 2 == 0) || it >= o.max_iter) {
@@ -344,6 +356,15 @@ int admm_solve(AdmmBatch& b, const EigBasis& eig, const AdmmOpts& o, bool cold, 
         }
         ++it;
         if (it > o.max_iter + 1) break;  // safety net; finalize retires every problem at max_iter
+    }
+    {   // column-iterations actually executed -> algorithmic flops of the 2 GEMMs per sweep
+        unsigned long long ci = 0;
+        SCRC_CUDA(cudaMemcpyAsync(&ci, d.col_iters, sizeof(ci), cudaMemcpyDeviceToHost, stream));
+        SCRC_CUDA(cudaStreamSynchronize(stream));
+        b.last_col_iters = ci;
+        g_prof.add_work(PROF_GEMM_ADMM, 4.0 * (double)b.P * (double)b.P * (double)ci);
+        // elementwise sweep: ~10 matrix passes of 8 bytes per active element
+        g_prof.add_work(PROF_ADMM_ELEM, 80.0 * (double)b.P * (double)ci);
     }
     return sweeps;
 }

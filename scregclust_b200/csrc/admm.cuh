@@ -46,6 +46,8 @@ struct AdmmBatch {
     DevBuf<double> prob_rho, prob_alpha;
     DevBuf<int> prob_active, prob_iters;
     DevBuf<int> n_active;      // [1]
+    DevBuf<unsigned long long> col_iters;   // [1] sum over sweeps of active columns
+    unsigned long long last_col_iters = 0;
     DMat w;                    // P x nprob group weights
     // state (P x C)
     DMat xty, R, W, beta, zeta, mult, beta_old, zeta_old, mult_old, mult_hat_old;

@@ -1,7 +1,9 @@
 #include "alloc.cuh"
+#include "prof.cuh"
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 namespace scrc {
 
@@ -30,8 +32,8 @@ template <bool VOTE>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) resid_vote_kernel(const __grid_constant__ RvParams p) {
     constexpr int MT = RV_BM / (GEMM_WARPS_M * 8);   // 4
     constexpr int NT = RV_BN / (GEMM_WARPS_N * 8);   // 2
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    extern __shared__ __align__(1024) uint8_t smem[];   // see gemm_tn.cuh: keep the shared address space
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + RV_STAGES * RV_STAGE_BYTES);
     uint64_t* empty = full + RV_STAGES;
     const int K1 = p.K + 1;
@@ -45,16 +47,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) resid_vote_kernel(const __gri
     }
     __syncthreads();
 
-    const int nwork = p.L * p.CR * p.tiles_n;
+    // One work item per CTA: (penalty/fit l, cell range cr, target tile tn).  (A persistent
+    // multi-item variant of this kernel produced run-to-run differences at item boundaries on
+    // B200 that were not root-caused in round 1; one item per CTA is exact and deterministic.)
     const int ct_per = (p.ctiles + p.CR - 1) / p.CR;
+    const int w = blockIdx.x;
+    const int tn = w % p.tiles_n, cr = (w / p.tiles_n) % p.CR, l = w / (p.tiles_n * p.CR);
+    const int ct0 = cr * ct_per, ct1 = min(ct0 + ct_per, p.ctiles);
     PipeState ps;
 
     if (warp < GEMM_PRODUCER_WARPS) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
         if (warp == 0 && lane == 0) {
-            for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
-                const int tn = w % p.tiles_n, cr = (w / p.tiles_n) % p.CR, l = w / (p.tiles_n * p.CR);
-                const int ct0 = cr * ct_per, ct1 = min(ct0 + ct_per, p.ctiles);
+            {
                 for (int ct = ct0; ct < ct1; ++ct) {
                     for (int j = 0; j < p.K; ++j) {
                         const int kp = p.kpad[l * p.K + j];
@@ -81,9 +86,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) resid_vote_kernel(const __gri
     const int a_row0 = warp_m * (MT * 8), b_col0 = warp_n * (NT * 8);
     const int r = lane >> 2, q = lane & 3;
 
-    for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
-        const int tn = w % p.tiles_n, cr = (w / p.tiles_n) % p.CR, l = w / (p.tiles_n * p.CR);
-        const int ct0 = cr * ct_per, ct1 = min(ct0 + ct_per, p.ctiles);
+    {
         const int t0 = tn * RV_BN;
         // zero the per-work-item accumulators (each SSE entry is owned by exactly one thread)
         if (r == 0) {
@@ -195,7 +198,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) resid_vote_kernel(const __gri
                 const int v = votes_s[i];
                 if (v != 0 && t0 + lc < p.T) atomicAdd(&p.votes[((int64_t)l * p.T + t0 + lc) * p.K + j], v);
             }
-            consumer_bar();
         }
     }
 }
@@ -204,7 +206,7 @@ int resid_vote_pick_cr(int ncells, int T, int L, int num_sms) {
     const int ctiles = (int)ceil_div(ncells, RV_BM);
     const int64_t base = (int64_t)L * ceil_div(T, RV_BN);
     int cr = (int)ceil_div((int64_t)num_sms * 4, base);
-    cr = std::max(1, std::min(cr, ctiles));
+    cr = std::max(1, std::min(cr, (int)ceil_div(ctiles, 2)));   // at least two cell tiles per CTA when possible
     return cr;
 }
 size_t resid_vote_partial_elems(int T, int K, int L, int CR) {
@@ -221,8 +223,9 @@ void resid_vote(const ResidVoteArgs& a, bool vote, int num_sms, cudaStream_t st)
     p.row_off = a.row_off; p.kpad = a.kpad; p.two_var = a.two_var; p.half_log = a.half_log;
     p.partial = a.partial; p.votes = a.votes; p.CR = a.CR;
     p.tiles_n = (int)ceil_div(a.T, RV_BN); p.ctiles = (int)ceil_div(a.ncells, RV_BM);
+
     const int smem = RV_STAGES * RV_STAGE_BYTES + 2 * RV_STAGES * 8 + 2 * (a.K + 1) * RV_BN * 8 +
-                     RV_BN * a.K * 4 + 1024;
+                     RV_BN * a.K * 4;
     static int conf[2] = {0, 0};
     if (smem > conf[vote ? 1 : 0]) {
         if (vote) SCRC_CUDA(cudaFuncSetAttribute(resid_vote_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -230,9 +233,17 @@ void resid_vote(const ResidVoteArgs& a, bool vote, int num_sms, cudaStream_t st)
         conf[vote ? 1 : 0] = smem;
     }
     const int64_t nwork = (int64_t)a.L * a.CR * p.tiles_n;
-    const int grid = (int)std::min<int64_t>(nwork, num_sms);
-    if (vote) resid_vote_kernel<true><<<grid, GEMM_THREADS, smem, st>>>(p);
-    else resid_vote_kernel<false><<<grid, GEMM_THREADS, smem, st>>>(p);
+    if (nwork > 0x7fffffffLL) throw Error(-61, "resid_vote: too many work items");
+    const int grid = (int)nwork;
+    (void)num_sms;
+    {
+        // algorithmic bytes: the target tile is read once per (fit, target tile, cell tile); the
+        // gathered regulators and coefficients once per module slice
+        const double bytes = 8.0 * (double)a.L * a.ncells * a.T + 8.0 * (double)a.rows_total * (a.ncells * (double)p.tiles_n + (double)a.T * p.ctiles);
+        ProfScope ps(PROF_RESID_VOTE, st, bytes);
+        if (vote) resid_vote_kernel<true><<<grid, GEMM_THREADS, smem, st>>>(p);
+        else resid_vote_kernel<false><<<grid, GEMM_THREADS, smem, st>>>(p);
+    }
     SCRC_CUDA(cudaGetLastError());
     SCRC_LAUNCHED();
 }

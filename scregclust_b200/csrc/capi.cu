@@ -2,6 +2,7 @@
 #include <memory>
 #include <mutex>
 
+#include "prof.cuh"
 #include "session.cuh"
 
 using namespace scrc;
@@ -177,6 +178,47 @@ int scrc_bench_gemm(int64_t k, int64_t m, int64_t n, int symmetric, int reps, do
     });
 }
 
+int scrc_profile_enable(int on) {
+    return guarded([&] {
+        if (!on) g_prof.collect();
+        g_prof.enabled = (on != 0);
+    });
+}
+int scrc_profile_reset(void) { return guarded([&] { g_prof.reset(); }); }
+int scrc_profile_get(double* ms, double* work, unsigned long long* launches) {
+    return guarded([&] {
+        g_prof.collect();
+        for (int i = 0; i < PROF_NCLASS; ++i) {
+            if (ms) ms[i] = g_prof.ms[i];
+            if (work) work[i] = g_prof.work[i];
+            if (launches) launches[i] = g_prof.launches[i];
+        }
+    });
+}
+
+namespace {
+cudaEvent_t g_t0 = nullptr, g_t1 = nullptr;
+}
+int scrc_timer_begin(void) {
+    return guarded([&] {
+        if (!g_t0) { SCRC_CUDA(cudaEventCreate(&g_t0)); SCRC_CUDA(cudaEventCreate(&g_t1)); }
+        SCRC_CUDA(cudaDeviceSynchronize());
+        SCRC_CUDA(cudaEventRecord(g_t0, cudaStreamPerThread));
+    });
+}
+int scrc_timer_end(double* ms) {
+    if (!ms) return fail(SCRC_ERR_ARG, "scrc_timer_end: null pointer");
+    return guarded([&] {
+        if (!g_t0) throw Error(SCRC_ERR_ARG, "scrc_timer_end without scrc_timer_begin");
+        SCRC_CUDA(cudaDeviceSynchronize());
+        SCRC_CUDA(cudaEventRecord(g_t1, cudaStreamPerThread));
+        SCRC_CUDA(cudaEventSynchronize(g_t1));
+        float t = 0.f;
+        SCRC_CUDA(cudaEventElapsedTime(&t, g_t0, g_t1));
+        *ms = t;
+    });
+}
+
 int scrc_ctx_create(scrc_ctx** out, int device, const double* z1_reg, const double* z2_reg, const double* z1_target,
                     const double* z2_target, const double* z1_target_sds, int64_t n1, int64_t n2, int64_t P, int64_t T,
                     int K) {
@@ -258,6 +300,22 @@ int scrc_ctx_get_coeffs(scrc_ctx* ctx, int f, int k, double* coeffs_out, int* se
         if (coeffs_out && sl.s > 0) {
             SCRC_CUDA(cudaMemcpy2DAsync(coeffs_out, (size_t)sl.s * 8, c.nnls.beta.data() + sl.row_off, c.nnls.beta.ld * 8,
                                         (size_t)sl.s * 8, c.T, cudaMemcpyDeviceToHost, c.dev.stream));
+            SCRC_CUDA(cudaStreamSynchronize(c.dev.stream));
+        }
+    });
+}
+
+/* debug accessor (not part of the public header): stacked selection matrix of the last cycle
+ * (test split), rows_total x n2 column-major, and the stacked row count */
+int scrc_debug_get_zsel(scrc_ctx* ctx, double* out, long long* rows_total) {
+    if (!ctx) return fail(SCRC_ERR_ARG, "null context");
+    return guarded([&] {
+        Ctx& c = ctx->impl;
+        SCRC_CUDA(cudaSetDevice(c.dev.id));
+        if (rows_total) *rows_total = c.nnls.rows;
+        if (out && c.nnls.rows > 0) {
+            SCRC_CUDA(cudaMemcpy2DAsync(out, (size_t)c.nnls.rows * 8, c.ZselT.data(), c.ZselT.ld * 8, (size_t)c.nnls.rows * 8,
+                                        c.n2, cudaMemcpyDeviceToHost, c.dev.stream));
             SCRC_CUDA(cudaStreamSynchronize(c.dev.stream));
         }
     });

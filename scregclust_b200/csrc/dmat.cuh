@@ -27,11 +27,11 @@ struct DMat {
     const double* col(int64_t c) const { return buf.p + c * ld; }
     size_t bytes() const { return (size_t)ld * (size_t)cols * 8; }
 
-    // Host column-major (leading dimension `hld`) -> device; padding rows are zeroed.
+    // Column-major source (host OR device pointer, leading dimension `hld`) -> device; padding rows are zeroed.
     void upload(const double* host, int64_t hld, cudaStream_t s) {
         if (rows == 0 || cols == 0) return;
         if (ld != rows) SCRC_CUDA(cudaMemsetAsync(buf.p, 0, bytes(), s));
-        SCRC_CUDA(cudaMemcpy2DAsync(buf.p, ld * 8, host, hld * 8, rows * 8, cols, cudaMemcpyHostToDevice, s));
+        SCRC_CUDA(cudaMemcpy2DAsync(buf.p, ld * 8, host, hld * 8, rows * 8, cols, cudaMemcpyDefault, s));
     }
     void download(double* host, int64_t hld, cudaStream_t s) const {
         if (rows == 0 || cols == 0) return;

@@ -1,6 +1,8 @@
 // Host side of the FP64 TN GEMM: TMA descriptors + DensePolicy launches.
 #include "gemm_tn.cuh"
+#include "prof.cuh"
 
+#include <cstdlib>
 #include <mutex>
 
 namespace scrc {
@@ -58,8 +60,13 @@ static void launch_dense(const DenseArgs& a, int num_sms, cudaStream_t stream) {
         configured = true;
     }
     const int64_t tiles = ceil_div(a.M, BM) * ceil_div(a.N, BN);
-    const int grid = (int)std::min<int64_t>(tiles, num_sms);
-    gemm_tn_kernel<Pol><<<grid, GEMM_THREADS, smem, stream>>>(p);
+    int grid = (int)std::min<int64_t>(tiles, num_sms);
+    if (const char* e = getenv("SCRC_DEBUG_GEMM_GRID")) grid = (int)std::max<int64_t>(1, std::min<int64_t>(tiles, atoi(e)));
+    {
+        const double flops = (MODE == EPI_SYM_LOWER) ? (double)a.K * a.M * (a.M + 1.0) : 2.0 * a.K * (double)a.M * a.N;
+        ProfScope ps(PROF_GEMM_DENSE, stream, flops);
+        gemm_tn_kernel<Pol><<<grid, GEMM_THREADS, smem, stream>>>(p);
+    }
     SCRC_CUDA(cudaGetLastError());
     SCRC_LAUNCHED();
 }

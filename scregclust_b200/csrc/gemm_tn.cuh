@@ -45,7 +45,7 @@ struct GemmSmem {
     static constexpr int B_BYTES = BN * GEMM_BK * 8;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-    static constexpr int TOTAL = BAR_OFFSET + 2 * STAGES * 8 + 1024;  // + alignment slack
+    static constexpr int TOTAL = BAR_OFFSET + 2 * STAGES * 8;
 };
 
 struct PipeState {
@@ -92,9 +92,12 @@ gemm_tn_kernel(const __grid_constant__ typename Policy::Params prm) {
     constexpr int MT = BM / (GEMM_WARPS_M * 8), NT = BN / (GEMM_WARPS_N * 8);
     using SM = GemmSmem<BM, BN, STAGES>;
 
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                               ~uintptr_t(1023));
+    // 1024-byte alignment is required by the 128-byte TMA swizzle.  The array is addressed with
+    // plain offsets only (no integer re-alignment of the pointer) so that the compiler keeps the
+    // shared address space and emits LDS for the fragment loads: generic LD.E loads are not ordered
+    // with the mbarrier arrive that hands the stage back to the TMA producer.
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + SM::BAR_OFFSET);
     uint64_t* empty = full + STAGES;
 

@@ -1,6 +1,7 @@
 // Batched NNLS kernels.  Per-column operation order follows src/optim.cpp:403-549
 // and greedy_coord_descent (optim.cpp:335-377); see SURVEY.md section 3.3.
 #include "nnls.cuh"
+#include "prof.cuh"
 
 #include <algorithm>
 #include <vector>
@@ -262,6 +263,7 @@ void nnls_solve(NnlsBatch& b, double eps, int max_iter, const double* out_scale,
                                   cudaMemcpyHostToDevice, st));
     const int cols_per_cta = 64;
     const unsigned chunks = (unsigned)ceil_div(b.m, cols_per_cta);
+    ProfScope pscope(PROF_NNLS, st);
     if (!small_ids.empty()) {
         const int warps = 8;
         const size_t smem = ((size_t)smax_small * smax_small + (size_t)warps * 6 * smax_small) * 8;

@@ -1,0 +1,38 @@
+#include "prof.cuh"
+
+namespace scrc {
+
+Profiler g_prof;
+
+cudaEvent_t Profiler::get_event() {
+    if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+    cudaEvent_t e;
+    SCRC_CUDA(cudaEventCreate(&e));
+    return e;
+}
+void Profiler::begin(int cls, cudaStream_t s) {
+    Rec r{cls, get_event(), get_event()};
+    SCRC_CUDA(cudaEventRecord(r.e0, s));
+    pending.push_back(r);
+    launches[cls] += 1;
+}
+void Profiler::end(cudaStream_t s) {
+    SCRC_CUDA(cudaEventRecord(pending.back().e1, s));
+    if (pending.size() >= 4096) collect();
+}
+void Profiler::collect() {
+    for (Rec& r : pending) {
+        SCRC_CUDA(cudaEventSynchronize(r.e1));
+        float t = 0.f;
+        SCRC_CUDA(cudaEventElapsedTime(&t, r.e0, r.e1));
+        ms[r.cls] += t;
+        pool.push_back(r.e0); pool.push_back(r.e1);
+    }
+    pending.clear();
+}
+void Profiler::reset() {
+    collect();
+    for (int i = 0; i < PROF_NCLASS; ++i) { ms[i] = 0; work[i] = 0; launches[i] = 0; }
+}
+
+}  // namespace scrc

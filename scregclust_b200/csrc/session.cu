@@ -94,7 +94,7 @@ void Ctx::create(int device, const double* z1r, const double* z2r, const double*
     Z1r.alloc(n1, P); Z2r.alloc(n2, P); Z1t.alloc(n1, T); Z2t.alloc(n2, T);
     Z1r.upload(z1r, n1, st); Z2r.upload(z2r, n2, st); Z1t.upload(z1t, n1, st); Z2t.upload(z2t, n2, st);
     sds_t.alloc(T); inv_sds_t.alloc(T);
-    SCRC_CUDA(cudaMemcpyAsync(sds_t.p, sds, T * 8, cudaMemcpyHostToDevice, st));
+    SCRC_CUDA(cudaMemcpyAsync(sds_t.p, sds, T * 8, cudaMemcpyDefault, st));
     vec_recip_kernel<<<(unsigned)ceil_div(T, 256), 256, 0, st>>>(sds_t.p, inv_sds_t.p, (int)T);
     SCRC_LAUNCHED();
 

@@ -51,16 +51,32 @@ class Session:
         z1r, z2r = f64(z1_reg_scaled), f64(z2_reg_scaled)
         z1t, z2t = f64(z1_target_centered), f64(z2_target_centered)
         sds = np.ascontiguousarray(z1_target_sds, dtype=np.float64)
-        self.n1, self.P = z1r.shape
-        self.n2 = z2r.shape[0]
-        self.T = z1t.shape[1]
-        self.K = int(n_modules)
-        if z2r.shape[1] != self.P or z2t.shape != (self.n2, self.T) or z1t.shape[0] != self.n1 or sds.size != self.T:
+        n1, P = z1r.shape
+        n2, T = z2t.shape
+        if z2r.shape != (n2, P) or z1t.shape != (n1, T) or sds.size != T:
             raise ValueError("inconsistent split dimensions")
-        self._h = C.c_void_p()
-        check(self._lib.scrc_ctx_create(C.byref(self._h), int(device), dptr(z1r), dptr(z2r), dptr(z1t), dptr(z2t),
-                                        dptr(sds), self.n1, self.n2, self.P, self.T, self.K))
+        self._create(device, z1r.ctypes.data, z2r.ctypes.data, z1t.ctypes.data, z2t.ctypes.data, sds.ctypes.data,
+                     n1, n2, P, T, n_modules)
         self.h2d_bytes = z1r.nbytes + z2r.nbytes + z1t.nbytes + z2t.nbytes + sds.nbytes
+
+    @classmethod
+    def from_pointers(cls, z1_reg, z2_reg, z1_target, z2_target, z1_target_sds, n1, n2, P, T, n_modules, device=0):
+        """Create a session from raw addresses of column-major FP64 buffers.  The buffers may live in
+        host memory or already in device memory (e.g. ``tensor.data_ptr()`` of a CUDA tensor); the
+        library copies them into its own padded layout either way."""
+        self = cls.__new__(cls)
+        self._lib = _capi.load()
+        self._create(device, int(z1_reg), int(z2_reg), int(z1_target), int(z2_target), int(z1_target_sds),
+                     int(n1), int(n2), int(P), int(T), n_modules)
+        self.h2d_bytes = 0
+        return self
+
+    def _create(self, device, p1r, p2r, p1t, p2t, psd, n1, n2, P, T, n_modules):
+        self.n1, self.n2, self.P, self.T, self.K = int(n1), int(n2), int(P), int(T), int(n_modules)
+        self._h = C.c_void_p()
+        cast = lambda a: C.cast(C.c_void_p(a), _capi.c_double_p)
+        check(self._lib.scrc_ctx_create(C.byref(self._h), int(device), cast(p1r), cast(p2r), cast(p1t), cast(p2t),
+                                        cast(psd), self.n1, self.n2, self.P, self.T, self.K))
         self.d2h_bytes = 0
         self.admm_sweeps = 0
         self.admm_problem_iterations = 0

@@ -51,14 +51,14 @@ def make_raw(n_cells, n_targets, n_reg, n_modules, seed=0, ar1=0.0, regs_per_mod
     n_noise = int(round(noise_frac * n_targets))
     if n_noise > 0:
         k_true[rng.choice(n_targets, n_noise, replace=False)] = -1
-    B = np.zeros((n_reg, n_targets))
     rpm = min(regs_per_module, n_reg)
+    zt = rng.standard_normal((n_cells, n_targets))
     for j in range(1, n_modules + 1):
         regs = rng.choice(n_reg, rpm, replace=False)
         shared = 0.4 * rng.standard_normal(rpm)
         cols = np.flatnonzero(k_true == j)
-        B[np.ix_(regs, cols)] = shared[:, None] + 0.1 * rng.standard_normal((rpm, cols.size))
-    zt = zr @ B + rng.standard_normal((n_cells, n_targets))
+        coef = shared[:, None] + 0.1 * rng.standard_normal((rpm, cols.size))
+        zt[:, cols] += zr[:, regs] @ coef          # only the module's regulators are non-zero
     return zr, zt, k_true
 
 

@@ -1,6 +1,16 @@
 """Loop-level parity: the batched session driver against the oracle's restatement of
 R/scregclust.R:996-1803 -- per-cycle module assignments, selected regulators, iteration
-counts (bit-exact) and coefficients / R2 / sigmas (1e-8 relative)."""
+counts (bit-exact) and coefficients / R2 / sigmas (1e-8 relative).
+
+Tie semantics.  When two modules predict a gene identically up to rounding (typical in the
+first cycles, where modules still share their regulators), the per-cell argmax of
+allocation.cpp:80-85 is decided by rounding noise of whatever BLAS computed the residuals --
+in the reference as much as here -- and different hosts give different votes for those cells.
+The oracle therefore reports, per gene, how many cells had a non-zero top-2 score gap below
+1e-9 relative (``ambiguity``).  Votes must agree exactly up to that many cells, and module
+assignments must agree exactly whenever the vote margin exceeds it.  Exact ties (identical
+models) are resolved by first index on both sides and are compared bit-exactly.
+"""
 import numpy as np
 import pytest
 
@@ -10,18 +20,90 @@ from scregclust_b200.synthetic import make_workload
 
 pytestmark = pytest.mark.gpu
 
+CASES = [("tiny", 0, 0.0), ("tiny", 1, 0.5), ("tiny", 3, 0.0), ("small", 0, 0.0), ("small", 2, 0.5), ("small", 3, 0.0)]
 
-def _compare(w, res_gpu, res_ref, tol=1e-8):
-    assert len(res_gpu) == len(res_ref)
-    for g, r in zip(res_gpu, res_ref):
-        assert len(g.k_history) == len(r.k_history), (g.penalization, len(g.k_history), len(r.k_history))
-        for c, (kg, kr) in enumerate(zip(g.k_history, r.k_history)):
-            if not np.array_equal(kg, kr):
-                bad = np.flatnonzero(kg != kr)
-                msg = f"lambda={g.penalization} cycle={c} genes={bad[:10]}"
-                if g.votes and c - 1 < len(g.votes):
-                    msg += f" votes_gpu={g.votes[c-1][bad[:3]]} votes_ref={r.votes[c-1][bad[:3]]}"
-                raise AssertionError(msg)
+
+def _check_votes(tag, vg, vr, amb, k_new_gpu):
+    """votes may differ by at most `amb` cells per gene; argmax must match when the margin is safe."""
+    moved = np.abs(vg.astype(np.int64) - vr.astype(np.int64)).sum(axis=1) // 2
+    bad = np.flatnonzero(moved > amb)
+    assert bad.size == 0, f"{tag}: unexplained vote differences for genes {bad[:8]}: gpu={vg[bad[:3]]} ref={vr[bad[:3]]} amb={amb[bad[:3]]}"
+    sv = np.sort(vr, axis=1)
+    margin = sv[:, -1] - sv[:, -2]
+    safe = margin > 2 * amb
+    k_ref = np.argmax(vr, axis=1) + 1
+    assert np.array_equal(k_new_gpu[safe], k_ref[safe]), f"{tag}: assignment differs for a gene with a safe vote margin"
+    assert np.array_equal(np.argmax(vg, axis=1) + 1, k_new_gpu), f"{tag}: k_new is not the first argmax of the votes"
+    return int(moved.sum())
+
+
+@pytest.mark.parametrize("name,seed,ar1", CASES)
+def test_cycle_parity_teacher_forced(name, seed, ar1):
+    """Every cycle of the oracle's trajectory is replayed on the GPU from the oracle's own
+    configuration, so one noise-decided vote cannot hide later cycles from the comparison."""
+    from scregclust_b200.driver import Session
+    w = make_workload(name, seed=seed, ar1=ar1)
+    K = w.n_modules
+    ref = orc.scregclust_fit(w.z1_reg, w.z2_reg, w.z1_target, w.z2_target, w.z1_target_sds, w.penalization, K,
+                             w.k_init, min_module_size=2, keep_history=True)
+    moved_total = 0
+    with Session(w.z1_reg, w.z2_reg, w.z1_target, w.z2_target, w.z1_target_sds, K) as s:
+        max_cycles = max(len(r.votes) for r in ref)
+        for c in range(max_cycles):
+            fits = [i for i, r in enumerate(ref) if c < len(r.votes)]
+            res = s.fit_cycle([ref[i].penalization for i in fits], np.stack([ref[i].k_history[c] for i in fits]),
+                              want_votes=True, want_nnls_iters=True)
+            s._last_nsel = res["n_selected"]
+            for f, i in enumerate(fits):
+                r = ref[i]
+                tag = f"{name}/{seed} lambda={r.penalization} cycle={c + 1}"
+                assert np.array_equal(res["admm_iterations"][f], r.admm_iterations[c]), tag
+                assert np.array_equal(res["models"][f].T.astype(bool), r.models_history[c]), tag
+                assert np.array_equal(res["nnls_iterations"][f], r.nnls_iterations[c]), tag
+                assert rel_err(res["resid_var"][f].T, r.resid_var_history[c]) < 1e-8, tag
+                assert np.max(np.abs(res["r2_test"][f].T - r.r2_history[c])) < 1e-8, tag
+                for j in range(K):
+                    cg, _ = s.coeffs(f, j)
+                    cr = r.coeffs_history[c][j]
+                    assert (cg is None) == (cr is None), tag
+                    if cg is not None:
+                        assert cg.shape == cr.shape and np.max(np.abs(cg - cr)) < 1e-8 * max(1.0, np.max(np.abs(cr))), tag
+                moved_total += _check_votes(tag, res["votes"][f], r.votes[c], r.ambiguity[c], res["k_new"][f])
+    print(f"{name}/{seed}: cells whose vote was decided by rounding noise and differed: {moved_total}")
+
+
+def _first_divergence(g, r):
+    for c, (kg, kr) in enumerate(zip(g.k_history, r.k_history)):
+        if not np.array_equal(kg, kr):
+            return c, np.flatnonzero(kg != kr)
+    if len(g.k_history) != len(r.k_history):
+        return min(len(g.k_history), len(r.k_history)), np.zeros(0, dtype=int)
+    return None, None
+
+
+@pytest.mark.parametrize("name,seed,ar1", CASES)
+def test_loop_free_running(name, seed, ar1):
+    """The driver, left alone, reproduces the oracle's whole trajectory and final results; a
+    divergence is only accepted at a gene whose vote the oracle itself flags as noise-decided."""
+    from scregclust_b200.driver import scregclust_fit
+    w = make_workload(name, seed=seed, ar1=ar1)
+    ref = orc.scregclust_fit(w.z1_reg, w.z2_reg, w.z1_target, w.z2_target, w.z1_target_sds, w.penalization,
+                             w.n_modules, w.k_init, min_module_size=2)
+    got = scregclust_fit(w.z1_reg, w.z2_reg, w.z1_target, w.z2_target, w.z1_target_sds, w.penalization,
+                         w.n_modules, w.k_init, min_module_size=2, keep_diagnostics=True)
+    tol = 1e-8
+    identical = 0
+    for g, r in zip(got, ref):
+        c, genes = _first_divergence(g, r)
+        if c is not None:
+            amb = r.ambiguity[c - 1]
+            sv = np.sort(r.votes[c - 1], axis=1)
+            margin = sv[:, -1] - sv[:, -2]
+            assert genes.size > 0 and np.all(margin[genes] <= 2 * amb[genes]), \
+                f"lambda={g.penalization}: trajectory diverges at cycle {c} for genes {genes[:8]} with safe margins " \
+                f"{margin[genes[:8]]} (noise-decided cells {amb[genes[:8]]})"
+            continue
+        identical += 1
         assert g.converged == r.converged and g.final_cycle_length == r.final_cycle_length
         assert g.n_cycles_run == r.n_cycles_run
         assert orc.adjusted_rand_index(g.k_final[0], r.k_final[0]) == 1.0
@@ -31,33 +113,22 @@ def _compare(w, res_gpu, res_ref, tol=1e-8):
             assert np.array_equal(a, b)
         for a, b in zip(g.nnls_iterations, r.nnls_iterations):
             assert np.array_equal(a, b)
-        for a, b in zip(g.votes, r.votes):
-            assert np.array_equal(a, b)
         for m in range(r.final_cycle_length):
             assert np.array_equal(g.k_final[m], r.k_final[m])
             assert np.array_equal(g.models[m], r.models[m])
             assert np.array_equal(np.isnan(g.signs[m]), np.isnan(r.signs[m]))
             assert np.array_equal(np.nan_to_num(g.signs[m]), np.nan_to_num(r.signs[m]))
             assert rel_err(g.weights[m], r.weights[m]) < tol
-            assert rel_err(g.r2[m], r.r2[m]) < tol
+            assert np.max(np.abs(g.r2[m] - r.r2[m])) < tol
             assert rel_err(g.sigmas[m], r.sigmas[m]) < tol
-            assert rel_err(g.best_r2[m], r.best_r2[m]) < tol
+            assert np.max(np.abs(g.best_r2[m] - r.best_r2[m])) < tol
             assert np.array_equal(g.best_r2_idx[m], r.best_r2_idx[m])
             for cg, cr in zip(g.coeffs[m], r.coeffs[m]):
                 assert (cg is None) == (cr is None)
                 if cg is not None:
-                    assert cg.shape == cr.shape and rel_err(cg, cr) < tol
-
-
-@pytest.mark.parametrize("name,seed,ar1", [("tiny", 0, 0.0), ("tiny", 1, 0.5), ("small", 0, 0.0), ("small", 2, 0.5)])
-def test_loop_parity(name, seed, ar1):
-    from scregclust_b200.driver import scregclust_fit
-    w = make_workload(name, seed=seed, ar1=ar1)
-    ref = orc.scregclust_fit(w.z1_reg, w.z2_reg, w.z1_target, w.z2_target, w.z1_target_sds, w.penalization,
-                             w.n_modules, w.k_init, min_module_size=2)
-    got = scregclust_fit(w.z1_reg, w.z2_reg, w.z1_target, w.z2_target, w.z1_target_sds, w.penalization,
-                         w.n_modules, w.k_init, min_module_size=2, keep_diagnostics=True)
-    _compare(w, got, ref)
+                    assert cg.shape == cr.shape and np.max(np.abs(cg - cr)) < tol * max(1.0, np.max(np.abs(cr)))
+    print(f"{name}/{seed}: {identical}/{len(ref)} penalties with trajectories identical to the oracle")
+    assert identical >= 1
 
 
 def test_session_precompute():
@@ -86,3 +157,22 @@ def test_session_ridge_init_when_few_cells():
         assert abs(init["init_df"] - pre["init_df"]) < 1e-8 * pre["init_df"]
         assert rel_err(init["beta_init"], pre["beta_init"]) < 1e-7
         assert rel_err(init["res_sds"], pre["res_sds"]) < 1e-7
+
+
+def test_empty_and_noise_modules():
+    """Edge cases of the driver: empty modules are skipped in Step 1 (R/scregclust.R:1345),
+    all-noise configurations leave every module without a model (zero-model residuals)."""
+    from scregclust_b200.driver import Session
+    w = make_workload("tiny", seed=4)
+    K, T = w.n_modules, w.z1_target.shape[1]
+    k_a = w.k_init.copy(); k_a[k_a == 2] = 1            # module 2 empty
+    k_b = np.full(T, -1, dtype=np.int32)                # everything in the noise module
+    with Session(w.z1_reg, w.z2_reg, w.z1_target, w.z2_target, w.z1_target_sds, K) as s:
+        res = s.fit_cycle([0.2, 0.2], np.stack([k_a, k_b]), want_votes=True)
+        assert res["admm_iterations"][0][1] == 0 and res["n_selected"][0][1] == 0
+        assert np.all(res["admm_iterations"][1] == 0) and np.all(res["n_selected"][1] == 0)
+        assert np.all(res["r2_test"][1] == 0.0)                     # 1 - SS/SS exactly (scregclust.R:1505-1515,1629)
+        assert np.all(res["k_new"][1] == 1)                         # all modules tie -> first index
+        assert np.all(res["votes"][1][:, 0] == w.z2_target.shape[0])
+        rv = (w.z1_target ** 2).sum(axis=0) / w.z1_target.shape[0]  # SS_train / (n1 - 0)
+        assert rel_err(res["resid_var"][1][0], rv) < 1e-12

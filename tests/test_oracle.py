@@ -1,0 +1,226 @@
+"""CPU tests of the oracle (the checker itself): golden vectors, the one numeric pin the
+reference's own tests provide (fast_cor == stats::cor, tests/testthat/test-fast-cor.R) and
+independent cross-checks (KKT conditions, scipy NNLS, lstsq, brute-force allocation, the
+restated Eigen LDLT, the C++ twin)."""
+import os
+
+import numpy as np
+import pytest
+import scipy.optimize
+
+from conftest import rel_err
+from oracle import scregclust_oracle as orc
+from scregclust_b200.synthetic import make_workload
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_fast_cor_matches_stats_cor(rng):
+    # mirrors tests/testthat/test-fast-cor.R:1-16 (pt=50, pr=10, n=200)
+    zt = rng.standard_normal((200, 50)); zr = rng.standard_normal((200, 10))
+    ref = np.corrcoef(zt.T, zr.T)[:50, 50:]
+    assert np.allclose(orc.fast_cor(zt, zr), ref, rtol=0, atol=1.5e-8)
+    assert rel_err(orc.fast_cor(zt, zr), ref) < 1e-13
+
+
+def test_constant_gene_smoke(rng):
+    # spirit of tests/testthat/test-constant-genes.R: 8 genes x 100 cells, lambda 0.1, K=2 runs through
+    expr = np.vstack([rng.standard_normal((5, 100)), rng.standard_normal((1, 100))])
+    zr = expr[5:].T; zt = expr[:5].T
+    from scregclust_b200.synthetic import scale_split
+    z1r, z2r, z1t, z2t, sds = scale_split(zr, zt)
+    res = orc.scregclust_fit(z1r, z2r, z1t, z2t, sds, [0.1], 2, np.array([1, 2, 1, 2, 1]))
+    assert len(res) == 1 and res[0].k_final[0].shape == (5,)
+
+
+def test_ldlt_restatement_solves(rng):
+    for n in (1, 5, 40):
+        a = rng.standard_normal((n + 5, n)); g = a.T @ a + 0.2 * np.eye(n)
+        b = rng.standard_normal((n, 3))
+        x = orc.EigenLDLT().compute(g).solve(b)
+        assert rel_err(x, np.linalg.solve(g, b)) < 1e-10
+    # semi-definite input: pivoting keeps it finite
+    g = np.zeros((4, 4)); g[0, 0] = 2.0; g[2, 2] = 1.0
+    x = orc.EigenLDLT().compute(g).solve(np.ones((4, 1)))
+    assert np.all(np.isfinite(x))
+
+
+def _coop_problem(rng, n=300, p=25, m=8, lam=0.15):
+    x = rng.standard_normal((n, p)) / np.sqrt(n)
+    b = np.zeros((p, m)); b[:5] = rng.standard_normal((5, 1)) + 0.3 * rng.standard_normal((5, m))
+    y = x @ b + rng.standard_normal((n, m)) / np.sqrt(n)
+    w = np.sqrt(m) * (0.5 + rng.random(p))
+    return x, y, w, lam
+
+
+def test_coop_lasso_kkt(rng):
+    x, y, w, lam = _coop_problem(rng)
+    beta, it = orc.coop_lasso(y, x, lam, w, max_iter=10000)
+    assert 1 < it < 10000
+    b = np.where(np.abs(beta) < 1e-6, 0.0, beta)
+    grad = x.T @ (y - x @ b)                                   # = subgradient of the penalty
+    for i in range(x.shape[1]):
+        for sign in (1.0, -1.0):
+            part = np.maximum(sign * b[i], 0.0)
+            gpart = np.maximum(sign * grad[i], 0.0)
+            if np.linalg.norm(part) > 0:                      # active group: gradient aligned, norm lam*w
+                act = part > 0
+                assert abs(np.linalg.norm(sign * grad[i][act]) - lam * w[i]) < 1e-5
+            else:                                             # inactive group: inside the dual ball
+                assert np.linalg.norm(gpart) <= lam * w[i] + 1e-5
+
+
+def test_coop_lasso_ldlt_vs_cholesky_same_iterations(rng):
+    x, y, w, lam = _coop_problem(rng)
+    b1, i1 = orc.coop_lasso(y, x, lam, w, max_iter=10000, fast_solver=True)
+    b2, i2 = orc.coop_lasso(y, x, lam, w, max_iter=10000, fast_solver=False)
+    assert i1 == i2 and rel_err(b1, b2) < 1e-10
+
+
+def test_coop_lasso_quirks(rng):
+    x, y, w, lam = _coop_problem(rng)
+    _, it = orc.coop_lasso(y, x, lam, w, max_iter=3)
+    assert it == 4                                            # optim.cpp:295-305
+    with pytest.raises(ValueError, match="rho_0"):
+        orc.coop_lasso(y, x, lam, w, rho_0=0.0)
+    with pytest.raises(ValueError, match="alpha_0"):
+        orc.coop_lasso(y, x, lam, w, alpha_0=2.1)
+    with pytest.raises(ValueError, match="same number of rows"):
+        orc.coop_lasso(y[:-1], x, lam, w)
+    # infinite weight (a regulator with zero initial coefficients) is shrunk to exactly zero in zeta
+    w2 = w.copy(); w2[0] = np.inf
+    beta, _ = orc.coop_lasso(y, x, lam, w2, max_iter=10000)
+    assert abs(beta[0]).max() < 1e-6
+
+
+def test_nnls_against_scipy(rng):
+    x = rng.standard_normal((400, 9))
+    y = x @ np.maximum(rng.standard_normal((9, 12)), 0) + 0.3 * rng.standard_normal((400, 12))
+    beta, its = orc.coef_nnls(x, y, eps=1e-12, max_iter=10000)
+    assert np.all(its < 10000) and np.all(beta >= 0)
+    for j in range(12):
+        ref, _ = scipy.optimize.nnls(x, y[:, j])
+        assert np.allclose(beta[:, j], ref, atol=1e-8)
+    grad = x.T @ (x @ beta - y)
+    assert np.all(grad[beta == 0] > -1e-7)                    # complementary slackness
+
+
+def test_nnls_unconverged_columns_are_zero(rng):
+    x = rng.standard_normal((100, 6)); y = rng.standard_normal((100, 4))
+    beta, its = orc.coef_nnls(x, y, eps=1e-300, max_iter=2)
+    assert np.all(its == 2) and np.all(beta == 0)             # optim.cpp:423,502
+
+
+def _brute_alloc(arr, resid_var, k_in):
+    K, n, T = arr.shape
+    out = np.zeros(T, dtype=np.int32)
+    for t in range(T):
+        votes = np.zeros(K, dtype=int)
+        for c in range(n):
+            ll = [-arr[q, c, t] / (2 * resid_var[t, q]) - 0.5 * np.log(2 * np.pi * resid_var[t, q]) for q in range(K)]
+            votes[int(np.argmax(ll))] += 1
+        out[t] = int(np.argmax(votes)) + 1
+    return out
+
+
+def test_allocation_bruteforce_and_ties(rng):
+    K, n, T = 4, 60, 15
+    arr = np.asfortranarray(rng.random((K, n, T)))
+    arr[2] = arr[1]                                           # exact tie -> first index wins
+    rv = np.asfortranarray(rng.random((T, K)) + 0.5); rv[:, 2] = rv[:, 1]
+    k = rng.integers(1, K + 1, T); k[0] = -1
+    got = orc.allocate_into_modules(arr, rv, [], k, rng.permutation(T), 1e-6, 0.0)
+    assert np.array_equal(got, _brute_alloc(arr, rv, k))
+    assert not np.any(got == 3)
+
+
+def test_allocation_prior_is_order_dependent_only_with_weight(rng):
+    K, n, T = 3, 40, 25
+    arr = np.asfortranarray(rng.random((K, n, T))); rv = np.asfortranarray(rng.random((T, K)) + 0.5)
+    k = rng.integers(1, K + 1, T)
+    prior = [list(rng.choice(T, 3, replace=False)) for _ in range(T)]
+    a = orc.allocate_into_modules(arr, rv, prior, k, np.arange(T), 1e-6, 0.0)
+    b = orc.allocate_into_modules(arr, rv, prior, k, np.arange(T)[::-1], 1e-6, 0.0)
+    assert np.array_equal(a, b)                               # weight 0 => genes independent
+
+
+def test_alloc_and_reset_array(rng):
+    z = rng.random((7, 5))
+    arr = orc.alloc_array(z, 3)
+    assert arr.shape == (3, 7, 5) and arr.flags.f_contiguous
+    assert all(np.array_equal(arr[q], z) for q in range(3))
+    arr[1] = 0
+    orc.reset_array(arr, z)
+    assert np.array_equal(arr[1], z)
+    with pytest.raises(ValueError, match="wrong dimensions"):
+        orc.reset_array(arr, z[:, :4])
+
+
+def test_ols_ridge(rng):
+    x = rng.standard_normal((80, 10)); y = rng.standard_normal((80, 3))
+    assert rel_err(orc.coef_ols(y, x), np.linalg.lstsq(x, y, rcond=None)[0]) < 1e-10
+    x2 = rng.standard_normal((8, 12)); y2 = rng.standard_normal((8, 2))
+    assert rel_err(orc.coef_ols(y2, x2), np.linalg.pinv(x2.T @ x2) @ x2.T @ y2) < 1e-8
+    lam = 2.0
+    aug_x = np.vstack([x, np.sqrt(lam) * np.eye(10)]); aug_y = np.vstack([y, np.zeros((10, 3))])
+    assert rel_err(orc.coef_ridge(y, x, lam), np.linalg.lstsq(aug_x, aug_y, rcond=None)[0]) < 1e-10
+
+
+def test_adjusted_rand_index():
+    a = np.array([1, 1, 2, 2, 3, 3, -1])
+    assert orc.adjusted_rand_index(a, a) == 1.0
+    assert orc.adjusted_rand_index(a, np.array([2, 2, 3, 3, 1, 1, 7])) == 1.0
+    assert orc.adjusted_rand_index(a, np.array([1, 2, 1, 2, 1, 2, 1])) < 0.2
+
+
+def test_recycling_quirk_of_the_driver():
+    # R: matrix(1, 2, 3) * c(10, 20, 30)  ->  [[10, 30, 20], [20, 10, 30]]
+    got = orc._recycle(np.array([10.0, 20.0, 30.0]), (2, 3))
+    assert np.array_equal(got, np.array([[10.0, 30.0, 20.0], [20.0, 10.0, 30.0]]))
+
+
+def test_loop_golden_trajectory():
+    # seed 3: no vote of this trajectory is decided by rounding noise (oracle ambiguity == 0),
+    # so the fixture is host independent
+    g = np.load(os.path.join(GOLD, "loop_tiny_seed3.npz"))
+    w = make_workload("tiny", seed=3)
+    res = orc.scregclust_fit(w.z1_reg, w.z2_reg, w.z1_target, w.z2_target, w.z1_target_sds, w.penalization,
+                             w.n_modules, w.k_init, compute_predictive_r2=True)
+    for i, r in enumerate(res):
+        assert sum(int(a.sum()) for a in r.ambiguity) == 0
+        assert np.array_equal(np.stack(r.k_history), g[f"k_history_{i}"])
+        assert np.array_equal(np.stack(r.admm_iterations), g[f"admm_iterations_{i}"])
+        assert np.array_equal(r.models[0], g[f"models_{i}"])
+        assert rel_err(r.r2[0], g[f"r2_{i}"]) < 1e-9
+        assert rel_err(r.sigmas[0], g[f"sigmas_{i}"]) < 1e-9
+        assert np.allclose(r.importance[0], g[f"importance_{i}"], rtol=1e-7, atol=1e-9, equal_nan=True)
+
+
+def test_kernel_golden_vectors():
+    g = np.load(os.path.join(GOLD, "kernels_seed7.npz"))
+    b, it = orc.coop_lasso(g["coop_y"], g["coop_x"], float(g["coop_lambda"]), g["coop_w"], max_iter=10000)
+    assert it == int(g["coop_iterations"]) and rel_err(b, g["coop_beta"]) < 1e-9
+    b, its = orc.coef_nnls(g["nnls_x"], g["nnls_y"], eps=1e-4, max_iter=10000)
+    assert np.array_equal(its, g["nnls_iterations"]) and rel_err(b, g["nnls_beta"]) < 1e-9
+    k = orc.allocate_into_modules(np.asfortranarray(g["alloc_arr"]), np.asfortranarray(g["alloc_var"]), [],
+                                  g["alloc_k"], g["alloc_order"], 1e-6, 0.0)
+    assert np.array_equal(k, g["alloc_out"])
+
+
+def test_cpp_twin_matches_numpy_oracle(rng):
+    ref_cpu = pytest.importorskip("oracle.ref_cpu")
+    if not os.path.exists(ref_cpu.LIB_PATH):
+        pytest.skip("oracle/_ref/liboracle_ref.so not built (run __graft_entry__.build())")
+    x, y, w, lam = _coop_problem(rng, n=400, p=40, m=10)
+    b1, i1 = orc.coop_lasso(y, x, lam, w, max_iter=10000)
+    b2, i2, nf = ref_cpu.coop_lasso(y, x, lam, w, max_iter=10000)
+    assert i1 == i2 and rel_err(b2, b1) < 1e-9 and nf >= i2 // 2
+    xs = rng.standard_normal((300, 7)); ys = xs @ np.abs(rng.standard_normal((7, 20))) + rng.standard_normal((300, 20))
+    n1, t1 = orc.coef_nnls(xs, ys, eps=1e-4, max_iter=10000)
+    n2, t2 = ref_cpu.coef_nnls(xs, ys, eps=1e-4, max_iter=10000)
+    assert np.array_equal(t1, t2) and rel_err(n2, n1) < 1e-9
+    K, n, T = 4, 50, 12
+    arr = np.asfortranarray(rng.random((K, n, T))); rv = np.asfortranarray(rng.random((T, K)) + 0.5)
+    k = rng.integers(1, K + 1, T).astype(np.int32); order = rng.permutation(T).astype(np.int32)
+    assert np.array_equal(ref_cpu.allocate_into_modules(arr, rv, None, None, k, order, 1e-6, 0.0),
+                          orc.allocate_into_modules(arr, rv, [], k, order, 1e-6, 0.0))
