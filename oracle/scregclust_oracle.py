@@ -408,15 +408,21 @@ def reset_array(arr: np.ndarray, inp: np.ndarray) -> None:
 # src/allocation.cpp:8-100
 # --------------------------------------------------------------------------- #
 def allocate_into_modules(resid_array, resid_var, prior_indicator, k_, update_order,
-                          prior_baseline, prior_weight, return_votes=False, ambiguity=None):
+                          prior_baseline, prior_weight, return_votes=False, ambiguity=None,
+                          distinct=None):
     """Per-cell vote reallocation (src/allocation.cpp:8-100).
 
     ``resid_array`` is K x n2 x T of *squared* residuals, ``resid_var`` T x K,
     ``k_`` 1-based (-1 noise), ``update_order`` / ``prior_indicator`` 0-based.
 
     ``ambiguity`` (optional int array of length T, filled in place) receives, per gene, the
-    number of cells whose two best module scores differ, but by less than 1e-9 relative -- i.e. cells whose
-    vote is decided by rounding noise (mathematically tied models).  Test diagnostics only.
+    number of cells whose two best scores -- over structurally distinct modules, ``distinct`` being
+    a boolean mask that keeps one representative of every group of modules with identical
+    regulator sets and signs -- agree to 1e-9 relative, i.e. cells whose vote is decided by
+    rounding noise.  (Modules with different regulator sets can predict a gene identically when
+    its coefficients live on the shared regulators; whether such a tie is exact or off by one ulp
+    depends on the summation order of the BLAS / tensor-core kernel.  Structurally identical
+    modules tie bit-exactly in every implementation and go to the first index.)  Diagnostics only.
     """
     n_modules, n_obs, n_genes = resid_array.shape
     k = np.asarray(k_, dtype=np.int64) - 1
@@ -440,11 +446,13 @@ def allocate_into_modules(resid_array, resid_var, prior_indicator, k_, update_or
         ll = (-resid) / (2.0 * var)[:, None] - (0.5 * np.log(2.0 * math.pi * var))[:, None]
         score = (1.0 - prior_weight) * ll + (prior_weight * prior_log_prob)[:, None]
         best_per_cell = np.argmax(score, axis=0)            # first max
-        if ambiguity is not None and n_modules > 1:
-            part = np.partition(score, n_modules - 2, axis=0)
-            top1 = part[n_modules - 1]; top2 = part[n_modules - 2]
-            gap = top1 - top2                               # exact ties (gap == 0) resolve to the first index
-            ambiguity[j] = int(np.sum((gap > 0.0) & (gap <= 1e-9 * np.maximum(1.0, np.abs(top1)))))
+        if ambiguity is not None:
+            sc = score if distinct is None else score[np.asarray(distinct, dtype=bool)]
+            nd = sc.shape[0]
+            if nd > 1:
+                part = np.partition(sc, nd - 2, axis=0)
+                top1 = part[nd - 1]; top2 = part[nd - 2]
+                ambiguity[j] = int(np.sum((top1 - top2) <= 1e-9 * np.maximum(1.0, np.abs(top1))))
         votes = np.bincount(best_per_cell, minlength=n_modules).astype(np.int32)
         best = int(np.argmax(votes))                        # first max
         if return_votes:
@@ -724,14 +732,20 @@ def scregclust_fit(z1_reg_scaled, z2_reg_scaled, z1_target_centered, z2_target_c
             order = (update_orders(li, cycle) if update_orders is not None
                      else np.arange(n_target))
             amb = np.zeros(n_target, dtype=np.int64)
+            seen, distinct = set(), np.zeros(n_modules, dtype=bool)
+            for j in range(n_modules):                      # one representative per identical model
+                reg_cl = np.flatnonzero(models[:, j])
+                key = (tuple(reg_cl), tuple(signs[reg_cl, j]))
+                if key not in seen:
+                    seen.add(key); distinct[j] = True
             if materialize_array:
                 idx, votes = allocate_into_modules(sq_arr, resid_var, prior_indicator, k, order,
                                                    prior_baseline, prior_weight, return_votes=True,
-                                                   ambiguity=amb)
+                                                   ambiguity=amb, distinct=distinct)
             else:
                 idx, votes = _allocate_streaming(z2t, z2r, models, betas, resid_var,
                                                  prior_indicator, k, order, prior_baseline,
-                                                 prior_weight, amb)
+                                                 prior_weight, amb, distinct)
             fr.votes.append(votes)
             fr.ambiguity.append(amb)
             idx = idx.copy()
@@ -761,7 +775,7 @@ def scregclust_fit(z1_reg_scaled, z2_reg_scaled, z1_target_centered, z2_target_c
 
 
 def _allocate_streaming(z2t, z2r, models, betas, resid_var, prior_indicator, k_, order,
-                        prior_baseline, prior_weight, ambiguity=None):
+                        prior_baseline, prior_weight, ambiguity=None, distinct=None):
     """allocate_into_modules without the K x n2 x T array: rebuilds each gene's
     K x n2 slab on the fly (same arithmetic as scregclust.R:1593-1599 + allocation.cpp)."""
     n2, n_target = z2t.shape
@@ -782,7 +796,8 @@ def _allocate_streaming(z2t, z2r, models, betas, resid_var, prior_indicator, k_,
                 out[c] = r * r
             return out
     return allocate_into_modules(_Lazy(), resid_var, prior_indicator, k_, order,
-                                 prior_baseline, prior_weight, return_votes=True, ambiguity=ambiguity)
+                                 prior_baseline, prior_weight, return_votes=True, ambiguity=ambiguity,
+                                 distinct=distinct)
 
 
 def _importance(fr, z1r, z2r, z1t, z2t, z1_target_sds, G_rr, G_rt_nnls, n_modules,

@@ -122,7 +122,10 @@ def test_loop_free_running(name, seed, ar1):
             assert np.max(np.abs(g.r2[m] - r.r2[m])) < tol
             assert rel_err(g.sigmas[m], r.sigmas[m]) < tol
             assert np.max(np.abs(g.best_r2[m] - r.best_r2[m])) < tol
-            assert np.array_equal(g.best_r2_idx[m], r.best_r2_idx[m])
+            # which.max over modules whose R2 agree to rounding is noise-decided (same tie semantics)
+            ig, ir = g.best_r2_idx[m] - 1, r.best_r2_idx[m] - 1
+            rows = np.arange(ig.size)
+            assert np.all(np.abs(r.r2[m][rows, ig] - r.r2[m][rows, ir]) < 1e-9)
             for cg, cr in zip(g.coeffs[m], r.coeffs[m]):
                 assert (cg is None) == (cr is None)
                 if cg is not None:
