@@ -49,7 +49,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default=os.environ.get("SCRC_BENCH_WORKLOAD", "config2"))
+    ap.add_argument("--workload", default=os.environ.get("SCRC_BENCH_WORKLOAD", "config3"))
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU-baseline sample work")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -249,8 +249,9 @@ def main():
     api.set_device(local_rank)
 
     w = make_workload(args.workload, seed=args.seed)
-    my_pens = [float(p) for p in pens[rank::world]]
-    my_idx = list(range(len(pens)))[rank::world]
+    from scregclust_b200 import parallel
+    my_idx = parallel.shard_penalties(len(pens), rank, world)
+    my_pens = [float(pens[i]) for i in my_idx]
     T = n_targets
     host = [np.asfortranarray(a) for a in (w.z1_reg, w.z2_reg, w.z1_target, w.z2_target)]
     pinned = []
@@ -284,15 +285,8 @@ def main():
         finally:
             ses.close()
         # exchange step: every rank learns every penalty's final module assignment (int32 x T)
-        mine = torch.full((max(1, (len(pens) + world - 1) // world), T), -9, dtype=torch.int32, device="cuda")
-        for i, r in enumerate(res):
-            mine[i] = torch.from_numpy(r.k_final[0]).to("cuda", non_blocking=True)
-        if world > 1:
-            allk = [torch.empty_like(mine) for _ in range(world)]
-            dist.all_gather(allk, mine)
-        else:
-            allk = [mine]
-        checksum = int(sum(int(a.clamp(min=0).sum().item()) for a in allk))
+        allk = parallel.gather_assignments([r.k_final[0] for r in res], len(pens), T, rank, world, device="cuda")
+        checksum = int(np.clip(allk, 0, None).sum())
         return res, stats, checksum
 
     def timed(resident: bool, steps: int):

@@ -1,0 +1,87 @@
+"""CPU-only checks of the drop-in boundary: the library builds for sm_100a, loads without a GPU,
+exports every symbol include/scregclust_b200.h declares, and the argument checks that run before
+any device work return the reference's error texts (src/optim.cpp:76-122,408-410; utils.cpp:20,52)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from scregclust_b200 import _capi
+    if not os.path.exists(_capi.LIB_PATH):
+        import __graft_entry__ as g
+        g.build()
+    return _capi.load()
+
+
+def test_header_symbols_exported(lib):
+    from scregclust_b200 import _capi
+    header = open(os.path.join(ROOT, "include", "scregclust_b200.h")).read()
+    declared = set(re.findall(r"\b(scrc_[a-z_0-9]+)\s*\(", header))
+    declared -= {"scrc_ctx", "scrc_options", "scrc_cycle_out"}
+    assert len(declared) >= 25
+    raw = C.CDLL(_capi.LIB_PATH)
+    missing = [s for s in sorted(declared) if not hasattr(raw, s)]
+    assert not missing, f"declared in the header but not exported: {missing}"
+    assert declared == set(_capi.SIGNATURES), (declared ^ set(_capi.SIGNATURES))
+
+
+def test_version_and_defaults(lib):
+    from scregclust_b200 import _capi
+    assert lib.scrc_version() == 100
+    o = _capi.Options()
+    lib.scrc_default_options(C.byref(o))
+    # R/scregclust.R:193-196 and src/optim.cpp:67-69
+    assert (o.max_optim_iter, o.tol_coop_rel, o.tol_coop_abs, o.tol_nnls) == (10000, 1e-8, 1e-12, 1e-4)
+    assert (o.rho0, o.alpha0, o.n_update, o.eps_corr) == (0.2, 1.5, 2, 0.2)
+
+
+def test_argument_errors_match_reference_texts(lib):
+    from scregclust_b200 import api
+    from scregclust_b200._capi import ScrcError
+    y = np.zeros((4, 2)); w = np.ones(3)
+    with pytest.raises(ScrcError, match="same number of rows"):
+        api.coop_lasso(y, np.zeros((5, 3)), 0.1, w)
+    with pytest.raises(ScrcError, match="COOP LASSO: Matrix dimensions of y and x need to be positive"):
+        api.coop_lasso(np.zeros((4, 0)), np.zeros((4, 3)), 0.1, w)
+    x = np.ones((4, 3))
+    with pytest.raises(ScrcError, match="beta_0 needs to be of size p x m"):
+        api.coop_lasso(y, x, 0.1, w, beta_0=np.zeros((2, 2)))
+    with pytest.raises(ScrcError, match="rho_0 > 0 needs to hold"):
+        api.coop_lasso(y, x, 0.1, w, rho_0=-1.0)
+    with pytest.raises(ScrcError, match="0 < alpha_0 < 2 needs to hold"):
+        api.coop_lasso(y, x, 0.1, w, alpha_0=0.0)
+    with pytest.raises(ScrcError, match="NNLS: Matrix dimensions of y and x need to be positive"):
+        api.coef_nnls(np.zeros((5, 0)), np.zeros((5, 2)))
+
+
+def test_host_side_array_helpers(lib):
+    # alloc_array / reset_array are host-side in the library (no device needed)
+    from scregclust_b200 import api
+    from scregclust_b200._capi import ScrcError
+    z = np.arange(12.0).reshape(4, 3)
+    arr = api.alloc_array(z, 5)
+    assert arr.shape == (5, 4, 3) and all(np.array_equal(arr[q], z) for q in range(5))
+    arr[2] = -1.0
+    api.reset_array(arr, z)
+    assert np.array_equal(arr[2], z)
+    with pytest.raises(ScrcError, match="reset_array: input has wrong dimensions"):
+        api.reset_array(arr, z[:, :2])
+
+
+def test_no_cpu_fallback_without_device(lib):
+    """Without a usable CUDA device the compute entry points fail loudly (no silent CPU path)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from scregclust_b200 import api
+    from scregclust_b200._capi import ScrcError
+    with pytest.raises(ScrcError) as ei:
+        api.fast_cor(np.random.rand(10, 3), np.random.rand(10, 2))
+    assert ei.value.code <= -100

@@ -1,0 +1,57 @@
+"""world_size-2 gloo test of the penalty-grid sharding and the assignment all-gather (CPU)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from oracle import scregclust_oracle as orc
+    from scregclust_b200 import parallel
+    from scregclust_b200.synthetic import make_workload
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    w = make_workload("tiny", seed=3, penalization=[0.1, 0.15, 0.2])
+    idx = parallel.shard_penalties(len(w.penalization), rank, world)
+    res = orc.scregclust_fit(w.z1_reg, w.z2_reg, w.z1_target, w.z2_target, w.z1_target_sds,
+                             [w.penalization[i] for i in idx], w.n_modules, w.k_init)
+    allk = parallel.gather_assignments([r.k_final[0] for r in res], len(w.penalization), w.z1_target.shape[1], rank, world)
+    np.save(os.path.join(out, f"rank{rank}.npy"), allk)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_shard_and_gather_world2(tmp_path):
+    import torch.multiprocessing as mp
+    from oracle import scregclust_oracle as orc
+    from scregclust_b200 import parallel
+    from scregclust_b200.synthetic import make_workload
+    assert parallel.shard_penalties(5, 0, 2) == [0, 2, 4] and parallel.shard_penalties(5, 1, 2) == [1, 3]
+    assert sorted(sum((parallel.shard_penalties(20, r, 8) for r in range(8)), [])) == list(range(20))
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    a = np.load(tmp_path / "rank0.npy"); b = np.load(tmp_path / "rank1.npy")
+    assert np.array_equal(a, b)
+    w = make_workload("tiny", seed=3, penalization=[0.1, 0.15, 0.2])
+    ref = orc.scregclust_fit(w.z1_reg, w.z2_reg, w.z1_target, w.z2_target, w.z1_target_sds, w.penalization,
+                             w.n_modules, w.k_init)
+    assert np.array_equal(a, np.stack([r.k_final[0] for r in ref]))
+
+
+def test_gather_single_rank():
+    from scregclust_b200 import parallel
+    k = [np.arange(5, dtype=np.int32), np.arange(5, dtype=np.int32) + 1]
+    out = parallel.gather_assignments(k, 2, 5, 0, 1)
+    assert np.array_equal(out, np.stack(k))
