@@ -25,11 +25,13 @@ struct AdmmDev {
     const double* xty;
     double *R, *W, *beta, *zeta, *mult, *beta_old, *zeta_old, *mult_old, *mult_hat_old;
     double* partial;
+    const int* prob_R;     // rows per update slab of each problem (32 / 16 / 8)
+    int max_nslab;
 };
 
 void AdmmBatch::resize(int P_, int C_, int nprob_) {
     P = P_; C = C_; nprob = nprob_;
-    nslab = (int)ceil_div(P, ADMM_SLAB);
+    nslab = (int)ceil_div(P, 8);   // worst case: 8-row slabs
     col_prob.ensure(C); prob_c0.ensure(nprob); prob_c1.ensure(nprob);
     prob_lambda.ensure(nprob); prob_rho.ensure(nprob); prob_alpha.ensure(nprob);
     prob_active.ensure(nprob); prob_iters.ensure(nprob);
@@ -38,6 +40,7 @@ void AdmmBatch::resize(int P_, int C_, int nprob_) {
     DMat* mats[] = {&xty, &R, &W, &beta, &zeta, &mult, &beta_old, &zeta_old, &mult_old, &mult_hat_old};
     for (DMat* m : mats) m->reshape(P, C);
     partial.ensure((size_t)nprob * nslab * ADMM_NSUM);
+    prob_R.ensure(nprob); class_ids.ensure(nprob);
 }
 
 static AdmmDev make_dev(AdmmBatch& b) {
@@ -53,6 +56,7 @@ static AdmmDev make_dev(AdmmBatch& b) {
     d.mult = b.mult.data(); d.beta_old = b.beta_old.data(); d.zeta_old = b.zeta_old.data();
     d.mult_old = b.mult_old.data(); d.mult_hat_old = b.mult_hat_old.data();
     d.partial = b.partial.p;
+    d.prob_R = b.prob_R.p; d.max_nslab = b.nslab;
     return d;
 }
 
@@ -72,7 +76,6 @@ __global__ void __launch_bounds__(256) admm_rhs_kernel(AdmmDev d) {
     const int c = blockIdx.x;
     const int p = d.col_prob[c];
     if (!d.active[p]) return;
-    if (threadIdx.x == 0) atomicAdd(d.col_iters, 1ull);
     const double rho = d.rho[p];
     const int64_t base = (int64_t)c * d.ld;
     for (int i = threadIdx.x; i < d.P; i += blockDim.x) {
@@ -157,72 +160,118 @@ static void launch_admm_gemm(const AdmmDev& d, const DMat& A, const double* Bm, 
 }
 
 // ------------------------------------------------------------------ relax / shrink / dual update / reductions
-// One CTA per (32-row slab, problem).  Lane = regulator row, warps interleave the
-// problem's columns.  optim.cpp:146-176 and the sums needed by :192-254.
-template <bool UPDATE_ITER>
-__global__ void __launch_bounds__(ADMM_UPD_WARPS * 32) admm_update_kernel(AdmmDev d) {
-    const int p = blockIdx.y;
-    if (!d.active[p]) return;
-    const int slab = blockIdx.x;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int row = slab * ADMM_SLAB + lane;
-    const bool rv = row < d.P;
-    const int c0 = d.c0[p], c1 = d.c1[p];
-    const double rho = d.rho[p], alpha = d.alpha[p], lam = d.lambda[p];
+// optim.cpp:146-176 and the sums needed by :192-254, one CTA per (R-row slab, problem).
+// Lane layout: row = lane % R, column sub-lane = lane / R, so a warp step covers 32/R columns and
+// 8 warps cover 8*32/R columns.  R is chosen per problem so that the whole slab of the three
+// input matrices (beta, zeta, mult: R x m x 24 B <= 96 KB) stays RESIDENT IN SHARED MEMORY between
+// the group-norm pass and the shrink / dual-update pass (m <= 128: R = 32, m <= 256: R = 16,
+// otherwise R = 8 with the columns beyond 512 re-read from L2/HBM).  Loads are issued in batches
+// before any store so that every thread keeps >= 12 independent 8-byte loads in flight.
+// FUSE_RHS (sweeps on which rho cannot change): also writes next sweep's rhs = xty + rho*zeta + mult.
+constexpr int UPD_CACHE = 4096;   // doubles per cached array (R * cached columns)
 
+template <int R, bool UPDATE_ITER, bool FUSE_RHS>
+__global__ void __launch_bounds__(ADMM_UPD_WARPS * 32) admm_update_kernel(AdmmDev d, const int* __restrict__ prob_ids) {
+    constexpr int CPW = 32 / R;
+    constexpr int CS = UPD_CACHE / R;
+    constexpr int STEP = ADMM_UPD_WARPS * CPW;
+    constexpr int U = UPDATE_ITER ? 2 : 4;
+    extern __shared__ double upd_sm[];
+    double* sb = upd_sm;
+    double* sz = upd_sm + UPD_CACHE;
+    double* smu = upd_sm + 2 * UPD_CACHE;
     __shared__ double s_norm[ADMM_UPD_WARPS][32][2];
     __shared__ double s_sum[ADMM_UPD_WARPS][ADMM_NSUM];
 
+    const int p = prob_ids[blockIdx.y];
+    if (!d.active[p]) return;
+    const int slab = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int row_l = lane % R, csub = lane / R;
+    const int row = slab * R + row_l;
+    const bool rv = row < d.P;
+    const int c0 = d.c0[p];
+    const int m = d.c1[p] - c0;
+    const double rho = d.rho[p], alpha = d.alpha[p], lam = d.lambda[p];
+    const int64_t base = row + (int64_t)c0 * d.ld;
+
+    // ---- pass 1: stage the slab, group norms of the positive / negative parts (optim.cpp:149-158)
     double np2 = 0.0, nn2 = 0.0;
-    if (rv) {
-        for (int c = c0 + warp; c < c1; c += ADMM_UPD_WARPS) {
-            const int64_t idx = row + (int64_t)c * d.ld;
-            const double b = d.beta[idx], z = d.zeta[idx], m = d.mult[idx];
-            const double br = alpha * b + (1.0 - alpha) * z;
-            const double zn = br - m / rho;
-            const double pos = fmax(zn, 0.0), neg = fmin(zn, 0.0);
-            np2 += pos * pos;
-            nn2 += neg * neg;
+#pragma unroll 4
+    for (int lc = warp * CPW + csub; lc < m; lc += STEP) {
+        double b = 0.0, z = 0.0, mu = 0.0;
+        if (rv) {
+            const int64_t idx = base + (int64_t)lc * d.ld;
+            b = d.beta[idx]; z = d.zeta[idx]; mu = d.mult[idx];
         }
+        if (lc < CS) { sb[lc * R + row_l] = b; sz[lc * R + row_l] = z; smu[lc * R + row_l] = mu; }
+        const double br = alpha * b + (1.0 - alpha) * z;
+        const double zn = br - mu / rho;
+        const double pos = fmax(zn, 0.0), neg = fmin(zn, 0.0);
+        np2 += pos * pos;
+        nn2 += neg * neg;
     }
-    s_norm[warp][lane][0] = np2;
-    s_norm[warp][lane][1] = nn2;
+#pragma unroll
+    for (int o = R; o < 32; o <<= 1) {
+        np2 += __shfl_xor_sync(0xffffffffu, np2, o);
+        nn2 += __shfl_xor_sync(0xffffffffu, nn2, o);
+    }
+    if (csub == 0) { s_norm[warp][row_l][0] = np2; s_norm[warp][row_l][1] = nn2; }
     __syncthreads();
     double tp = 0.0, tn = 0.0;
 #pragma unroll
-    for (int w = 0; w < ADMM_UPD_WARPS; ++w) { tp += s_norm[w][lane][0]; tn += s_norm[w][lane][1]; }
+    for (int w = 0; w < ADMM_UPD_WARPS; ++w) { tp += s_norm[w][row_l][0]; tn += s_norm[w][row_l][1]; }
     const double wi = rv ? d.w[row + (int64_t)p * d.ldw] : 0.0;
     // optim.cpp:151-158 (a zero norm gives 1 - inf -> 0)
     const double sp = fmax(1.0 - lam * wi / (rho * sqrt(tp)), 0.0);
     const double sn = fmax(1.0 - lam * wi / (rho * sqrt(tn)), 0.0);
 
+    // ---- pass 2: shrink, dual update, residual / adaptation sums, stores
     double s[ADMM_NSUM];
 #pragma unroll
     for (int k = 0; k < ADMM_NSUM; ++k) s[k] = 0.0;
-    if (rv) {
-        for (int c = c0 + warp; c < c1; c += ADMM_UPD_WARPS) {
-            const int64_t idx = row + (int64_t)c * d.ld;
-            const double b = d.beta[idx], z = d.zeta[idx], m = d.mult[idx];
-            const double br = alpha * b + (1.0 - alpha) * z;
-            double zn = br - m / rho;
+    for (int lc0 = warp * CPW + csub; lc0 < m; lc0 += STEP * U) {
+        double b[U], z[U], mu[U], xt[U], bo[U], zo[U], mo[U], mho[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int lc = lc0 + u * STEP;
+            b[u] = z[u] = mu[u] = xt[u] = bo[u] = zo[u] = mo[u] = mho[u] = 0.0;
+            if (lc < m) {
+                const int64_t idx = base + (int64_t)lc * d.ld;
+                if (lc < CS) { b[u] = sb[lc * R + row_l]; z[u] = sz[lc * R + row_l]; mu[u] = smu[lc * R + row_l]; }
+                else if (rv) { b[u] = d.beta[idx]; z[u] = d.zeta[idx]; mu[u] = d.mult[idx]; }
+                if (rv) {
+                    if (FUSE_RHS) xt[u] = d.xty[idx];
+                    if (UPDATE_ITER) { bo[u] = d.beta_old[idx]; zo[u] = d.zeta_old[idx]; mo[u] = d.mult_old[idx]; mho[u] = d.mult_hat_old[idx]; }
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int lc = lc0 + u * STEP;
+            if (lc >= m || !rv) continue;
+            const int64_t idx = base + (int64_t)lc * d.ld;
+            const double br = alpha * b[u] + (1.0 - alpha) * z[u];
+            double zn = br - mu[u] / rho;
             zn = (zn >= 0.0) ? zn * sp : zn * sn;                       // optim.cpp:160-168
-            const double mn = m + rho * (-br + zn);                     // optim.cpp:171
-            const double pr = -b + zn;                                  // optim.cpp:175
-            const double du = rho * (z - zn);                           // optim.cpp:176
-            s[0] += pr * pr; s[1] += du * du; s[2] += b * b; s[3] += zn * zn; s[4] += mn * mn;
+            const double mn = mu[u] + rho * (-br + zn);                 // optim.cpp:171
+            const double pr = -b[u] + zn;                               // optim.cpp:175
+            const double du = rho * (z[u] - zn);                        // optim.cpp:176
+            s[0] += pr * pr; s[1] += du * du; s[2] += b[u] * b[u]; s[3] += zn * zn; s[4] += mn * mn;
             if (UPDATE_ITER) {
-                const double mh = mn + rho * (-b + z);                  // optim.cpp:203
-                const double dmh = mh - d.mult_hat_old[idx];
-                const double dh = b - d.beta_old[idx];
-                const double dm = mn - d.mult_old[idx];
-                const double dg = d.zeta_old[idx] - z;
+                const double mh = mn + rho * (-b[u] + z[u]);            // optim.cpp:203
+                const double dmh = mh - mho[u];
+                const double dh = b[u] - bo[u];
+                const double dm = mn - mo[u];
+                const double dg = zo[u] - z[u];
                 s[5] += dmh * dmh; s[6] += dh * dh; s[7] += dh * dmh;
                 s[8] += dm * dm; s[9] += dg * dg; s[10] += dg * dm;
-                d.beta_old[idx] = b; d.zeta_old[idx] = zn;              // optim.cpp:282-285
+                d.beta_old[idx] = b[u]; d.zeta_old[idx] = zn;           // optim.cpp:282-285
                 d.mult_old[idx] = mn; d.mult_hat_old[idx] = mh;
             }
             d.zeta[idx] = zn;                                           // optim.cpp:292
             d.mult[idx] = mn;
+            if (FUSE_RHS) d.R[idx] = (xt[u] + rho * zn) + mn;           // optim.cpp:143 of the next sweep
         }
     }
 #pragma unroll
@@ -235,26 +284,34 @@ __global__ void __launch_bounds__(ADMM_UPD_WARPS * 32) admm_update_kernel(AdmmDe
         double v = 0.0;
 #pragma unroll
         for (int w = 0; w < ADMM_UPD_WARPS; ++w) v += s_sum[w][threadIdx.x];
-        d.partial[((int64_t)p * d.nslab + slab) * ADMM_NSUM + threadIdx.x] = v;
+        d.partial[((int64_t)p * d.max_nslab + slab) * ADMM_NSUM + threadIdx.x] = v;
     }
 }
 
 // ------------------------------------------------------------------ stop test + adaptive rho / alpha
 // optim.cpp:192-196 (stop), :199-289 (spectral step-size / relaxation update), :295-305.
-__global__ void __launch_bounds__(256) admm_finalize_kernel(AdmmDev d, AdmmOpts o, int it, int is_update) {
+// One CTA; one warp per problem (lanes stride the slab partials, fixed shuffle tree).
+__global__ void __launch_bounds__(1024) admm_finalize_kernel(AdmmDev d, AdmmOpts o, int it, int is_update) {
     __shared__ int s_cnt;
-    if (threadIdx.x == 0) s_cnt = 0;
+    __shared__ unsigned long long s_cols;
+    if (threadIdx.x == 0) { s_cnt = 0; s_cols = 0ull; }
     __syncthreads();
-    for (int p = threadIdx.x; p < d.nprob; p += blockDim.x) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int p = warp; p < d.nprob; p += nwarps) {
         if (!d.active[p]) continue;
+        const int nsl = (d.P + d.prob_R[p] - 1) / d.prob_R[p];
         double s[ADMM_NSUM];
 #pragma unroll
         for (int k = 0; k < ADMM_NSUM; ++k) s[k] = 0.0;
-        for (int sl = 0; sl < d.nslab; ++sl) {
-            const double* q = d.partial + ((int64_t)p * d.nslab + sl) * ADMM_NSUM;
+        for (int sl = lane; sl < nsl; sl += 32) {
+            const double* q = d.partial + ((int64_t)p * d.max_nslab + sl) * ADMM_NSUM;
 #pragma unroll
             for (int k = 0; k < ADMM_NSUM; ++k) s[k] += q[k];
         }
+#pragma unroll
+        for (int k = 0; k < ADMM_NSUM; ++k) s[k] = warp_sum(s[k]);
+        if (lane != 0) continue;
+        atomicAdd(&s_cols, (unsigned long long)(d.c1[p] - d.c0[p]));   // columns swept this iteration
         const double n_primal = sqrt(s[0]), n_dual = sqrt(s[1]);
         const double n_beta = sqrt(s[2]), n_zeta = sqrt(s[3]), n_mult = sqrt(s[4]);
         const bool conv = (n_primal <= fmax(o.eps_rel * fmax(n_beta, n_zeta), o.eps_abs)) &&
@@ -305,7 +362,7 @@ __global__ void __launch_bounds__(256) admm_finalize_kernel(AdmmDev d, AdmmOpts 
         atomicAdd(&s_cnt, 1);
     }
     __syncthreads();
-    if (threadIdx.x == 0) *d.n_active = s_cnt;
+    if (threadIdx.x == 0) { *d.n_active = s_cnt; *d.col_iters += s_cols; }
 }
 
 // ------------------------------------------------------------------ driver
@@ -323,15 +380,58 @@ int admm_solve(AdmmBatch& b, const EigBasis& eig, const AdmmOpts& o, bool cold, 
     SCRC_LAUNCHED();
 
     const bool big = ceil_div(b.P, 128) * ceil_div(b.C, 128) >= num_sms;
-    const dim3 ugrid(b.nslab, b.nprob);
+    // problems grouped by slab height (see admm_update_kernel); lists live in class_ids
+    if ((int)b.h_cols.size() != b.nprob) throw Error(-71, "admm_solve: host column counts missing");
+    std::vector<int> hR(b.nprob), ids[3];
+    for (int p = 0; p < b.nprob; ++p) {
+        const int m = b.h_cols[p];
+        const int cls = (m <= 128) ? 0 : (m <= 256) ? 1 : 2;
+        hR[p] = 32 >> cls;
+        if (m > 0) ids[cls].push_back(p);
+    }
+    std::vector<int> flat;
+    int off[3];
+    for (int c = 0; c < 3; ++c) { off[c] = (int)flat.size(); flat.insert(flat.end(), ids[c].begin(), ids[c].end()); }
+    SCRC_CUDA(cudaMemcpyAsync(b.prob_R.p, hR.data(), b.nprob * 4, cudaMemcpyHostToDevice, stream));
+    if (!flat.empty()) SCRC_CUDA(cudaMemcpyAsync(b.class_ids.p, flat.data(), flat.size() * 4, cudaMemcpyHostToDevice, stream));
+    SCRC_CUDA(cudaStreamSynchronize(stream));   // hR / flat are stack temporaries
+    constexpr int upd_smem = 3 * UPD_CACHE * 8;
+    static bool upd_configured = false;
+    if (!upd_configured) {
+#define SCRC_SET_UPD(R_) \
+        SCRC_CUDA(cudaFuncSetAttribute(admm_update_kernel<R_, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, upd_smem)); \
+        SCRC_CUDA(cudaFuncSetAttribute(admm_update_kernel<R_, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, upd_smem)); \
+        SCRC_CUDA(cudaFuncSetAttribute(admm_update_kernel<R_, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, upd_smem)); \
+        SCRC_CUDA(cudaFuncSetAttribute(admm_update_kernel<R_, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, upd_smem));
+        SCRC_SET_UPD(32) SCRC_SET_UPD(16) SCRC_SET_UPD(8)
+#undef SCRC_SET_UPD
+        upd_configured = true;
+    }
+    auto launch_update = [&](bool upd, bool fuse) {
+        for (int c = 0; c < 3; ++c) {
+            if (ids[c].empty()) continue;
+            const int R = 32 >> c;
+            const dim3 grid((unsigned)ceil_div(b.P, R), (unsigned)ids[c].size());
+            const int* lst = b.class_ids.p + off[c];
+#define SCRC_UPD(R_) \
+            if (upd && fuse) admm_update_kernel<R_, true, true><<<grid, ADMM_UPD_WARPS * 32, upd_smem, stream>>>(d, lst); \
+            else if (upd) admm_update_kernel<R_, true, false><<<grid, ADMM_UPD_WARPS * 32, upd_smem, stream>>>(d, lst); \
+            else if (fuse) admm_update_kernel<R_, false, true><<<grid, ADMM_UPD_WARPS * 32, upd_smem, stream>>>(d, lst); \
+            else admm_update_kernel<R_, false, false><<<grid, ADMM_UPD_WARPS * 32, upd_smem, stream>>>(d, lst);
+            if (R == 32) { SCRC_UPD(32) } else if (R == 16) { SCRC_UPD(16) } else { SCRC_UPD(8) }
+#undef SCRC_UPD
+            SCRC_LAUNCHED();
+        }
+    };
     int it = 1;
     int sweeps = 0;
+    bool need_rhs = true;   // the first sweep and every sweep after a possible rho change build the rhs explicitly
     while (true) {
-        {
+        if (need_rhs) {
             ProfScope ps(PROF_ADMM_ELEM, stream);
             admm_rhs_kernel<<<b.C, 256, 0, stream>>>(d);
+            SCRC_LAUNCHED();
         }
-        SCRC_LAUNCHED();
         if (big) {
             launch_admm_gemm<128, 128, 6, 1>(d, eig.V, d.R, d.W, num_sms, eig.lam.p, stream);
             launch_admm_gemm<128, 128, 6, 2>(d, eig.Vt, d.W, d.beta, num_sms, eig.lam.p, stream);
@@ -342,11 +442,11 @@ int admm_solve(AdmmBatch& b, const EigBasis& eig, const AdmmOpts& o, bool cold, 
         const int is_update = (it % o.n_update == 0) ? 1 : 0;
         {
             ProfScope ps(PROF_ADMM_ELEM, stream);
-            if (is_update) admm_update_kernel<true><<<ugrid, ADMM_UPD_WARPS * 32, 0, stream>>>(d);
-            else admm_update_kernel<false><<<ugrid, ADMM_UPD_WARPS * 32, 0, stream>>>(d);
-            admm_finalize_kernel<<<1, 256, 0, stream>>>(d, o, it, is_update);
+            launch_update(is_update != 0, /*fuse rhs=*/!is_update);
+            admm_finalize_kernel<<<1, 1024, 0, stream>>>(d, o, it, is_update);
+            SCRC_LAUNCHED();
         }
-        SCRC_LAUNCHED(); SCRC_LAUNCHED();
+        need_rhs = (is_update != 0);
         SCRC_CUDA(cudaGetLastError());
         ++sweeps;
         if ((it >= 4 && it % 2 == 0) || it >= o.max_iter) {

@@ -11,6 +11,8 @@
 // refactorisation is ever needed when rho changes (the reference refactors a
 // P x P LDL^T per problem per rho change).
 #pragma once
+#include <vector>
+
 #include "dmat.cuh"
 #include "gemm_tn.cuh"
 
@@ -52,6 +54,9 @@ struct AdmmBatch {
     // state (P x C)
     DMat xty, R, W, beta, zeta, mult, beta_old, zeta_old, mult_old, mult_hat_old;
     DevBuf<double> partial;    // nprob x nslab x ADMM_NSUM
+    DevBuf<int> prob_R;        // rows per update slab (32 / 16 / 8), chosen from the column count
+    DevBuf<int> class_ids;     // problem ids grouped by slab height
+    std::vector<int> h_cols;   // host copy of the column count of every problem (set by the caller)
 
     void resize(int P_, int C_, int nprob_);
 };

@@ -47,9 +47,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) resid_vote_kernel(const __gri
     }
     __syncthreads();
 
-    // One work item per CTA: (penalty/fit l, cell range cr, target tile tn).  (A persistent
-    // multi-item variant of this kernel produced run-to-run differences at item boundaries on
-    // B200 that were not root-caused in round 1; one item per CTA is exact and deterministic.)
+    // One work item per CTA: (penalty/fit l, cell range cr, target tile tn).
     const int ct_per = (p.ctiles + p.CR - 1) / p.CR;
     const int w = blockIdx.x;
     const int tn = w % p.tiles_n, cr = (w / p.tiles_n) % p.CR, l = w / (p.tiles_n * p.CR);
@@ -126,12 +124,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) resid_vote_kernel(const __gri
                 if (j < p.K) {
                     const int kp = p.kpad[l * p.K + j];
                     for (int kk = 0; kk < kp; kk += GEMM_BK) {
-                        mbar_wait(&full[ps.stage], ps.phase);
+                        mbar_wait_warp(&full[ps.stage], ps.phase, lane);
                         const double* As = reinterpret_cast<const double*>(smem + ps.stage * RV_STAGE_BYTES);
                         const double* Bs = reinterpret_cast<const double*>(smem + ps.stage * RV_STAGE_BYTES + RV_A_BYTES);
                         mma_kslice<MT, NT>(As, Bs, a_row0, b_col0, lane, acc);
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&empty[ps.stage]);
+                        stage_release_warp(&empty[ps.stage], lane);
                         ps.advance<RV_STAGES>();
                     }
                 }

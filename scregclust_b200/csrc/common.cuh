@@ -102,6 +102,27 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(addr, parity)) {
     }
 }
+// Warp-collective wait used by the consumer warps: ONE lane polls the mbarrier, the rest of the
+// warp joins at __syncwarp() (which also orders their subsequent shared-memory reads after the
+// polling lane's acquire).  Do NOT let all 32 lanes spin on try_wait in front of warp-collective
+// instructions: ptxas treats the try_wait predicate as warp-uniform (uniform operands) and emits
+// no reconvergence, but on B200 lanes were observed to leave the spin loop on different
+// iterations when the phase completes mid-poll; the early lanes then ran LDS + DMMA with a
+// partial warp (rare, run-to-run varying ~1e-3 errors in one warp's tile).
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, int lane) {
+    if (lane == 0) mbar_wait(bar, parity);
+    __syncwarp();
+}
+// Consumer release of a TMA stage.  The fragment loads are generic-proxy reads; the refill is an
+// async-proxy (TMA) write.  Every lane fences its own reads against the async proxy, the warp
+// joins, then one lane arrives on the `empty` barrier.  Without the cross-proxy fence the arrive
+// (which ptxas is free to schedule right behind the last LDS *issue*) can be observed before
+// queued LDS have read the stage, and the producer's next TMA load overwrites data still in use.
+__device__ __forceinline__ void stage_release_warp(uint64_t* empty_bar, int lane) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty_bar);
+}
 // 2-D tiled TMA load: coordinates are (c0 = contiguous dim, c1 = strided dim).
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1,
                                             uint64_t* bar) {

@@ -147,13 +147,12 @@ gemm_tn_kernel(const __grid_constant__ typename Policy::Params prm) {
 #pragma unroll
                 for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
             for (int k = ti.k0; k < ti.k1; k += GEMM_BK) {
-                mbar_wait(&full[ps.stage], ps.phase);
+                mbar_wait_warp(&full[ps.stage], ps.phase, lane);
                 const double* As = reinterpret_cast<const double*>(smem + ps.stage * SM::STAGE_BYTES);
                 const double* Bs = reinterpret_cast<const double*>(smem + ps.stage * SM::STAGE_BYTES +
                                                                    SM::A_BYTES);
                 mma_kslice<MT, NT>(As, Bs, a_row0, b_col0, lane, acc);
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&empty[ps.stage]);
+                stage_release_warp(&empty[ps.stage], lane);
                 ps.template advance<STAGES>();
             }
             Policy::epilogue(prm, ti, acc, warp_m, warp_n, lane);

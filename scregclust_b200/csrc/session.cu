@@ -240,6 +240,8 @@ void Ctx::fit_cycle(int F, const double* lambda, const int* k_in, const scrc_opt
     long long sweeps = 0;
     if (nprob > 0) {
         admm.resize((int)P, C, nprob);
+        admm.h_cols.resize(nprob);
+        for (int p = 0; p < nprob; ++p) admm.h_cols[p] = h_c1[p] - h_c0[p];
         col_target.ensure(C); prob_fit.ensure(nprob); prob_mod.ensure(nprob);
         SCRC_CUDA(cudaMemcpyAsync(col_target.p, h_col_target.data(), C * 4, cudaMemcpyHostToDevice, st));
         SCRC_CUDA(cudaMemcpyAsync(admm.col_prob.p, h_col_prob.data(), C * 4, cudaMemcpyHostToDevice, st));
@@ -456,6 +458,7 @@ void dropin_coop_lasso(Device& dev, const double* y, int64_t n, int64_t m, const
     build_eig(G, 1.0, eig, dev);
     AdmmBatch b;
     b.resize((int)p, (int)m, 1);
+    b.h_cols.assign(1, (int)m);
     std::vector<int> cp(m, 0);
     const int c0 = 0, c1 = (int)m;
     SCRC_CUDA(cudaMemcpyAsync(b.col_prob.p, cp.data(), m * 4, cudaMemcpyHostToDevice, st));

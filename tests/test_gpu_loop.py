@@ -179,3 +179,34 @@ def test_empty_and_noise_modules():
         assert np.all(res["votes"][1][:, 0] == w.z2_target.shape[0])
         rv = (w.z1_target ** 2).sum(axis=0) / w.z1_target.shape[0]  # SS_train / (n1 - 0)
         assert rel_err(res["resid_var"][1][0], rv) < 1e-12
+
+
+def test_run_to_run_determinism_at_bench_scale():
+    """Three identical cycles at the config-2 shape must be bit-identical (no float atomics, fixed
+    reduction orders, warp-collective mbarrier waits): this is the regression test for the two
+    pipeline hazards found in round 1."""
+    from scregclust_b200.driver import Session
+    w = make_workload("config2", seed=0)
+    pens = w.penalization[[0, 2, 5, 9]]
+    with Session(w.z1_reg, w.z2_reg, w.z1_target, w.z2_target, w.z1_target_sds, w.n_modules) as s:
+        outs = [s.fit_cycle(pens, np.stack([w.k_init] * len(pens)), want_votes=True, want_nnls_iters=True)
+                for _ in range(3)]
+    for rep in (1, 2):
+        for key, v in outs[0].items():
+            if v is not None:
+                assert np.array_equal(v, outs[rep][key], equal_nan=True), f"{key} differs between identical runs"
+
+
+def test_large_contraction_parity_property():
+    """BASELINE-scale size-independent property: the session's Gram matrices equal NumPy's on a
+    config-2 sized split, and the residual variance of modules without a model is SS/n1 exactly."""
+    from scregclust_b200.driver import Session
+    w = make_workload("config2", seed=1)
+    K = w.n_modules
+    with Session(w.z1_reg, w.z2_reg, w.z1_target, w.z2_target, w.z1_target_sds, K) as s:
+        g_rr, g_rt = s.gram()
+        assert rel_err(g_rr, w.z1_reg.T @ w.z1_reg) < 1e-12 and rel_err(g_rt, w.z1_reg.T @ w.z1_target) < 1e-12
+        k = np.full(w.z1_target.shape[1], -1, dtype=np.int32)
+        res = s.fit_cycle([0.3], k[None, :], want_votes=True)
+        assert np.all(res["r2_test"] == 0.0) and np.all(res["votes"][0][:, 0] == w.z2_target.shape[0])
+        assert rel_err(res["resid_var"][0][0], (w.z1_target ** 2).sum(axis=0) / w.z1_target.shape[0]) < 1e-12
