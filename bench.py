@@ -213,7 +213,9 @@ def main():
                           f"{n_modules} modules, {len(pens)}-value penalty grid (seed {args.seed})",
               "n1": n_cells // 2, "n2": n_cells - n_cells // 2, "targets": n_targets, "regulators": n_reg,
               "modules": n_modules, "penalties": [float(p) for p in pens],
-              "parallelism": f"penalty grid sharded round-robin over {world} GPU(s)",
+              "parallelism": (f"penalization values claimed dynamically from a shared counter by {world} GPUs, "
+                               f"{max(1, len(pens) // (2 * world))} in flight per GPU"
+                              if world > 1 else "whole penalty grid advanced in lock-step on 1 GPU"),
               "l2": "working set (FP64 state of all problems) exceeds the 126 MB L2; no flush between steps"}
 
     if args.impl == "reference":
@@ -243,6 +245,7 @@ def main():
     from scregclust_b200.driver import Session, scregclust_fit
 
     torch.cuda.set_device(local_rank)
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout for the one JSON line
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     lib = _capi.load()
@@ -250,8 +253,13 @@ def main():
 
     w = make_workload(args.workload, seed=args.seed)
     from scregclust_b200 import parallel
-    my_idx = parallel.shard_penalties(len(pens), rank, world)
-    my_pens = [float(pens[i]) for i in my_idx]
+    all_pens = [float(p) for p in pens]
+    store = None
+    if world > 1:   # shared counter for dynamic claiming of penalization values (host side)
+        store = dist.TCPStore("127.0.0.1", int(os.environ.get("MASTER_PORT", "29500")) + 17, world, rank == 0,
+                              wait_for_workers=True)
+    counter = parallel.GridCounter(len(all_pens), store)
+    step_no = [0]
     T = n_targets
     host = [np.asfortranarray(a) for a in (w.z1_reg, w.z2_reg, w.z1_target, w.z2_target)]
     pinned = []
@@ -276,8 +284,18 @@ def main():
                                         device=local_rank)
             ses.h2d_bytes = sum(t.numel() * 8 for t in pinned) + sds_pinned.numel() * 8
         try:
-            res = scregclust_fit(penalization=my_pens, n_modules=n_modules, initial_target_modules=w.k_init,
-                                 session=ses, return_coeffs=not resident) if my_pens else []
+            step_no[0] += 1
+            counter.reset(f"scrc_next_{step_no[0]}")
+            # one GPU: the whole grid advances in lock-step; several GPUs: each rank keeps
+            # L / (2 N) penalization values in flight and claims the next one from the shared counter
+            # (most expensive first) whenever one of them finishes -- the longest fit (about twice
+            # the average number of cycles) then still fits inside a rank's share of the work
+            allres = scregclust_fit(penalization=all_pens, n_modules=n_modules, initial_target_modules=w.k_init,
+                                    session=ses, return_coeffs=not resident,
+                                    claim=counter if world > 1 else None,
+                                    concurrency=max(1, len(all_pens) // (2 * world)) if world > 1 else None)
+            res = [r for r in allres if r is not None]
+            local_k = {i: r.k_final[0] for i, r in enumerate(allres) if r is not None}
             stats = dict(h2d=ses.h2d_bytes, d2h=ses.d2h_bytes, sweeps=ses.admm_sweeps,
                          admm_iters=ses.admm_problem_iterations,
                          fit_cycles=sum(r.n_cycles_run - 1 for r in res),
@@ -285,7 +303,8 @@ def main():
         finally:
             ses.close()
         # exchange step: every rank learns every penalty's final module assignment (int32 x T)
-        allk = parallel.gather_assignments([r.k_final[0] for r in res], len(pens), T, rank, world, device="cuda")
+        allk = parallel.merge_assignments(local_k, len(pens), T, world, device="cuda")
+        assert allk.min() >= -1, "a penalization value was not fitted by any rank"
         checksum = int(np.clip(allk, 0, None).sum())
         return res, stats, checksum
 

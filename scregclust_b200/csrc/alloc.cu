@@ -200,11 +200,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) resid_vote_kernel(const __gri
 }
 
 int resid_vote_pick_cr(int ncells, int T, int L, int num_sms) {
+    // The split of the cells into ranges fixes the association order of the SSE sums, so it must
+    // depend on the number of cells only -- not on how many fits share the launch -- or a fit's
+    // result would change with the batch it is computed in (and with the number of GPUs).
+    (void)T; (void)L; (void)num_sms;
     const int ctiles = (int)ceil_div(ncells, RV_BM);
-    const int64_t base = (int64_t)L * ceil_div(T, RV_BN);
-    int cr = (int)ceil_div((int64_t)num_sms * 4, base);
-    cr = std::max(1, std::min(cr, (int)ceil_div(ctiles, 2)));   // at least two cell tiles per CTA when possible
-    return cr;
+    return std::max(1, (int)ceil_div(ctiles, 16));   // 16 cell tiles (1024 cells) per CTA
 }
 size_t resid_vote_partial_elems(int T, int K, int L, int CR) {
     return (size_t)L * CR * 2 * (K + 1) * T;

@@ -200,11 +200,18 @@ def scregclust_fit(z1_reg_scaled=None, z2_reg_scaled=None, z1_target_centered=No
                    z1_target_sds=None, penalization=(), n_modules=1, initial_target_modules=None,
                    min_module_size=0, noise_threshold=0.025, n_cycles=50, max_optim_iter=10000,
                    tol_coop_rel=1e-8, tol_coop_abs=1e-12, tol_nnls=1e-4, device=0, session=None,
-                   keep_diagnostics=False, return_coeffs=True):
+                   keep_diagnostics=False, return_coeffs=True, claim=None, concurrency=None):
     """The alternating loop of ``scregclust()`` (R/scregclust.R:1222-1803) for all penalization values.
 
     Returns one :class:`FitResult` per penalization value, in order.  ``session`` may be passed to
     reuse the device-resident precompute (R/scregclust.R:996-1183) across calls.
+
+    Multi-GPU work sharing: the fits of different penalization values are independent
+    (R/scregclust.R:1223,1245), so ``claim`` may be a callable returning the index of the next
+    penalization value this process should fit (or ``None`` when the grid is exhausted) --
+    e.g. an atomic counter shared by all ranks -- and ``concurrency`` bounds how many claimed
+    values are advanced together by one batched device call.  Values never claimed here come
+    back as ``None``.  A fit's result does not depend on what it is batched with.
     """
     own = session is None
     ses = session or Session(z1_reg_scaled, z2_reg_scaled, z1_target_centered, z2_target_centered, z1_target_sds,
@@ -217,20 +224,32 @@ def scregclust_fit(z1_reg_scaled=None, z2_reg_scaled=None, z1_target_centered=No
         k_start = np.asarray(initial_target_modules, dtype=np.int32)
         if k_start.size != T:
             raise ValueError("initial_target_modules needs one entry per target gene")
-        states = [_PenState(k=k_start.copy(), k_history=[k_start.copy()]) for _ in pens]
-        results = [FitResult(penalization=p) for p in pens]
-        for fr, stt in zip(results, states):
-            fr.k_history = stt.k_history
+        if claim is None:
+            queue = iter(range(len(pens)))
+            claim = lambda: next(queue, None)
+        concurrency = len(pens) if concurrency is None else max(1, int(concurrency))
+        states, results = {}, [None] * len(pens)
+        active = []
 
-        while not all(s.done for s in states):
+        while True:
+            while len(active) < concurrency:
+                i = claim()
+                if i is None:
+                    break
+                states[i] = _PenState(k=k_start.copy(), k_history=[k_start.copy()])
+                results[i] = FitResult(penalization=pens[i])
+                results[i].k_history = states[i].k_history
+                active.append(i)
+            if not active:
+                break
             # R/scregclust.R:1269-1284: cycle counter, forced last cycle after n_cycles
-            for s in states:
-                if not s.done:
-                    s.cycle += 1
-                    if s.cycle == n_cycles + 1:
-                        s.last_cycle = True
-            run = [i for i, s in enumerate(states) if not s.done and not s.last_cycle]
-            fin = [i for i, s in enumerate(states) if not s.done and s.last_cycle]
+            for i in active:
+                s = states[i]
+                s.cycle += 1
+                if s.cycle == n_cycles + 1:
+                    s.last_cycle = True
+            run = [i for i in active if not states[i].last_cycle]
+            fin = [i for i in active if states[i].last_cycle]
 
             if run:
                 res = ses.fit_cycle([pens[i] for i in run], np.stack([states[i].k for i in run]), opt,
@@ -289,6 +308,7 @@ def scregclust_fit(z1_reg_scaled=None, z2_reg_scaled=None, z1_target_centered=No
                     fr.converged = s.converged
                     fr.final_cycle_length = s.final_cycle_length
                     fr.n_cycles_run = s.cycle
+                active = [i for i in active if not states[i].done]
         return results
     finally:
         if own:

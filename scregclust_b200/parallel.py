@@ -42,3 +42,44 @@ def gather_assignments(local_k, n_penalties: int, n_targets: int, rank: int, wor
         for i, p in enumerate(shard_penalties(n_penalties, r, world)):
             out[p] = parts[r][i].cpu().numpy()
     return out
+
+
+class GridCounter:
+    """Atomic "next penalization value" counter shared by all ranks (dynamic load balancing).
+
+    The cost of a fit is not known in advance (small penalties select more regulators and need
+    more cycles), so ranks claim values one at a time, cheapest last (ascending penalty =
+    descending expected cost), from a counter kept in the job's TCP store.  Host side only; no
+    GPU data moves."""
+
+    def __init__(self, n_penalties: int, store=None, key="scrc_next"):
+        self.n = int(n_penalties)
+        self.store = store
+        self.key = key
+        self._local = 0
+
+    def reset(self, key: str):
+        self.key = key
+        self._local = 0
+
+    def __call__(self):
+        if self.store is None:
+            i = self._local
+            self._local += 1
+        else:
+            i = int(self.store.add(self.key, 1)) - 1
+        return i if i < self.n else None
+
+
+def merge_assignments(local: dict, n_penalties: int, n_targets: int, world: int, device="cpu"):
+    """Every rank contributes the rows (penalization values) it fitted; an all-reduce(MAX) over an
+    (L, T) int32 table filled with the sentinel -9 gives every rank the complete table."""
+    import torch
+    import torch.distributed as dist
+
+    tab = torch.full((n_penalties, n_targets), -9, dtype=torch.int32, device=device)
+    for i, k in local.items():
+        tab[i] = torch.as_tensor(np.ascontiguousarray(k, dtype=np.int32)).to(device)
+    if world > 1:
+        dist.all_reduce(tab, op=dist.ReduceOp.MAX)
+    return tab.cpu().numpy()

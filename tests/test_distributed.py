@@ -55,3 +55,35 @@ def test_gather_single_rank():
     k = [np.arange(5, dtype=np.int32), np.arange(5, dtype=np.int32) + 1]
     out = parallel.gather_assignments(k, 2, 5, 0, 1)
     assert np.array_equal(out, np.stack(k))
+
+
+def _worker_dynamic(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from scregclust_b200 import parallel
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    store = dist.TCPStore("127.0.0.1", port + 17, world, rank == 0, wait_for_workers=True)
+    counter = parallel.GridCounter(7, store, key="scrc_next_1")
+    mine = {}
+    while True:
+        i = counter()
+        if i is None:
+            break
+        mine[i] = np.full(5, i + 1, dtype=np.int32)          # stand-in for a fitted assignment vector
+    table = parallel.merge_assignments(mine, 7, 5, world)
+    np.save(os.path.join(out, f"dyn{rank}.npy"), table)
+    np.save(os.path.join(out, f"mine{rank}.npy"), np.array(sorted(mine), dtype=np.int64))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_dynamic_counter_and_merge_world2(tmp_path):
+    import torch.multiprocessing as mp
+    port = _free_port()
+    mp.spawn(_worker_dynamic, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    a = np.load(tmp_path / "dyn0.npy"); b = np.load(tmp_path / "dyn1.npy")
+    assert np.array_equal(a, b)
+    assert np.array_equal(a, np.repeat(np.arange(1, 8, dtype=np.int32)[:, None], 5, axis=1))   # every value fitted once
+    m0 = set(np.load(tmp_path / "mine0.npy").tolist()); m1 = set(np.load(tmp_path / "mine1.npy").tolist())
+    assert not (m0 & m1) and (m0 | m1) == set(range(7))

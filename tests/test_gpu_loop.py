@@ -210,3 +210,36 @@ def test_large_contraction_parity_property():
         res = s.fit_cycle([0.3], k[None, :], want_votes=True)
         assert np.all(res["r2_test"] == 0.0) and np.all(res["votes"][0][:, 0] == w.z2_target.shape[0])
         assert rel_err(res["resid_var"][0][0], (w.z1_target ** 2).sum(axis=0) / w.z1_target.shape[0]) < 1e-12
+
+
+def test_fit_is_independent_of_batch_composition():
+    """A fit's numbers must not depend on which other fits share the batched launch (and therefore
+    not on the number of GPUs the grid is spread over): same bits alone and in a batch of three."""
+    from scregclust_b200.driver import Session
+    w = make_workload("small", seed=1)
+    pens = np.array([0.1, 0.2, 0.3])
+    with Session(w.z1_reg, w.z2_reg, w.z1_target, w.z2_target, w.z1_target_sds, w.n_modules) as s:
+        together = s.fit_cycle(pens, np.stack([w.k_init] * 3), want_votes=True, want_nnls_iters=True)
+        for f in range(3):
+            alone = s.fit_cycle(pens[f:f + 1], w.k_init[None, :], want_votes=True, want_nnls_iters=True)
+            for key, v in alone.items():
+                if v is not None:
+                    assert np.array_equal(v[0], together[key][f], equal_nan=True), f"{key} of fit {f} depends on the batch"
+
+
+def test_dynamic_claiming_matches_lockstep():
+    """concurrency=1 with a claim counter (the multi-GPU schedule) == the lock-step single-GPU run."""
+    from scregclust_b200.driver import Session, scregclust_fit
+    from scregclust_b200.parallel import GridCounter
+    w = make_workload("small", seed=2)
+    with Session(w.z1_reg, w.z2_reg, w.z1_target, w.z2_target, w.z1_target_sds, w.n_modules) as s:
+        a = scregclust_fit(penalization=w.penalization, n_modules=w.n_modules, initial_target_modules=w.k_init, session=s)
+        b = scregclust_fit(penalization=w.penalization, n_modules=w.n_modules, initial_target_modules=w.k_init, session=s,
+                           claim=GridCounter(len(w.penalization)), concurrency=1)
+        c = scregclust_fit(penalization=w.penalization, n_modules=w.n_modules, initial_target_modules=w.k_init, session=s,
+                           claim=GridCounter(2), concurrency=2)       # this "rank" only gets the first two values
+    assert c[2] is None and c[0] is not None and c[1] is not None
+    for x, y in list(zip(a, b)) + list(zip(a[:2], c[:2])):
+        assert len(x.k_history) == len(y.k_history) and all(np.array_equal(p, q) for p, q in zip(x.k_history, y.k_history))
+        assert np.array_equal(x.models[0], y.models[0]) and np.array_equal(x.r2[0], y.r2[0])
+        assert all((p is None and q is None) or np.array_equal(p, q) for p, q in zip(x.coeffs[0], y.coeffs[0]))
