@@ -5,6 +5,7 @@
 #include "prof.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace scrc {
 
@@ -380,6 +381,9 @@ int admm_solve(AdmmBatch& b, const EigBasis& eig, const AdmmOpts& o, bool cold, 
     SCRC_LAUNCHED();
 
     const bool big = ceil_div(b.P, 128) * ceil_div(b.C, 128) >= num_sms;
+    // 160-row tiles when they waste fewer padded rows than 128-row tiles (e.g. P = 1600: 0 % vs 4 %)
+    const bool tall = (getenv("SCRC_NO_TALL_TILES") == nullptr) &&
+                      (ceil_div(b.P, 160) * 160 < ceil_div(b.P, 128) * 128);
     // problems grouped by slab height (see admm_update_kernel); lists live in class_ids
     if ((int)b.h_cols.size() != b.nprob) throw Error(-71, "admm_solve: host column counts missing");
     std::vector<int> hR(b.nprob), ids[3];
@@ -432,7 +436,10 @@ int admm_solve(AdmmBatch& b, const EigBasis& eig, const AdmmOpts& o, bool cold, 
             admm_rhs_kernel<<<b.C, 256, 0, stream>>>(d);
             SCRC_LAUNCHED();
         }
-        if (big) {
+        if (big && tall) {
+            launch_admm_gemm<160, 128, 5, 1>(d, eig.V, d.R, d.W, num_sms, eig.lam.p, stream);
+            launch_admm_gemm<160, 128, 5, 2>(d, eig.Vt, d.W, d.beta, num_sms, eig.lam.p, stream);
+        } else if (big) {
             launch_admm_gemm<128, 128, 6, 1>(d, eig.V, d.R, d.W, num_sms, eig.lam.p, stream);
             launch_admm_gemm<128, 128, 6, 2>(d, eig.Vt, d.W, d.beta, num_sms, eig.lam.p, stream);
         } else {
