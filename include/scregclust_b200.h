@@ -176,6 +176,14 @@ typedef struct scrc_cycle_out {
 int scrc_fit_cycle(scrc_ctx* ctx, int F, const double* lambda, const int* k_in, const scrc_options* opt,
                    int skip_allocation, scrc_cycle_out* out);
 
+/* Leave-one-regulator-out importance and module R2 of F final configurations
+ * (R/scregclust.R:1823-1912, compute_predictive_r2 = TRUE).  k_final: F x T module assignments,
+ * models / signs: F x K x P exactly as returned by scrc_fit_cycle for those configurations.
+ * r2_module: F x K, importance: F x K x P ([f][k][p] = R's P x K matrix), NaN where the
+ * reference leaves NA (modules without targets or with fewer than two regulators). */
+int scrc_importance(scrc_ctx* ctx, int F, const int* k_final, const unsigned char* models, const double* signs,
+                    const scrc_options* opt, double* r2_module, double* importance);
+
 /* NNLS coefficients of module k (0-based) of fit f from the last scrc_fit_cycle call:
  * n_selected x T (R/scregclust.R:1588); sel_out receives the 0-based regulator indices. */
 int scrc_ctx_get_coeffs(scrc_ctx* ctx, int f, int k, double* coeffs_out, int* sel_out);

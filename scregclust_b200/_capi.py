@@ -74,6 +74,8 @@ SIGNATURES = {
     "scrc_ctx_get_gram": (C.c_int, [C.c_void_p, c_double_p, c_double_p]),
     "scrc_fit_cycle": (C.c_int, [C.c_void_p, C.c_int, c_double_p, c_int_p, C.POINTER(Options), C.c_int,
                                  C.POINTER(CycleOut)]),
+    "scrc_importance": (C.c_int, [C.c_void_p, C.c_int, c_int_p, c_ubyte_p, c_double_p, C.POINTER(Options), c_double_p,
+                                  c_double_p]),
     "scrc_ctx_get_coeffs": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_double_p, c_int_p]),
 }
 

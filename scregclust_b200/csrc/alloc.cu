@@ -18,6 +18,10 @@ struct RvParams {
     double* partial;
     int* votes;
     int CR, tiles_n, ctiles;
+    const int* row_off_b;
+    const int* col_index;
+    const int* col_off;
+    const int* col_cnt;
 };
 
 constexpr int RV_A_BYTES = RV_BM * GEMM_BK * 8;
@@ -52,6 +56,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) resid_vote_kernel(const __gri
     const int w = blockIdx.x;
     const int tn = w % p.tiles_n, cr = (w / p.tiles_n) % p.CR, l = w / (p.tiles_n * p.CR);
     const int ct0 = cr * ct_per, ct1 = min(ct0 + ct_per, p.ctiles);
+    const int ncol = p.col_cnt ? p.col_cnt[l] : p.T;      // columns of this fit
+    if (tn * RV_BN >= ncol) return;                       // whole CTA: nothing to do for this tile
+    const int* cidx = p.col_index ? p.col_index + p.col_off[l] : nullptr;
     PipeState ps;
 
     if (warp < GEMM_PRODUCER_WARPS) {
@@ -62,12 +69,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) resid_vote_kernel(const __gri
                     for (int j = 0; j < p.K; ++j) {
                         const int kp = p.kpad[l * p.K + j];
                         const int ro = p.row_off[l * p.K + j];
+                        const int rob = p.row_off_b ? p.row_off_b[l * p.K + j] : ro;
                         for (int kk = 0; kk < kp; kk += GEMM_BK) {
                             mbar_wait(&empty[ps.stage], ps.phase ^ 1);
                             uint8_t* sa = smem + ps.stage * RV_STAGE_BYTES;
                             mbar_expect_tx(&full[ps.stage], RV_STAGE_BYTES);
                             tma_load_2d(sa, &p.ta, ro + kk, ct * RV_BM, &full[ps.stage]);
-                            tma_load_2d(sa + RV_A_BYTES, &p.tb, ro + kk, tn * RV_BN, &full[ps.stage]);
+                            tma_load_2d(sa + RV_A_BYTES, &p.tb, rob + kk, tn * RV_BN, &full[ps.stage]);
                             ps.advance<RV_STAGES>();
                         }
                     }
@@ -111,7 +119,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) resid_vote_kernel(const __gri
                     for (int e = 0; e < 2; ++e) {
                         const int row = c0 + a_row0 + i * 8 + r;
                         const int col = t0 + b_col0 + jj * 8 + q * 2 + e;
-                        z[i][jj][e] = (row < p.ncells && col < p.T) ? p.Z[row + (int64_t)col * p.ldz] : 0.0;
+                        double zv = 0.0;
+                        if (row < p.ncells && col < ncol) zv = p.Z[row + (int64_t)(cidx ? cidx[col] : col) * p.ldz];
+                        z[i][jj][e] = zv;
                         best[i][jj][e] = -INFINITY;
                         bidx[i][jj][e] = 0;
                     }
@@ -140,7 +150,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) resid_vote_kernel(const __gri
                         const int lc = b_col0 + jj * 8 + q * 2 + e;
                         const int col = t0 + lc;
                         double tv = 1.0, hl = 0.0;
-                        if (VOTE && j < p.K && col < p.T) {
+                        if (VOTE && j < p.K && col < ncol) {
                             const int64_t vi = ((int64_t)l * p.K + j) * p.T + col;
                             tv = p.two_var[vi];
                             hl = p.half_log[vi];
@@ -171,7 +181,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) resid_vote_kernel(const __gri
                         for (int e = 0; e < 2; ++e) {
                             const int row = c0 + a_row0 + i * 8 + r;
                             const int lc = b_col0 + jj * 8 + q * 2 + e;
-                            if (row < p.ncells && t0 + lc < p.T) atomicAdd(&votes_s[lc * p.K + bidx[i][jj][e]], 1);
+                            if (row < p.ncells && t0 + lc < ncol) atomicAdd(&votes_s[lc * p.K + bidx[i][jj][e]], 1);
                         }
             }
         }
@@ -183,7 +193,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) resid_vote_kernel(const __gri
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
                         const int lc = b_col0 + jj * 8 + q * 2 + e;
-                        if (t0 + lc < p.T)
+                        if (t0 + lc < ncol)
                             p.partial[((((int64_t)l * p.CR + cr) * 2 + warp_m) * K1 + j) * p.T + t0 + lc] =
                                 sse_s[(warp_m * K1 + j) * RV_BN + lc];
                     }
@@ -193,7 +203,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) resid_vote_kernel(const __gri
             for (int i = ctid; i < RV_BN * p.K; i += 256) {
                 const int lc = i / p.K, j = i % p.K;
                 const int v = votes_s[i];
-                if (v != 0 && t0 + lc < p.T) atomicAdd(&p.votes[((int64_t)l * p.T + t0 + lc) * p.K + j], v);
+                if (v != 0 && t0 + lc < ncol) atomicAdd(&p.votes[((int64_t)l * p.T + t0 + lc) * p.K + j], v);
             }
         }
     }
@@ -215,11 +225,13 @@ void resid_vote(const ResidVoteArgs& a, bool vote, int num_sms, cudaStream_t st)
     if (a.K + 1 > RV_MAX_K + 1) throw Error(-60, "resid_vote: at most 64 modules are supported");
     RvParams p;
     // operands are allocated with at least one 16-row block so that the maps are never empty
-    p.ta = make_tmap_f64(a.ZselT, std::max<int64_t>(a.rows_total, 16), a.ncells, a.ldzs, RV_BM);
+    p.ta = make_tmap_f64(a.ZselT, std::max<int64_t>(a.rows_total_a >= 0 ? a.rows_total_a : a.rows_total, 16), a.ncells,
+                         a.ldzs, RV_BM);
     p.tb = make_tmap_f64(a.beta, std::max<int64_t>(a.rows_total, 16), a.T, a.ldb, RV_BN);
     p.Z = a.Z; p.ldz = a.ldz; p.ncells = a.ncells; p.T = a.T; p.K = a.K; p.L = a.L;
     p.row_off = a.row_off; p.kpad = a.kpad; p.two_var = a.two_var; p.half_log = a.half_log;
     p.partial = a.partial; p.votes = a.votes; p.CR = a.CR;
+    p.row_off_b = a.row_off_b; p.col_index = a.col_index; p.col_off = a.col_off; p.col_cnt = a.col_cnt;
     p.tiles_n = (int)ceil_div(a.T, RV_BN); p.ctiles = (int)ceil_div(a.ncells, RV_BM);
 
     const int smem = RV_STAGES * RV_STAGE_BYTES + 2 * RV_STAGES * 8 + 2 * (a.K + 1) * RV_BN * 8 +

@@ -26,6 +26,12 @@ struct ResidVoteArgs {
     double* partial;                     // device [L][CR][2][K+1][T]
     int* votes;                          // device [L][T][K]   (vote mode, pre-zeroed)
     int CR;                              // cell ranges per (penalty, target tile)
+    // optional generalisations (used by the leave-one-regulator-out post-processing):
+    int64_t rows_total_a = -1;           // rows of ZselT when they differ from the rows of `beta` (-1: same)
+    const int* row_off_b = nullptr;      // device [L*K]: rows of `beta` when they differ from the rows of ZselT
+    const int* col_index = nullptr;      // device: flattened per-fit lists of target columns of Z
+    const int* col_off = nullptr;        // device [L]: start of fit l's list in col_index
+    const int* col_cnt = nullptr;        // device [L]: number of columns of fit l (<= T = columns of beta)
 };
 int resid_vote_pick_cr(int ncells, int T, int L, int num_sms);
 size_t resid_vote_partial_elems(int T, int K, int L, int CR);

@@ -289,6 +289,15 @@ int scrc_fit_cycle(scrc_ctx* ctx, int F, const double* lambda, const int* k_in, 
     return guarded([&] { ctx->impl.fit_cycle(F, lambda, k_in, o, skip_allocation != 0, out); });
 }
 
+int scrc_importance(scrc_ctx* ctx, int F, const int* k_final, const unsigned char* models, const double* signs,
+                    const scrc_options* opt, double* r2_module, double* importance) {
+    if (!ctx || !k_final || !models || !signs || !r2_module || !importance)
+        return fail(SCRC_ERR_ARG, "scrc_importance: null pointer");
+    scrc_options o;
+    if (opt) o = *opt; else scrc_default_options(&o);
+    return guarded([&] { ctx->impl.importance(F, k_final, models, signs, o, r2_module, importance); });
+}
+
 int scrc_ctx_get_coeffs(scrc_ctx* ctx, int f, int k, double* coeffs_out, int* sel_out) {
     if (!ctx) return fail(SCRC_ERR_ARG, "null context");
     return guarded([&] {

@@ -63,6 +63,24 @@ void col_center_ss(double* x, int64_t ld, int64_t rows, int64_t cols, double* ss
     SCRC_LAUNCHED();
 }
 
+__global__ void __launch_bounds__(256) col_centered_ss_kernel(const double* x, int64_t ld, int64_t rows, double* css) {
+    __shared__ double s_buf[8];
+    const double* col = x + (int64_t)blockIdx.x * ld;
+    double a = 0.0;
+    for (int64_t i = threadIdx.x; i < rows; i += 256) a += col[i];
+    const double mean = block_sum_256(a, s_buf) / (double)rows;
+    double q = 0.0;
+    for (int64_t i = threadIdx.x; i < rows; i += 256) { const double v = col[i] - mean; q += v * v; }
+    q = block_sum_256(q, s_buf);
+    if (threadIdx.x == 0) css[blockIdx.x] = q;
+}
+void col_centered_ss(const double* x, int64_t ld, int64_t rows, int64_t cols, double* css, cudaStream_t s) {
+    if (cols == 0) return;
+    col_centered_ss_kernel<<<(unsigned)cols, 256, 0, s>>>(x, ld, rows, css);
+    SCRC_CUDA(cudaGetLastError());
+    SCRC_LAUNCHED();
+}
+
 __global__ void __launch_bounds__(256) col_sumsq_kernel(const double* x, int64_t ld, int64_t rows, double* ss) {
     __shared__ double s_buf[8];
     const double* col = x + (int64_t)blockIdx.x * ld;

@@ -12,6 +12,9 @@ void transpose(const double* in, int64_t ldi, int64_t rows, int64_t cols, double
 // (R/utils.R:534-537).  One CTA per column, deterministic reductions.
 void col_center_ss(double* x, int64_t ld, int64_t rows, int64_t cols, double* ss, cudaStream_t s);
 
+// css[c] = sum_r (x[r,c] - mean_c)^2 without modifying x (R: colSums(scale(x, center=TRUE, scale=FALSE)^2))
+void col_centered_ss(const double* x, int64_t ld, int64_t rows, int64_t cols, double* css, cudaStream_t s);
+
 // ss[c] = sum_r x[r,c]^2
 void col_sumsq(const double* x, int64_t ld, int64_t rows, int64_t cols, double* ss, cudaStream_t s);
 

@@ -11,6 +11,8 @@ namespace scrc {
 struct NnlsDev {
     const NnlsProblem* prob;
     const int* sel;
+    const int* pos;
+    const int* cols;
     const double* sign;
     double* Q;
     double* dvec;
@@ -48,11 +50,13 @@ __global__ void __launch_bounds__(256) nnls_setup_grad_kernel(NnlsDev d, const d
     const int* sel = d.sel + pr.sel_off;
     const double* sg = d.sign + pr.sel_off;
     const int col0 = blockIdx.x * 32;
+    const int ncols = pr.ncols < 0 ? d.m : pr.ncols;
     for (int e = threadIdx.x; e < s * 32; e += blockDim.x) {
         const int a = e % s, col = col0 + e / s;
-        if (col >= d.m) break;
-        const double cs = colscale ? colscale[col] : 1.0;
-        const double v = sg[a] * (xty[sel[a] + (int64_t)col * ldy] * cs);
+        if (col >= ncols) break;
+        const int xc = pr.xcol_off < 0 ? col : d.cols[pr.xcol_off + col];
+        const double cs = colscale ? colscale[xc] : 1.0;
+        const double v = sg[a] * (xty[sel[a] + (int64_t)xc * ldy] * cs);
         d.grad0[pr.row_off + a + (int64_t)col * d.ldg] = (-v) * d.dvec[pr.row_off + a];
     }
 }
@@ -60,7 +64,7 @@ __global__ void __launch_bounds__(256) nnls_setup_grad_kernel(NnlsDev d, const d
 void nnls_setup(NnlsBatch& b, const double* xtx, int64_t ldx, const double* xty, int64_t ldy,
                 const double* colscale, cudaStream_t st) {
     if (b.nprob == 0) return;
-    NnlsDev d{b.prob.p, b.sel.p, b.sign.p, b.Q.p, b.dvec.p, b.grad0.data(), b.grad0.ld,
+    NnlsDev d{b.prob.p, b.sel.p, b.pos.p, b.cols.p, b.sign.p, b.Q.p, b.dvec.p, b.grad0.data(), b.grad0.ld,
               b.beta.data(), b.beta.ld, b.iters.p, b.m};
     nnls_setup_q_kernel<<<b.nprob, 256, 0, st>>>(d, xtx, ldx);
     SCRC_LAUNCHED();
@@ -154,7 +158,11 @@ __global__ void nnls_kernel(NnlsDev d, const int* __restrict__ prob_ids, int col
     double *beta = vec, *grad = vec + s, *gb = vec + 2 * s, *bsave = vec + 3 * s, *db = vec + 4 * s,
            *tmp = vec + 5 * s;
     const double* sg = d.sign + pr.sel_off;
-    const int col_end = min((int)((blockIdx.x + 1) * cols_per_cta), d.m);
+    const int ncols = pr.ncols < 0 ? d.m : pr.ncols;
+    const int col_end = min((int)((blockIdx.x + 1) * cols_per_cta), ncols);
+    const double* oscale = out_scale ? out_scale + pr.scale_off : nullptr;
+    const int oscale_len = pr.scale_len > 0 ? pr.scale_len : n_out_scale;
+    const int* opos = pr.pos_off < 0 ? nullptr : d.pos + pr.pos_off;
 
     for (int col = blockIdx.x * cols_per_cta + warp; col < col_end; col += nwarps) {
         const double* g0 = d.grad0 + pr.row_off + (int64_t)col * d.ldg;
@@ -230,8 +238,8 @@ __global__ void nnls_kernel(NnlsDev d, const int* __restrict__ prob_ids, int col
         for (int a = lane; a < s; a += 32) {
             double v = conv ? beta[a] * d.dvec[pr.row_off + a] : 0.0;
             v = v * sg[a];
-            if (out_scale) v = v * out_scale[((int64_t)a + (int64_t)col * s) % n_out_scale];
-            out[a] = v;
+            if (oscale) v = v * oscale[((int64_t)a + (int64_t)col * s) % oscale_len];
+            out[opos ? opos[a] : a] = v;
         }
         if (lane == 0) d.iters[(int64_t)pid * d.m + col] = iters;
         __syncwarp();
@@ -241,7 +249,7 @@ __global__ void nnls_kernel(NnlsDev d, const int* __restrict__ prob_ids, int col
 void nnls_solve(NnlsBatch& b, double eps, int max_iter, const double* out_scale, int n_out_scale,
                 int num_sms, cudaStream_t st) {
     if (b.nprob == 0 || b.m == 0) return;
-    NnlsDev d{b.prob.p, b.sel.p, b.sign.p, b.Q.p, b.dvec.p, b.grad0.data(), b.grad0.ld,
+    NnlsDev d{b.prob.p, b.sel.p, b.pos.p, b.cols.p, b.sign.p, b.Q.p, b.dvec.p, b.grad0.data(), b.grad0.ld,
               b.beta.data(), b.beta.ld, b.iters.p, b.m};
     SCRC_CUDA(cudaMemsetAsync(b.beta.data(), 0, b.beta.bytes(), st));
     // classify problems by size (host copy of the descriptors is cheap: nprob <= K*L)

@@ -12,10 +12,23 @@ namespace scrc {
 // One NNLS problem group = one (penalty, module): `s` variables, all `m` columns.
 struct NnlsProblem {
     int s;            // number of variables (selected regulators)
-    int sel_off;      // offset into sel / sign arrays
+    int sel_off;      // offset into sel / sign (/ pos) arrays
     int64_t q_off;    // offset of Q (s x s, ld = s) in the Q workspace
     int64_t row_off;  // first row of this problem in the stacked grad0 / beta_hat matrices
+    // --- optional generalisations (defaults reproduce the plain "all columns" problem) ---
+    int ncols;        // number of columns of this problem (<= batch m); -1 = all m columns
+    int xcol_off;     // local column c reads column cols[xcol_off + c] of xty / colscale; -1 = identity
+    int pos_off;      // variable a is written to row row_off + pos[pos_off + a] of beta; -1 = identity
+    int scale_off;    // out_scale window starts at out_scale[scale_off] ...
+    int scale_len;    // ... and has this length (R's recycling modulus); 0 = use the batch default
+    int pad_;
 };
+inline NnlsProblem make_nnls_problem(int s, int sel_off, int64_t q_off, int64_t row_off) {
+    NnlsProblem p;
+    p.s = s; p.sel_off = sel_off; p.q_off = q_off; p.row_off = row_off;
+    p.ncols = -1; p.xcol_off = -1; p.pos_off = -1; p.scale_off = 0; p.scale_len = 0; p.pad_ = 0;
+    return p;
+}
 
 struct NnlsBatch {
     int nprob = 0;
@@ -24,6 +37,8 @@ struct NnlsBatch {
     DevBuf<NnlsProblem> prob;      // device copy
     DevBuf<int> sel;               // selected variable indices (into xtx / xty rows)
     DevBuf<double> sign;           // +-1 per selected variable
+    DevBuf<int> pos;               // optional output row positions (see NnlsProblem::pos_off)
+    DevBuf<int> cols;              // optional column index lists (see NnlsProblem::xcol_off)
     DevBuf<double> Q;              // normalised Gram blocks
     DevBuf<double> dvec;           // 1/sqrt(diag) per stacked row
     DMat grad0;                    // rows x m : initial gradient

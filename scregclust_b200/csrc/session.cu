@@ -291,8 +291,7 @@ void Ctx::fit_cycle(int F, const double* lambda, const int* k_in, const scrc_opt
         const int kp = (int)round_up(sl.s, 16);
         sl.row_off = (int)rows_total;
         h_row_off[fk] = sl.row_off; h_kpad[fk] = kp;
-        NnlsProblem np;
-        np.s = sl.s; np.sel_off = (int)h_sel.size(); np.q_off = q_total; np.row_off = rows_total;
+        NnlsProblem np = make_nnls_problem(sl.s, (int)h_sel.size(), q_total, rows_total);
         for (int a = 0; a < sl.s; ++a) { h_sel.push_back(sl.sel[a]); h_sign.push_back(h_signs[fk * P + sl.sel[a]]); h_row_src.push_back(sl.sel[a]); }
         for (int a = sl.s; a < kp; ++a) h_row_src.push_back(-1);
         h_np.push_back(np); h_np_slot.push_back((int)fk);
@@ -378,6 +377,138 @@ void Ctx::fit_cycle(int F, const double* lambda, const int* k_in, const scrc_opt
         }
     }
     SCRC_CUDA(cudaStreamSynchronize(st));
+}
+
+// ============================================================================ importance (next row f1)
+// R/scregclust.R:1823-1912.  For every final configuration f and module j with >1 regulators and
+// >0 targets: refit the sign-constrained NNLS on the module's targets with each regulator left out
+// in turn (r = 0: none), measure the test SSE per target, and derive
+//   r2_removed_vec[r] = 1 - sum_t ssq[t, r] / sum(scale(z2[, targets], center = TRUE)^2)
+//   r2_module[j] = r2_removed_vec[0],  importance[reg_r, j] = 1 - r2_removed_vec[r] / r2_module[j].
+// All (f, j, r) problems run in one batched NNLS launch and one batched residual launch; the s + 1
+// problems of a module share one gathered regulator block (the removed regulator's coefficient row
+// is kept as an exact zero row) and differ only in their coefficient rows.
+void Ctx::importance(int F, const int* k_final, const unsigned char* models, const double* signs,
+                     const scrc_options& opt, double* r2_module, double* importance_out) {
+    if (F <= 0) throw Error(SCRC_ERR_ARG, "scrc_importance: F must be positive");
+    SCRC_CUDA(cudaSetDevice(dev.id));
+    cudaStream_t st = dev.stream;
+    const int64_t FK = (int64_t)F * K;
+    const double nan_v = std::nan("");
+    for (int64_t i = 0; i < FK; ++i) r2_module[i] = nan_v;
+    for (int64_t i = 0; i < FK * P; ++i) importance_out[i] = nan_v;
+
+    struct Group { int f, j, s, spad, m; int arow; int col_off; std::vector<int> regs; int first_prob; };
+    std::vector<Group> groups;
+    std::vector<NnlsProblem> h_np;
+    std::vector<int> h_sel, h_pos, h_cols, h_row_src, h_arow, h_brow, h_kpad, h_coff, h_ccnt;
+    std::vector<double> h_sign;
+    int64_t rows_a = 0, rows_b = 0, q_total = 0;
+    int Tmax = 0;
+    for (int f = 0; f < F; ++f) {
+        const int* k = k_final + (int64_t)f * T;
+        for (int j = 0; j < K; ++j) {
+            Group g;
+            g.f = f; g.j = j;
+            const unsigned char* mk = models + ((int64_t)f * K + j) * P;
+            for (int64_t i = 0; i < P; ++i) if (mk[i]) g.regs.push_back((int)i);
+            g.s = (int)g.regs.size();
+            g.col_off = (int)h_cols.size();
+            for (int64_t t = 0; t < T; ++t) if (k[t] == j + 1) h_cols.push_back((int)t);
+            g.m = (int)h_cols.size() - g.col_off;
+            if (!(g.m > 0 && g.s > 1)) { h_cols.resize(g.col_off); continue; }      // scregclust.R:1839
+            g.spad = (int)round_up(g.s, 16);
+            g.arow = (int)rows_a;
+            g.first_prob = (int)h_np.size();
+            for (int a = 0; a < g.s; ++a) h_row_src.push_back(g.regs[a]);
+            for (int a = g.s; a < g.spad; ++a) h_row_src.push_back(-1);
+            rows_a += g.spad;
+            Tmax = std::max(Tmax, g.m);
+            const double* sg = signs + ((int64_t)f * K + j) * P;
+            for (int r = 0; r <= g.s; ++r) {                                        // scregclust.R:1844-1847
+                const int sp = g.s - (r > 0 ? 1 : 0);
+                NnlsProblem np = make_nnls_problem(sp, (int)h_sel.size(), q_total, rows_b);
+                np.ncols = g.m; np.xcol_off = g.col_off; np.pos_off = (int)h_sel.size();
+                np.scale_off = g.col_off; np.scale_len = g.m;
+                for (int a = 0; a < g.s; ++a) {
+                    if (r > 0 && a == r - 1) continue;
+                    h_sel.push_back(g.regs[a]); h_sign.push_back(sg[g.regs[a]]); h_pos.push_back(a);
+                }
+                h_np.push_back(np);
+                h_arow.push_back(g.arow); h_brow.push_back((int)rows_b); h_kpad.push_back(g.spad);
+                h_coff.push_back(g.col_off); h_ccnt.push_back(g.m);
+                rows_b += g.spad; q_total += (int64_t)sp * sp;
+            }
+            groups.push_back(std::move(g));
+        }
+    }
+    if (groups.empty()) return;
+    if (rows_b > 0x7fffff00LL) throw Error(SCRC_ERR_UNSUPPORTED, "scrc_importance: batch too large; pass fewer configurations per call");
+    const int nprob = (int)h_np.size();
+
+    // gathered per-group scale vector z1_target_sds[target_cl] shares the layout of h_cols
+    NnlsBatch nb;
+    nb.nprob = nprob; nb.m = Tmax; nb.rows = rows_b;
+    nb.prob.alloc(nprob); nb.sel.alloc(h_sel.size()); nb.sign.alloc(h_sign.size()); nb.pos.alloc(h_pos.size());
+    nb.cols.alloc(h_cols.size()); nb.Q.alloc(q_total); nb.dvec.alloc(rows_b);
+    nb.grad0.alloc(rows_b, Tmax); nb.beta.alloc(rows_b, Tmax); nb.iters.alloc((size_t)nprob * Tmax);
+    DevBuf<double> scale_vals(h_cols.size());
+    std::vector<double> h_sds(T), h_scale(h_cols.size());
+    SCRC_CUDA(cudaMemcpyAsync(h_sds.data(), sds_t.p, T * 8, cudaMemcpyDeviceToHost, st));
+    SCRC_CUDA(cudaStreamSynchronize(st));
+    for (size_t i = 0; i < h_cols.size(); ++i) h_scale[i] = h_sds[h_cols[i]];
+    SCRC_CUDA(cudaMemcpyAsync(nb.prob.p, h_np.data(), nprob * sizeof(NnlsProblem), cudaMemcpyHostToDevice, st));
+    SCRC_CUDA(cudaMemcpyAsync(nb.sel.p, h_sel.data(), h_sel.size() * 4, cudaMemcpyHostToDevice, st));
+    SCRC_CUDA(cudaMemcpyAsync(nb.sign.p, h_sign.data(), h_sign.size() * 8, cudaMemcpyHostToDevice, st));
+    SCRC_CUDA(cudaMemcpyAsync(nb.pos.p, h_pos.data(), h_pos.size() * 4, cudaMemcpyHostToDevice, st));
+    SCRC_CUDA(cudaMemcpyAsync(nb.cols.p, h_cols.data(), h_cols.size() * 4, cudaMemcpyHostToDevice, st));
+    SCRC_CUDA(cudaMemcpyAsync(scale_vals.p, h_scale.data(), h_scale.size() * 8, cudaMemcpyHostToDevice, st));
+    SCRC_CUDA(cudaMemsetAsync(nb.grad0.data(), 0, nb.grad0.bytes(), st));
+    nnls_setup(nb, G_rr.data(), G_rr.ld, G_rt.data(), G_rt.ld, inv_sds_t.p, st);
+    nnls_solve(nb, opt.tol_nnls, opt.max_optim_iter, scale_vals.p, 1, dev.num_sms, st);   // scregclust.R:1865-1873
+
+    // test residuals: SSE per (problem, target of the module)                          scregclust.R:1875-1878
+    DevBuf<int> d_row_src(rows_a), d_arow(nprob), d_brow(nprob), d_kpad(nprob), d_coff(nprob), d_ccnt(nprob);
+    SCRC_CUDA(cudaMemcpyAsync(d_row_src.p, h_row_src.data(), rows_a * 4, cudaMemcpyHostToDevice, st));
+    SCRC_CUDA(cudaMemcpyAsync(d_arow.p, h_arow.data(), nprob * 4, cudaMemcpyHostToDevice, st));
+    SCRC_CUDA(cudaMemcpyAsync(d_brow.p, h_brow.data(), nprob * 4, cudaMemcpyHostToDevice, st));
+    SCRC_CUDA(cudaMemcpyAsync(d_kpad.p, h_kpad.data(), nprob * 4, cudaMemcpyHostToDevice, st));
+    SCRC_CUDA(cudaMemcpyAsync(d_coff.p, h_coff.data(), nprob * 4, cudaMemcpyHostToDevice, st));
+    SCRC_CUDA(cudaMemcpyAsync(d_ccnt.p, h_ccnt.data(), nprob * 4, cudaMemcpyHostToDevice, st));
+    DMat Zs(rows_a, n2);
+    gather_transpose(Z2r.data(), Z2r.ld, (int)n2, d_row_src.p, rows_a, Zs.data(), Zs.ld, st);
+    const int CR = resid_vote_pick_cr((int)n2, Tmax, nprob, dev.num_sms);
+    DevBuf<double> part(resid_vote_partial_elems(Tmax, 1, nprob, CR)), sse((size_t)nprob * 2 * Tmax);
+    ResidVoteArgs ra;
+    ra.ZselT = Zs.data(); ra.ldzs = Zs.ld; ra.beta = nb.beta.data(); ra.ldb = nb.beta.ld; ra.rows_total = rows_b;
+    ra.Z = Z2t.data(); ra.ldz = Z2t.ld; ra.ncells = (int)n2; ra.T = Tmax; ra.K = 1; ra.L = nprob;
+    ra.row_off = d_arow.p; ra.kpad = d_kpad.p; ra.two_var = nullptr; ra.half_log = nullptr;
+    ra.partial = part.p; ra.votes = nullptr; ra.CR = CR;
+    ra.row_off_b = d_brow.p; ra.col_index = nb.cols.p; ra.col_off = d_coff.p; ra.col_cnt = d_ccnt.p;
+    // the A operand (rows_a rows) and the B operand (rows_b rows) need tensor maps of their own extent
+    ra.rows_total_a = rows_a;
+    resid_vote(ra, false, dev.num_sms, st);
+    reduce_sse(part.p, Tmax, 1, nprob, CR, sse.p, st);
+    if (z2t_css.n == 0) { z2t_css.alloc(T); col_centered_ss(Z2t.data(), Z2t.ld, n2, T, z2t_css.p, st); }
+    std::vector<double> h_sse((size_t)nprob * 2 * Tmax), h_css(T);
+    SCRC_CUDA(cudaMemcpyAsync(h_sse.data(), sse.p, h_sse.size() * 8, cudaMemcpyDeviceToHost, st));
+    SCRC_CUDA(cudaMemcpyAsync(h_css.data(), z2t_css.p, T * 8, cudaMemcpyDeviceToHost, st));
+    SCRC_CUDA(cudaStreamSynchronize(st));
+
+    for (const Group& g : groups) {
+        long double denom = 0.0L;
+        for (int c = 0; c < g.m; ++c) denom += h_css[h_cols[g.col_off + c]];            // scregclust.R:1883-1887
+        std::vector<double> vec(g.s + 1);
+        for (int r = 0; r <= g.s; ++r) {
+            const double* q = h_sse.data() + ((size_t)(g.first_prob + r) * 2 + 0) * Tmax;
+            long double tot = 0.0L;
+            for (int c = 0; c < g.m; ++c) tot += q[c];
+            vec[r] = 1.0 - (double)(tot / denom);                                       // scregclust.R:1882
+        }
+        r2_module[(int64_t)g.f * K + g.j] = vec[0];                                     // scregclust.R:1901
+        for (int r = 1; r <= g.s; ++r)
+            importance_out[((int64_t)g.f * K + g.j) * P + g.regs[r - 1]] = 1.0 - vec[r] / vec[0];   // scregclust.R:1904-1909
+    }
 }
 
 // ============================================================================ drop-ins
@@ -494,7 +625,7 @@ void dropin_nnls(Device& dev, const double* x, int64_t nobs, int64_t nvar, const
     b.nprob = 1; b.m = (int)m;
     const int64_t rows = round_up(nvar, 16);
     b.rows = rows;
-    NnlsProblem np{(int)nvar, 0, 0, 0};
+    NnlsProblem np = make_nnls_problem((int)nvar, 0, 0, 0);
     std::vector<int> sel(nvar);
     std::iota(sel.begin(), sel.end(), 0);
     std::vector<double> sg(nvar, 1.0);

@@ -65,6 +65,10 @@ struct Ctx {
                 const double* sds, int64_t n1, int64_t n2, int64_t P, int64_t T, int K);
     void fit_cycle(int F, const double* lambda, const int* k_in, const scrc_options& opt, bool skip_alloc,
                    scrc_cycle_out* out);
+    // Leave-one-regulator-out importance and module R2 (R/scregclust.R:1823-1912) for F final configurations.
+    void importance(int F, const int* k_final, const unsigned char* models, const double* signs,
+                    const scrc_options& opt, double* r2_module, double* importance_out);
+    DevBuf<double> z2t_css;      // centred sums of squares of the test targets (lazy)
     ~Ctx() { dev.destroy(); }
 };
 

@@ -40,6 +40,8 @@ class FitResult:
     nnls_iterations: list = field(default_factory=list)
     votes: list = field(default_factory=list)
     models_history: list = field(default_factory=list)
+    r2_module: list = field(default_factory=list)     # per final configuration: K (nan = NA)
+    importance: list = field(default_factory=list)    # per final configuration: P x K (nan = NA)
 
 
 class Session:
@@ -157,6 +159,23 @@ class Session:
         self.admm_problem_iterations += int(res["admm_iterations"].sum())
         return res
 
+    def importance(self, k_final, models, signs, options=None):
+        """Leave-one-regulator-out importance (R/scregclust.R:1823-1912) for F final configurations.
+
+        ``k_final``: F x T, ``models``: F x K x P (bool/uint8), ``signs``: F x K x P (nan where unselected).
+        Returns ``(r2_module[F, K], importance[F, K, P])`` with nan where the reference leaves NA."""
+        k = np.ascontiguousarray(k_final, dtype=np.int32).reshape(-1, self.T)
+        F = k.shape[0]
+        md = np.ascontiguousarray(models, dtype=np.uint8).reshape(F, self.K, self.P)
+        sg = np.ascontiguousarray(signs, dtype=np.float64).reshape(F, self.K, self.P)
+        opt = options if options is not None else default_options()
+        r2m = np.zeros((F, self.K)); imp = np.zeros((F, self.K, self.P))
+        check(self._lib.scrc_importance(self._h, F, iptr(k), md.ctypes.data_as(_capi.c_ubyte_p), dptr(sg), C.byref(opt),
+                                        dptr(r2m), dptr(imp)))
+        self.h2d_bytes += k.nbytes + md.nbytes + sg.nbytes
+        self.d2h_bytes += r2m.nbytes + imp.nbytes
+        return r2m, imp
+
     def coeffs(self, f, module):
         """NNLS coefficients (s x T) and 0-based regulator indices of ``module`` (0-based) of fit ``f``."""
         s = self._last_nsel[f, module]
@@ -200,7 +219,8 @@ def scregclust_fit(z1_reg_scaled=None, z2_reg_scaled=None, z1_target_centered=No
                    z1_target_sds=None, penalization=(), n_modules=1, initial_target_modules=None,
                    min_module_size=0, noise_threshold=0.025, n_cycles=50, max_optim_iter=10000,
                    tol_coop_rel=1e-8, tol_coop_abs=1e-12, tol_nnls=1e-4, device=0, session=None,
-                   keep_diagnostics=False, return_coeffs=True, claim=None, concurrency=None):
+                   keep_diagnostics=False, return_coeffs=True, claim=None, concurrency=None,
+                   compute_predictive_r2=False):
     """The alternating loop of ``scregclust()`` (R/scregclust.R:1222-1803) for all penalization values.
 
     Returns one :class:`FitResult` per penalization value, in order.  ``session`` may be passed to
@@ -302,6 +322,11 @@ def scregclust_fit(z1_reg_scaled=None, z2_reg_scaled=None, z1_target_centered=No
                     fr.best_r2_idx.append(res["best_r2_idx"][f].copy())
                     if return_coeffs:
                         fr.coeffs.append([ses.coeffs(f, j)[0] for j in range(K)])
+                if compute_predictive_r2:                             # R/scregclust.R:1823-1912
+                    r2m, imp = ses.importance(np.stack(k_f), res["models"], res["signs"], opt)
+                    for f, i in enumerate(owner):
+                        results[i].r2_module.append(r2m[f].copy())
+                        results[i].importance.append(imp[f].T.copy())
                 for i in fin:
                     s, fr = states[i], results[i]
                     s.done = True

@@ -243,3 +243,36 @@ def test_dynamic_claiming_matches_lockstep():
         assert len(x.k_history) == len(y.k_history) and all(np.array_equal(p, q) for p, q in zip(x.k_history, y.k_history))
         assert np.array_equal(x.models[0], y.models[0]) and np.array_equal(x.r2[0], y.r2[0])
         assert all((p is None and q is None) or np.array_equal(p, q) for p, q in zip(x.coeffs[0], y.coeffs[0]))
+
+
+@pytest.mark.parametrize("name,seed", [("tiny", 3), ("small", 1)])
+def test_importance_matches_oracle(name, seed):
+    """Next-row f1: leave-one-regulator-out importance and module R2 (R/scregclust.R:1823-1912)."""
+    from scregclust_b200.driver import Session
+    w = make_workload(name, seed=seed)
+    K = w.n_modules
+    ref = orc.scregclust_fit(w.z1_reg, w.z2_reg, w.z1_target, w.z2_target, w.z1_target_sds, w.penalization, K,
+                             w.k_init, min_module_size=2, compute_predictive_r2=True)
+    ks = np.stack([r.k_final[0] for r in ref])
+    models = np.stack([r.models[0].T for r in ref]).astype(np.uint8)       # F x K x P
+    signs = np.stack([r.signs[0].T for r in ref])
+    with Session(w.z1_reg, w.z2_reg, w.z1_target, w.z2_target, w.z1_target_sds, K) as s:
+        r2m, imp = s.importance(ks, models, signs)
+    for f, r in enumerate(ref):
+        assert np.array_equal(np.isnan(r2m[f]), np.isnan(r.r2_module[0]))
+        assert np.allclose(r2m[f], r.r2_module[0], rtol=1e-8, atol=1e-10, equal_nan=True)
+        assert np.array_equal(np.isnan(imp[f].T), np.isnan(r.importance[0]))
+        assert np.allclose(imp[f].T, r.importance[0], rtol=1e-7, atol=1e-9, equal_nan=True)
+    assert np.isfinite(r2m).any()
+
+
+def test_driver_importance_end_to_end():
+    from scregclust_b200.driver import scregclust_fit
+    w = make_workload("tiny", seed=3)
+    ref = orc.scregclust_fit(w.z1_reg, w.z2_reg, w.z1_target, w.z2_target, w.z1_target_sds, w.penalization,
+                             w.n_modules, w.k_init, compute_predictive_r2=True)
+    got = scregclust_fit(w.z1_reg, w.z2_reg, w.z1_target, w.z2_target, w.z1_target_sds, w.penalization,
+                         w.n_modules, w.k_init, compute_predictive_r2=True)
+    for g, r in zip(got, ref):
+        assert np.allclose(g.r2_module[0], r.r2_module[0], rtol=1e-8, atol=1e-10, equal_nan=True)
+        assert np.allclose(g.importance[0], r.importance[0], rtol=1e-7, atol=1e-9, equal_nan=True)
