@@ -3,9 +3,10 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload config2|config3|...] [--impl reference]
 
-A *step* is one complete penalization-grid fit of the alternating loop (R/scregclust.R:996-1803:
-Gram / eigenbasis / initial fit, then Step 1 + 2a + 2b cycles until every penalty has converged
-and its final configurations are re-fitted) on one seeded synthetic workload of a BASELINE.json
+A *step* is one complete penalization-grid fit of the alternating loop (R/scregclust.R:996-1912:
+Gram / eigenbasis / initial fit, then Step 1 + 2a + 2b cycles until every penalty has converged,
+its final configurations are re-fitted and their leave-one-regulator-out importances computed,
+i.e. the default compute_predictive_r2 = TRUE) on one seeded synthetic workload of a BASELINE.json
 shape.  With N > 1 (torchrun, one rank per GPU) the penalty grid is sharded round-robin over the
 ranks -- the fits are independent (R/scregclust.R:1223,1245) -- and the per-penalty module
 assignments are all-gathered over NCCL at the end of the step ("scaling": "strong": the grid is
@@ -179,13 +180,34 @@ def cpu_sample(w, budget_s, total_fit_cycles, total_last_cycles, lam):
     ref_cpu.allocate_into_modules(arr, rv, None, None, np.ones(g, dtype=np.int32), np.arange(g, dtype=np.int32), 1e-6, 0.0)
     t_alloc = time.perf_counter() - t0
     step2b_est = (t_fill * (1 + (nonempty - 1) * 0.5) + t_alloc) * T / g
+    # ---- post-processing: leave-one-regulator-out NNLS importance (R/scregclust.R:1823-1912) on one module ----
+    t_imp, imp_mods = 0.0, 0
+    for j, reg in models.items():
+        cl = np.flatnonzero(k == j)
+        if reg.size < 2 or cl.size == 0:
+            continue
+        t0 = time.perf_counter()
+        y_cl = np.asfortranarray(w.z1_target[:, cl] / w.z1_target_sds[cl][None, :])
+        for r in range(reg.size + 1):
+            keep = np.ones(reg.size, dtype=bool)
+            if r > 0:
+                keep[r - 1] = False
+            xs = np.asfortranarray(w.z1_reg[:, reg[keep]] * signs[j][keep][None, :])
+            b, _ = ref_cpu.coef_nnls(xs, y_cl, eps=1e-4, max_iter=10000)
+            bh = b * signs[j][keep][:, None] * orc._recycle(w.z1_target_sds[cl], b.shape)
+            rt = w.z2_target[:, cl] - w.z2_reg[:, reg[keep]] @ bh
+            _ = (rt * rt).sum(axis=0)
+        t_imp += time.perf_counter() - t0
+        imp_mods += 1
+        break
+    imp_est = t_imp * nonempty / max(imp_mods, 1)
     cycle_est = step1_est + step2a_est + step2b_est
-    last_est = step1_est + step2a_est
+    last_est = step1_est + step2a_est + imp_est
     total = t_pre + cycle_est * total_fit_cycles + last_est * total_last_cycles
     desc = (f"reference-faithful C++ twin (oracle/ref_cpu.cpp: Gram per call, LDL^T per iteration, K x n2 x T array), "
             f"lambda={lam:.3g}, first cycle from the initial configuration: Step 1 on {done1}/{nonempty} modules "
             f"({admm_it} ADMM iterations, {t1:.1f} s), Step 2a on {done2} modules ({t2:.1f} s), reset+allocate on {g}/{T} genes "
-            f"({t_fill + t_alloc:.2f} s), precompute {t_pre:.1f} s; extrapolated to {total_fit_cycles} fit cycles + "
+            f"({t_fill + t_alloc:.2f} s), importance refits of {imp_mods} module ({t_imp:.1f} s), precompute {t_pre:.1f} s; extrapolated to {total_fit_cycles} fit cycles + "
             f"{total_last_cycles} final re-fits of the grid")
     return total, desc, threads
 
@@ -291,7 +313,7 @@ def main():
             # (most expensive first) whenever one of them finishes -- the longest fit (about twice
             # the average number of cycles) then still fits inside a rank's share of the work
             allres = scregclust_fit(penalization=all_pens, n_modules=n_modules, initial_target_modules=w.k_init,
-                                    session=ses, return_coeffs=not resident,
+                                    session=ses, return_coeffs=not resident, compute_predictive_r2=True,
                                     claim=counter if world > 1 else None,
                                     concurrency=max(1, len(all_pens) // (2 * world)) if world > 1 else None)
             res = [r for r in allres if r is not None]

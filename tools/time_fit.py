@@ -18,6 +18,10 @@ for rep in range(reps):
     res = scregclust_fit(penalization=w.penalization, n_modules=w.n_modules, initial_target_modules=w.k_init, session=ses,
                          return_coeffs=False)
     t2 = time.time()
+    if "--importance" in sys.argv:
+        ks = np.stack([r.k_final[0] for r in res]); md = np.stack([r.models[0].T for r in res]); sg = np.stack([r.signs[0].T for r in res])
+        ti = time.time(); r2m, imp = ses.importance(ks, md, sg); ti = time.time() - ti
+        print(f"    importance for {len(res)} final configurations: {ti:.3f} s; r2_module[0][:5] = {np.round(r2m[0][:5], 4)}", flush=True)
     pm = (C.c_double * 6)(); pw = (C.c_double * 6)(); pl = (C.c_ulonglong * 6)()
     _capi.check(lib.scrc_profile_get(pm, pw, pl)); _capi.check(lib.scrc_profile_enable(0))
     print(f"rep {rep}: create {t1 - t0:.3f} s, loop {t2 - t1:.3f} s, cycles/penalty {[r.n_cycles_run for r in res]}, "
