@@ -379,6 +379,11 @@ def main():
         adm = prof["gemm_admm"]
         achieved = adm["work_per_step"] / (adm["ms_per_step"] * 1e-3) / 1e12 if adm["ms_per_step"] > 0 else 0.0
         sweeps = max(stats["sweeps"], 1)
+        traffic = None
+        try:   # DRAM bytes of one (all-columns-active) launch of the dominant kernel from the committed ncu capture
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[args.workload]
+        except Exception:
+            pass
         line = {
             "metric": METRIC, "value": ms_dev * 1e-3, "unit": "s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": False, "scaling": "strong",
@@ -391,7 +396,10 @@ def main():
                      "fit_cycles_rank0": int(stats["fit_cycles"]), "final_refits_rank0": int(stats["last_cycles"])},
             "roofline": {"kernel": "gemm_tn_kernel<AdmmGemmPolicy> (two eigenbasis GEMMs per ADMM sweep)",
                          "bound": "tensor", "achieved": achieved, "peak": dgemm_tf, "unit": "TFLOP/s",
-                         "frac": achieved / dgemm_tf if dgemm_tf > 0 else None, "traffic": None,
+                         "frac": achieved / dgemm_tf if dgemm_tf > 0 else None,
+                         "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
+                         "traffic_note": (f"ncu dram bytes of a launch with every column active; algorithmic "
+                                          f"{traffic['algorithmic_bytes_per_launch']} B for that launch") if traffic else None,
                          "share_of_step": adm["ms_per_step"] / ms_dev if ms_dev > 0 else None,
                          "launches_per_step": 2 * sweeps / max(args.steps, 1),
                          "peak_source": "cuBLAS DGEMM 8192^3 (torch.matmul float64) measured in this run; "

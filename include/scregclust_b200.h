@@ -184,6 +184,21 @@ int scrc_fit_cycle(scrc_ctx* ctx, int F, const double* lambda, const int* k_in, 
 int scrc_importance(scrc_ctx* ctx, int F, const int* k_final, const unsigned char* models, const double* signs,
                     const scrc_options* opt, double* r2_module, double* importance);
 
+/* Network prior for Step 2b (src/allocation.cpp:39-56,74-77; R/scregclust.R:584-615,1666-1675).
+ * prior_off / prior_idx: CSR form of `prior_indicator` over the T target genes (0-based neighbours);
+ * update_order: F x T, the 0-based permutation R draws with sample() for each fit and cycle
+ * (R/scregclust.R:1666) -- the caller owns the RNG, so the result matches a serial R run only if it
+ * replays R's draws.  With prior_weight == 0 this is identical to scrc_fit_cycle. */
+typedef struct scrc_prior {
+    const int* prior_off;      /* T + 1 */
+    const int* prior_idx;      /* prior_off[T] entries */
+    double baseline;           /* prior_baseline (1e-6) */
+    double weight;             /* prior_weight   (0.5)  */
+    const int* update_order;   /* F x T */
+} scrc_prior;
+int scrc_fit_cycle_prior(scrc_ctx* ctx, int F, const double* lambda, const int* k_in, const scrc_options* opt,
+                         const scrc_prior* prior, scrc_cycle_out* out);
+
 /* NNLS coefficients of module k (0-based) of fit f from the last scrc_fit_cycle call:
  * n_selected x T (R/scregclust.R:1588); sel_out receives the 0-based regulator indices. */
 int scrc_ctx_get_coeffs(scrc_ctx* ctx, int f, int k, double* coeffs_out, int* sel_out);

@@ -40,6 +40,11 @@ class CycleOut(C.Structure):
                 ("nnls_iterations", c_int_p), ("n_selected", c_int_p), ("admm_sweeps", C.POINTER(C.c_longlong))]
 
 
+class Prior(C.Structure):
+    _fields_ = [("prior_off", c_int_p), ("prior_idx", c_int_p), ("baseline", C.c_double), ("weight", C.c_double),
+                ("update_order", c_int_p)]
+
+
 # name -> (restype, argtypes); also the list of symbols the header declares
 SIGNATURES = {
     "scrc_version": (C.c_int, []),
@@ -74,6 +79,8 @@ SIGNATURES = {
     "scrc_ctx_get_gram": (C.c_int, [C.c_void_p, c_double_p, c_double_p]),
     "scrc_fit_cycle": (C.c_int, [C.c_void_p, C.c_int, c_double_p, c_int_p, C.POINTER(Options), C.c_int,
                                  C.POINTER(CycleOut)]),
+    "scrc_fit_cycle_prior": (C.c_int, [C.c_void_p, C.c_int, c_double_p, c_int_p, C.POINTER(Options), C.POINTER(Prior),
+                                       C.POINTER(CycleOut)]),
     "scrc_importance": (C.c_int, [C.c_void_p, C.c_int, c_int_p, c_ubyte_p, c_double_p, C.POINTER(Options), c_double_p,
                                   c_double_p]),
     "scrc_ctx_get_coeffs": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_double_p, c_int_p]),

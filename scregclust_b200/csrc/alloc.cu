@@ -22,6 +22,7 @@ struct RvParams {
     const int* col_index;
     const int* col_off;
     const int* col_cnt;
+    double* sq_out;      // MODE 2: K x ncells x T squared test residuals of ONE fit (module fastest)
 };
 
 constexpr int RV_A_BYTES = RV_BM * GEMM_BK * 8;
@@ -32,8 +33,11 @@ __device__ __forceinline__ void consumer_bar() {   // the 8 consumer warps only
     asm volatile("bar.sync 1, 256;" ::: "memory");
 }
 
-template <bool VOTE>
+// MODE 0: SSE only; MODE 1: SSE + per-cell votes; MODE 2: SSE + squared residuals written out
+// (only used for the sequential network-prior sweep, which needs every gene's K x n2 slab).
+template <int MODE>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) resid_vote_kernel(const __grid_constant__ RvParams p) {
+    constexpr bool VOTE = (MODE == 1);
     constexpr int MT = RV_BM / (GEMM_WARPS_M * 8);   // 4
     constexpr int NT = RV_BN / (GEMM_WARPS_N * 8);   // 2
     extern __shared__ __align__(1024) uint8_t smem[];   // see gemm_tn.cuh: keep the shared address space
@@ -161,6 +165,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) resid_vote_kernel(const __gri
                             const double res = z[i][jj][e] - acc[i][jj][e];   // scregclust.R:1593-1595
                             const double sq = res * res;
                             csum += sq;
+                            if (MODE == 2 && j < p.K) {
+                                const int row = c0 + a_row0 + i * 8 + r;
+                                if (row < p.ncells && col < ncol)
+                                    p.sq_out[j + (int64_t)p.K * (row + (int64_t)p.ncells * col)] = sq;   // scregclust.R:1599
+                            }
                             if (VOTE && j < p.K) {
                                 const double sc = (-sq) / tv - hl;            // allocation.cpp:59-62
                                 if (sc > best[i][jj][e]) { best[i][jj][e] = sc; bidx[i][jj][e] = j; }
@@ -221,7 +230,7 @@ size_t resid_vote_partial_elems(int T, int K, int L, int CR) {
     return (size_t)L * CR * 2 * (K + 1) * T;
 }
 
-void resid_vote(const ResidVoteArgs& a, bool vote, int num_sms, cudaStream_t st) {
+void resid_vote(const ResidVoteArgs& a, int mode, int num_sms, cudaStream_t st) {
     if (a.K + 1 > RV_MAX_K + 1) throw Error(-60, "resid_vote: at most 64 modules are supported");
     RvParams p;
     // operands are allocated with at least one 16-row block so that the maps are never empty
@@ -232,15 +241,18 @@ void resid_vote(const ResidVoteArgs& a, bool vote, int num_sms, cudaStream_t st)
     p.row_off = a.row_off; p.kpad = a.kpad; p.two_var = a.two_var; p.half_log = a.half_log;
     p.partial = a.partial; p.votes = a.votes; p.CR = a.CR;
     p.row_off_b = a.row_off_b; p.col_index = a.col_index; p.col_off = a.col_off; p.col_cnt = a.col_cnt;
+    p.sq_out = a.sq_out;
+    if (mode == 2 && (a.L != 1 || !a.sq_out)) throw Error(-62, "resid_vote: store mode handles one fit per launch");
     p.tiles_n = (int)ceil_div(a.T, RV_BN); p.ctiles = (int)ceil_div(a.ncells, RV_BM);
 
     const int smem = RV_STAGES * RV_STAGE_BYTES + 2 * RV_STAGES * 8 + 2 * (a.K + 1) * RV_BN * 8 +
                      RV_BN * a.K * 4;
-    static int conf[2] = {0, 0};
-    if (smem > conf[vote ? 1 : 0]) {
-        if (vote) SCRC_CUDA(cudaFuncSetAttribute(resid_vote_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        else SCRC_CUDA(cudaFuncSetAttribute(resid_vote_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        conf[vote ? 1 : 0] = smem;
+    static int conf[3] = {0, 0, 0};
+    if (smem > conf[mode]) {
+        if (mode == 1) SCRC_CUDA(cudaFuncSetAttribute(resid_vote_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        else if (mode == 2) SCRC_CUDA(cudaFuncSetAttribute(resid_vote_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        else SCRC_CUDA(cudaFuncSetAttribute(resid_vote_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        conf[mode] = smem;
     }
     const int64_t nwork = (int64_t)a.L * a.CR * p.tiles_n;
     if (nwork > 0x7fffffffLL) throw Error(-61, "resid_vote: too many work items");
@@ -251,8 +263,9 @@ void resid_vote(const ResidVoteArgs& a, bool vote, int num_sms, cudaStream_t st)
         // gathered regulators and coefficients once per module slice
         const double bytes = 8.0 * (double)a.L * a.ncells * a.T + 8.0 * (double)a.rows_total * (a.ncells * (double)p.tiles_n + (double)a.T * p.ctiles);
         ProfScope ps(PROF_RESID_VOTE, st, bytes);
-        if (vote) resid_vote_kernel<true><<<grid, GEMM_THREADS, smem, st>>>(p);
-        else resid_vote_kernel<false><<<grid, GEMM_THREADS, smem, st>>>(p);
+        if (mode == 1) resid_vote_kernel<1><<<grid, GEMM_THREADS, smem, st>>>(p);
+        else if (mode == 2) resid_vote_kernel<2><<<grid, GEMM_THREADS, smem, st>>>(p);
+        else resid_vote_kernel<0><<<grid, GEMM_THREADS, smem, st>>>(p);
     }
     SCRC_CUDA(cudaGetLastError());
     SCRC_LAUNCHED();
@@ -272,6 +285,58 @@ __global__ void reduce_sse_kernel(const double* __restrict__ partial, int T, int
 void reduce_sse(const double* partial, int T, int K, int L, int CR, double* sse, cudaStream_t st) {
     const int64_t n = (int64_t)L * (K + 1) * T;
     reduce_sse_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(partial, T, K + 1, L, CR, sse);
+    SCRC_CUDA(cudaGetLastError());
+    SCRC_LAUNCHED();
+}
+
+// One CTA per (fit*module, 128-target chunk); the module's Gram block lives in shared memory.
+constexpr int SSG_MAX_S = 72;   // 72^2 doubles = 41 KB of static shared memory
+__global__ void __launch_bounds__(128) sse_train_gram_kernel(const double* __restrict__ G_rr, int64_t ldrr,
+                                                             const double* __restrict__ G_rt, int64_t ldrt,
+                                                             const double* __restrict__ gtt,
+                                                             const double* __restrict__ beta, int64_t ldb,
+                                                             const int* __restrict__ sel, const int* __restrict__ row_off,
+                                                             const int* __restrict__ nsel, int T, int K, double* sse) {
+    __shared__ double s_g[SSG_MAX_S * SSG_MAX_S];
+    __shared__ int s_sel[SSG_MAX_S];
+    const int fk = blockIdx.y;
+    const int l = fk / K, j = fk % K;
+    const int s = nsel[fk];
+    const int ro = row_off[fk];
+    const int t = blockIdx.x * 128 + threadIdx.x;
+    const bool in_smem = s <= SSG_MAX_S;
+    if (in_smem) {
+        for (int a = threadIdx.x; a < s; a += 128) s_sel[a] = sel[ro + a];
+        __syncthreads();
+        for (int e = threadIdx.x; e < s * s; e += 128) s_g[e] = G_rr[s_sel[e % s] + (int64_t)s_sel[e / s] * ldrr];
+        __syncthreads();
+    }
+    if (t >= T) return;
+    double acc = gtt[t];
+    if (s > 0) {
+        const double* b = beta + ro + (int64_t)t * ldb;
+        double cross = 0.0, quad = 0.0;
+        for (int a = 0; a < s; ++a) {
+            const double ba = b[a];
+            const int ia = in_smem ? s_sel[a] : sel[ro + a];
+            cross += ba * G_rt[ia + (int64_t)t * ldrt];
+            double row = 0.0;
+            for (int c = 0; c < s; ++c) {
+                const double g = in_smem ? s_g[a + c * s] : G_rr[ia + (int64_t)sel[ro + c] * ldrr];
+                row += g * b[c];
+            }
+            quad += ba * row;
+        }
+        acc = (acc - 2.0 * cross) + quad;
+    }
+    sse[((int64_t)l * (K + 1) + j) * T + t] = acc;
+}
+void sse_train_gram(const double* G_rr, int64_t ldrr, const double* G_rt, int64_t ldrt, const double* gtt,
+                    const double* beta, int64_t ldb, const int* sel, const int* row_off, const int* nsel, int T, int K,
+                    int L, double* sse, cudaStream_t st) {
+    dim3 grid((unsigned)ceil_div(T, 128), (unsigned)(L * K));
+    ProfScope ps(PROF_RESID_VOTE, st, 0.0);
+    sse_train_gram_kernel<<<grid, 128, 0, st>>>(G_rr, ldrr, G_rt, ldrt, gtt, beta, ldb, sel, row_off, nsel, T, K, sse);
     SCRC_CUDA(cudaGetLastError());
     SCRC_LAUNCHED();
 }

@@ -32,13 +32,24 @@ struct ResidVoteArgs {
     const int* col_index = nullptr;      // device: flattened per-fit lists of target columns of Z
     const int* col_off = nullptr;        // device [L]: start of fit l's list in col_index
     const int* col_cnt = nullptr;        // device [L]: number of columns of fit l (<= T = columns of beta)
+    double* sq_out = nullptr;            // mode 2: K x ncells x T squared residuals (module fastest, one fit)
 };
 int resid_vote_pick_cr(int ncells, int T, int L, int num_sms);
 size_t resid_vote_partial_elems(int T, int K, int L, int CR);
-void resid_vote(const ResidVoteArgs& a, bool vote, int num_sms, cudaStream_t s);
+// mode 0: SSE only, 1: SSE + votes, 2: SSE + squared residuals of one fit written to sq_out
+void resid_vote(const ResidVoteArgs& a, int mode, int num_sms, cudaStream_t s);
 
 // sse[l][j][t] (j = 0..K, the last one is the "no model" pseudo module) = fixed-order sum of partials
 void reduce_sse(const double* partial, int T, int K, int L, int CR, double* sse, cudaStream_t s);
+
+// Training SSE of every (fit, module, target) from the Gram matrices instead of the n1 cells:
+//   ||y_t - X_sel b||^2 = y_t'y_t - 2 b'(X_sel'y_t) + b'(X_sel'X_sel) b
+// with y'y = gtt[t], X'y = G_rt[sel, t], X'X = G_rr[sel, sel]  (same quantity as
+// colSums(residuals_train_nnls^2), R/scregclust.R:1590-1602, in O(s^2) instead of O(n1 s) per pair).
+// Modules without a model get gtt[t] exactly.  Output layout = sse[l][j][t] with K+1 module slots.
+void sse_train_gram(const double* G_rr, int64_t ldrr, const double* G_rt, int64_t ldrt, const double* gtt,
+                    const double* beta, int64_t ldb, const int* sel /* per stacked row: regulator or -1 */,
+                    const int* row_off, const int* nsel, int T, int K, int L, double* sse, cudaStream_t s);
 
 // resid_var = SSE_train / (n1 - s_j); two_var = 2 var; half_log = 0.5 log(2 pi var)
 // (R/scregclust.R:1635-1638, allocation.cpp:59-62).  nsel: device [L*K].

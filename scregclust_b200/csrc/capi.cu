@@ -289,6 +289,16 @@ int scrc_fit_cycle(scrc_ctx* ctx, int F, const double* lambda, const int* k_in, 
     return guarded([&] { ctx->impl.fit_cycle(F, lambda, k_in, o, skip_allocation != 0, out); });
 }
 
+int scrc_fit_cycle_prior(scrc_ctx* ctx, int F, const double* lambda, const int* k_in, const scrc_options* opt,
+                         const scrc_prior* prior, scrc_cycle_out* out) {
+    if (!ctx || !lambda || !k_in || !prior) return fail(SCRC_ERR_ARG, "scrc_fit_cycle_prior: null pointer");
+    scrc_options o;
+    if (opt) o = *opt; else scrc_default_options(&o);
+    if (o.max_optim_iter <= 0 || o.n_update <= 0 || !(o.rho0 > 0.0) || o.alpha0 <= 0.0 || o.alpha0 > 2.0)
+        return fail(SCRC_ERR_ARG, "scrc_fit_cycle_prior: invalid options");
+    return guarded([&] { ctx->impl.fit_cycle(F, lambda, k_in, o, false, out, prior); });
+}
+
 int scrc_importance(scrc_ctx* ctx, int F, const int* k_final, const unsigned char* models, const double* signs,
                     const scrc_options* opt, double* r2_module, double* importance) {
     if (!ctx || !k_final || !models || !signs || !r2_module || !importance)

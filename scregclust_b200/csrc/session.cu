@@ -2,6 +2,8 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
+#include <ctime>
 #include <numeric>
 
 namespace scrc {
@@ -91,17 +93,33 @@ void Ctx::create(int device, const double* z1r, const double* z2r, const double*
     dev.init(device);
     n1 = n1_; n2 = n2_; P = P_; T = T_; K = K_;
     cudaStream_t st = dev.stream;
+    const bool dbg = getenv("SCRC_DEBUG_TIMING") != nullptr;
+    auto tick = [&](const char* what) {
+        static double t_prev = 0.0;
+        if (!dbg) return;
+        cudaStreamSynchronize(st);
+        timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);
+        const double t = ts.tv_sec + 1e-9 * ts.tv_nsec;
+        if (what) fprintf(stderr, "[scrc create] %-28s %8.2f ms\n", what, (t - t_prev) * 1e3);
+        t_prev = t;
+    };
+    tick(nullptr);
     Z1r.alloc(n1, P); Z2r.alloc(n2, P); Z1t.alloc(n1, T); Z2t.alloc(n2, T);
     Z1r.upload(z1r, n1, st); Z2r.upload(z2r, n2, st); Z1t.upload(z1t, n1, st); Z2t.upload(z2t, n2, st);
     sds_t.alloc(T); inv_sds_t.alloc(T);
     SCRC_CUDA(cudaMemcpyAsync(sds_t.p, sds, T * 8, cudaMemcpyDefault, st));
     vec_recip_kernel<<<(unsigned)ceil_div(T, 256), 256, 0, st>>>(sds_t.p, inv_sds_t.p, (int)T);
     SCRC_LAUNCHED();
+    tick("alloc + upload");
 
     // Gram matrices (optim.cpp:17-27,99,414,421) -- computed once, the reference redoes them per call
     gram(Z1r, Z1r, G_rr, true, dev);
     gram(Z1r, Z1t, G_rt, false, dev);
+    tick("gram");
     build_eig(G_rr, 1.0 / (double)n1, eig, dev);   // eigenbasis of X'X with X = Z1r / sqrt(n1)
+    tick("eigen-decomposition");
+    gtt.alloc(T);
+    col_sumsq(Z1t.data(), Z1t.ld, n1, T, gtt.p, st);
 
     // Initial fit (scregclust.R:1049-1101): OLS when n1 >= P, ridge with the df search otherwise.
     DMat tmp;
@@ -121,6 +139,7 @@ void Ctx::create(int device, const double* z1r, const double* z2r, const double*
         while (init_df >= (double)n1) { ridge *= 2.0; init_df = df(ridge); }
     }
     eig_solve(eig, (double)n1, ridge, 0.0, G_rt, beta_init, tmp, dev);
+    tick("initial fit solve");
 
     // res_sds = sqrt(colSums((Y - X beta)^2) / (n1 - df))  -- explicit residuals (scregclust.R:1104-1107)
     {
@@ -141,6 +160,7 @@ void Ctx::create(int device, const double* z1r, const double* z2r, const double*
     bas_kernel<<<(unsigned)ceil_div(P * T, 256), 256, 0, st>>>(beta_init.data(), beta_init.ld, res_sds.p, bas.data(), bas.ld, P, T);
     SCRC_LAUNCHED();
     SCRC_CUDA(cudaStreamSynchronize(st));
+    tick("residual sds + weights");
 }
 
 // ============================================================================ Step 1 helper kernels
@@ -202,6 +222,10 @@ __global__ void __launch_bounds__(256) admm_extract_kernel(const double* __restr
         signs[o] = a ? (double)((wt > 0.0) - (wt < 0.0)) : nan("");
     }
 }
+__global__ void add_one_kernel(int* x, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[i] += 1;
+}
 __global__ void fill_nan_kernel(double* x, int64_t n) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) x[i] = nan("");
@@ -209,7 +233,10 @@ __global__ void fill_nan_kernel(double* x, int64_t n) {
 
 // ============================================================================ one batched cycle
 void Ctx::fit_cycle(int F, const double* lambda, const int* k_in, const scrc_options& opt, bool skip_alloc,
-                    scrc_cycle_out* out) {
+                    scrc_cycle_out* out, const scrc_prior* prior) {
+    const bool use_prior = prior && prior->weight != 0.0 && !skip_alloc;
+    if (use_prior && (!prior->update_order || !prior->prior_off))
+        throw Error(SCRC_ERR_ARG, "scrc_fit_cycle_prior: prior_off and update_order are required when prior_weight != 0");
     if (F <= 0) throw Error(SCRC_ERR_ARG, "scrc_fit_cycle: F must be positive");
     SCRC_CUDA(cudaSetDevice(dev.id));
     cudaStream_t st = dev.stream;
@@ -322,26 +349,20 @@ void Ctx::fit_cycle(int F, const double* lambda, const int* k_in, const scrc_opt
     }
 
     // ---------------- Step 2a/2b: residuals, SSE, variances, votes ----------------
-    const int CRtr = resid_vote_pick_cr((int)n1, (int)T, F, dev.num_sms);
     const int CRte = resid_vote_pick_cr((int)n2, (int)T, F, dev.num_sms);
-    partial.ensure(std::max(resid_vote_partial_elems((int)T, K, F, CRtr), resid_vote_partial_elems((int)T, K, F, CRte)));
+    partial.ensure(resid_vote_partial_elems((int)T, K, F, CRte));
     const size_t fkt = (size_t)F * K * T, fk1t = (size_t)F * (K + 1) * T;
     sse_train.ensure(fk1t); sse_test.ensure(fk1t); var.ensure(fkt); two_var.ensure(fkt); half_log.ensure(fkt);
     r2.ensure(fkt); best_r2.ensure((size_t)F * T); best_idx.ensure((size_t)F * T); k_new.ensure((size_t)F * T);
     votes.ensure(fkt);
-    ZselT.reshape(rows_alloc, std::max(n1, n2));
 
     ResidVoteArgs ra;
     ra.beta = nnls.beta.data(); ra.ldb = nnls.beta.ld; ra.rows_total = rows_total;
     ra.T = (int)T; ra.K = K; ra.L = F; ra.row_off = row_off_d.p; ra.kpad = kpad_d.p;
     ra.two_var = two_var.p; ra.half_log = half_log.p; ra.partial = partial.p; ra.votes = votes.p;
-    // train split
-    ZselT.reshape(rows_alloc, n1);
-    if (rows_total == 0) SCRC_CUDA(cudaMemsetAsync(ZselT.data(), 0, ZselT.bytes(), st));
-    gather_transpose(Z1r.data(), Z1r.ld, (int)n1, row_src.p, rows_total, ZselT.data(), ZselT.ld, st);
-    ra.ZselT = ZselT.data(); ra.ldzs = ZselT.ld; ra.Z = Z1t.data(); ra.ldz = Z1t.ld; ra.ncells = (int)n1; ra.CR = CRtr;
-    resid_vote(ra, false, dev.num_sms, st);
-    reduce_sse(partial.p, (int)T, K, F, CRtr, sse_train.p, st);
+    // train split: SSE from the Gram matrices (no pass over the n1 cells), then the variances
+    sse_train_gram(G_rr.data(), G_rr.ld, G_rt.data(), G_rt.ld, gtt.p, nnls.beta.data(), nnls.beta.ld, row_src.p,
+                   row_off_d.p, nsel_d.p, (int)T, K, F, sse_train.p, st);
     make_resid_var(sse_train.p, nsel_d.p, (int)n1, (int)T, K, F, var.p, two_var.p, half_log.p, st);
     // test split
     ZselT.reshape(rows_alloc, n2);
@@ -349,10 +370,46 @@ void Ctx::fit_cycle(int F, const double* lambda, const int* k_in, const scrc_opt
     gather_transpose(Z2r.data(), Z2r.ld, (int)n2, row_src.p, rows_total, ZselT.data(), ZselT.ld, st);
     ra.ZselT = ZselT.data(); ra.ldzs = ZselT.ld; ra.Z = Z2t.data(); ra.ldz = Z2t.ld; ra.ncells = (int)n2; ra.CR = CRte;
     const bool vote = !skip_alloc;
-    if (vote) SCRC_CUDA(cudaMemsetAsync(votes.p, 0, fkt * 4, st));
-    resid_vote(ra, vote, dev.num_sms, st);
-    reduce_sse(partial.p, (int)T, K, F, CRte, sse_test.p, st);
-    finish_alloc(sse_test.p, vote ? votes.p : nullptr, (int)T, K, F, r2.p, best_r2.p, best_idx.p, k_new.p, st);
+    if (!use_prior) {
+        if (vote) SCRC_CUDA(cudaMemsetAsync(votes.p, 0, fkt * 4, st));
+        resid_vote(ra, vote ? 1 : 0, dev.num_sms, st);
+        reduce_sse(partial.p, (int)T, K, F, CRte, sse_test.p, st);
+        finish_alloc(sse_test.p, vote ? votes.p : nullptr, (int)T, K, F, r2.p, best_r2.p, best_idx.p, k_new.p, st);
+    } else {
+        // Network prior (allocation.cpp:39-56,74-77): the sweep is sequential in update_order because every
+        // reassignment changes the prior of the genes that follow, so each fit materialises its K x n2 x T
+        // squared residuals on the device (never on the host) and one CTA walks the genes in order.
+        const size_t need = (size_t)K * n2 * T;
+        size_t free_b = 0, total_b = 0;
+        SCRC_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        if (sq_arr.n < need && need * 8 + (1ull << 30) > free_b + sq_arr.n * 8)
+            throw Error(SCRC_ERR_UNSUPPORTED, "network prior: the K x n2 x T residual array does not fit in device memory");
+        sq_arr.ensure(need);
+        const int nidx = prior->prior_off[T];
+        DevBuf<int> d_off(T + 1), d_idx(std::max(nidx, 1)), d_order(T), d_k(T);
+        SCRC_CUDA(cudaMemcpyAsync(d_off.p, prior->prior_off, (T + 1) * 4, cudaMemcpyHostToDevice, st));
+        if (nidx > 0) SCRC_CUDA(cudaMemcpyAsync(d_idx.p, prior->prior_idx, (size_t)nidx * 4, cudaMemcpyHostToDevice, st));
+        std::vector<int> k0(T);
+        ResidVoteArgs r1 = ra;
+        r1.L = 1; r1.sq_out = sq_arr.p;
+        for (int f = 0; f < F; ++f) {
+            r1.row_off = row_off_d.p + (size_t)f * K; r1.kpad = kpad_d.p + (size_t)f * K;
+            r1.partial = partial.p + (size_t)f * CRte * 2 * (K + 1) * T;
+            resid_vote(r1, 2, dev.num_sms, st);
+            for (int64_t t = 0; t < T; ++t) k0[t] = k_in[(int64_t)f * T + t] - 1;     // allocation.cpp:23
+            SCRC_CUDA(cudaMemcpyAsync(d_k.p, k0.data(), T * 4, cudaMemcpyHostToDevice, st));
+            SCRC_CUDA(cudaMemcpyAsync(d_order.p, prior->update_order + (int64_t)f * T, T * 4, cudaMemcpyHostToDevice, st));
+            alloc_sequential_device(sq_arr.p, K, n2, T, var.p + (size_t)f * K * T, d_off.p, d_idx.p, d_k.p, d_order.p,
+                                    prior->baseline, prior->weight, votes.p + (size_t)f * T * K, st);
+            SCRC_CUDA(cudaMemcpyAsync(k_new.p + (size_t)f * T, d_k.p, T * 4, cudaMemcpyDeviceToDevice, st));
+            SCRC_CUDA(cudaStreamSynchronize(st));   // k0 is reused by the next fit
+        }
+        reduce_sse(partial.p, (int)T, K, F, CRte, sse_test.p, st);
+        // r2 / best_r2 from the SSEs; k_new (0-based from the sweep) is shifted to 1-based below
+        finish_alloc(sse_test.p, nullptr, (int)T, K, F, r2.p, best_r2.p, best_idx.p, nullptr, st);
+        add_one_kernel<<<(unsigned)ceil_div((int64_t)F * T, 256), 256, 0, st>>>(k_new.p, (int64_t)F * T);   // allocation.cpp:99
+        SCRC_LAUNCHED();
+    }
 
     // ---------------- outputs ----------------
     if (out) {
@@ -487,7 +544,7 @@ void Ctx::importance(int F, const int* k_final, const unsigned char* models, con
     ra.row_off_b = d_brow.p; ra.col_index = nb.cols.p; ra.col_off = d_coff.p; ra.col_cnt = d_ccnt.p;
     // the A operand (rows_a rows) and the B operand (rows_b rows) need tensor maps of their own extent
     ra.rows_total_a = rows_a;
-    resid_vote(ra, false, dev.num_sms, st);
+    resid_vote(ra, 0, dev.num_sms, st);
     reduce_sse(part.p, Tmax, 1, nprob, CR, sse.p, st);
     if (z2t_css.n == 0) { z2t_css.alloc(T); col_centered_ss(Z2t.data(), Z2t.ld, n2, T, z2t_css.p, st); }
     std::vector<double> h_sse((size_t)nprob * 2 * Tmax), h_css(T);
@@ -731,6 +788,15 @@ __global__ void __launch_bounds__(1024) alloc_sequential_kernel(const double* __
         }
         __syncthreads();
     }
+}
+
+void alloc_sequential_device(const double* d_arr, int K, int64_t n2, int64_t T, const double* d_resid_var,
+                             const int* d_prior_off, const int* d_prior_idx, int* d_k, const int* d_order,
+                             double baseline, double weight, int* d_votes, cudaStream_t st) {
+    alloc_sequential_kernel<<<1, 1024, 0, st>>>(d_arr, K, n2, T, d_resid_var, d_prior_off, d_prior_idx, d_k, d_order,
+                                                baseline, weight, d_votes);
+    SCRC_CUDA(cudaGetLastError());
+    SCRC_LAUNCHED();
 }
 
 void dropin_allocate(Device& dev, const double* sq_resid, int K, int64_t n2, int64_t T, const double* resid_var,

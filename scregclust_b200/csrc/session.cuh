@@ -64,11 +64,13 @@ struct Ctx {
     void create(int device, const double* z1r, const double* z2r, const double* z1t, const double* z2t,
                 const double* sds, int64_t n1, int64_t n2, int64_t P, int64_t T, int K);
     void fit_cycle(int F, const double* lambda, const int* k_in, const scrc_options& opt, bool skip_alloc,
-                   scrc_cycle_out* out);
+                   scrc_cycle_out* out, const scrc_prior* prior = nullptr);
+    DevBuf<double> sq_arr;       // K x n2 x T squared residuals, only with a network prior
     // Leave-one-regulator-out importance and module R2 (R/scregclust.R:1823-1912) for F final configurations.
     void importance(int F, const int* k_final, const unsigned char* models, const double* signs,
                     const scrc_options& opt, double* r2_module, double* importance_out);
     DevBuf<double> z2t_css;      // centred sums of squares of the test targets (lazy)
+    DevBuf<double> gtt;          // colSums(z1_target_centered^2)
     ~Ctx() { dev.destroy(); }
 };
 
@@ -81,6 +83,10 @@ void dropin_fast_cor(Device& dev, const double* x, const double* y, int64_t n, i
 void dropin_ols(Device& dev, const double* y, const double* x, int64_t n, int64_t p, int64_t m, double lambda,
                 bool ridge, double* beta_out);
 void dropin_crossprod(Device& dev, const double* x, const double* y, int64_t n, int64_t px, int64_t py, double* out);
+// Sequential Gauss-Seidel allocation sweep on a device-resident array (allocation.cpp:33-97).
+void alloc_sequential_device(const double* d_arr, int K, int64_t n2, int64_t T, const double* d_resid_var,
+                             const int* d_prior_off, const int* d_prior_idx, int* d_k /* 0-based, -2 noise, in/out */,
+                             const int* d_order, double baseline, double weight, int* d_votes, cudaStream_t st);
 void dropin_allocate(Device& dev, const double* sq_resid, int K, int64_t n2, int64_t T, const double* resid_var,
                      const int* prior_off, const int* prior_idx, const int* k_in, const int* order, double baseline,
                      double weight, int* k_out, int* votes_out);

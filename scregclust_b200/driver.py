@@ -16,7 +16,7 @@ from dataclasses import dataclass, field
 import numpy as np
 
 from . import _capi
-from ._capi import CycleOut, Options, check, dptr, f64, iptr
+from ._capi import CycleOut, Options, Prior, check, dptr, f64, iptr
 
 
 @dataclass
@@ -120,8 +120,13 @@ class Session:
         return out
 
     # ------------------------------------------------------------------ one batched cycle
-    def fit_cycle(self, lambdas, ks, options=None, skip_allocation=False, want_votes=False, want_nnls_iters=False):
-        """Step 1 + 2a (+ 2b) for ``F`` (lambda, k) pairs; returns a dict of arrays in R's layouts."""
+    def fit_cycle(self, lambdas, ks, options=None, skip_allocation=False, want_votes=False, want_nnls_iters=False,
+                  prior=None):
+        """Step 1 + 2a (+ 2b) for ``F`` (lambda, k) pairs; returns a dict of arrays in R's layouts.
+
+        ``prior``: optional ``(prior_indicator, prior_baseline, prior_weight, update_orders)`` with
+        ``prior_indicator`` a list of T lists of 0-based neighbour targets and ``update_orders`` an
+        ``F x T`` array of 0-based permutations (R/scregclust.R:1666; src/allocation.cpp:39-56)."""
         lam = np.ascontiguousarray(lambdas, dtype=np.float64)
         F = lam.size
         k = np.ascontiguousarray(ks, dtype=np.int32).reshape(F, self.T)
@@ -151,8 +156,17 @@ class Session:
         out.admm_iterations = iptr(res["admm_iterations"]); out.nnls_iterations = iptr(res["nnls_iterations"])
         out.n_selected = iptr(res["n_selected"])
         out.admm_sweeps = C.pointer(sweeps)
-        check(self._lib.scrc_fit_cycle(self._h, F, dptr(lam), iptr(k), C.byref(opt), 1 if skip_allocation else 0,
-                                       C.byref(out)))
+        if prior is not None and not skip_allocation and float(prior[2]) != 0.0:
+            from .api import _csr
+            off, idx = _csr(prior[0], T)
+            if off is None:
+                off = np.zeros(T + 1, dtype=np.int32); idx = np.zeros(1, dtype=np.int32)
+            orders = np.ascontiguousarray(prior[3], dtype=np.int32).reshape(F, T)
+            pr = Prior(iptr(off), iptr(idx), float(prior[1]), float(prior[2]), iptr(orders))
+            check(self._lib.scrc_fit_cycle_prior(self._h, F, dptr(lam), iptr(k), C.byref(opt), C.byref(pr), C.byref(out)))
+        else:
+            check(self._lib.scrc_fit_cycle(self._h, F, dptr(lam), iptr(k), C.byref(opt), 1 if skip_allocation else 0,
+                                           C.byref(out)))
         self.h2d_bytes += lam.nbytes + k.nbytes
         self.d2h_bytes += sum(v.nbytes for v in res.values() if v is not None)
         self.admm_sweeps += int(sweeps.value)
@@ -220,11 +234,16 @@ def scregclust_fit(z1_reg_scaled=None, z2_reg_scaled=None, z1_target_centered=No
                    min_module_size=0, noise_threshold=0.025, n_cycles=50, max_optim_iter=10000,
                    tol_coop_rel=1e-8, tol_coop_abs=1e-12, tol_nnls=1e-4, device=0, session=None,
                    keep_diagnostics=False, return_coeffs=True, claim=None, concurrency=None,
-                   compute_predictive_r2=False):
+                   compute_predictive_r2=False, prior_indicator=None, prior_baseline=1e-6, prior_weight=0.0,
+                   update_orders=None):
     """The alternating loop of ``scregclust()`` (R/scregclust.R:1222-1803) for all penalization values.
 
     Returns one :class:`FitResult` per penalization value, in order.  ``session`` may be passed to
     reuse the device-resident precompute (R/scregclust.R:996-1183) across calls.
+
+    Network prior (R/scregclust.R:584-615): ``prior_indicator`` is a list of T lists of 0-based
+    neighbour targets, ``update_orders(penalty_index, cycle)`` returns the permutation R's
+    ``sample()`` would draw (R/scregclust.R:1666; identity when omitted).
 
     Multi-GPU work sharing: the fits of different penalization values are independent
     (R/scregclust.R:1223,1245), so ``claim`` may be a callable returning the index of the next
@@ -272,9 +291,14 @@ def scregclust_fit(z1_reg_scaled=None, z2_reg_scaled=None, z1_target_centered=No
             fin = [i for i in active if states[i].last_cycle]
 
             if run:
+                prior = None
+                if prior_indicator is not None and len(prior_indicator) > 0 and prior_weight != 0.0:
+                    orders = np.stack([np.asarray(update_orders(i, states[i].cycle), dtype=np.int32)
+                                       if update_orders is not None else np.arange(T, dtype=np.int32) for i in run])
+                    prior = (prior_indicator, prior_baseline, prior_weight, orders)
                 res = ses.fit_cycle([pens[i] for i in run], np.stack([states[i].k for i in run]), opt,
                                     skip_allocation=False, want_votes=keep_diagnostics,
-                                    want_nnls_iters=keep_diagnostics)
+                                    want_nnls_iters=keep_diagnostics, prior=prior)
                 for f, i in enumerate(run):
                     s, fr = states[i], results[i]
                     _unpack(fr, res, f, K, keep_diagnostics)

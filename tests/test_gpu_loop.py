@@ -276,3 +276,46 @@ def test_driver_importance_end_to_end():
     for g, r in zip(got, ref):
         assert np.allclose(g.r2_module[0], r.r2_module[0], rtol=1e-8, atol=1e-10, equal_nan=True)
         assert np.allclose(g.importance[0], r.importance[0], rtol=1e-7, atol=1e-9, equal_nan=True)
+
+
+@pytest.mark.parametrize("name,seed", [("tiny", 3), ("small", 1)])
+def test_network_prior_loop(name, seed):
+    """Next-row f2: Step 2b with a network prior (sequential Gauss-Seidel sweep in update_order,
+    src/allocation.cpp:39-56,74-77) through the session path, against the oracle."""
+    from scregclust_b200.driver import scregclust_fit
+    w = make_workload(name, seed=seed)
+    T = w.z1_target.shape[1]
+    prng = np.random.default_rng(99)
+    # genes of the same planted module are neighbours (sparse, like a PPI prior)
+    prior = []
+    for t in range(T):
+        same = np.flatnonzero((w.k_true == w.k_true[t]) & (np.arange(T) != t) & (w.k_true > 0))
+        prior.append(sorted(prng.choice(same, size=min(4, same.size), replace=False).tolist()) if same.size else [])
+    orders = {}
+    def update_orders(li, cycle):
+        return orders.setdefault((li, cycle), np.random.default_rng(1000 * li + cycle).permutation(T).astype(np.int32))
+    kw = dict(prior_indicator=prior, prior_baseline=1e-6, prior_weight=0.5, update_orders=update_orders, min_module_size=2)
+    ref = orc.scregclust_fit(w.z1_reg, w.z2_reg, w.z1_target, w.z2_target, w.z1_target_sds, w.penalization,
+                             w.n_modules, w.k_init, **kw)
+    got = scregclust_fit(w.z1_reg, w.z2_reg, w.z1_target, w.z2_target, w.z1_target_sds, w.penalization,
+                         w.n_modules, w.k_init, keep_diagnostics=True, **kw)
+    same = 0
+    for g, r in zip(got, ref):
+        c, genes = _first_divergence(g, r)
+        if c is not None:
+            # with a prior one flipped gene changes the prior of its neighbours, so only the first
+            # divergence can be classified: it must sit on a noise-decided vote
+            amb = r.ambiguity[c - 1]
+            sv = np.sort(r.votes[c - 1], axis=1)
+            assert np.any((sv[:, -1] - sv[:, -2])[genes] <= 2 * amb[genes]), (g.penalization, c, genes[:8])
+            continue
+        same += 1
+        assert g.n_cycles_run == r.n_cycles_run and np.array_equal(g.k_final[0], r.k_final[0])
+        for a, b in zip(g.votes, r.votes):
+            assert np.array_equal(a, b)
+        assert np.max(np.abs(g.r2[0] - r.r2[0])) < 1e-8
+    assert same >= 1
+    # the prior changes the result (otherwise this test would not test anything)
+    plain = orc.scregclust_fit(w.z1_reg, w.z2_reg, w.z1_target, w.z2_target, w.z1_target_sds, w.penalization,
+                               w.n_modules, w.k_init, min_module_size=2)
+    assert any(not np.array_equal(a.k_history[1], b.k_history[1]) for a, b in zip(plain, ref))
