@@ -223,8 +223,22 @@ def load_cycles(name, seed, n_pen):
 
 
 # --------------------------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The one JSON line goes to the process's original stdout."""
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (json.dumps(line) + "\n").encode())
+
+
 def main():
+    global _REAL_STDOUT
     args = parse()
+    # Native libraries (NCCL's version banner, cuSOLVER notices) write to file descriptor 1 directly; keep the
+    # original stdout for the JSON line only and send everything else to stderr.
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     from scregclust_b200.synthetic import CONFIGS, make_workload
 
     rank = int(os.environ.get("RANK", "0"))
@@ -257,7 +271,7 @@ def main():
                 "cpu_baseline": {"value": v, "unit": "s", "cores": threads, "kind": "port",
                                  "sample": desc + f" [cycle counts: {src}]"},
                 "e2e": {"value": v, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     import torch
@@ -424,7 +438,7 @@ def main():
                 except Exception as exc:   # the checker library is optional for the GPU arm
                     line["cpu_baseline"] = {"value": None, "unit": "s", "cores": 0, "kind": "port",
                                             "sample": f"unavailable: {exc}"}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

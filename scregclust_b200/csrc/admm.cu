@@ -170,19 +170,24 @@ static void launch_admm_gemm(const AdmmDev& d, const DMat& A, const double* Bm, 
 // before any store so that every thread keeps >= 12 independent 8-byte loads in flight.
 // FUSE_RHS (sweeps on which rho cannot change): also writes next sweep's rhs = xty + rho*zeta + mult.
 constexpr int UPD_CACHE = 4096;   // doubles per cached array (R * cached columns)
+constexpr int UPD_BOXC = 64;      // columns per TMA box
+
+struct UpdMaps { CUtensorMap b, z, m; };   // beta, zeta, mult viewed as (P x C) with an (R x 64) box
 
 template <int R, bool UPDATE_ITER, bool FUSE_RHS>
-__global__ void __launch_bounds__(ADMM_UPD_WARPS * 32) admm_update_kernel(AdmmDev d, const int* __restrict__ prob_ids) {
+__global__ void __launch_bounds__(ADMM_UPD_WARPS * 32) admm_update_kernel(AdmmDev d, const int* __restrict__ prob_ids,
+                                                                          const __grid_constant__ UpdMaps maps) {
     constexpr int CPW = 32 / R;
     constexpr int CS = UPD_CACHE / R;
     constexpr int STEP = ADMM_UPD_WARPS * CPW;
     constexpr int U = UPDATE_ITER ? 2 : 4;
-    extern __shared__ double upd_sm[];
+    extern __shared__ __align__(128) double upd_sm[];
     double* sb = upd_sm;
     double* sz = upd_sm + UPD_CACHE;
     double* smu = upd_sm + 2 * UPD_CACHE;
     __shared__ double s_norm[ADMM_UPD_WARPS][32][2];
     __shared__ double s_sum[ADMM_UPD_WARPS][ADMM_NSUM];
+    __shared__ __align__(8) uint64_t s_bar;
 
     const int p = prob_ids[blockIdx.y];
     if (!d.active[p]) return;
@@ -196,16 +201,36 @@ __global__ void __launch_bounds__(ADMM_UPD_WARPS * 32) admm_update_kernel(AdmmDe
     const double rho = d.rho[p], alpha = d.alpha[p], lam = d.lambda[p];
     const int64_t base = row + (int64_t)c0 * d.ld;
 
-    // ---- pass 1: stage the slab, group norms of the positive / negative parts (optim.cpp:149-158)
+    // ---- stage the slab of beta / zeta / mult with TMA: every box is in flight at once, no registers
+    // are tied up, and the image in shared memory is [column][row] exactly as the passes index it.
+    // (Boxes may run past the problem's last column or past row P; those entries are never used.)
+    const int mc = min(m, CS);
+    const int nbox = (mc + UPD_BOXC - 1) / UPD_BOXC;
+    if (threadIdx.x == 0) {
+        mbar_init(&s_bar, 1);
+        mbar_fence_init();
+        mbar_expect_tx(&s_bar, (uint32_t)(3 * nbox * UPD_BOXC * R * 8));
+        for (int bx = 0; bx < nbox; ++bx) {
+            const int cc = c0 + bx * UPD_BOXC;
+            tma_load_2d(sb + bx * UPD_BOXC * R, &maps.b, slab * R, cc, &s_bar);
+            tma_load_2d(sz + bx * UPD_BOXC * R, &maps.z, slab * R, cc, &s_bar);
+            tma_load_2d(smu + bx * UPD_BOXC * R, &maps.m, slab * R, cc, &s_bar);
+        }
+    }
+    __syncthreads();                       // barrier initialised and armed before anyone polls it
+    mbar_wait_warp(&s_bar, 0, lane);
+
+    // ---- pass 1: group norms of the positive / negative parts (optim.cpp:149-158)
     double np2 = 0.0, nn2 = 0.0;
 #pragma unroll 4
     for (int lc = warp * CPW + csub; lc < m; lc += STEP) {
         double b = 0.0, z = 0.0, mu = 0.0;
-        if (rv) {
+        if (lc < CS) {
+            if (rv) { b = sb[lc * R + row_l]; z = sz[lc * R + row_l]; mu = smu[lc * R + row_l]; }
+        } else if (rv) {
             const int64_t idx = base + (int64_t)lc * d.ld;
             b = d.beta[idx]; z = d.zeta[idx]; mu = d.mult[idx];
         }
-        if (lc < CS) { sb[lc * R + row_l] = b; sz[lc * R + row_l] = z; smu[lc * R + row_l] = mu; }
         const double br = alpha * b + (1.0 - alpha) * z;
         const double zn = br - mu / rho;
         const double pos = fmax(zn, 0.0), neg = fmin(zn, 0.0);
@@ -239,7 +264,7 @@ __global__ void __launch_bounds__(ADMM_UPD_WARPS * 32) admm_update_kernel(AdmmDe
             b[u] = z[u] = mu[u] = xt[u] = bo[u] = zo[u] = mo[u] = mho[u] = 0.0;
             if (lc < m) {
                 const int64_t idx = base + (int64_t)lc * d.ld;
-                if (lc < CS) { b[u] = sb[lc * R + row_l]; z[u] = sz[lc * R + row_l]; mu[u] = smu[lc * R + row_l]; }
+                if (lc < CS) { if (rv) { b[u] = sb[lc * R + row_l]; z[u] = sz[lc * R + row_l]; mu[u] = smu[lc * R + row_l]; } }
                 else if (rv) { b[u] = d.beta[idx]; z[u] = d.zeta[idx]; mu[u] = d.mult[idx]; }
                 if (rv) {
                     if (FUSE_RHS) xt[u] = d.xty[idx];
@@ -411,6 +436,14 @@ int admm_solve(AdmmBatch& b, const EigBasis& eig, const AdmmOpts& o, bool cold, 
 #undef SCRC_SET_UPD
         upd_configured = true;
     }
+    UpdMaps umaps[3];
+    for (int c = 0; c < 3; ++c) {
+        if (ids[c].empty()) continue;
+        const int R = 32 >> c;
+        umaps[c].b = make_tmap_f64_plain(d.beta, b.P, b.C, d.ld, R, UPD_BOXC);
+        umaps[c].z = make_tmap_f64_plain(d.zeta, b.P, b.C, d.ld, R, UPD_BOXC);
+        umaps[c].m = make_tmap_f64_plain(d.mult, b.P, b.C, d.ld, R, UPD_BOXC);
+    }
     auto launch_update = [&](bool upd, bool fuse) {
         for (int c = 0; c < 3; ++c) {
             if (ids[c].empty()) continue;
@@ -418,10 +451,10 @@ int admm_solve(AdmmBatch& b, const EigBasis& eig, const AdmmOpts& o, bool cold, 
             const dim3 grid((unsigned)ceil_div(b.P, R), (unsigned)ids[c].size());
             const int* lst = b.class_ids.p + off[c];
 #define SCRC_UPD(R_) \
-            if (upd && fuse) admm_update_kernel<R_, true, true><<<grid, ADMM_UPD_WARPS * 32, upd_smem, stream>>>(d, lst); \
-            else if (upd) admm_update_kernel<R_, true, false><<<grid, ADMM_UPD_WARPS * 32, upd_smem, stream>>>(d, lst); \
-            else if (fuse) admm_update_kernel<R_, false, true><<<grid, ADMM_UPD_WARPS * 32, upd_smem, stream>>>(d, lst); \
-            else admm_update_kernel<R_, false, false><<<grid, ADMM_UPD_WARPS * 32, upd_smem, stream>>>(d, lst);
+            if (upd && fuse) admm_update_kernel<R_, true, true><<<grid, ADMM_UPD_WARPS * 32, upd_smem, stream>>>(d, lst, umaps[c]); \
+            else if (upd) admm_update_kernel<R_, true, false><<<grid, ADMM_UPD_WARPS * 32, upd_smem, stream>>>(d, lst, umaps[c]); \
+            else if (fuse) admm_update_kernel<R_, false, true><<<grid, ADMM_UPD_WARPS * 32, upd_smem, stream>>>(d, lst, umaps[c]); \
+            else admm_update_kernel<R_, false, false><<<grid, ADMM_UPD_WARPS * 32, upd_smem, stream>>>(d, lst, umaps[c]);
             if (R == 32) { SCRC_UPD(32) } else if (R == 16) { SCRC_UPD(16) } else { SCRC_UPD(8) }
 #undef SCRC_UPD
             SCRC_LAUNCHED();

@@ -155,5 +155,9 @@ __device__ __forceinline__ double warp_sum(double v) {
 // ----------------------------------------------------------------------------
 CUtensorMap make_tmap_f64(const double* base, int64_t rows, int64_t cols, int64_t ld,
                           int box_cols);
+// Same matrix view, unswizzled box of (box_rows x box_cols): shared-memory image is dense
+// column-major [box_cols][box_rows] (used to stage slabs of the ADMM state).
+CUtensorMap make_tmap_f64_plain(const double* base, int64_t rows, int64_t cols, int64_t ld,
+                                int box_rows, int box_cols);
 
 }  // namespace scrc

@@ -45,6 +45,24 @@ CUtensorMap make_tmap_f64(const double* base, int64_t rows, int64_t cols, int64_
     return m;
 }
 
+CUtensorMap make_tmap_f64_plain(const double* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+                                int box_cols) {
+    if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld * 8) % 16 != 0 || (box_rows * 8) % 16 != 0)
+        throw Error(-91, "TMA operand must be 16-byte aligned with an even leading dimension");
+    if (rows <= 0 || cols <= 0) throw Error(-92, "TMA operand with empty extent");
+    CUtensorMap m;
+    cuuint64_t dims[2] = {(cuuint64_t)rows, (cuuint64_t)cols};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 8};
+    cuuint32_t box[2] = {(cuuint32_t)box_rows, (cuuint32_t)box_cols};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), dims, strides, box,
+                              estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        throw Error(-93, "cuTensorMapEncodeTiled (plain) failed with CUresult " + std::to_string((int)r));
+    return m;
+}
+
 template <int BM, int BN, int STAGES, int MODE>
 static void launch_dense(const DenseArgs& a, int num_sms, cudaStream_t stream) {
     using Pol = DensePolicy<BM, BN, STAGES, MODE>;
