@@ -142,6 +142,27 @@ int scrc_ctx_create(scrc_ctx** out, int device, const double* z1_reg, const doub
                     int64_t n1, int64_t n2, int64_t P, int64_t T, int K);
 void scrc_ctx_destroy(scrc_ctx* ctx);
 
+/* Same session, but from the raw p x n expression matrix (genes x cells, column-major, as the
+ * reference's `expression` argument): sample split with explicit `split_indices`, optional
+ * per-stratum centring with split-1 means (split_sample, R/scregclust.R:2280-2326 -- including
+ * its column re-ordering by stratum when center is set), removal of genes that are constant in
+ * either split (R/scregclust.R:899-964) and the scaling of R/scregclust.R:996-1009, all on the
+ * device after one upload.
+ *   is_regulator[p]   : 1 = regulator, 0 = target, anything else = gene in neither matrix
+ *   split_indices[n]  : 1 / 2 = data split, anything else (R's NA) = cell not used
+ *   stratification[n] : integer stratum labels, or NULL for a single stratum
+ *   keep_gene[p]      : out, 1 where the gene survived the constant filter (may be NULL)
+ *   dims_out[4]       : out, n1, n2, P, T of the session (may be NULL)
+ * `expr` may be a host or a device pointer.  The random draw of split_indices when the user gives
+ * none stays with the caller (it consumes R's RNG stream, R/scregclust.R:2283-2301). */
+int scrc_ctx_create_raw(scrc_ctx** out, int device, const double* expr, int64_t p, int64_t n,
+                        const int* is_regulator, const int* split_indices, const int* stratification,
+                        int center, int K, unsigned char* keep_gene, int64_t* dims_out);
+/* The staged inputs of a session: z1_reg_scaled (n1 x P), z2_reg_scaled (n2 x P),
+ * z1_target_centered (n1 x T), z2_target_centered (n2 x T), z1_target_sds (T); any may be NULL. */
+int scrc_ctx_get_inputs(scrc_ctx* ctx, double* z1_reg, double* z2_reg, double* z1_target, double* z2_target,
+                        double* z1_target_sds);
+
 /* res_sds (T), init_df (1), beta_init (P x T) -- any pointer may be NULL. */
 int scrc_ctx_get_init(scrc_ctx* ctx, double* res_sds, double* init_df, double* beta_init);
 /* cross_corr1 = fast_cor(z1_target_centered, z1_reg_scaled), T x P (R/scregclust.R:1116). */

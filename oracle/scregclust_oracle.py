@@ -519,6 +519,56 @@ def _sd(a):
     return np.std(a, axis=0, ddof=1)
 
 
+def split_sample(z, stratification, is_regulator, split_indices, center=True):
+    """split_sample with explicit ``split_indices`` (R/scregclust.R:2302-2325).
+
+    ``z``: p x n expression (genes x cells); ``split_indices``: 1 / 2 / NaN (= NA) per cell.
+    Quirk kept on purpose: with ``center`` the reference rebuilds ``z_`` with ``cbind`` over the
+    strata (:2309-2316), which re-orders its columns stratum by stratum, and then still selects the
+    first split by the positions computed on the original order (:2320-2323).
+    Returns z1_reg, z2_reg, z1_target, z2_target (cells x genes)."""
+    z = np.asarray(z, dtype=np.float64)
+    si = np.asarray(split_indices, dtype=np.float64)
+    is_included = np.flatnonzero(~np.isnan(si))                 # which(!is.na(split_indices))
+    is_split1 = np.flatnonzero(si[is_included] == 1)            # positions inside is_included
+    z_ = z[:, is_included]
+    if center:
+        strat = (np.zeros(is_included.size, dtype=np.int64) if stratification is None
+                 else np.asarray(stratification)[is_included])
+        blocks = []
+        for lev in np.unique(strat):                            # split(): sorted factor levels
+            s_ = np.flatnonzero(strat == lev)
+            idx = np.intersect1d(s_, is_split1)
+            blocks.append(z_[:, s_] - z_[:, idx].mean(axis=1, keepdims=True))
+        z_ = np.concatenate(blocks, axis=1)
+    in1 = np.zeros(z_.shape[1], dtype=bool)
+    in1[is_split1] = True
+    isr = np.asarray(is_regulator)
+    reg, tgt = isr == 1, isr == 0
+    return (np.asfortranarray(z_[:, in1][reg].T), np.asfortranarray(z_[:, ~in1][reg].T),
+            np.asfortranarray(z_[:, in1][tgt].T), np.asfortranarray(z_[:, ~in1][tgt].T))
+
+
+def constant_genes(z1, z2):
+    """Columns with ``sd == 0`` in either split (R/scregclust.R:900-907).  R's ``sd`` of a column of
+    identical values is exactly 0 (long-double mean with a refinement pass), which a plain float64
+    two-pass formula does not guarantee -- so the test is stated as "all values coincide"."""
+    return (np.ptp(z1, axis=0) == 0) | (np.ptp(z2, axis=0) == 0)
+
+
+def stage_inputs(z, stratification, is_regulator, split_indices, center=True):
+    """Raw expression -> the five scaled inputs of the loop + per-gene keep mask
+    (R/scregclust.R:880-964 + 996-1009)."""
+    z1r, z2r, z1t, z2t = split_sample(z, stratification, is_regulator, split_indices, center)
+    creg, ctgt = constant_genes(z1r, z2r), constant_genes(z1t, z2t)
+    isr = np.asarray(is_regulator)
+    keep = np.zeros(isr.size, dtype=bool)
+    keep[np.flatnonzero(isr == 1)[~creg]] = True
+    keep[np.flatnonzero(isr == 0)[~ctgt]] = True
+    out = scale_inputs(z1r[:, ~creg], z2r[:, ~creg], z1t[:, ~ctgt], z2t[:, ~ctgt])
+    return out + (keep,)
+
+
 def scale_inputs(z1_reg, z2_reg, z1_target, z2_target):
     """Scaling with split-1 statistics (R/scregclust.R:998-1009)."""
     m1t = z1_target.mean(axis=0)

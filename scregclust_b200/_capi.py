@@ -73,6 +73,9 @@ SIGNATURES = {
     "scrc_timer_end": (C.c_int, [c_double_p]),
     "scrc_ctx_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, c_double_p, c_double_p, c_double_p, c_double_p,
                                   c_double_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int]),
+    "scrc_ctx_create_raw": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, c_double_p, C.c_int64, C.c_int64, c_int_p, c_int_p,
+                                      c_int_p, C.c_int, C.c_int, c_ubyte_p, C.POINTER(C.c_int64)]),
+    "scrc_ctx_get_inputs": (C.c_int, [C.c_void_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p]),
     "scrc_ctx_destroy": (None, [C.c_void_p]),
     "scrc_ctx_get_init": (C.c_int, [C.c_void_p, c_double_p, c_double_p, c_double_p]),
     "scrc_ctx_cross_corr": (C.c_int, [C.c_void_p, c_double_p]),

@@ -14,6 +14,7 @@ struct RvParams {
     const int* row_off;
     const int* kpad;
     const double* two_var;
+    const double* inv_two_var;
     const double* half_log;
     double* partial;
     int* votes;
@@ -153,12 +154,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) resid_vote_kernel(const __gri
                     for (int e = 0; e < 2; ++e) {
                         const int lc = b_col0 + jj * 8 + q * 2 + e;
                         const int col = t0 + lc;
-                        double tv = 1.0, hl = 0.0;
+                        double tv = 1.0, hl = 0.0, iv = 1.0;
                         if (VOTE && j < p.K && col < ncol) {
                             const int64_t vi = ((int64_t)l * p.K + j) * p.T + col;
                             tv = p.two_var[vi];
+                            iv = p.inv_two_var[vi];
                             hl = p.half_log[vi];
                         }
+                        // sq / tv through the correctly rounded reciprocal iv = RN(1 / tv): each step
+                        // q <- q + RN(sq - tv q) iv is Markstein's quotient correction; after the first
+                        // one q is a faithful quotient, so the second returns RN(sq / tv) -- the same bits
+                        // as the IEEE division of allocation.cpp:61 at a quarter of the FP64 instructions.
+                        // Outside the range where the remainders are exact the division itself is used.
+                        const bool fastq = tv > 1e-280 && tv < 1e280;
                         double csum = 0.0;
 #pragma unroll
                         for (int i = 0; i < MT; ++i) {
@@ -171,7 +179,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) resid_vote_kernel(const __gri
                                     p.sq_out[j + (int64_t)p.K * (row + (int64_t)p.ncells * col)] = sq;   // scregclust.R:1599
                             }
                             if (VOTE && j < p.K) {
-                                const double sc = (-sq) / tv - hl;            // allocation.cpp:59-62
+                                double qd;
+                                if (fastq && sq > 1e-280 && sq < 1e280) {
+                                    qd = sq * iv;
+                                    qd = fma(fma(-qd, tv, sq), iv, qd);
+                                    qd = fma(fma(-qd, tv, sq), iv, qd);
+                                } else {
+                                    qd = sq / tv;
+                                }
+                                const double sc = -qd - hl;                   // allocation.cpp:59-62
                                 if (sc > best[i][jj][e]) { best[i][jj][e] = sc; bidx[i][jj][e] = j; }
                             }
                         }
@@ -238,10 +254,11 @@ void resid_vote(const ResidVoteArgs& a, int mode, int num_sms, cudaStream_t st) 
                          a.ldzs, RV_BM);
     p.tb = make_tmap_f64(a.beta, std::max<int64_t>(a.rows_total, 16), a.T, a.ldb, RV_BN);
     p.Z = a.Z; p.ldz = a.ldz; p.ncells = a.ncells; p.T = a.T; p.K = a.K; p.L = a.L;
-    p.row_off = a.row_off; p.kpad = a.kpad; p.two_var = a.two_var; p.half_log = a.half_log;
+    p.row_off = a.row_off; p.kpad = a.kpad; p.two_var = a.two_var; p.inv_two_var = a.inv_two_var; p.half_log = a.half_log;
     p.partial = a.partial; p.votes = a.votes; p.CR = a.CR;
     p.row_off_b = a.row_off_b; p.col_index = a.col_index; p.col_off = a.col_off; p.col_cnt = a.col_cnt;
     p.sq_out = a.sq_out;
+    if (mode == 1 && !a.inv_two_var) throw Error(-63, "resid_vote: vote mode needs the reciprocal table");
     if (mode == 2 && (a.L != 1 || !a.sq_out)) throw Error(-62, "resid_vote: store mode handles one fit per launch");
     p.tiles_n = (int)ceil_div(a.T, RV_BN); p.ctiles = (int)ceil_div(a.ncells, RV_BM);
 
@@ -342,7 +359,7 @@ void sse_train_gram(const double* G_rr, int64_t ldrr, const double* G_rt, int64_
 }
 
 __global__ void resid_var_kernel(const double* __restrict__ sse_train, const int* __restrict__ nsel, int n1, int T,
-                                 int K, int L, double* var, double* two_var, double* half_log) {
+                                 int K, int L, double* var, double* two_var, double* inv_two_var, double* half_log) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // over L*K*T
     if (i >= (int64_t)L * K * T) return;
     const int t = (int)(i % T);
@@ -352,12 +369,14 @@ __global__ void resid_var_kernel(const double* __restrict__ sse_train, const int
     const double v = sse / (double)(n1 - nsel[l * K + j]);             // scregclust.R:1636-1638
     var[i] = v;
     two_var[i] = 2.0 * v;                                               // allocation.cpp:60
+    if (inv_two_var) inv_two_var[i] = 1.0 / (2.0 * v);                  // correctly rounded (IEEE division)
     half_log[i] = 0.5 * log((2.0 * M_PI) * v);                          // allocation.cpp:62
 }
 void make_resid_var(const double* sse_train, const int* nsel, int n1, int T, int K, int L, double* var,
-                    double* two_var, double* half_log, cudaStream_t st) {
+                    double* two_var, double* inv_two_var, double* half_log, cudaStream_t st) {
     const int64_t n = (int64_t)L * K * T;
-    resid_var_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(sse_train, nsel, n1, T, K, L, var, two_var, half_log);
+    resid_var_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(sse_train, nsel, n1, T, K, L, var, two_var,
+                                                                 inv_two_var, half_log);
     SCRC_CUDA(cudaGetLastError());
     SCRC_LAUNCHED();
 }

@@ -22,6 +22,7 @@ struct ResidVoteArgs {
     const int* row_off;                  // device [L*K]
     const int* kpad;                     // device [L*K]  (0 = module without a model)
     const double* two_var;               // device [L][K][T]   (vote mode)
+    const double* inv_two_var = nullptr; // device [L][K][T]   (vote mode): RN(1 / two_var)
     const double* half_log;              // device [L][K][T]   (vote mode)
     double* partial;                     // device [L][CR][2][K+1][T]
     int* votes;                          // device [L][T][K]   (vote mode, pre-zeroed)
@@ -51,10 +52,10 @@ void sse_train_gram(const double* G_rr, int64_t ldrr, const double* G_rt, int64_
                     const double* beta, int64_t ldb, const int* sel /* per stacked row: regulator or -1 */,
                     const int* row_off, const int* nsel, int T, int K, int L, double* sse, cudaStream_t s);
 
-// resid_var = SSE_train / (n1 - s_j); two_var = 2 var; half_log = 0.5 log(2 pi var)
+// resid_var = SSE_train / (n1 - s_j); two_var = 2 var; inv_two_var = RN(1 / two_var); half_log = 0.5 log(2 pi var)
 // (R/scregclust.R:1635-1638, allocation.cpp:59-62).  nsel: device [L*K].
 void make_resid_var(const double* sse_train, const int* nsel, int n1, int T, int K, int L, double* var,
-                    double* two_var, double* half_log, cudaStream_t s);
+                    double* two_var, double* inv_two_var, double* half_log, cudaStream_t s);
 
 // r2[l][t][j] = 1 - SSE_test / SS0 ; best_r2 = row max ; best_idx = first argmax (1-based)
 // (R/scregclust.R:1628-1632, 1646).  k_new = first argmax of votes (1-based, allocation.cpp:88-94).

@@ -231,6 +231,32 @@ int scrc_ctx_create(scrc_ctx** out, int device, const double* z1_reg, const doub
         *out = c.release();
     });
 }
+int scrc_ctx_create_raw(scrc_ctx** out, int device, const double* expr, int64_t p, int64_t n, const int* is_regulator,
+                        const int* split_indices, const int* stratification, int center, int K,
+                        unsigned char* keep_gene, int64_t* dims_out) {
+    if (!out || !expr || !is_regulator || !split_indices) return fail(SCRC_ERR_ARG, "scrc_ctx_create_raw: null pointer");
+    *out = nullptr;
+    return guarded([&] {
+        std::unique_ptr<scrc_ctx> c(new scrc_ctx());
+        c->impl.create_raw(device, expr, p, n, is_regulator, split_indices, stratification, center, K, keep_gene, dims_out);
+        *out = c.release();
+    });
+}
+int scrc_ctx_get_inputs(scrc_ctx* ctx, double* z1_reg, double* z2_reg, double* z1_target, double* z2_target,
+                        double* z1_target_sds) {
+    if (!ctx) return fail(SCRC_ERR_ARG, "null context");
+    return guarded([&] {
+        Ctx& c = ctx->impl;
+        SCRC_CUDA(cudaSetDevice(c.dev.id));
+        cudaStream_t st = c.dev.stream;
+        if (z1_reg) c.Z1r.download(z1_reg, c.n1, st);
+        if (z2_reg) c.Z2r.download(z2_reg, c.n2, st);
+        if (z1_target) c.Z1t.download(z1_target, c.n1, st);
+        if (z2_target) c.Z2t.download(z2_target, c.n2, st);
+        if (z1_target_sds) SCRC_CUDA(cudaMemcpyAsync(z1_target_sds, c.sds_t.p, c.T * 8, cudaMemcpyDeviceToHost, st));
+        SCRC_CUDA(cudaStreamSynchronize(st));
+    });
+}
 void scrc_ctx_destroy(scrc_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->impl.dev.id);

@@ -86,12 +86,27 @@ __global__ void bas_kernel(const double* beta, int64_t ldb, const double* res_sd
 }
 
 // ============================================================================ session creation
+void Ctx::begin(int64_t n1_, int64_t n2_, int64_t P_, int64_t T_, int K_) {
+    if (n1_ <= 1 || n2_ <= 0 || P_ <= 0 || T_ <= 0 || K_ <= 0) throw Error(SCRC_ERR_ARG, "scrc_ctx_create: non-positive dimension");
+    if (K_ > RV_MAX_K) throw Error(SCRC_ERR_UNSUPPORTED, "scrc_ctx_create: at most 64 modules are supported");
+    n1 = n1_; n2 = n2_; P = P_; T = T_; K = K_;
+    Z1r.alloc(n1, P); Z2r.alloc(n2, P); Z1t.alloc(n1, T); Z2t.alloc(n2, T);
+    sds_t.alloc(T); inv_sds_t.alloc(T);
+}
+
 void Ctx::create(int device, const double* z1r, const double* z2r, const double* z1t, const double* z2t,
                  const double* sds, int64_t n1_, int64_t n2_, int64_t P_, int64_t T_, int K_) {
     if (n1_ <= 1 || n2_ <= 0 || P_ <= 0 || T_ <= 0 || K_ <= 0) throw Error(SCRC_ERR_ARG, "scrc_ctx_create: non-positive dimension");
-    if (K_ > RV_MAX_K) throw Error(SCRC_ERR_UNSUPPORTED, "scrc_ctx_create: at most 64 modules are supported");
     dev.init(device);
-    n1 = n1_; n2 = n2_; P = P_; T = T_; K = K_;
+    begin(n1_, n2_, P_, T_, K_);
+    cudaStream_t st = dev.stream;
+    Z1r.upload(z1r, n1, st); Z2r.upload(z2r, n2, st); Z1t.upload(z1t, n1, st); Z2t.upload(z2t, n2, st);
+    SCRC_CUDA(cudaMemcpyAsync(sds_t.p, sds, T * 8, cudaMemcpyDefault, st));
+    finish();
+}
+
+// Everything after the four scaled matrices and z1_target_sds are resident.
+void Ctx::finish() {
     cudaStream_t st = dev.stream;
     const bool dbg = getenv("SCRC_DEBUG_TIMING") != nullptr;
     auto tick = [&](const char* what) {
@@ -104,13 +119,9 @@ void Ctx::create(int device, const double* z1r, const double* z2r, const double*
         t_prev = t;
     };
     tick(nullptr);
-    Z1r.alloc(n1, P); Z2r.alloc(n2, P); Z1t.alloc(n1, T); Z2t.alloc(n2, T);
-    Z1r.upload(z1r, n1, st); Z2r.upload(z2r, n2, st); Z1t.upload(z1t, n1, st); Z2t.upload(z2t, n2, st);
-    sds_t.alloc(T); inv_sds_t.alloc(T);
-    SCRC_CUDA(cudaMemcpyAsync(sds_t.p, sds, T * 8, cudaMemcpyDefault, st));
     vec_recip_kernel<<<(unsigned)ceil_div(T, 256), 256, 0, st>>>(sds_t.p, inv_sds_t.p, (int)T);
     SCRC_LAUNCHED();
-    tick("alloc + upload");
+    tick("inputs resident");
 
     // Gram matrices (optim.cpp:17-27,99,414,421) -- computed once, the reference redoes them per call
     gram(Z1r, Z1r, G_rr, true, dev);
@@ -352,18 +363,18 @@ void Ctx::fit_cycle(int F, const double* lambda, const int* k_in, const scrc_opt
     const int CRte = resid_vote_pick_cr((int)n2, (int)T, F, dev.num_sms);
     partial.ensure(resid_vote_partial_elems((int)T, K, F, CRte));
     const size_t fkt = (size_t)F * K * T, fk1t = (size_t)F * (K + 1) * T;
-    sse_train.ensure(fk1t); sse_test.ensure(fk1t); var.ensure(fkt); two_var.ensure(fkt); half_log.ensure(fkt);
+    sse_train.ensure(fk1t); sse_test.ensure(fk1t); var.ensure(fkt); two_var.ensure(fkt); inv_two_var.ensure(fkt); half_log.ensure(fkt);
     r2.ensure(fkt); best_r2.ensure((size_t)F * T); best_idx.ensure((size_t)F * T); k_new.ensure((size_t)F * T);
     votes.ensure(fkt);
 
     ResidVoteArgs ra;
     ra.beta = nnls.beta.data(); ra.ldb = nnls.beta.ld; ra.rows_total = rows_total;
     ra.T = (int)T; ra.K = K; ra.L = F; ra.row_off = row_off_d.p; ra.kpad = kpad_d.p;
-    ra.two_var = two_var.p; ra.half_log = half_log.p; ra.partial = partial.p; ra.votes = votes.p;
+    ra.two_var = two_var.p; ra.inv_two_var = inv_two_var.p; ra.half_log = half_log.p; ra.partial = partial.p; ra.votes = votes.p;
     // train split: SSE from the Gram matrices (no pass over the n1 cells), then the variances
     sse_train_gram(G_rr.data(), G_rr.ld, G_rt.data(), G_rt.ld, gtt.p, nnls.beta.data(), nnls.beta.ld, row_src.p,
                    row_off_d.p, nsel_d.p, (int)T, K, F, sse_train.p, st);
-    make_resid_var(sse_train.p, nsel_d.p, (int)n1, (int)T, K, F, var.p, two_var.p, half_log.p, st);
+    make_resid_var(sse_train.p, nsel_d.p, (int)n1, (int)T, K, F, var.p, two_var.p, inv_two_var.p, half_log.p, st);
     // test split
     ZselT.reshape(rows_alloc, n2);
     if (rows_total == 0) SCRC_CUDA(cudaMemsetAsync(ZselT.data(), 0, ZselT.bytes(), st));

@@ -54,7 +54,7 @@ struct Ctx {
     NnlsBatch nnls;
     DevBuf<int> row_src, row_off_d, kpad_d, nsel_d;
     DMat ZselT;
-    DevBuf<double> partial, sse_train, sse_test, var, two_var, half_log, r2, best_r2;
+    DevBuf<double> partial, sse_train, sse_test, var, two_var, inv_two_var, half_log, r2, best_r2;
     DevBuf<int> votes, best_idx, k_new;
     DevBuf<unsigned char> models_d;
     DevBuf<double> weights_d, signs_d;
@@ -63,6 +63,14 @@ struct Ctx {
 
     void create(int device, const double* z1r, const double* z2r, const double* z1t, const double* z2t,
                 const double* sds, int64_t n1, int64_t n2, int64_t P, int64_t T, int K);
+    // Raw p x n expression matrix in; split, per-stratum centring, constant-gene filter and scaling on
+    // the device (stage.cu).  keep_gene[p] (may be null) marks the genes that survive the filter;
+    // dims_out[4] = n1, n2, P, T after filtering.
+    void create_raw(int device, const double* expr, int64_t p, int64_t n, const int* is_regulator,
+                    const int* split_indices, const int* stratification, int center, int K,
+                    unsigned char* keep_gene, int64_t* dims_out);
+    void begin(int64_t n1, int64_t n2, int64_t P, int64_t T, int K);   // dimensions + input buffers
+    void finish();                                                      // Gram, eigenbasis, initial fit
     void fit_cycle(int F, const double* lambda, const int* k_in, const scrc_options& opt, bool skip_alloc,
                    scrc_cycle_out* out, const scrc_prior* prior = nullptr);
     DevBuf<double> sq_arr;       // K x n2 x T squared residuals, only with a network prior

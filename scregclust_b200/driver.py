@@ -73,6 +73,51 @@ class Session:
         self.h2d_bytes = 0
         return self
 
+    @classmethod
+    def from_expression(cls, expression, is_regulator, split_indices, n_modules, stratification=None, center=True,
+                        device=0):
+        """Session from the raw ``p x n`` expression matrix (genes x cells): sample split, per-stratum
+        centring, constant-gene filter and scaling run on the device (R/scregclust.R:2280-2326,
+        899-964, 996-1009).  ``split_indices``: 1 / 2 per cell, anything else (NaN / NA) = unused.
+        The surviving genes are in ``self.keep_gene``; ``is_regulator`` refers to the rows of ``expression``."""
+        self = cls.__new__(cls)
+        self._lib = _capi.load()
+        ex = f64(expression)
+        p, n = ex.shape
+        isr = np.ascontiguousarray(is_regulator, dtype=np.int32)
+        si = np.asarray(split_indices, dtype=np.float64)
+        si = np.ascontiguousarray(np.where(np.isfinite(si), si, 0.0).astype(np.int32))
+        if isr.size != p or si.size != n:
+            raise ValueError("is_regulator / split_indices do not match the expression matrix")
+        st = None
+        if stratification is not None:
+            _, st = np.unique(np.asarray(stratification), return_inverse=True)   # sorted levels, like split()
+            st = np.ascontiguousarray(st, dtype=np.int32)
+            if st.size != n:
+                raise ValueError("stratification does not match the expression matrix")
+        keep = np.zeros(p, dtype=np.uint8)
+        dims = (C.c_int64 * 4)()
+        self._h = C.c_void_p()
+        check(self._lib.scrc_ctx_create_raw(C.byref(self._h), int(device), dptr(ex), p, n, iptr(isr), iptr(si), iptr(st),
+                                            1 if center else 0, int(n_modules),
+                                            keep.ctypes.data_as(_capi.c_ubyte_p), dims))
+        self.n1, self.n2, self.P, self.T, self.K = int(dims[0]), int(dims[1]), int(dims[2]), int(dims[3]), int(n_modules)
+        self.keep_gene = keep.astype(bool)
+        self.h2d_bytes = ex.nbytes + isr.nbytes + si.nbytes + (st.nbytes if st is not None else 0)
+        self.d2h_bytes = keep.nbytes
+        self.admm_sweeps = 0
+        self.admm_problem_iterations = 0
+        return self
+
+    def inputs(self):
+        """The staged matrices as R would hold them: z1_reg_scaled, z2_reg_scaled, z1_target_centered,
+        z2_target_centered, z1_target_sds."""
+        z1r = np.zeros((self.n1, self.P), order="F"); z2r = np.zeros((self.n2, self.P), order="F")
+        z1t = np.zeros((self.n1, self.T), order="F"); z2t = np.zeros((self.n2, self.T), order="F")
+        sds = np.zeros(self.T)
+        check(self._lib.scrc_ctx_get_inputs(self._h, dptr(z1r), dptr(z2r), dptr(z1t), dptr(z2t), dptr(sds)))
+        return z1r, z2r, z1t, z2t, sds
+
     def _create(self, device, p1r, p2r, p1t, p2t, psd, n1, n2, P, T, n_modules):
         self.n1, self.n2, self.P, self.T, self.K = int(n1), int(n2), int(P), int(T), int(n_modules)
         self._h = C.c_void_p()

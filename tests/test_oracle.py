@@ -224,3 +224,68 @@ def test_cpp_twin_matches_numpy_oracle(rng):
     k = rng.integers(1, K + 1, T).astype(np.int32); order = rng.permutation(T).astype(np.int32)
     assert np.array_equal(ref_cpu.allocate_into_modules(arr, rv, None, None, k, order, 1e-6, 0.0),
                           orc.allocate_into_modules(arr, rv, [], k, order, 1e-6, 0.0))
+
+
+def _raw_expression(seed, p=60, n=90, n_strata=3, sort_strata=False):
+    r = np.random.default_rng(seed)
+    z = np.round(r.gamma(1.5, 1.0, size=(p, n)), 3)
+    is_reg = (r.random(p) < 0.3).astype(np.int32)
+    is_reg[:2] = 1; is_reg[2:4] = 0
+    strat = r.integers(0, n_strata, size=n) * 7 + 3          # arbitrary integer labels
+    if sort_strata:
+        strat = np.sort(strat)
+    split = np.where(r.random(n) < 0.5, 1.0, 2.0)
+    split[r.random(n) < 0.1] = np.nan                        # unused cells
+    z[5, :] = 0.0                                            # constant everywhere
+    z[9, split == 2] = 4.0                                   # constant in the second split only
+    return z, is_reg, strat, split
+
+
+def test_split_sample_single_stratum_is_split1_row_centring():
+    z, is_reg, _, split = _raw_expression(1)
+    z1r, z2r, z1t, z2t = orc.split_sample(z, None, is_reg, split, center=True)
+    inc = ~np.isnan(split)
+    mu = z[:, split == 1].mean(axis=1, keepdims=True)
+    assert np.allclose(z1r, (z[:, split == 1] - mu)[is_reg == 1].T, rtol=0, atol=1e-14)
+    assert np.allclose(z2t, (z[:, inc & (split == 2)] - mu)[is_reg == 0].T, rtol=0, atol=1e-14)
+    # no centring: plain selection
+    a1r, _, _, a2t = orc.split_sample(z, None, is_reg, split, center=False)
+    assert np.array_equal(a1r, z[:, split == 1][is_reg == 1].T)
+    assert np.array_equal(a2t, z[:, inc & (split == 2)][is_reg == 0].T)
+
+
+def test_split_sample_reorders_columns_by_stratum_when_centring():
+    """R/scregclust.R:2309-2323: cbind over strata permutes the cells, the split positions stay."""
+    z, is_reg, strat, split = _raw_expression(2)
+    z1r, z2r, z1t, z2t = orc.split_sample(z, strat, is_reg, split, center=True)
+    inc = np.flatnonzero(~np.isnan(split))
+    pos1 = np.flatnonzero(split[inc] == 1)
+    perm = np.argsort(strat[inc], kind="stable")
+    # centred values cell by cell
+    cen = np.empty((z.shape[0], inc.size))
+    for lev in np.unique(strat[inc]):
+        s_ = np.flatnonzero(strat[inc] == lev)
+        idx = np.intersect1d(s_, pos1)
+        cen[:, s_] = z[:, inc[s_]] - z[:, inc[idx]].mean(axis=1, keepdims=True)
+    expect = cen[:, perm][:, pos1][is_reg == 1].T
+    assert np.allclose(z1r, expect, rtol=0, atol=1e-14)
+    assert z1r.shape[0] + z2r.shape[0] == inc.size
+    # with strata already sorted the permutation is the identity
+    zs, ir, st, sp = _raw_expression(2, sort_strata=True)
+    b1r, *_ = orc.split_sample(zs, st, ir, sp, center=True)
+    incs = np.flatnonzero(~np.isnan(sp))
+    assert np.array_equal(np.argsort(st[incs], kind="stable"), np.arange(incs.size))
+    assert b1r.shape == (int((sp == 1).sum()), int((ir == 1).sum()))
+
+
+def test_stage_inputs_filters_constant_genes_and_scales():
+    z, is_reg, strat, split = _raw_expression(3)
+    # per-stratum centring makes gene 9 vary across strata again; gene 5 (all zero) stays constant
+    *_, keep_c = orc.stage_inputs(z, strat, is_reg, split, center=True)
+    assert not keep_c[5] and keep_c[9] and keep_c.sum() == z.shape[0] - 1
+    z1r, z2r, z1t, z2t, sds, keep = orc.stage_inputs(z, strat, is_reg, split, center=False)
+    assert not keep[5] and not keep[9] and keep.sum() == z.shape[0] - 2
+    assert z1r.shape[1] == int((is_reg[keep] == 1).sum()) and z1t.shape[1] == int((is_reg[keep] == 0).sum())
+    assert np.allclose(z1r.mean(axis=0), 0, atol=1e-13) and np.allclose(z1r.std(axis=0, ddof=1), 1, atol=1e-12)
+    assert np.allclose(z1t.mean(axis=0), 0, atol=1e-13) and np.allclose(z1t.std(axis=0, ddof=1), sds, rtol=1e-12)
+    assert abs(z2r.mean()) > 1e-6                               # the test split keeps split-1 statistics
