@@ -223,6 +223,10 @@ int scrc_fit_cycle_prior(scrc_ctx* ctx, int F, const double* lambda, const int* 
 /* NNLS coefficients of module k (0-based) of fit f from the last scrc_fit_cycle call:
  * n_selected x T (R/scregclust.R:1588); sel_out receives the 0-based regulator indices. */
 int scrc_ctx_get_coeffs(scrc_ctx* ctx, int f, int k, double* coeffs_out, int* sel_out);
+/* The same for every module of fit f in one transfer: the K coefficient matrices (n_selected_k x T,
+ * column-major each) packed one after the other in coeffs_out (sum_k n_selected_k * T doubles) and
+ * the regulator indices in sel_out (sum_k n_selected_k); n_selected as returned by the cycle. */
+int scrc_ctx_get_coeffs_fit(scrc_ctx* ctx, int f, double* coeffs_out, int* sel_out);
 
 #ifdef __cplusplus
 }

@@ -10,7 +10,9 @@ allocate_into_modules / coef_ols / coef_ridge (the reference ships no golden
 vectors for them, R + Eigen are absent in the build container so the reference
 cannot be executed, and ``datasets/*.rds`` are Git-LFS pointers).  ``fast_cor``
 is pinned through the reference's own test (tests/testthat/test-fast-cor.R:1-16:
-equal to ``stats::cor`` == ``numpy.corrcoef`` at tolerance 1.5e-8).  Independent
+equal to ``stats::cor`` == ``numpy.corrcoef`` at tolerance 1.5e-8), and the
+constant-gene filter of the input staging through the reference's other test
+(tests/testthat/test-constant-genes.R:1-24: T1 / R1 dropped).  Independent
 cross-checks (KKT conditions, scipy.optimize.nnls, lstsq, brute-force
 allocation) live in tests/test_oracle.py.
 

@@ -87,6 +87,7 @@ SIGNATURES = {
     "scrc_importance": (C.c_int, [C.c_void_p, C.c_int, c_int_p, c_ubyte_p, c_double_p, C.POINTER(Options), c_double_p,
                                   c_double_p]),
     "scrc_ctx_get_coeffs": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_double_p, c_int_p]),
+    "scrc_ctx_get_coeffs_fit": (C.c_int, [C.c_void_p, C.c_int, c_double_p, c_int_p]),
 }
 
 _lib = None

@@ -136,6 +136,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) resid_vote_kernel(const __gri
                 for (int i = 0; i < MT; ++i)
 #pragma unroll
                     for (int jj = 0; jj < NT; ++jj) acc[i][jj][0] = acc[i][jj][1] = 0.0;
+                // score constants of this module's columns, requested before the mainloop hides their latency
+                double tv[NT][2], hl[NT][2], iv[NT][2];
+#pragma unroll
+                for (int jj = 0; jj < NT; ++jj)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        tv[jj][e] = 1.0; hl[jj][e] = 0.0; iv[jj][e] = 1.0;
+                        const int col = t0 + b_col0 + jj * 8 + q * 2 + e;
+                        if (VOTE && j < p.K && col < ncol) {
+                            const int64_t vi = ((int64_t)l * p.K + j) * p.T + col;
+                            tv[jj][e] = p.two_var[vi];
+                            iv[jj][e] = p.inv_two_var[vi];
+                            hl[jj][e] = p.half_log[vi];
+                        }
+                    }
                 if (j < p.K) {
                     const int kp = p.kpad[l * p.K + j];
                     for (int kk = 0; kk < kp; kk += GEMM_BK) {
@@ -147,67 +162,106 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) resid_vote_kernel(const __gri
                         ps.advance<RV_STAGES>();
                     }
                 }
-                // residual, squared residual, column sums, per-cell score
+                // residual, squared residual, column sums (scregclust.R:1593-1599)
+                double csum[NT][2];
+                bool fast = true;
+#pragma unroll
+                for (int jj = 0; jj < NT; ++jj)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        if (VOTE) fast &= (((unsigned)__double2hiint(tv[jj][e]) >> 20) - 93u) < 1860u;
+                        double cs = 0.0;
+#pragma unroll
+                        for (int i = 0; i < MT; ++i) {
+                            const double res = z[i][jj][e] - acc[i][jj][e];
+                            const double sq = res * res;
+                            acc[i][jj][e] = sq;
+                            cs += sq;
+                            // biased exponent in [93, 1953) <=> 2^-930 <= sq < 2^930 (integer pipe, not FP64)
+                            if (VOTE) fast &= (((unsigned)__double2hiint(sq) >> 20) - 93u) < 1860u;
+                        }
+                        csum[jj][e] = cs;
+                    }
+                if (MODE == 2 && j < p.K) {
+#pragma unroll
+                    for (int jj = 0; jj < NT; ++jj)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e)
+#pragma unroll
+                            for (int i = 0; i < MT; ++i) {
+                                const int row = c0 + a_row0 + i * 8 + r;
+                                const int col = t0 + b_col0 + jj * 8 + q * 2 + e;
+                                if (row < p.ncells && col < ncol)
+                                    p.sq_out[j + (int64_t)p.K * (row + (int64_t)p.ncells * col)] = acc[i][jj][e];
+                            }
+                }
+                // per-cell score -sq / (2 var) - 0.5 log(2 pi var) and running first maximum (allocation.cpp:59-62,80-85).
+                // sq / tv goes through the correctly rounded reciprocal iv = RN(1 / tv): each step
+                // q <- q + RN(sq - tv q) iv is Markstein's quotient correction; after the first one q is a
+                // faithful quotient, so the second returns RN(sq / tv) -- the bits of the IEEE division at a
+                // quarter of its instructions and, unlike the division subroutine, as 16 independent
+                // straight-line chains per thread.  If any operand of the thread lies outside the range where
+                // the remainders are exact (zero residuals of padding rows, degenerate variances) the whole
+                // thread takes the division.
+                if (VOTE && j < p.K) {
+                    if (fast) {
+#pragma unroll
+                        for (int jj = 0; jj < NT; ++jj)
+#pragma unroll
+                            for (int e = 0; e < 2; ++e)
+#pragma unroll
+                                for (int i = 0; i < MT; ++i) {
+                                    const double sq = acc[i][jj][e];
+                                    double qd = sq * iv[jj][e];
+                                    qd = fma(fma(-qd, tv[jj][e], sq), iv[jj][e], qd);
+                                    qd = fma(fma(-qd, tv[jj][e], sq), iv[jj][e], qd);
+                                    const double sc = -qd - hl[jj][e];
+                                    if (sc > best[i][jj][e]) { best[i][jj][e] = sc; bidx[i][jj][e] = j; }
+                                }
+                    } else {
+#pragma unroll
+                        for (int jj = 0; jj < NT; ++jj)
+#pragma unroll
+                            for (int e = 0; e < 2; ++e)
+#pragma unroll
+                                for (int i = 0; i < MT; ++i) {
+                                    const double sc = (-acc[i][jj][e]) / tv[jj][e] - hl[jj][e];
+                                    if (sc > best[i][jj][e]) { best[i][jj][e] = sc; bidx[i][jj][e] = j; }
+                                }
+                    }
+                }
+#pragma unroll
+                for (int jj = 0; jj < NT; ++jj)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        double cs = csum[jj][e];
+                        cs += __shfl_xor_sync(0xffffffffu, cs, 4);
+                        cs += __shfl_xor_sync(0xffffffffu, cs, 8);
+                        cs += __shfl_xor_sync(0xffffffffu, cs, 16);
+                        if (r == 0) sse_s[(warp_m * K1 + j) * RV_BN + b_col0 + jj * 8 + q * 2 + e] += cs;
+                    }
+            }
+            if (VOTE) {
+                // The 8 lanes that share a target column mostly vote for the same module: lanes with the
+                // same (column, module) key elect a leader that adds the group's count once.
 #pragma unroll
                 for (int jj = 0; jj < NT; ++jj)
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
                         const int lc = b_col0 + jj * 8 + q * 2 + e;
-                        const int col = t0 + lc;
-                        double tv = 1.0, hl = 0.0, iv = 1.0;
-                        if (VOTE && j < p.K && col < ncol) {
-                            const int64_t vi = ((int64_t)l * p.K + j) * p.T + col;
-                            tv = p.two_var[vi];
-                            iv = p.inv_two_var[vi];
-                            hl = p.half_log[vi];
-                        }
-                        // sq / tv through the correctly rounded reciprocal iv = RN(1 / tv): each step
-                        // q <- q + RN(sq - tv q) iv is Markstein's quotient correction; after the first
-                        // one q is a faithful quotient, so the second returns RN(sq / tv) -- the same bits
-                        // as the IEEE division of allocation.cpp:61 at a quarter of the FP64 instructions.
-                        // Outside the range where the remainders are exact the division itself is used.
-                        const bool fastq = tv > 1e-280 && tv < 1e280;
-                        double csum = 0.0;
+                        const bool cvalid = t0 + lc < ncol;
+                        const int b0 = bidx[0][jj][e];
+                        int cnt = 0;
 #pragma unroll
                         for (int i = 0; i < MT; ++i) {
-                            const double res = z[i][jj][e] - acc[i][jj][e];   // scregclust.R:1593-1595
-                            const double sq = res * res;
-                            csum += sq;
-                            if (MODE == 2 && j < p.K) {
-                                const int row = c0 + a_row0 + i * 8 + r;
-                                if (row < p.ncells && col < ncol)
-                                    p.sq_out[j + (int64_t)p.K * (row + (int64_t)p.ncells * col)] = sq;   // scregclust.R:1599
-                            }
-                            if (VOTE && j < p.K) {
-                                double qd;
-                                if (fastq && sq > 1e-280 && sq < 1e280) {
-                                    qd = sq * iv;
-                                    qd = fma(fma(-qd, tv, sq), iv, qd);
-                                    qd = fma(fma(-qd, tv, sq), iv, qd);
-                                } else {
-                                    qd = sq / tv;
-                                }
-                                const double sc = -qd - hl;                   // allocation.cpp:59-62
-                                if (sc > best[i][jj][e]) { best[i][jj][e] = sc; bidx[i][jj][e] = j; }
-                            }
+                            const bool valid = cvalid && (c0 + a_row0 + i * 8 + r < p.ncells);
+                            if (valid && bidx[i][jj][e] == b0) ++cnt;
+                            else if (valid) atomicAdd(&votes_s[lc * p.K + bidx[i][jj][e]], 1);
                         }
-                        csum += __shfl_xor_sync(0xffffffffu, csum, 4);
-                        csum += __shfl_xor_sync(0xffffffffu, csum, 8);
-                        csum += __shfl_xor_sync(0xffffffffu, csum, 16);
-                        if (r == 0) sse_s[(warp_m * K1 + j) * RV_BN + lc] += csum;
+                        const unsigned peers = __match_any_sync(0xffffffffu, (q << 8) | b0);
+                        const int total = __reduce_add_sync(peers, cnt);
+                        if (lane == __ffs(peers) - 1 && total > 0) atomicAdd(&votes_s[lc * p.K + b0], total);
                     }
-            }
-            if (VOTE) {
-#pragma unroll
-                for (int i = 0; i < MT; ++i)
-#pragma unroll
-                    for (int jj = 0; jj < NT; ++jj)
-#pragma unroll
-                        for (int e = 0; e < 2; ++e) {
-                            const int row = c0 + a_row0 + i * 8 + r;
-                            const int lc = b_col0 + jj * 8 + q * 2 + e;
-                            if (row < p.ncells && t0 + lc < ncol) atomicAdd(&votes_s[lc * p.K + bidx[i][jj][e]], 1);
-                        }
             }
         }
         // flush

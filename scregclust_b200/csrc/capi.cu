@@ -50,6 +50,19 @@ int guarded(F&& f) {
 }
 }  // namespace
 
+namespace {
+// out[base[r] + a[r] + s[r] * t] = beta[src[r] + ld * t]: drops the 16-row padding of the stacked layout and
+// lays every module's s x T block out contiguously, so that one linear copy brings a whole fit to the host.
+__global__ void coeff_pack_kernel(const double* __restrict__ beta, int64_t ld, int T, int nrows,
+                                  const int* __restrict__ src, const int* __restrict__ s_of, const int* __restrict__ a_of,
+                                  const long long* __restrict__ base, double* out) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    const int t = blockIdx.y;
+    if (r >= nrows || t >= T) return;
+    out[base[r] + a_of[r] + (long long)s_of[r] * t] = beta[src[r] + ld * t];
+}
+}  // namespace
+
 extern "C" {
 
 int scrc_version(void) { return 100; }
@@ -343,10 +356,50 @@ int scrc_ctx_get_coeffs(scrc_ctx* ctx, int f, int k, double* coeffs_out, int* se
         const FitSlot& sl = c.slots[(size_t)f * c.K + k];
         if (sel_out) for (int a = 0; a < sl.s; ++a) sel_out[a] = sl.sel[a];
         if (coeffs_out && sl.s > 0) {
-            SCRC_CUDA(cudaMemcpy2DAsync(coeffs_out, (size_t)sl.s * 8, c.nnls.beta.data() + sl.row_off, c.nnls.beta.ld * 8,
-                                        (size_t)sl.s * 8, c.T, cudaMemcpyDeviceToHost, c.dev.stream));
+            // compact on the device first: a strided device-to-host copy of T rows of s doubles is slow
+            DevBuf<double> packed((size_t)sl.s * c.T);
+            SCRC_CUDA(cudaMemcpy2DAsync(packed.p, (size_t)sl.s * 8, c.nnls.beta.data() + sl.row_off, c.nnls.beta.ld * 8,
+                                        (size_t)sl.s * 8, c.T, cudaMemcpyDeviceToDevice, c.dev.stream));
+            SCRC_CUDA(cudaMemcpyAsync(coeffs_out, packed.p, (size_t)sl.s * c.T * 8, cudaMemcpyDeviceToHost, c.dev.stream));
             SCRC_CUDA(cudaStreamSynchronize(c.dev.stream));
         }
+    });
+}
+
+int scrc_ctx_get_coeffs_fit(scrc_ctx* ctx, int f, double* coeffs_out, int* sel_out) {
+    if (!ctx) return fail(SCRC_ERR_ARG, "null context");
+    return guarded([&] {
+        Ctx& c = ctx->impl;
+        if (f < 0 || f >= c.last_F) throw Error(SCRC_ERR_ARG, "scrc_ctx_get_coeffs_fit: index out of range");
+        SCRC_CUDA(cudaSetDevice(c.dev.id));
+        cudaStream_t st = c.dev.stream;
+        std::vector<int> src, s_of, a_of;
+        std::vector<long long> base;
+        long long off = 0;
+        size_t nsel = 0;
+        for (int k = 0; k < c.K; ++k) {
+            const FitSlot& sl = c.slots[(size_t)f * c.K + k];
+            for (int a = 0; a < sl.s; ++a) {
+                src.push_back(sl.row_off + a); s_of.push_back(sl.s); a_of.push_back(a); base.push_back(off);
+                if (sel_out) sel_out[nsel] = sl.sel[a];
+                ++nsel;
+            }
+            off += (long long)sl.s * c.T;
+        }
+        if (!coeffs_out || src.empty()) return;
+        const int nrows = (int)src.size();
+        DevBuf<int> d_src(nrows), d_s(nrows), d_a(nrows);
+        DevBuf<long long> d_base(nrows);
+        DevBuf<double> packed((size_t)off);
+        SCRC_CUDA(cudaMemcpyAsync(d_src.p, src.data(), nrows * 4, cudaMemcpyHostToDevice, st));
+        SCRC_CUDA(cudaMemcpyAsync(d_s.p, s_of.data(), nrows * 4, cudaMemcpyHostToDevice, st));
+        SCRC_CUDA(cudaMemcpyAsync(d_a.p, a_of.data(), nrows * 4, cudaMemcpyHostToDevice, st));
+        SCRC_CUDA(cudaMemcpyAsync(d_base.p, base.data(), nrows * 8, cudaMemcpyHostToDevice, st));
+        coeff_pack_kernel<<<dim3((unsigned)ceil_div(nrows, 128), (unsigned)c.T), 128, 0, st>>>(
+            c.nnls.beta.data(), c.nnls.beta.ld, (int)c.T, nrows, d_src.p, d_s.p, d_a.p, d_base.p, packed.p);
+        SCRC_LAUNCHED();
+        SCRC_CUDA(cudaMemcpyAsync(coeffs_out, packed.p, (size_t)off * 8, cudaMemcpyDeviceToHost, st));
+        SCRC_CUDA(cudaStreamSynchronize(st));
     });
 }
 

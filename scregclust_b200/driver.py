@@ -247,6 +247,23 @@ class Session:
         return co, sel
 
 
+    def coeffs_fit(self, f):
+        """All modules of fit ``f`` in one transfer: list of K coefficient matrices (s_k x T, ``None``
+        where the module has no model) -- views into one packed buffer -- and the list of index vectors."""
+        ns = [int(v) for v in self._last_nsel[f]]
+        tot = sum(ns)
+        buf = np.zeros(max(tot, 1) * self.T)
+        sel = np.zeros(max(tot, 1), dtype=np.int32)
+        check(self._lib.scrc_ctx_get_coeffs_fit(self._h, int(f), dptr(buf), iptr(sel)))
+        self.d2h_bytes += tot * self.T * 8 + tot * 4
+        cos, sels, o, r = [], [], 0, 0
+        for s_ in ns:
+            cos.append(buf[o:o + s_ * self.T].reshape((s_, self.T), order="F") if s_ else None)
+            sels.append(sel[r:r + s_].copy())
+            o += s_ * self.T; r += s_
+        return cos, sels
+
+
 def default_options(**kw) -> Options:
     o = Options()
     _capi.load().scrc_default_options(C.byref(o))
@@ -313,7 +330,7 @@ def scregclust_fit(z1_reg_scaled=None, z2_reg_scaled=None, z1_target_centered=No
             claim = lambda: next(queue, None)
         concurrency = len(pens) if concurrency is None else max(1, int(concurrency))
         states, results = {}, [None] * len(pens)
-        active = []
+        active, pending_final = [], []
 
         while True:
             while len(active) < concurrency:
@@ -369,40 +386,57 @@ def scregclust_fit(z1_reg_scaled=None, z2_reg_scaled=None, z1_target_centered=No
                     s.k = k
                     fr.n_cycles_run = s.cycle
 
-            if fin:
-                lam_f, k_f, owner = [], [], []
-                for i in fin:
-                    s = states[i]
-                    for m in range(1, s.final_cycle_length + 1):     # R/scregclust.R:1307-1311
-                        lam_f.append(pens[i]); k_f.append(s.k_history[len(s.k_history) - m]); owner.append(i)
-                res = ses.fit_cycle(lam_f, np.stack(k_f), opt, skip_allocation=True,
-                                    want_nnls_iters=keep_diagnostics)
-                ses._last_nsel = res["n_selected"]
+            # Penalization values entering their last cycle only need the re-fit of their final
+            # configuration(s) (R/scregclust.R:1307-1311, Step 2b skipped) and the post-processing.
+            # Nothing depends on those results, so they are deferred and batched into as few device
+            # calls as possible instead of one small call whenever a value happens to finish.
+            pending_final.extend(fin)
+            active = [i for i in active if i not in fin]
+
+        def finalize(batch):
+            lam_f, k_f, owner = [], [], []
+            for i in batch:
+                s = states[i]
+                for m in range(1, s.final_cycle_length + 1):     # R/scregclust.R:1307-1311
+                    lam_f.append(pens[i]); k_f.append(s.k_history[len(s.k_history) - m]); owner.append(i)
+            res = ses.fit_cycle(lam_f, np.stack(k_f), opt, skip_allocation=True,
+                                want_nnls_iters=keep_diagnostics)
+            ses._last_nsel = res["n_selected"]
+            for f, i in enumerate(owner):
+                s, fr = states[i], results[i]
+                _unpack(fr, res, f, K, keep_diagnostics)
+                fr.k_final.append(np.asarray(k_f[f]).copy())
+                fr.models.append(res["models"][f].T.astype(bool))
+                fr.signs.append(res["signs"][f].T.copy())
+                fr.weights.append(res["weights"][f].T.copy())
+                fr.sigmas.append(np.sqrt(res["resid_var"][f].T))
+                fr.r2.append(res["r2_test"][f].T.copy())
+                fr.best_r2.append(res["best_r2"][f].copy())
+                fr.best_r2_idx.append(res["best_r2_idx"][f].copy())
+                if return_coeffs:
+                    fr.coeffs.append(ses.coeffs_fit(f)[0])
+            if compute_predictive_r2:                             # R/scregclust.R:1823-1912
+                r2m, imp = ses.importance(np.stack(k_f), res["models"], res["signs"], opt)
                 for f, i in enumerate(owner):
-                    s, fr = states[i], results[i]
-                    _unpack(fr, res, f, K, keep_diagnostics)
-                    fr.k_final.append(np.asarray(k_f[f]).copy())
-                    fr.models.append(res["models"][f].T.astype(bool))
-                    fr.signs.append(res["signs"][f].T.copy())
-                    fr.weights.append(res["weights"][f].T.copy())
-                    fr.sigmas.append(np.sqrt(res["resid_var"][f].T))
-                    fr.r2.append(res["r2_test"][f].T.copy())
-                    fr.best_r2.append(res["best_r2"][f].copy())
-                    fr.best_r2_idx.append(res["best_r2_idx"][f].copy())
-                    if return_coeffs:
-                        fr.coeffs.append([ses.coeffs(f, j)[0] for j in range(K)])
-                if compute_predictive_r2:                             # R/scregclust.R:1823-1912
-                    r2m, imp = ses.importance(np.stack(k_f), res["models"], res["signs"], opt)
-                    for f, i in enumerate(owner):
-                        results[i].r2_module.append(r2m[f].copy())
-                        results[i].importance.append(imp[f].T.copy())
-                for i in fin:
-                    s, fr = states[i], results[i]
-                    s.done = True
-                    fr.converged = s.converged
-                    fr.final_cycle_length = s.final_cycle_length
-                    fr.n_cycles_run = s.cycle
-                active = [i for i in active if not states[i].done]
+                    results[i].r2_module.append(r2m[f].copy())
+                    results[i].importance.append(imp[f].T.copy())
+            for i in batch:
+                s, fr = states[i], results[i]
+                s.done = True
+                fr.converged = s.converged
+                fr.final_cycle_length = s.final_cycle_length
+                fr.n_cycles_run = s.cycle
+
+        # at most ~2x the regular batch width per call (bounds the state matrices of the re-fit)
+        batch, width = [], 0
+        for i in pending_final:
+            w_i = states[i].final_cycle_length
+            if batch and width + w_i > 2 * concurrency:
+                finalize(batch)
+                batch, width = [], 0
+            batch.append(i); width += w_i
+        if batch:
+            finalize(batch)
         return results
     finally:
         if own:

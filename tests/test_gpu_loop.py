@@ -319,3 +319,40 @@ def test_network_prior_loop(name, seed):
     plain = orc.scregclust_fit(w.z1_reg, w.z2_reg, w.z1_target, w.z2_target, w.z1_target_sds, w.penalization,
                                w.n_modules, w.k_init, min_module_size=2)
     assert any(not np.array_equal(a.k_history[1], b.k_history[1]) for a, b in zip(plain, ref))
+
+
+@pytest.mark.parametrize("shape,seed", [((331, 67, 19, 4), 2), ((402, 130, 33, 7), 6), ((258, 65, 17, 2), 9)])
+def test_ragged_shapes_match_oracle(shape, seed):
+    """Nothing on the path may assume multiples of the tile sizes: odd cell counts (TMA boxes run past
+    the matrix), 64k+1 / 64k+3 targets, regulator counts that are not multiples of 8 or 16."""
+    from scregclust_b200.driver import Session
+    w = make_workload(shape=shape, penalization=[0.08, 0.25], seed=seed)
+    K = w.n_modules
+    ref = orc.scregclust_fit(w.z1_reg, w.z2_reg, w.z1_target, w.z2_target, w.z1_target_sds, w.penalization, K,
+                             w.k_init, n_cycles=1, keep_history=True)
+    with Session(w.z1_reg, w.z2_reg, w.z1_target, w.z2_target, w.z1_target_sds, K) as s:
+        res = s.fit_cycle(w.penalization, np.stack([w.k_init] * 2), want_votes=True, want_nnls_iters=True)
+    for f, r in enumerate(ref):
+        assert np.array_equal(res["admm_iterations"][f], r.admm_iterations[0])
+        assert np.array_equal(res["models"][f].T.astype(bool), r.models_history[0])
+        assert np.array_equal(res["nnls_iterations"][f], r.nnls_iterations[0])
+        assert np.max(np.abs(res["r2_test"][f].T - r.r2_history[0])) < 1e-8
+        assert rel_err(res["resid_var"][f].T, r.resid_var_history[0]) < 1e-8
+        _check_votes(f"ragged{shape}/{f}", res["votes"][f], r.votes[0], r.ambiguity[0], res["k_new"][f])
+
+
+def test_module_count_limit():
+    """64 modules (the shared-memory vote histogram's limit) work, most of them empty; 65 are refused
+    with SCRC_ERR_UNSUPPORTED instead of a silent fallback."""
+    from scregclust_b200 import _capi
+    from scregclust_b200.driver import Session
+    w = make_workload(shape=(300, 96, 24, 64), penalization=[0.2], seed=12)
+    with Session(w.z1_reg, w.z2_reg, w.z1_target, w.z2_target, w.z1_target_sds, 64) as s:
+        res = s.fit_cycle([0.2], w.k_init[None, :], want_votes=True)
+        assert res["votes"][0].sum(axis=1).tolist() == [w.z2_target.shape[0]] * 96      # one vote per test cell
+        ref = orc.scregclust_fit(w.z1_reg, w.z2_reg, w.z1_target, w.z2_target, w.z1_target_sds, [0.2], 64, w.k_init,
+                                 n_cycles=1, keep_history=True)[0]
+        assert np.array_equal(res["models"][0].T.astype(bool), ref.models_history[0])
+        _check_votes("K64", res["votes"][0], ref.votes[0], ref.ambiguity[0], res["k_new"][0])
+    with pytest.raises(_capi.ScrcError):
+        Session(w.z1_reg, w.z2_reg, w.z1_target, w.z2_target, w.z1_target_sds, 65)

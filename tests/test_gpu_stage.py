@@ -72,3 +72,19 @@ def test_staging_rejects_bad_inputs():
     strat2 = strat.copy(); strat2[:] = 1; strat2[0] = 99; split2 = split.copy(); split2[0] = 2.0
     with pytest.raises(_capi.ScrcError):
         Session.from_expression(z, is_reg, split2, n_modules=3, stratification=strat2)   # stratum without split-1 cells
+
+
+@pytest.mark.parametrize("center", [True, False])
+def test_constant_genes_are_discarded_correctly(center):
+    """The reference's own test of this step (tests/testthat/test-constant-genes.R:1-24), through the C ABI:
+    after staging, T1 (all 1) and R1 (all 0.5) are gone and a fit on the remaining genes runs."""
+    from test_oracle import _constant_genes_case
+    from scregclust_b200.driver import Session, scregclust_fit
+    expression, genesymbols, is_regulator, split = _constant_genes_case()
+    with Session.from_expression(expression, is_regulator, split, n_modules=2, center=center) as ses:
+        assert genesymbols[ses.keep_gene].tolist() == ["T2", "T3", "T4", "T5", "T6", "R2"]
+        assert (is_regulator[ses.keep_gene] == 1).tolist() == [False, False, False, False, False, True]
+        assert (ses.P, ses.T) == (1, 5)
+        res = scregclust_fit(penalization=[0.1], n_modules=2, initial_target_modules=np.array([1, 2, 1, 2, 1], dtype=np.int32),
+                             session=ses)
+        assert res[0].k_final[0].shape == (5,)

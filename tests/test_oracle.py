@@ -289,3 +289,23 @@ def test_stage_inputs_filters_constant_genes_and_scales():
     assert np.allclose(z1r.mean(axis=0), 0, atol=1e-13) and np.allclose(z1r.std(axis=0, ddof=1), 1, atol=1e-12)
     assert np.allclose(z1t.mean(axis=0), 0, atol=1e-13) and np.allclose(z1t.std(axis=0, ddof=1), sds, rtol=1e-12)
     assert abs(z2r.mean()) > 1e-6                               # the test split keeps split-1 statistics
+
+
+def _constant_genes_case():
+    """The fixture of the reference's tests/testthat/test-constant-genes.R:1-10."""
+    r = np.random.default_rng(0)
+    expression = np.vstack([np.ones((1, 100)), r.standard_normal((5, 100)), np.full((1, 100), 0.5),
+                            r.standard_normal((1, 100))])
+    genesymbols = np.array(["T1", "T2", "T3", "T4", "T5", "T6", "R1", "R2"])
+    is_regulator = np.array([0, 0, 0, 0, 0, 0, 1, 1], dtype=np.int32)
+    split = np.where(r.permutation(100) < 50, 1.0, 2.0)           # split_indices drawn by the caller
+    return expression, genesymbols, is_regulator, split
+
+
+@pytest.mark.parametrize("center", [True, False])
+def test_constant_genes_are_discarded_correctly(center):
+    """tests/testthat/test-constant-genes.R:12-23: T1 and R1 are constant and must be dropped."""
+    expression, genesymbols, is_regulator, split = _constant_genes_case()
+    *_, keep = orc.stage_inputs(expression, None, is_regulator, split, center=center)
+    assert genesymbols[keep].tolist() == ["T2", "T3", "T4", "T5", "T6", "R2"]
+    assert (is_regulator[keep] == 1).tolist() == [False, False, False, False, False, True]

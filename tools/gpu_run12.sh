@@ -1,0 +1,9 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout -s KILL 1500 python -m pytest tests -m gpu -q --no-header -p no:cacheprovider --timeout=600 > gpurun_out/pytest_gpu.log 2>&1
+echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
+grep -E "passed|failed|Error|error|assert" gpurun_out/pytest_gpu.log | tail -15
+timeout -s KILL 900 python tools/time_fit.py config3 1 --importance 2>&1 | tail -4
+bash tools/gpu_profile_final.sh
+python -c "
+import json; d=json.load(open('gpurun_out/bench_config3_n1.json')); print({k:d[k] for k in ('value','e2e','gpu_launches') if k in d}); print(d.get('assignment_checksum'), d['kernel_classes_rank0'])"
