@@ -36,7 +36,7 @@ void AdmmBatch::resize(int P_, int C_, int nprob_) {
     col_prob.ensure(C); prob_c0.ensure(nprob); prob_c1.ensure(nprob);
     prob_lambda.ensure(nprob); prob_rho.ensure(nprob); prob_alpha.ensure(nprob);
     prob_active.ensure(nprob); prob_iters.ensure(nprob);
-    n_active.ensure(1); col_iters.ensure(1);
+    n_active.ensure(2); col_iters.ensure(1);   // n_active[0] = active problems, [1] = their columns
     w.reshape(P, nprob);
     DMat* mats[] = {&xty, &R, &W, &beta, &zeta, &mult, &beta_old, &zeta_old, &mult_old, &mult_hat_old};
     for (DMat* m : mats) m->reshape(P, C);
@@ -69,7 +69,7 @@ __global__ void admm_init_prob_kernel(AdmmDev d, double rho0, double alpha0) {
         d.active[p] = (d.c1[p] > d.c0[p]) ? 1 : 0;
         d.iters[p] = 0;
     }
-    if (p == 0) { *d.n_active = d.nprob; *d.col_iters = 0ull; }
+    if (p == 0) { d.n_active[0] = d.nprob; d.n_active[1] = d.C; *d.col_iters = 0ull; }
 }
 
 // ------------------------------------------------------------------ rhs = xty + rho*zeta + mult   (optim.cpp:143)
@@ -320,7 +320,8 @@ __global__ void __launch_bounds__(ADMM_UPD_WARPS * 32) admm_update_kernel(AdmmDe
 __global__ void __launch_bounds__(1024) admm_finalize_kernel(AdmmDev d, AdmmOpts o, int it, int is_update) {
     __shared__ int s_cnt;
     __shared__ unsigned long long s_cols;
-    if (threadIdx.x == 0) { s_cnt = 0; s_cols = 0ull; }
+    __shared__ int s_act_cols;
+    if (threadIdx.x == 0) { s_cnt = 0; s_cols = 0ull; s_act_cols = 0; }
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     for (int p = warp; p < d.nprob; p += nwarps) {
@@ -386,9 +387,10 @@ __global__ void __launch_bounds__(1024) admm_finalize_kernel(AdmmDev d, AdmmOpts
             continue;
         }
         atomicAdd(&s_cnt, 1);
+        atomicAdd(&s_act_cols, d.c1[p] - d.c0[p]);
     }
     __syncthreads();
-    if (threadIdx.x == 0) { *d.n_active = s_cnt; *d.col_iters += s_cols; }
+    if (threadIdx.x == 0) { d.n_active[0] = s_cnt; d.n_active[1] = s_act_cols; *d.col_iters += s_cols; }
 }
 
 // ------------------------------------------------------------------ driver
@@ -462,6 +464,7 @@ int admm_solve(AdmmBatch& b, const EigBasis& eig, const AdmmOpts& o, bool cold, 
     };
     int it = 1;
     int sweeps = 0;
+    int active_cols = b.C;   // refreshed whenever the host polls the device counters
     bool need_rhs = true;   // the first sweep and every sweep after a possible rho change build the rhs explicitly
     while (true) {
         if (need_rhs) {
@@ -469,15 +472,19 @@ int admm_solve(AdmmBatch& b, const EigBasis& eig, const AdmmOpts& o, bool cold, 
             admm_rhs_kernel<<<b.C, 256, 0, stream>>>(d);
             SCRC_LAUNCHED();
         }
-        if (big && tall) {
-            launch_admm_gemm<160, 128, 5, 1>(d, eig.V, d.R, d.W, num_sms, eig.lam.p, stream);
-            launch_admm_gemm<160, 128, 5, 2>(d, eig.Vt, d.W, d.beta, num_sms, eig.lam.p, stream);
-        } else if (big) {
-            launch_admm_gemm<128, 128, 6, 1>(d, eig.V, d.R, d.W, num_sms, eig.lam.p, stream);
-            launch_admm_gemm<128, 128, 6, 2>(d, eig.Vt, d.W, d.beta, num_sms, eig.lam.p, stream);
-        } else {
+        // Tail of the solve: once the surviving problems fill less than about half of the SMs with
+        // large tiles, 64 x 64 tiles give 4-5x the CTAs (the accumulation order along k does not depend
+        // on the tile shape, so the bits are the same).
+        const bool small_tiles = !big || (int64_t)ceil_div(b.P, 128) * ceil_div((int64_t)active_cols, 128) * 20 < (int64_t)num_sms * 9;
+        if (small_tiles) {
             launch_admm_gemm<64, 64, 8, 1>(d, eig.V, d.R, d.W, num_sms, eig.lam.p, stream);
             launch_admm_gemm<64, 64, 8, 2>(d, eig.Vt, d.W, d.beta, num_sms, eig.lam.p, stream);
+        } else if (tall) {
+            launch_admm_gemm<160, 128, 5, 1>(d, eig.V, d.R, d.W, num_sms, eig.lam.p, stream);
+            launch_admm_gemm<160, 128, 5, 2>(d, eig.Vt, d.W, d.beta, num_sms, eig.lam.p, stream);
+        } else {
+            launch_admm_gemm<128, 128, 6, 1>(d, eig.V, d.R, d.W, num_sms, eig.lam.p, stream);
+            launch_admm_gemm<128, 128, 6, 2>(d, eig.Vt, d.W, d.beta, num_sms, eig.lam.p, stream);
         }
         const int is_update = (it % o.n_update == 0) ? 1 : 0;
         {
@@ -490,9 +497,10 @@ int admm_solve(AdmmBatch& b, const EigBasis& eig, const AdmmOpts& o, bool cold, 
         SCRC_CUDA(cudaGetLastError());
         ++sweeps;
         if ((it >= 4 && it % 2 == 0) || it >= o.max_iter) {
-            SCRC_CUDA(cudaMemcpyAsync(h_scratch, d.n_active, sizeof(int), cudaMemcpyDeviceToHost, stream));
+            SCRC_CUDA(cudaMemcpyAsync(h_scratch, d.n_active, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream));
             SCRC_CUDA(cudaStreamSynchronize(stream));
-            if (*h_scratch == 0) break;
+            if (h_scratch[0] == 0) break;
+            active_cols = h_scratch[1];
         }
         ++it;
         if (it > o.max_iter + 1) break;  // safety net; finalize retires every problem at max_iter

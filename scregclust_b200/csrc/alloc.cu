@@ -13,6 +13,7 @@ struct RvParams {
     int ncells, T, K, L;
     const int* row_off;
     const int* kpad;
+    const int* nsel;     // optional: rows of each block that are not zero padding
     const double* two_var;
     const double* inv_two_var;
     const double* half_log;
@@ -153,11 +154,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) resid_vote_kernel(const __gri
                     }
                 if (j < p.K) {
                     const int kp = p.kpad[l * p.K + j];
+                    // rows beyond the selection are zero padding up to the 16-row box: their 4-deep slices
+                    // add exact zeros and are skipped
+                    const int s4 = p.nsel ? ((p.nsel[l * p.K + j] + 3) & ~3) : kp;
                     for (int kk = 0; kk < kp; kk += GEMM_BK) {
                         mbar_wait_warp(&full[ps.stage], ps.phase, lane);
                         const double* As = reinterpret_cast<const double*>(smem + ps.stage * RV_STAGE_BYTES);
                         const double* Bs = reinterpret_cast<const double*>(smem + ps.stage * RV_STAGE_BYTES + RV_A_BYTES);
-                        mma_kslice<MT, NT>(As, Bs, a_row0, b_col0, lane, acc);
+                        mma_kslice_n<MT, NT>(As, Bs, a_row0, b_col0, lane, min(4, (s4 - kk) >> 2), acc);
                         stage_release_warp(&empty[ps.stage], lane);
                         ps.advance<RV_STAGES>();
                     }
@@ -308,7 +312,7 @@ void resid_vote(const ResidVoteArgs& a, int mode, int num_sms, cudaStream_t st) 
                          a.ldzs, RV_BM);
     p.tb = make_tmap_f64(a.beta, std::max<int64_t>(a.rows_total, 16), a.T, a.ldb, RV_BN);
     p.Z = a.Z; p.ldz = a.ldz; p.ncells = a.ncells; p.T = a.T; p.K = a.K; p.L = a.L;
-    p.row_off = a.row_off; p.kpad = a.kpad; p.two_var = a.two_var; p.inv_two_var = a.inv_two_var; p.half_log = a.half_log;
+    p.row_off = a.row_off; p.kpad = a.kpad; p.nsel = a.nsel; p.two_var = a.two_var; p.inv_two_var = a.inv_two_var; p.half_log = a.half_log;
     p.partial = a.partial; p.votes = a.votes; p.CR = a.CR;
     p.row_off_b = a.row_off_b; p.col_index = a.col_index; p.col_off = a.col_off; p.col_cnt = a.col_cnt;
     p.sq_out = a.sq_out;

@@ -21,6 +21,7 @@ struct ResidVoteArgs {
     int ncells, T, K, L;
     const int* row_off;                  // device [L*K]
     const int* kpad;                     // device [L*K]  (0 = module without a model)
+    const int* nsel = nullptr;           // device [L*K], optional: selected rows (<= kpad; the rest of a block is zero)
     const double* two_var;               // device [L][K][T]   (vote mode)
     const double* inv_two_var = nullptr; // device [L][K][T]   (vote mode): RN(1 / two_var)
     const double* half_log;              // device [L][K][T]   (vote mode)

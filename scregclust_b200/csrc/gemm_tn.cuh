@@ -79,6 +79,28 @@ __device__ __forceinline__ void mma_kslice(const double* __restrict__ As,
     }
 }
 
+// Same, but only the first `nslices` (1..4) 4-deep slices of the stage: the rest is known to be zero padding.
+template <int MT, int NT>
+__device__ __forceinline__ void mma_kslice_n(const double* __restrict__ As,
+                                             const double* __restrict__ Bs, int a_row0, int b_col0,
+                                             int lane, int nslices, double (&acc)[MT][NT][2]) {
+    const int r = lane >> 2, q = lane & 3;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+        if (kk >= nslices) break;
+        const int off = ((((kk * 2) + (q >> 1)) ^ r) << 1) + (q & 1);
+        double a[MT], b[NT];
+#pragma unroll
+        for (int i = 0; i < MT; ++i) a[i] = As[(a_row0 + i * 8 + r) * GEMM_BK + off];
+#pragma unroll
+        for (int j = 0; j < NT; ++j) b[j] = Bs[(b_col0 + j * 8 + r) * GEMM_BK + off];
+#pragma unroll
+        for (int i = 0; i < MT; ++i)
+#pragma unroll
+            for (int j = 0; j < NT; ++j) dmma_8x8x4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+}
+
 // Policy interface:
 //   struct Params;                               (trivially copyable, < 4 KB)
 //   static constexpr int BM, BN, STAGES;

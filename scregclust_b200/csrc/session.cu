@@ -369,7 +369,7 @@ void Ctx::fit_cycle(int F, const double* lambda, const int* k_in, const scrc_opt
 
     ResidVoteArgs ra;
     ra.beta = nnls.beta.data(); ra.ldb = nnls.beta.ld; ra.rows_total = rows_total;
-    ra.T = (int)T; ra.K = K; ra.L = F; ra.row_off = row_off_d.p; ra.kpad = kpad_d.p;
+    ra.T = (int)T; ra.K = K; ra.L = F; ra.row_off = row_off_d.p; ra.kpad = kpad_d.p; ra.nsel = nsel_d.p;
     ra.two_var = two_var.p; ra.inv_two_var = inv_two_var.p; ra.half_log = half_log.p; ra.partial = partial.p; ra.votes = votes.p;
     // train split: SSE from the Gram matrices (no pass over the n1 cells), then the variances
     sse_train_gram(G_rr.data(), G_rr.ld, G_rt.data(), G_rt.ld, gtt.p, nnls.beta.data(), nnls.beta.ld, row_src.p,
@@ -405,6 +405,7 @@ void Ctx::fit_cycle(int F, const double* lambda, const int* k_in, const scrc_opt
         r1.L = 1; r1.sq_out = sq_arr.p;
         for (int f = 0; f < F; ++f) {
             r1.row_off = row_off_d.p + (size_t)f * K; r1.kpad = kpad_d.p + (size_t)f * K;
+            r1.nsel = nsel_d.p + (size_t)f * K;
             r1.partial = partial.p + (size_t)f * CRte * 2 * (K + 1) * T;
             resid_vote(r1, 2, dev.num_sms, st);
             for (int64_t t = 0; t < T; ++t) k0[t] = k_in[(int64_t)f * T + t] - 1;     // allocation.cpp:23

@@ -166,7 +166,7 @@ class Session:
 
     # ------------------------------------------------------------------ one batched cycle
     def fit_cycle(self, lambdas, ks, options=None, skip_allocation=False, want_votes=False, want_nnls_iters=False,
-                  prior=None):
+                  prior=None, light=False):
         """Step 1 + 2a (+ 2b) for ``F`` (lambda, k) pairs; returns a dict of arrays in R's layouts.
 
         ``prior``: optional ``(prior_indicator, prior_baseline, prior_weight, update_orders)`` with
@@ -181,12 +181,13 @@ class Session:
             "k_new": None if skip_allocation else np.zeros((F, T), dtype=np.int32),
             "votes": np.zeros((F, T, K), dtype=np.int32) if (want_votes and not skip_allocation) else None,
             "models": np.zeros((F, K, P), dtype=np.uint8),
-            "weights": np.zeros((F, K, P)),
-            "signs": np.zeros((F, K, P)),
-            "r2_test": np.zeros((F, K, T)),
-            "resid_var": np.zeros((F, K, T)),
+            # ``light``: an intermediate cycle of the loop only needs k_new, best_r2 and models back
+            "weights": None if light else np.zeros((F, K, P)),
+            "signs": None if light else np.zeros((F, K, P)),
+            "r2_test": None if light else np.zeros((F, K, T)),
+            "resid_var": None if light else np.zeros((F, K, T)),
             "best_r2": np.zeros((F, T)),
-            "best_r2_idx": np.zeros((F, T), dtype=np.int32),
+            "best_r2_idx": None if light else np.zeros((F, T), dtype=np.int32),
             "admm_iterations": np.zeros((F, K), dtype=np.int32),
             "nnls_iterations": np.zeros((F, K, T), dtype=np.int32) if want_nnls_iters else None,
             "n_selected": np.zeros((F, K), dtype=np.int32),
@@ -360,7 +361,7 @@ def scregclust_fit(z1_reg_scaled=None, z2_reg_scaled=None, z1_target_centered=No
                     prior = (prior_indicator, prior_baseline, prior_weight, orders)
                 res = ses.fit_cycle([pens[i] for i in run], np.stack([states[i].k for i in run]), opt,
                                     skip_allocation=False, want_votes=keep_diagnostics,
-                                    want_nnls_iters=keep_diagnostics, prior=prior)
+                                    want_nnls_iters=keep_diagnostics, prior=prior, light=True)
                 for f, i in enumerate(run):
                     s, fr = states[i], results[i]
                     _unpack(fr, res, f, K, keep_diagnostics)

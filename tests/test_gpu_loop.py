@@ -311,8 +311,10 @@ def test_network_prior_loop(name, seed):
             continue
         same += 1
         assert g.n_cycles_run == r.n_cycles_run and np.array_equal(g.k_final[0], r.k_final[0])
-        for a, b in zip(g.votes, r.votes):
-            assert np.array_equal(a, b)
+        for a, b, amb in zip(g.votes, r.votes, r.ambiguity):
+            # the per-cell votes do not depend on the prior; noise-decided cells may differ (module docstring)
+            moved = np.abs(a.astype(np.int64) - b.astype(np.int64)).sum(axis=1) // 2
+            assert np.all(moved <= amb), (g.penalization, np.flatnonzero(moved > amb)[:8])
         assert np.max(np.abs(g.r2[0] - r.r2[0])) < 1e-8
     assert same >= 1
     # the prior changes the result (otherwise this test would not test anything)

@@ -15,9 +15,20 @@ for rep in range(reps):
     t0 = time.time()
     ses = Session(w.z1_reg, w.z2_reg, w.z1_target, w.z2_target, w.z1_target_sds, w.n_modules)
     t1 = time.time()
+    acc = {"fit_cycle": 0.0, "calls": 0, "importance": 0.0, "coeffs": 0.0}
+    _fc, _imp, _cf = ses.fit_cycle, ses.importance, ses.coeffs_fit
+    def fc(*a, **k):
+        t = time.perf_counter(); r = _fc(*a, **k); acc["fit_cycle"] += time.perf_counter() - t; acc["calls"] += 1; return r
+    def im(*a, **k):
+        t = time.perf_counter(); r = _imp(*a, **k); acc["importance"] += time.perf_counter() - t; return r
+    def cf(*a, **k):
+        t = time.perf_counter(); r = _cf(*a, **k); acc["coeffs"] += time.perf_counter() - t; return r
+    ses.fit_cycle, ses.importance, ses.coeffs_fit = fc, im, cf
     res = scregclust_fit(penalization=w.penalization, n_modules=w.n_modules, initial_target_modules=w.k_init, session=ses,
-                         return_coeffs=False)
+                         return_coeffs="--coeffs" in sys.argv, compute_predictive_r2="--r2" in sys.argv)
     t2 = time.time()
+    print(f"    host split: {acc['calls']} fit_cycle calls {acc['fit_cycle']:.3f} s, importance {acc['importance']:.3f} s, "
+          f"coeffs {acc['coeffs']:.3f} s, python remainder {t2 - t1 - acc['fit_cycle'] - acc['importance'] - acc['coeffs']:.3f} s", flush=True)
     if "--importance" in sys.argv:
         ks = np.stack([r.k_final[0] for r in res]); md = np.stack([r.models[0].T for r in res]); sg = np.stack([r.signs[0].T for r in res])
         ti = time.time(); r2m, imp = ses.importance(ks, md, sg); ti = time.time() - ti
