@@ -1,0 +1,133 @@
+"""Host logic of the session driver (scregclust_b200/driver.py) without a GPU.
+
+The driver's control flow -- noise threshold, minimum module size, history match / limit cycles,
+forced last cycle, deferral and batching of the final re-fits, dynamic claiming with a bounded
+number of penalization values in flight -- is exercised against the oracle's monolithic loop by
+substituting the device session with one that answers each batched cycle from the oracle
+(tests may import oracle/, the product path never does)."""
+import numpy as np
+import pytest
+
+from oracle import scregclust_oracle as orc
+from scregclust_b200.synthetic import make_workload
+
+
+class OracleSession:
+    """Implements the slice of driver.Session that scregclust_fit() uses."""
+
+    def __init__(self, w):
+        self.w = w
+        self.K = w.n_modules
+        self.T = w.z1_target.shape[1]
+        self.P = w.z1_reg.shape[1]
+        self.pre = orc.precompute(w.z1_reg, w.z1_target)
+        self.calls = []          # (n_fits, skip_allocation) per batched call
+        self._last = None
+
+    def _one(self, lam, k, n_cycles):
+        w = self.w
+        return orc.scregclust_fit(w.z1_reg, w.z2_reg, w.z1_target, w.z2_target, w.z1_target_sds, [lam], self.K, k,
+                                  n_cycles=n_cycles, pre=self.pre, keep_history=True, materialize_array=False)[0]
+
+    def fit_cycle(self, lambdas, ks, options=None, skip_allocation=False, want_votes=False, want_nnls_iters=False,
+                  prior=None, light=False):
+        F, K, T, P = len(lambdas), self.K, self.T, self.P
+        ks = np.asarray(ks).reshape(F, T)
+        self.calls.append((F, bool(skip_allocation)))
+        res = {"k_new": np.zeros((F, T), np.int32), "models": np.zeros((F, K, P), np.uint8),
+               "best_r2": np.zeros((F, T)), "admm_iterations": np.zeros((F, K), np.int32),
+               "n_selected": np.zeros((F, K), np.int32), "votes": None, "nnls_iterations": None,
+               "signs": np.zeros((F, K, P)), "weights": np.zeros((F, K, P)), "r2_test": np.zeros((F, K, T)),
+               "resid_var": np.zeros((F, K, T)), "best_r2_idx": np.zeros((F, T), np.int32)}
+        self._last = []
+        for f in range(F):
+            if skip_allocation:                     # the forced last cycle of the reference: re-fit only
+                r = self._one(lambdas[f], ks[f], 0)
+                res["models"][f] = r.models[0].T
+                res["signs"][f] = r.signs[0].T; res["weights"][f] = r.weights[0].T
+                res["r2_test"][f] = r.r2[0].T; res["resid_var"][f] = (r.sigmas[0] ** 2).T
+                res["best_r2"][f] = r.best_r2[0]; res["best_r2_idx"][f] = r.best_r2_idx[0]
+                res["admm_iterations"][f] = r.admm_iterations[0]
+                res["n_selected"][f] = r.models[0].sum(axis=0)
+                self._last.append(r.coeffs[0])
+            else:
+                r = self._one(lambdas[f], ks[f], 1)
+                res["models"][f] = r.models_history[0].T
+                res["k_new"][f] = np.argmax(r.votes[0], axis=1) + 1
+                res["best_r2"][f] = r.r2_history[0].max(axis=1)
+                res["admm_iterations"][f] = r.admm_iterations[0]
+                res["n_selected"][f] = r.models_history[0].sum(axis=0)
+                self._last.append(None)
+        return res
+
+    def coeffs_fit(self, f):
+        return self._last[f], None
+
+    def close(self):
+        pass
+
+
+def _same(got, ref):
+    assert len(got) == len(ref)
+    for g, r in zip(got, ref):
+        assert g.n_cycles_run == r.n_cycles_run and g.converged == r.converged
+        assert g.final_cycle_length == r.final_cycle_length
+        assert len(g.k_history) == len(r.k_history)
+        assert all(np.array_equal(a, b) for a, b in zip(g.k_history, r.k_history))
+        for m in range(r.final_cycle_length):
+            assert np.array_equal(g.k_final[m], r.k_final[m])
+            assert np.array_equal(g.models[m], r.models[m])
+            assert np.allclose(g.r2[m], r.r2[m], rtol=0, atol=1e-12)
+            assert np.allclose(g.sigmas[m], r.sigmas[m], rtol=1e-12, atol=0)
+            for cg, cr in zip(g.coeffs[m], r.coeffs[m]):
+                assert (cg is None) == (cr is None)
+                if cg is not None:
+                    assert np.array_equal(cg, cr)
+
+
+@pytest.fixture(scope="module")
+def case():
+    w = make_workload("tiny", seed=3)
+    kw = dict(min_module_size=2, noise_threshold=0.025)
+    ref = orc.scregclust_fit(w.z1_reg, w.z2_reg, w.z1_target, w.z2_target, w.z1_target_sds, w.penalization,
+                             w.n_modules, w.k_init, **kw)
+    return w, kw, ref
+
+
+def test_lockstep_driver_reproduces_the_oracle_loop(case):
+    from scregclust_b200.driver import scregclust_fit
+    w, kw, ref = case
+    ses = OracleSession(w)
+    got = scregclust_fit(penalization=w.penalization, n_modules=w.n_modules, initial_target_modules=w.k_init,
+                         session=ses, **kw)
+    _same(got, ref)
+    # the final re-fits of all penalization values arrive in ONE batched call, after the last cycle
+    assert [c for c in ses.calls if c[1]] == [(sum(r.final_cycle_length for r in ref), True)]
+    assert ses.calls[-1][1] is True
+
+
+def test_forced_last_cycle_after_n_cycles(case):
+    from scregclust_b200.driver import scregclust_fit
+    w, kw, _ = case
+    ref = orc.scregclust_fit(w.z1_reg, w.z2_reg, w.z1_target, w.z2_target, w.z1_target_sds, w.penalization,
+                             w.n_modules, w.k_init, n_cycles=2, **kw)
+    got = scregclust_fit(penalization=w.penalization, n_modules=w.n_modules, initial_target_modules=w.k_init,
+                         session=OracleSession(w), n_cycles=2, **kw)
+    _same(got, ref)
+    assert all(g.n_cycles_run <= 3 for g in got)
+
+
+@pytest.mark.parametrize("concurrency", [1, 2])
+def test_claiming_with_bounded_concurrency_gives_the_same_fits(case, concurrency):
+    from scregclust_b200.driver import scregclust_fit
+    w, kw, ref = case
+    pens = list(w.penalization) + [0.3]
+    ref = ref + orc.scregclust_fit(w.z1_reg, w.z2_reg, w.z1_target, w.z2_target, w.z1_target_sds, [0.3],
+                                   w.n_modules, w.k_init, **kw)
+    order = iter([2, 0])                             # this "rank" is handed values 2 and 0, never 1
+    ses = OracleSession(w)
+    got = scregclust_fit(penalization=pens, n_modules=w.n_modules, initial_target_modules=w.k_init, session=ses,
+                         claim=lambda: next(order, None), concurrency=concurrency, **kw)
+    assert got[1] is None
+    _same([got[0], got[2]], [ref[0], ref[2]])
+    assert max(c[0] for c in ses.calls if not c[1]) <= concurrency
