@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(ADMM_UPD_WARPS * 32) admm_update_kernel(AdmmDe
     double* smu = upd_sm + 2 * UPD_CACHE;
     __shared__ double s_norm[ADMM_UPD_WARPS][32][2];
     __shared__ double s_sum[ADMM_UPD_WARPS][ADMM_NSUM];
-    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ __align__(8) uint64_t s_bar[UPD_CACHE / (8 * UPD_BOXC)];   // one per staged box (R >= 8)
 
     const int p = prob_ids[blockIdx.y];
     if (!d.active[p]) return;
@@ -200,6 +200,10 @@ __global__ void __launch_bounds__(ADMM_UPD_WARPS * 32) admm_update_kernel(AdmmDe
     const int m = d.c1[p] - c0;
     const double rho = d.rho[p], alpha = d.alpha[p], lam = d.lambda[p];
     const int64_t base = row + (int64_t)c0 * d.ld;
+    // mult / rho (optim.cpp:149,160) is needed for every element in both passes: one real division
+    // per thread gives RN(1 / rho), the elements use the exact quotient correction (common.cuh).
+    const double inv_rho = 1.0 / rho;
+    const bool rho_ok = quot_in_range(rho);
 
     // ---- stage the slab of beta / zeta / mult with TMA: every box is in flight at once, no registers
     // are tied up, and the image in shared memory is [column][row] exactly as the passes index it.
@@ -207,35 +211,48 @@ __global__ void __launch_bounds__(ADMM_UPD_WARPS * 32) admm_update_kernel(AdmmDe
     const int mc = min(m, CS);
     const int nbox = (mc + UPD_BOXC - 1) / UPD_BOXC;
     if (threadIdx.x == 0) {
-        mbar_init(&s_bar, 1);
+        for (int bx = 0; bx < nbox; ++bx) mbar_init(&s_bar[bx], 1);
         mbar_fence_init();
-        mbar_expect_tx(&s_bar, (uint32_t)(3 * nbox * UPD_BOXC * R * 8));
-        for (int bx = 0; bx < nbox; ++bx) {
+        for (int bx = 0; bx < nbox; ++bx) {       // one barrier per 64-column box: pass 1 starts on the first arrival
             const int cc = c0 + bx * UPD_BOXC;
-            tma_load_2d(sb + bx * UPD_BOXC * R, &maps.b, slab * R, cc, &s_bar);
-            tma_load_2d(sz + bx * UPD_BOXC * R, &maps.z, slab * R, cc, &s_bar);
-            tma_load_2d(smu + bx * UPD_BOXC * R, &maps.m, slab * R, cc, &s_bar);
+            mbar_expect_tx(&s_bar[bx], (uint32_t)(3 * UPD_BOXC * R * 8));
+            tma_load_2d(sb + bx * UPD_BOXC * R, &maps.b, slab * R, cc, &s_bar[bx]);
+            tma_load_2d(sz + bx * UPD_BOXC * R, &maps.z, slab * R, cc, &s_bar[bx]);
+            tma_load_2d(smu + bx * UPD_BOXC * R, &maps.m, slab * R, cc, &s_bar[bx]);
         }
     }
-    __syncthreads();                       // barrier initialised and armed before anyone polls it
-    mbar_wait_warp(&s_bar, 0, lane);
+    __syncthreads();                       // barriers initialised and armed before anyone polls them
 
-    // ---- pass 1: group norms of the positive / negative parts (optim.cpp:149-158)
+    // ---- pass 1: group norms of the positive / negative parts (optim.cpp:149-158), box by box as the
+    // loads land (every lane walks its columns in increasing order, exactly as a single loop would)
     double np2 = 0.0, nn2 = 0.0;
-#pragma unroll 4
-    for (int lc = warp * CPW + csub; lc < m; lc += STEP) {
-        double b = 0.0, z = 0.0, mu = 0.0;
-        if (lc < CS) {
-            if (rv) { b = sb[lc * R + row_l]; z = sz[lc * R + row_l]; mu = smu[lc * R + row_l]; }
-        } else if (rv) {
-            const int64_t idx = base + (int64_t)lc * d.ld;
-            b = d.beta[idx]; z = d.zeta[idx]; mu = d.mult[idx];
-        }
+    auto norm_term = [&](double b, double z, double mu) {
         const double br = alpha * b + (1.0 - alpha) * z;
-        const double zn = br - mu / rho;
+        const double qm = (rho_ok && (quot_in_range(mu) || mu == 0.0)) ? quot_exact(mu, rho, inv_rho) : mu / rho;
+        const double zn = br - qm;
         const double pos = fmax(zn, 0.0), neg = fmin(zn, 0.0);
         np2 += pos * pos;
         nn2 += neg * neg;
+    };
+    int lc = warp * CPW + csub;
+    for (int bx = 0; bx < nbox; ++bx) {
+        const int end = min((bx + 1) * UPD_BOXC, mc);
+        if (lc - csub < end) mbar_wait_warp(&s_bar[bx], 0, lane);    // warp-uniform: the warp has columns in this box
+#pragma unroll 4
+        for (; lc < end; lc += STEP) {
+            double b = 0.0, z = 0.0, mu = 0.0;
+            if (rv) { b = sb[lc * R + row_l]; z = sz[lc * R + row_l]; mu = smu[lc * R + row_l]; }
+            norm_term(b, z, mu);
+        }
+    }
+#pragma unroll 4
+    for (; lc < m; lc += STEP) {               // columns beyond the cached slab
+        double b = 0.0, z = 0.0, mu = 0.0;
+        if (rv) {
+            const int64_t idx = base + (int64_t)lc * d.ld;
+            b = d.beta[idx]; z = d.zeta[idx]; mu = d.mult[idx];
+        }
+        norm_term(b, z, mu);
     }
 #pragma unroll
     for (int o = R; o < 32; o <<= 1) {
@@ -272,13 +289,24 @@ __global__ void __launch_bounds__(ADMM_UPD_WARPS * 32) admm_update_kernel(AdmmDe
                 }
             }
         }
+        bool fastq = rho_ok;
+#pragma unroll
+        for (int u = 0; u < U; ++u) fastq &= quot_in_range(mu[u]) || mu[u] == 0.0;
+        double qm[U];
+        if (fastq) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) qm[u] = quot_exact(mu[u], rho, inv_rho);
+        } else {
+#pragma unroll
+            for (int u = 0; u < U; ++u) qm[u] = mu[u] / rho;
+        }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int lc = lc0 + u * STEP;
             if (lc >= m || !rv) continue;
             const int64_t idx = base + (int64_t)lc * d.ld;
             const double br = alpha * b[u] + (1.0 - alpha) * z[u];
-            double zn = br - mu[u] / rho;
+            double zn = br - qm[u];
             zn = (zn >= 0.0) ? zn * sp : zn * sn;                       // optim.cpp:160-168
             const double mn = mu[u] + rho * (-br + zn);                 // optim.cpp:171
             const double pr = -b[u] + zn;                               // optim.cpp:175

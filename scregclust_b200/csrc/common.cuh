@@ -135,6 +135,21 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
+// a / b with the bits of the IEEE division but ~5 FP64 instructions: rb = RN(1 / b) (computed once with a real
+// division), then two Markstein quotient corrections q <- q + RN(a - b q) rb.  After the first one q is a
+// faithful quotient, so the second returns RN(a / b).  Valid while the remainders are exact, i.e. for
+// 2^-930 <= |a| < 2^930 (or a == 0) and b in the same range: callers test quot_in_range() and fall back to `/`.
+__device__ __forceinline__ bool quot_in_range(double a) {
+    const unsigned e = ((unsigned)__double2hiint(a) >> 20) & 0x7ffu;
+    return (e - 93u) < 1860u;
+}
+__device__ __forceinline__ double quot_exact(double a, double b, double rb) {
+    double q = a * rb;
+    q = fma(fma(-q, b, a), rb, q);
+    q = fma(fma(-q, b, a), rb, q);
+    return q;
+}
+
 // D(8x8) += A(8x4, row) * B(4x8, col), all FP64 -> SASS DMMA.8x8x4
 __device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
