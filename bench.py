@@ -231,6 +231,13 @@ def emit(line):
     os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (json.dumps(line) + "\n").encode())
 
 
+def in_flight(n_pens, world):
+    """Penalization values a rank advances together when the grid is shared dynamically."""
+    if os.environ.get("SCRC_BENCH_CONCURRENCY"):
+        return max(1, int(os.environ["SCRC_BENCH_CONCURRENCY"]))
+    return max(1, n_pens // (2 * world))
+
+
 def main():
     global _REAL_STDOUT
     args = parse()
@@ -250,7 +257,7 @@ def main():
               "n1": n_cells // 2, "n2": n_cells - n_cells // 2, "targets": n_targets, "regulators": n_reg,
               "modules": n_modules, "penalties": [float(p) for p in pens],
               "parallelism": (f"penalization values claimed dynamically from a shared counter by {world} GPUs, "
-                               f"{max(1, len(pens) // (2 * world))} in flight per GPU"
+                               f"{in_flight(len(pens), world)} in flight per GPU"
                               if world > 1 else "whole penalty grid advanced in lock-step on 1 GPU"),
               "l2": "working set (FP64 state of all problems) exceeds the 126 MB L2; no flush between steps"}
 
@@ -310,7 +317,10 @@ def main():
     n1, P = w.z1_reg.shape
     n2 = w.z2_reg.shape[0]
 
+    dbg = os.environ.get("SCRC_BENCH_DEBUG") is not None
+
     def run_step(resident: bool):
+        t_a = time.perf_counter()
         if resident:
             ses = Session.from_pointers(dev[0].data_ptr(), dev[1].data_ptr(), dev[2].data_ptr(), dev[3].data_ptr(),
                                         sds_dev.data_ptr(), n1, n2, P, T, n_modules, device=local_rank)
@@ -320,6 +330,7 @@ def main():
                                         device=local_rank)
             ses.h2d_bytes = sum(t.numel() * 8 for t in pinned) + sds_pinned.numel() * 8
         try:
+            t_b = time.perf_counter()
             step_no[0] += 1
             counter.reset(f"scrc_next_{step_no[0]}")
             # one GPU: the whole grid advances in lock-step; several GPUs: each rank keeps
@@ -329,19 +340,24 @@ def main():
             allres = scregclust_fit(penalization=all_pens, n_modules=n_modules, initial_target_modules=w.k_init,
                                     session=ses, return_coeffs=not resident, compute_predictive_r2=True,
                                     claim=counter if world > 1 else None,
-                                    concurrency=max(1, len(all_pens) // (2 * world)) if world > 1 else None)
+                                    concurrency=in_flight(len(all_pens), world) if world > 1 else None)
             res = [r for r in allres if r is not None]
             local_k = {i: r.k_final[0] for i, r in enumerate(allres) if r is not None}
             stats = dict(h2d=ses.h2d_bytes, d2h=ses.d2h_bytes, sweeps=ses.admm_sweeps,
                          admm_iters=ses.admm_problem_iterations,
                          fit_cycles=sum(r.n_cycles_run - 1 for r in res),
                          last_cycles=sum(r.final_cycle_length for r in res))
+            t_c = time.perf_counter()
         finally:
             ses.close()
+        t_d = time.perf_counter()
         # exchange step: every rank learns every penalty's final module assignment (int32 x T)
         allk = parallel.merge_assignments(local_k, len(pens), T, world, device="cuda")
         assert allk.min() >= -1, "a penalization value was not fitted by any rank"
         checksum = int(np.clip(allk, 0, None).sum())
+        if dbg:
+            print(f"[bench step {step_no[0]} resident={resident}] create {t_b - t_a:.3f} s, fit {t_c - t_b:.3f} s, "
+                  f"close {t_d - t_c:.3f} s, merge {time.perf_counter() - t_d:.3f} s", file=sys.stderr, flush=True)
         return res, stats, checksum
 
     def timed(resident: bool, steps: int):

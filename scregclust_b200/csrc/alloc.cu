@@ -38,7 +38,7 @@ __device__ __forceinline__ void consumer_bar() {   // the 8 consumer warps only
 // MODE 0: SSE only; MODE 1: SSE + per-cell votes; MODE 2: SSE + squared residuals written out
 // (only used for the sequential network-prior sweep, which needs every gene's K x n2 slab).
 template <int MODE>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) resid_vote_kernel(const __grid_constant__ RvParams p) {
+__global__ void __launch_bounds__(GEMM_THREADS, 2) resid_vote_kernel(const __grid_constant__ RvParams p) {
     constexpr bool VOTE = (MODE == 1);
     constexpr int MT = RV_BM / (GEMM_WARPS_M * 8);   // 4
     constexpr int NT = RV_BN / (GEMM_WARPS_N * 8);   // 2
@@ -91,7 +91,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) resid_vote_kernel(const __gri
         return;
     }
 
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    // Register pool of the CTA = 384 threads x 80 registers (2 CTAs/SM).  The producer warpgroup gives back
+    // (80 - 24) x 128 = 7168 registers, which lets the 256 consumer threads grow by 28 -> 104 (multiple of 8).
+    // Asking for more than the pool holds makes setmaxnreg.inc wait forever.
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
     const int cw = warp - GEMM_PRODUCER_WARPS;
     const int ctid = threadIdx.x - GEMM_PRODUCER_WARPS * 32;
     const int warp_m = cw / GEMM_WARPS_N, warp_n = cw % GEMM_WARPS_N;
