@@ -85,3 +85,26 @@ def test_no_cpu_fallback_without_device(lib):
     with pytest.raises(ScrcError) as ei:
         api.fast_cor(np.random.rand(10, 3), np.random.rand(10, 2))
     assert ei.value.code <= -100
+
+
+def build_c_client(tmp_path):
+    """Compiles tests/c/abi_smoke.c as strict C99 against the public header and the shared library."""
+    import subprocess
+    from scregclust_b200 import _capi
+    exe = str(tmp_path / "abi_smoke")
+    libdir = os.path.dirname(_capi.LIB_PATH)
+    cmd = ["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "tests", "c", "abi_smoke.c"), "-o", exe, "-L", libdir, "-lscregclust_b200", "-lm",
+           f"-Wl,-rpath,{libdir}"]
+    out = subprocess.run(cmd, capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    return exe
+
+
+def test_plain_c_client_links_and_reports_errors(lib, tmp_path):
+    """The boundary is usable from plain C (what cgo / JNI / .Call glue binds): header is valid C99,
+    argument errors carry the reference's texts, and without a device nothing computes."""
+    import subprocess
+    exe = build_c_client(tmp_path)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "C ABI smoke: ok" in out.stdout, out.stdout + out.stderr

@@ -158,3 +158,12 @@ def test_allocate_into_modules(api, rng, K, n2, T, weight):
         assert not np.any(got == 2)
     api.reset_array(got_arr, z2 * z2)
     assert np.array_equal(got_arr, orc.alloc_array(z2 * z2, K))
+
+
+def test_plain_c_client_runs_on_the_device(tmp_path):
+    """tests/c/abi_smoke.c --gpu: coop_lasso and coef_nnls through the C ABI from a C program."""
+    import subprocess
+    from test_capi_cpu import build_c_client
+    exe = build_c_client(tmp_path)
+    out = subprocess.run([exe, "--gpu"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "C ABI smoke: ok" in out.stdout, out.stdout + out.stderr
