@@ -145,11 +145,8 @@ static void launch_admm_gemm(const AdmmDev& d, const DMat& A, const double* Bm, 
     p.out = out; p.ld = d.ld; p.P = d.P; p.C = d.C;
     p.col_prob = d.col_prob; p.active = d.active; p.rho = d.rho; p.lam = lam;
     constexpr int smem = GemmSmem<BM, BN, STAGES>::TOTAL;
-    static bool configured = false;
-    if (!configured) {
-        SCRC_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<Pol>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = true;
-    }
+    static SmemAttr attr;
+    attr.ensure(gemm_tn_kernel<Pol>, smem);
     const int64_t tiles = ceil_div(d.P, BM) * ceil_div(d.C, BN);
     const int grid = (int)std::min<int64_t>(tiles, num_sms);
     {
@@ -455,16 +452,13 @@ int admm_solve(AdmmBatch& b, const EigBasis& eig, const AdmmOpts& o, bool cold, 
     if (!flat.empty()) SCRC_CUDA(cudaMemcpyAsync(b.class_ids.p, flat.data(), flat.size() * 4, cudaMemcpyHostToDevice, stream));
     SCRC_CUDA(cudaStreamSynchronize(stream));   // hR / flat are stack temporaries
     constexpr int upd_smem = 3 * UPD_CACHE * 8;
-    static bool upd_configured = false;
-    if (!upd_configured) {
-#define SCRC_SET_UPD(R_) \
-        SCRC_CUDA(cudaFuncSetAttribute(admm_update_kernel<R_, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, upd_smem)); \
-        SCRC_CUDA(cudaFuncSetAttribute(admm_update_kernel<R_, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, upd_smem)); \
-        SCRC_CUDA(cudaFuncSetAttribute(admm_update_kernel<R_, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, upd_smem)); \
-        SCRC_CUDA(cudaFuncSetAttribute(admm_update_kernel<R_, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, upd_smem));
-        SCRC_SET_UPD(32) SCRC_SET_UPD(16) SCRC_SET_UPD(8)
+    {
+        static SmemAttr attr[12];
+#define SCRC_SET_UPD(R_, I_) \
+        attr[I_].ensure(admm_update_kernel<R_, false, false>, upd_smem); attr[I_ + 1].ensure(admm_update_kernel<R_, false, true>, upd_smem); \
+        attr[I_ + 2].ensure(admm_update_kernel<R_, true, false>, upd_smem); attr[I_ + 3].ensure(admm_update_kernel<R_, true, true>, upd_smem);
+        SCRC_SET_UPD(32, 0) SCRC_SET_UPD(16, 4) SCRC_SET_UPD(8, 8)
 #undef SCRC_SET_UPD
-        upd_configured = true;
     }
     UpdMaps umaps[3];
     for (int c = 0; c < 3; ++c) {

@@ -325,13 +325,10 @@ void resid_vote(const ResidVoteArgs& a, int mode, int num_sms, cudaStream_t st) 
 
     const int smem = RV_STAGES * RV_STAGE_BYTES + 2 * RV_STAGES * 8 + 2 * (a.K + 1) * RV_BN * 8 +
                      RV_BN * a.K * 4;
-    static int conf[3] = {0, 0, 0};
-    if (smem > conf[mode]) {
-        if (mode == 1) SCRC_CUDA(cudaFuncSetAttribute(resid_vote_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        else if (mode == 2) SCRC_CUDA(cudaFuncSetAttribute(resid_vote_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        else SCRC_CUDA(cudaFuncSetAttribute(resid_vote_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        conf[mode] = smem;
-    }
+    static SmemAttr attr[3];
+    if (mode == 1) attr[1].ensure(resid_vote_kernel<1>, smem);
+    else if (mode == 2) attr[2].ensure(resid_vote_kernel<2>, smem);
+    else attr[0].ensure(resid_vote_kernel<0>, smem);
     const int64_t nwork = (int64_t)a.L * a.CR * p.tiles_n;
     if (nwork > 0x7fffffffLL) throw Error(-61, "resid_vote: too many work items");
     const int grid = (int)nwork;

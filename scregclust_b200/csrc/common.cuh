@@ -168,6 +168,22 @@ __device__ __forceinline__ double warp_sum(double v) {
 // Host: TMA descriptor for a column-major FP64 matrix with `rows` contiguous.
 // Tensor dims = (rows, cols); box = (16, box_cols); 128-byte swizzle.
 // ----------------------------------------------------------------------------
+// Opt-in to more than 48 KB of dynamic shared memory, remembered per kernel AND per device (the
+// attribute belongs to the device's copy of the function; a process may drive several devices).
+struct SmemAttr {
+    int sizes[64] = {};
+    template <class Kernel>
+    void ensure(Kernel kernel, size_t smem) {
+        int dev = 0;
+        SCRC_CUDA(cudaGetDevice(&dev));
+        dev &= 63;
+        if ((int)smem > sizes[dev]) {
+            SCRC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            sizes[dev] = (int)smem;
+        }
+    }
+};
+
 CUtensorMap make_tmap_f64(const double* base, int64_t rows, int64_t cols, int64_t ld,
                           int box_cols);
 // Same matrix view, unswizzled box of (box_rows x box_cols): shared-memory image is dense

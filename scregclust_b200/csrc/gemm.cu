@@ -72,11 +72,8 @@ static void launch_dense(const DenseArgs& a, int num_sms, cudaStream_t stream) {
     p.C = a.C; p.ldc = a.ldc; p.M = a.M; p.N = a.N; p.K = a.K; p.alpha = a.alpha;
     p.rvec = a.rvec; p.cvec = a.cvec; p.D = a.D; p.ldd = a.ldd; p.shift = a.shift; p.cut = a.cut;
     constexpr int smem = GemmSmem<BM, BN, STAGES>::TOTAL;
-    static bool configured = false;
-    if (!configured) {
-        SCRC_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<Pol>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = true;
-    }
+    static SmemAttr attr;
+    attr.ensure(gemm_tn_kernel<Pol>, smem);
     const int64_t tiles = ceil_div(a.M, BM) * ceil_div(a.N, BN);
     int grid = (int)std::min<int64_t>(tiles, num_sms);
     if (const char* e = getenv("SCRC_DEBUG_GEMM_GRID")) grid = (int)std::max<int64_t>(1, std::min<int64_t>(tiles, atoi(e)));

@@ -275,11 +275,8 @@ void nnls_solve(NnlsBatch& b, double eps, int max_iter, const double* out_scale,
     if (!small_ids.empty()) {
         const int warps = 8;
         const size_t smem = ((size_t)smax_small * smax_small + (size_t)warps * 6 * smax_small) * 8;
-        static size_t configured = 0;
-        if (smem > configured) {
-            SCRC_CUDA(cudaFuncSetAttribute(nnls_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = smem;
-        }
+        static SmemAttr attr;
+        attr.ensure(nnls_kernel<true>, smem);
         nnls_kernel<true><<<dim3(chunks, (unsigned)small_ids.size()), warps * 32, smem, st>>>(
             d, ids.p, cols_per_cta, eps, max_iter, out_scale, n_out_scale);
         SCRC_LAUNCHED();
@@ -288,11 +285,8 @@ void nnls_solve(NnlsBatch& b, double eps, int max_iter, const double* out_scale,
         int warps = (int)std::min<size_t>(8, (200 * 1024) / ((size_t)48 * smax_large));
         if (warps < 1) throw Error(-70, "NNLS: too many selected regulators for the shared-memory work vectors");
         const size_t smem = (size_t)warps * 6 * smax_large * 8;
-        static size_t configured = 0;
-        if (smem > configured) {
-            SCRC_CUDA(cudaFuncSetAttribute(nnls_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = smem;
-        }
+        static SmemAttr attr;
+        attr.ensure(nnls_kernel<false>, smem);
         nnls_kernel<false><<<dim3(chunks, (unsigned)large_ids.size()), warps * 32, smem, st>>>(
             d, ids.p + small_ids.size(), cols_per_cta, eps, max_iter, out_scale, n_out_scale);
         SCRC_LAUNCHED();

@@ -8,6 +8,7 @@ if [ $rc -ne 0 ]; then echo "QUICK TEST FAILED rc=$rc -- stopping"; exit 1; fi
 timeout -s KILL 400 python -m pytest tests -m gpu -q --no-header -p no:cacheprovider --timeout=200 > gpurun_out/pytest_gpu.log 2>&1
 echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
 grep -E "passed|failed|Error|error|assert" gpurun_out/pytest_gpu.log | tail -15
+if [ "$1" == "--tests-only" ]; then exit 0; fi
 timeout -s KILL 200 python tools/time_fit.py config3 1 2>&1 | grep -E "rep|gemm" | cut -c1-330
 timeout -s KILL 400 python bench.py --steps 2 --warmup 3 > gpurun_out/bench_config3_n1.json 2> gpurun_out/bench_config3_n1.err
 echo "bench exit $?"
