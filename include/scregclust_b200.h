@@ -204,6 +204,15 @@ int scrc_fit_cycle(scrc_ctx* ctx, int F, const double* lambda, const int* k_in, 
  * reference leaves NA (modules without targets or with fewer than two regulators). */
 int scrc_importance(scrc_ctx* ctx, int F, const int* k_final, const unsigned char* models, const double* signs,
                     const scrc_options* opt, double* r2_module, double* importance);
+/* The same, plus the per-target matrices `r2_removed[[m]][[j]]` (R/scregclust.R:1890-1898): for every
+ * (fit, module) in order that has targets and more than one regulator, an m_j x (s_j + 1) column-major
+ * block (rows = the module's targets in increasing index, column 0 = "None", column r = r-th selected
+ * regulator removed), packed one after the other into r2_removed (capacity in doubles; the caller
+ * knows m_j and s_j from k_final and models).  R divides t(ssq) by a length-m_j vector there, which
+ * recycles down the columns of the (s_j + 1) x m_j matrix; the values reproduce that. */
+int scrc_importance_ex(scrc_ctx* ctx, int F, const int* k_final, const unsigned char* models, const double* signs,
+                       const scrc_options* opt, double* r2_module, double* importance, double* r2_removed,
+                       int64_t r2_removed_capacity);
 
 /* Network prior for Step 2b (src/allocation.cpp:39-56,74-77; R/scregclust.R:584-615,1666-1675).
  * prior_off / prior_idx: CSR form of `prior_indicator` over the T target genes (0-based neighbours);

@@ -634,6 +634,7 @@ class FitResult:
     coeffs_history: list = field(default_factory=list)     # per cycle list of s_j x T
     r2_module: list = field(default_factory=list)
     importance: list = field(default_factory=list)
+    r2_removed: list = field(default_factory=list)         # per final configuration: list over modules
 
 
 def _recycle(v, shape):
@@ -860,6 +861,7 @@ def _importance(fr, z1r, z2r, z1t, z2t, z1_target_sds, G_rr, G_rt_nnls, n_module
         k = fr.k_final[m]
         r2_module = np.full(n_modules, np.nan)
         importance = np.full((n_reg, n_modules), np.nan)
+        removed = [None] * n_modules
         for j in range(n_modules):
             reg_cl = np.flatnonzero(fr.models[m][:, j])
             target_cl = np.flatnonzero(k == j + 1)
@@ -876,7 +878,12 @@ def _importance(fr, z1r, z2r, z1t, z2t, z1_target_sds, G_rr, G_rt_nnls, n_module
                     ssq[:, r] = np.sum(rt * rt, axis=0)
                 zc = z2t[:, target_cl] - z2t[:, target_cl].mean(axis=0)
                 r2_removed = 1.0 - ssq.sum(axis=0) / np.sum(zc * zc)
+                # scregclust.R:1890-1896: 1 - t(t(ssq) / colSums(zc^2)) -- the length-m vector is recycled
+                # down the columns of the (s+1) x m matrix t(ssq), not matched to its columns
+                tss = ssq.T
+                removed[j] = 1.0 - (tss / _recycle(np.sum(zc * zc, axis=0), tss.shape)).T
                 r2_module[j] = r2_removed[0]
                 importance[reg_cl, j] = 1.0 - r2_removed[1:] / r2_module[j]
         fr.r2_module.append(r2_module)
         fr.importance.append(importance)
+        fr.r2_removed.append(removed)

@@ -86,6 +86,8 @@ SIGNATURES = {
                                        C.POINTER(CycleOut)]),
     "scrc_importance": (C.c_int, [C.c_void_p, C.c_int, c_int_p, c_ubyte_p, c_double_p, C.POINTER(Options), c_double_p,
                                   c_double_p]),
+    "scrc_importance_ex": (C.c_int, [C.c_void_p, C.c_int, c_int_p, c_ubyte_p, c_double_p, C.POINTER(Options), c_double_p,
+                                     c_double_p, c_double_p, C.c_int64]),
     "scrc_ctx_get_coeffs": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_double_p, c_int_p]),
     "scrc_ctx_get_coeffs_fit": (C.c_int, [C.c_void_p, C.c_int, c_double_p, c_int_p]),
 }

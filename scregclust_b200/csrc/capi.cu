@@ -347,6 +347,18 @@ int scrc_importance(scrc_ctx* ctx, int F, const int* k_final, const unsigned cha
     return guarded([&] { ctx->impl.importance(F, k_final, models, signs, o, r2_module, importance); });
 }
 
+int scrc_importance_ex(scrc_ctx* ctx, int F, const int* k_final, const unsigned char* models, const double* signs,
+                       const scrc_options* opt, double* r2_module, double* importance, double* r2_removed,
+                       int64_t r2_removed_capacity) {
+    if (!ctx || !k_final || !models || !signs || !r2_module || !importance)
+        return fail(SCRC_ERR_ARG, "scrc_importance_ex: null pointer");
+    scrc_options o;
+    if (opt) o = *opt; else scrc_default_options(&o);
+    return guarded([&] {
+        ctx->impl.importance(F, k_final, models, signs, o, r2_module, importance, r2_removed, r2_removed_capacity);
+    });
+}
+
 int scrc_ctx_get_coeffs(scrc_ctx* ctx, int f, int k, double* coeffs_out, int* sel_out) {
     if (!ctx) return fail(SCRC_ERR_ARG, "null context");
     return guarded([&] {

@@ -458,7 +458,8 @@ void Ctx::fit_cycle(int F, const double* lambda, const int* k_in, const scrc_opt
 // problems of a module share one gathered regulator block (the removed regulator's coefficient row
 // is kept as an exact zero row) and differ only in their coefficient rows.
 void Ctx::importance(int F, const int* k_final, const unsigned char* models, const double* signs,
-                     const scrc_options& opt, double* r2_module, double* importance_out) {
+                     const scrc_options& opt, double* r2_module, double* importance_out, double* r2_removed,
+                     int64_t r2_removed_capacity) {
     if (F <= 0) throw Error(SCRC_ERR_ARG, "scrc_importance: F must be positive");
     SCRC_CUDA(cudaSetDevice(dev.id));
     cudaStream_t st = dev.stream;
@@ -564,7 +565,24 @@ void Ctx::importance(int F, const int* k_final, const unsigned char* models, con
     SCRC_CUDA(cudaMemcpyAsync(h_css.data(), z2t_css.p, T * 8, cudaMemcpyDeviceToHost, st));
     SCRC_CUDA(cudaStreamSynchronize(st));
 
+    int64_t rr_off = 0;
     for (const Group& g : groups) {
+        if (r2_removed) {
+            // r2_removed[[m]][[j]] = 1 - t(t(ssq) / colSums(scale(z2...)^2))   (scregclust.R:1890-1896): the
+            // (s+1) x m matrix t(ssq) is divided by a length-m vector, which R recycles down ITS columns, so
+            // entry (target c, removal r) is divided by css[(r + c (s+1)) mod m] -- reproduced as is.
+            const int64_t need = (int64_t)g.m * (g.s + 1);
+            if (rr_off + need > r2_removed_capacity) throw Error(SCRC_ERR_ARG, "scrc_importance_ex: r2_removed buffer too small");
+            for (int r = 0; r <= g.s; ++r) {
+                const double* q = h_sse.data() + ((size_t)(g.first_prob + r) * 2 + 0) * Tmax;
+                for (int c = 0; c < g.m; ++c) {
+                    const int64_t flat = (int64_t)r + (int64_t)c * (g.s + 1);
+                    const double css = h_css[h_cols[g.col_off + (int)(flat % g.m)]];
+                    r2_removed[rr_off + c + (int64_t)r * g.m] = 1.0 - q[c] / css;
+                }
+            }
+            rr_off += need;
+        }
         long double denom = 0.0L;
         for (int c = 0; c < g.m; ++c) denom += h_css[h_cols[g.col_off + c]];            // scregclust.R:1883-1887
         std::vector<double> vec(g.s + 1);

@@ -75,8 +75,11 @@ struct Ctx {
                    scrc_cycle_out* out, const scrc_prior* prior = nullptr);
     DevBuf<double> sq_arr;       // K x n2 x T squared residuals, only with a network prior
     // Leave-one-regulator-out importance and module R2 (R/scregclust.R:1823-1912) for F final configurations.
+    // r2_removed (optional): the per-target matrices of scregclust.R:1890-1898, packed in (fit, module) order --
+    // see scrc_importance_ex in the public header.
     void importance(int F, const int* k_final, const unsigned char* models, const double* signs,
-                    const scrc_options& opt, double* r2_module, double* importance_out);
+                    const scrc_options& opt, double* r2_module, double* importance_out,
+                    double* r2_removed = nullptr, int64_t r2_removed_capacity = 0);
     DevBuf<double> z2t_css;      // centred sums of squares of the test targets (lazy)
     DevBuf<double> gtt;          // colSums(z1_target_centered^2)
     ~Ctx() { dev.destroy(); }

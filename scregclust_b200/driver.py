@@ -42,6 +42,7 @@ class FitResult:
     models_history: list = field(default_factory=list)
     r2_module: list = field(default_factory=list)     # per final configuration: K (nan = NA)
     importance: list = field(default_factory=list)    # per final configuration: P x K (nan = NA)
+    r2_removed: list = field(default_factory=list)    # per final configuration: list over modules of m_j x (s_j+1)
 
 
 class Session:
@@ -219,22 +220,42 @@ class Session:
         self.admm_problem_iterations += int(res["admm_iterations"].sum())
         return res
 
-    def importance(self, k_final, models, signs, options=None):
+    def importance(self, k_final, models, signs, options=None, want_r2_removed=False):
         """Leave-one-regulator-out importance (R/scregclust.R:1823-1912) for F final configurations.
 
         ``k_final``: F x T, ``models``: F x K x P (bool/uint8), ``signs``: F x K x P (nan where unselected).
-        Returns ``(r2_module[F, K], importance[F, K, P])`` with nan where the reference leaves NA."""
+        Returns ``(r2_module[F, K], importance[F, K, P])`` with nan where the reference leaves NA and, with
+        ``want_r2_removed``, a third item: per fit a list over modules of the ``m_j x (s_j + 1)`` matrices
+        ``r2_removed`` (``None`` where the reference leaves the list entry empty)."""
         k = np.ascontiguousarray(k_final, dtype=np.int32).reshape(-1, self.T)
         F = k.shape[0]
         md = np.ascontiguousarray(models, dtype=np.uint8).reshape(F, self.K, self.P)
         sg = np.ascontiguousarray(signs, dtype=np.float64).reshape(F, self.K, self.P)
         opt = options if options is not None else default_options()
         r2m = np.zeros((F, self.K)); imp = np.zeros((F, self.K, self.P))
-        check(self._lib.scrc_importance(self._h, F, iptr(k), md.ctypes.data_as(_capi.c_ubyte_p), dptr(sg), C.byref(opt),
-                                        dptr(r2m), dptr(imp)))
         self.h2d_bytes += k.nbytes + md.nbytes + sg.nbytes
         self.d2h_bytes += r2m.nbytes + imp.nbytes
-        return r2m, imp
+        if not want_r2_removed:
+            check(self._lib.scrc_importance(self._h, F, iptr(k), md.ctypes.data_as(_capi.c_ubyte_p), dptr(sg),
+                                            C.byref(opt), dptr(r2m), dptr(imp)))
+            return r2m, imp
+        shapes = []                                   # (f, j, m_j, s_j) of every block, in the library's order
+        for f in range(F):
+            for j in range(self.K):
+                m_j, s_j = int(np.count_nonzero(k[f] == j + 1)), int(md[f, j].sum())
+                if m_j > 0 and s_j > 1:
+                    shapes.append((f, j, m_j, s_j))
+        cap = sum(m_j * (s_j + 1) for _, _, m_j, s_j in shapes)
+        buf = np.zeros(max(cap, 1))
+        check(self._lib.scrc_importance_ex(self._h, F, iptr(k), md.ctypes.data_as(_capi.c_ubyte_p), dptr(sg),
+                                           C.byref(opt), dptr(r2m), dptr(imp), dptr(buf), cap))
+        self.d2h_bytes += cap * 8
+        removed = [[None] * self.K for _ in range(F)]
+        o = 0
+        for f, j, m_j, s_j in shapes:
+            removed[f][j] = buf[o:o + m_j * (s_j + 1)].reshape((m_j, s_j + 1), order="F")
+            o += m_j * (s_j + 1)
+        return r2m, imp, removed
 
     def coeffs(self, f, module):
         """NNLS coefficients (s x T) and 0-based regulator indices of ``module`` (0-based) of fit ``f``."""
@@ -417,10 +438,11 @@ def scregclust_fit(z1_reg_scaled=None, z2_reg_scaled=None, z1_target_centered=No
                 if return_coeffs:
                     fr.coeffs.append(ses.coeffs_fit(f)[0])
             if compute_predictive_r2:                             # R/scregclust.R:1823-1912
-                r2m, imp = ses.importance(np.stack(k_f), res["models"], res["signs"], opt)
+                r2m, imp, rem = ses.importance(np.stack(k_f), res["models"], res["signs"], opt, want_r2_removed=True)
                 for f, i in enumerate(owner):
                     results[i].r2_module.append(r2m[f].copy())
                     results[i].importance.append(imp[f].T.copy())
+                    results[i].r2_removed.append(rem[f])
             for i in batch:
                 s, fr = states[i], results[i]
                 s.done = True

@@ -258,12 +258,22 @@ def test_importance_matches_oracle(name, seed):
     signs = np.stack([r.signs[0].T for r in ref])
     with Session(w.z1_reg, w.z2_reg, w.z1_target, w.z2_target, w.z1_target_sds, K) as s:
         r2m, imp = s.importance(ks, models, signs)
+        r2m_x, imp_x, removed = s.importance(ks, models, signs, want_r2_removed=True)
+    assert np.array_equal(r2m, r2m_x, equal_nan=True) and np.array_equal(imp, imp_x, equal_nan=True)
+    n_blocks = 0
     for f, r in enumerate(ref):
         assert np.array_equal(np.isnan(r2m[f]), np.isnan(r.r2_module[0]))
         assert np.allclose(r2m[f], r.r2_module[0], rtol=1e-8, atol=1e-10, equal_nan=True)
         assert np.array_equal(np.isnan(imp[f].T), np.isnan(r.importance[0]))
         assert np.allclose(imp[f].T, r.importance[0], rtol=1e-7, atol=1e-9, equal_nan=True)
-    assert np.isfinite(r2m).any()
+        # per-target matrices incl. the reference's recycling of the column sums (scregclust.R:1890-1896)
+        for j in range(K):
+            a, b = removed[f][j], r.r2_removed[0][j]
+            assert (a is None) == (b is None)
+            if a is not None:
+                n_blocks += 1
+                assert a.shape == b.shape and np.allclose(a, b, rtol=1e-8, atol=1e-9)
+    assert np.isfinite(r2m).any() and n_blocks > 0
 
 
 def test_driver_importance_end_to_end():
@@ -276,6 +286,10 @@ def test_driver_importance_end_to_end():
     for g, r in zip(got, ref):
         assert np.allclose(g.r2_module[0], r.r2_module[0], rtol=1e-8, atol=1e-10, equal_nan=True)
         assert np.allclose(g.importance[0], r.importance[0], rtol=1e-7, atol=1e-9, equal_nan=True)
+        for a, b in zip(g.r2_removed[0], r.r2_removed[0]):
+            assert (a is None) == (b is None)
+            if a is not None:
+                assert np.allclose(a, b, rtol=1e-8, atol=1e-9)
 
 
 @pytest.mark.parametrize("name,seed", [("tiny", 3), ("small", 1)])

@@ -309,3 +309,30 @@ def test_constant_genes_are_discarded_correctly(center):
     *_, keep = orc.stage_inputs(expression, None, is_regulator, split, center=center)
     assert genesymbols[keep].tolist() == ["T2", "T3", "T4", "T5", "T6", "R2"]
     assert (is_regulator[keep] == 1).tolist() == [False, False, False, False, False, True]
+
+
+def test_r2_removed_recycles_the_column_sums_like_r():
+    """scregclust.R:1890-1896: `t(ssq) / v` with an (s+1) x m matrix and a length-m vector divides the
+    element with column-major flat index i by v[i mod m]."""
+    w = make_workload("tiny", seed=3)
+    r = orc.scregclust_fit(w.z1_reg, w.z2_reg, w.z1_target, w.z2_target, w.z1_target_sds, w.penalization[:1],
+                           w.n_modules, w.k_init, compute_predictive_r2=True)[0]
+    k = r.k_final[0]
+    checked = 0
+    for j, blk in enumerate(r.r2_removed[0]):
+        if blk is None:
+            continue
+        tc = np.flatnonzero(k == j + 1)
+        zc = w.z2_target[:, tc] - w.z2_target[:, tc].mean(axis=0)
+        css = (zc * zc).sum(axis=0)
+        m, s1 = blk.shape
+        assert m == tc.size and s1 == int(r.models[0][:, j].sum()) + 1
+        # recover ssq from column 0 of a correctly aligned entry: flat index of (r=0, c) is c*(s+1)
+        for c in range(m):
+            ssq_c0 = (1.0 - blk[c, 0]) * css[(c * s1) % m]
+            assert ssq_c0 > 0
+        # module R2 is the properly summed version of column 0
+        ssq0 = np.array([(1.0 - blk[c, 0]) * css[(c * s1) % m] for c in range(m)])
+        assert abs((1.0 - ssq0.sum() / css.sum()) - r.r2_module[0][j]) < 1e-12
+        checked += 1
+    assert checked > 0
