@@ -88,3 +88,16 @@ def test_constant_genes_are_discarded_correctly(center):
         res = scregclust_fit(penalization=[0.1], n_modules=2, initial_target_modules=np.array([1, 2, 1, 2, 1], dtype=np.int32),
                              session=ses)
         assert res[0].k_final[0].shape == (5,)
+
+
+def test_reference_constant_genes_test_through_the_frontend():
+    """tests/testthat/test-constant-genes.R:1-24 with the reference's own call shape:
+    ``scregclust(expression, genesymbols, is_regulator, 0.1, 2)`` -> genesymbols / is_regulator of the result."""
+    from test_oracle import _constant_genes_case
+    from scregclust_b200.frontend import scregclust
+    expression, genesymbols, is_regulator, split = _constant_genes_case()
+    fit = scregclust(expression, genesymbols, is_regulator, 0.1, 2, split_indices=split, seed=1, n_initializations=2)
+    assert fit["results"][0]["genesymbols"] == ["T2", "T3", "T4", "T5", "T6", "R2"]
+    assert fit["results"][0]["is_regulator"].tolist() == [False, False, False, False, False, True]
+    out = fit["results"][0]["output"][0]
+    assert out["module"].shape == (6,) and np.isnan(out["module"][5])          # NA for the regulator
