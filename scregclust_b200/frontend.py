@@ -68,8 +68,8 @@ def _validate(expression, genesymbols, is_regulator, penalization, n_modules, in
         _abort("n_cycles needs to be a positive integer.")
     if not (isinstance(min_module_size, (int, np.integer)) and min_module_size >= 0):
         _abort("min_module_size needs to be a non-negative integer.")
-    if not (0 <= float(prior_weight) < 1):
-        _abort("prior_weight needs to be a number in [0, 1).")
+    if not (0 <= float(prior_weight) <= 1):
+        _abort("prior_weight needs to be a number between 0 and 1.")                   # R/scregclust.R:567-579
     return ex, isr.astype(np.int32), pen
 
 
@@ -98,16 +98,58 @@ def initial_modules_kmeans(cross_corr1, n_modules, n_initializations, rng):
     return km.fit_predict(np.ascontiguousarray(cross_corr1)).astype(np.int32) + 1
 
 
+def prior_to_target_lists(prior_indicator, prior_genesymbols, genesymbols_target):
+    """``prior_indicator`` (q x q, dense or scipy.sparse) + ``prior_genesymbols`` -> per target gene the sorted
+    0-based indices of the target genes it is linked to (R/scregclust.R:584-608 and 1026-1047): the diagonal is
+    dropped, row l lists the columns with a non-zero entry, and both sides are matched to the target symbols
+    (first match, like ``match``)."""
+    pg = [str(g) for g in prior_genesymbols]
+    gt = [str(g) for g in genesymbols_target]
+    q = len(pg)
+    pi = prior_indicator.toarray() if hasattr(prior_indicator, "toarray") else np.asarray(prior_indicator)
+    if pi.shape != (q, q):
+        _abort("prior_genesymbols needs to have one element for each row/column of prior_indicator")
+    pi = pi.copy()
+    np.fill_diagonal(pi, 0)
+    first = {}
+    for i, g in enumerate(pg):
+        first.setdefault(g, i)
+    out = [[] for _ in gt]
+    done = set()
+    for t, g in enumerate(gt):
+        if g in first and g not in done:                  # match(genes_overlap, genesymbols_target): first hit only
+            done.add(g)
+            linked = {pg[c] for c in np.flatnonzero(pi[first[g]] != 0)}
+            out[t] = [u for u, h in enumerate(gt) if h in linked]
+    return out
+
+
+def silhouette_from_r2(r2, k):
+    """R/scregclust.R:1973-1985: (a - b) / max(a, b) with a = own-module R2 and b = best other module (>= 0)."""
+    r2 = np.asarray(r2)
+    out = np.full(len(k), np.nan)
+    for i, c in enumerate(k):
+        if c != -1:
+            others = np.delete(r2[i], c - 1)
+            b = max(float(np.max(others)), 0.0) if others.size else 0.0
+            a = float(r2[i, c - 1])
+            with np.errstate(invalid="ignore", divide="ignore"):
+                out[i] = np.float64(a - b) / np.float64(max(a, b))
+    return out
+
+
 def scregclust(expression, genesymbols, is_regulator, penalization, n_modules, initial_target_modules=None,
                sample_assignment=None, center=True, split1_proportion=0.5, total_proportion=1, split_indices=None,
-               prior_indicator=None, prior_baseline=1e-6, prior_weight=0.5, min_module_size=0, noise_threshold=0.025,
-               n_cycles=50, n_initializations=50, max_optim_iter=10000, tol_coop_rel=1e-8, tol_coop_abs=1e-12,
-               tol_nnls=1e-4, compute_predictive_r2=True, update_orders=None, seed=None, device=0,
-               session_factory=None):
+               prior_indicator=None, prior_genesymbols=None, prior_baseline=1e-6, prior_weight=0.5, min_module_size=0,
+               noise_threshold=0.025, n_cycles=50, n_initializations=50, max_optim_iter=10000, tol_coop_rel=1e-8,
+               tol_coop_abs=1e-12, tol_nnls=1e-4, compute_predictive_r2=True, compute_silhouette=False,
+               update_orders=None, seed=None, device=0, session_factory=None):
     """``scregclust(expression, genesymbols, is_regulator, penalization, n_modules, ...)`` of the reference.
 
-    ``expression``: p x n (genes x cells).  ``prior_indicator``: list of T lists of 0-based neighbour targets
-    (target order after the constant-gene filter), or ``None``.  Returns a dict with the fields of the R object
+    ``expression``: p x n (genes x cells).  ``prior_indicator``: the reference's q x q indicator matrix together
+    with ``prior_genesymbols`` (R/scregclust.R:52-63), or -- without ``prior_genesymbols`` -- a ready list of T lists
+    of 0-based neighbour targets in target order after the constant-gene filter; ``None`` = no prior.  With a prior
+    the caller supplies ``update_orders(penalty_index, cycle)`` to replay R's ``sample()`` (identity otherwise).  Returns a dict with the fields of the R object
     (R/scregclust.R:2056-2120): ``penalization``, ``results`` (one per penalization value, each with
     ``genesymbols``, ``is_regulator``, ``n_modules``, ``converged`` and ``output`` = one entry per final
     configuration), ``initial_target_modules`` and ``split_indices``.  NA is ``nan``.
@@ -134,6 +176,10 @@ def scregclust(expression, genesymbols, is_regulator, penalization, n_modules, i
             k_start = np.asarray(initial_target_modules, dtype=np.int32)[tgt_keep]      # :947-949
         else:
             k_start = initial_modules_kmeans(cross_corr1, int(n_modules), n_initializations, rng)
+        if prior_indicator is not None and prior_genesymbols is not None:
+            prior_indicator = prior_to_target_lists(prior_indicator, prior_genesymbols, gs[isr_k == 0])
+        elif prior_indicator is not None and not isinstance(prior_indicator, (list, tuple)):
+            _abort("prior_genesymbols missing, but prior_indicator supplied.")          # R/scregclust.R:523-533
         use_prior = prior_indicator is not None and len(prior_indicator) > 0 and float(prior_weight) != 0.0
         fits = driver.scregclust_fit(
             penalization=pen, n_modules=int(n_modules), initial_target_modules=k_start, session=ses,
@@ -169,6 +215,8 @@ def scregclust(expression, genesymbols, is_regulator, penalization, n_modules, i
                 "r2_module": fr.r2_module[m] if compute_predictive_r2 else None,
                 "importance": fr.importance[m] if compute_predictive_r2 else None,
                 "r2_removed": fr.r2_removed[m] if compute_predictive_r2 else None,
+                "r2_cross_module_per_target": fr.r2[m] if compute_silhouette else None,         # :1961
+                "silhouette": silhouette_from_r2(fr.r2[m], k) if compute_silhouette else None,
                 "models": fr.models[m], "signs": fr.signs[m], "weights": fr.weights[m], "coeffs": fr.coeffs[m],
                 "sigmas": fr.sigmas[m]})
         results.append({"penalization": fr.penalization, "genesymbols": gs.tolist(), "is_regulator": isr_k == 1,

@@ -120,3 +120,49 @@ def test_frontend_argument_errors(kwargs, needle):
     args.update(kwargs)
     with pytest.raises(ScregclustError, match=needle):
         scregclust(**args)
+
+
+def test_prior_matrix_is_mapped_to_target_neighbour_lists():
+    """R/scregclust.R:584-608,1026-1047 on a small example worked out by hand."""
+    from scregclust_b200.frontend import prior_to_target_lists
+    prior_genes = ["A", "B", "X", "C", "D"]                      # X is not a target gene
+    pi = np.zeros((5, 5), dtype=int)
+    pi[0, 1] = pi[1, 0] = 1      # A - B
+    pi[0, 2] = pi[2, 0] = 1      # A - X  (dropped: X is no target)
+    pi[3, 3] = 1                 # C - C  (diagonal: dropped)
+    pi[4, 0] = 1                 # D -> A (directed entry: only D's list gets A)
+    targets = ["B", "A", "E", "D", "C"]                           # E is not in the prior
+    got = prior_to_target_lists(pi, prior_genes, targets)
+    assert got == [[1], [0], [], [1], []]
+    import scipy.sparse
+    assert prior_to_target_lists(scipy.sparse.csr_matrix(pi), prior_genes, targets) == got
+
+
+def test_silhouette_follows_the_reference_formula():
+    from scregclust_b200.frontend import silhouette_from_r2
+    r2 = np.array([[0.5, 0.2, -0.1], [0.1, -0.3, -0.2], [0.0, 0.4, 0.6], [0.3, 0.3, 0.3]])
+    k = np.array([1, 2, -1, 3])
+    s = silhouette_from_r2(r2, k)
+    assert np.isclose(s[0], (0.5 - 0.2) / 0.5)
+    assert np.isclose(s[1], (-0.3 - 0.1) / 0.1)                  # b = max(0.1, -0.2) = 0.1
+    assert np.isnan(s[2])
+    assert np.isclose(s[3], 0.0)
+
+
+def test_frontend_accepts_the_prior_matrix_form():
+    from scregclust_b200.frontend import ScregclustError, scregclust
+    z, is_reg, strat, split = _raw_expression(23, p=40, n=120, n_strata=1)
+    genes = [f"g{i}" for i in range(40)]
+    tgt = [g for g, r in zip(genes, is_reg) if r == 0]
+    q = len(tgt)
+    pi = (np.random.default_rng(1).random((q, q)) < 0.1).astype(int)
+    common = dict(expression=z, genesymbols=genes, is_regulator=is_reg, penalization=0.2, n_modules=2,
+                  split_indices=split, n_cycles=2, compute_predictive_r2=False, compute_silhouette=True, seed=0,
+                  n_initializations=2, session_factory=OracleExpressionSession)
+    with pytest.raises(ScregclustError, match="prior_genesymbols missing"):
+        scregclust(prior_indicator=pi, **common)
+    # weight 0 keeps the sweep order-independent (the oracle-backed session has no prior path)
+    fit = scregclust(prior_indicator=pi, prior_genesymbols=tgt, prior_weight=0.0, **common)
+    out = fit["results"][0]["output"][0]
+    assert out["silhouette"].shape == (len(fit["initial_target_modules"]),)
+    assert out["r2_cross_module_per_target"] is out["r2"]
