@@ -167,3 +167,19 @@ def test_plain_c_client_runs_on_the_device(tmp_path):
     exe = build_c_client(tmp_path)
     out = subprocess.run([exe, "--gpu"], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "C ABI smoke: ok" in out.stdout, out.stdout + out.stderr
+
+
+def test_kernels_match_golden_fixtures(api):
+    """The committed golden vectors (tests/golden/kernels_seed7.npz, written by tests/golden/make_golden.py and
+    checked against the oracle in tests/test_oracle.py) through the C ABI."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "kernels_seed7.npz"))
+    got = api.coop_lasso(g["coop_y"], g["coop_x"], float(g["coop_lambda"]), g["coop_w"], max_iter=10000)
+    assert got["iterations"] == int(g["coop_iterations"])
+    assert rel_err(got["beta"], g["coop_beta"]) < 1e-8
+    got = api.coef_nnls(g["nnls_x"], g["nnls_y"], eps=1e-4, max_iter=10000)
+    assert np.array_equal(got["iterations"], g["nnls_iterations"])
+    assert rel_err(got["beta"], g["nnls_beta"]) < 1e-8
+    k = api.allocate_into_modules(np.asfortranarray(g["alloc_arr"]), np.asfortranarray(g["alloc_var"]), [],
+                                  g["alloc_k"], g["alloc_order"], 1e-6, 0.0)
+    assert np.array_equal(k, g["alloc_out"])

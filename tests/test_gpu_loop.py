@@ -372,3 +372,22 @@ def test_module_count_limit():
         _check_votes("K64", res["votes"][0], ref.votes[0], ref.ambiguity[0], res["k_new"][0])
     with pytest.raises(_capi.ScrcError):
         Session(w.z1_reg, w.z2_reg, w.z1_target, w.z2_target, w.z1_target_sds, 65)
+
+
+def test_loop_matches_golden_trajectory():
+    """tests/golden/loop_tiny_seed3.npz (an oracle trajectory without a single noise-decided vote, so it is host
+    independent): module assignments of every cycle, ADMM iteration counts and selected regulators bit-exact;
+    R2, sigmas and importances at the tolerances of the oracle's own golden test."""
+    import os
+    from scregclust_b200.driver import scregclust_fit
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "loop_tiny_seed3.npz"))
+    w = make_workload("tiny", seed=3)
+    res = scregclust_fit(w.z1_reg, w.z2_reg, w.z1_target, w.z2_target, w.z1_target_sds, w.penalization,
+                         w.n_modules, w.k_init, compute_predictive_r2=True)
+    for i, r in enumerate(res):
+        assert np.array_equal(np.stack(r.k_history), g[f"k_history_{i}"])
+        assert np.array_equal(np.stack(r.admm_iterations), g[f"admm_iterations_{i}"])
+        assert np.array_equal(r.models[0], g[f"models_{i}"])
+        assert rel_err(r.r2[0], g[f"r2_{i}"]) < 1e-8
+        assert rel_err(r.sigmas[0], g[f"sigmas_{i}"]) < 1e-8
+        assert np.allclose(r.importance[0], g[f"importance_{i}"], rtol=1e-7, atol=1e-9, equal_nan=True)
