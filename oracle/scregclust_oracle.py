@@ -13,8 +13,9 @@ is pinned through the reference's own test (tests/testthat/test-fast-cor.R:1-16:
 equal to ``stats::cor`` == ``numpy.corrcoef`` at tolerance 1.5e-8), and the
 constant-gene filter of the input staging through the reference's other test
 (tests/testthat/test-constant-genes.R:1-24: T1 / R1 dropped).  Independent
-cross-checks (KKT conditions, scipy.optimize.nnls, lstsq, brute-force
-allocation) live in tests/test_oracle.py.
+cross-checks (KKT conditions, the single-column case against scikit-learn's
+weighted lasso, scipy.optimize.nnls, lstsq, brute-force allocation) live in
+tests/test_oracle.py.
 
 Third-party arithmetic restated here (absent from /root/reference):
   * Eigen 3.4.0 (bundled by RcppEigen 0.3.4.x; DESCRIPTION:39 "LinkingTo: Rcpp,

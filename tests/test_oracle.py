@@ -336,3 +336,24 @@ def test_r2_removed_recycles_the_column_sums_like_r():
         assert abs((1.0 - ssq0.sum() / css.sum()) - r.r2_module[0][j]) < 1e-12
         checked += 1
     assert checked > 0
+
+
+def test_coop_lasso_single_column_is_the_weighted_lasso(rng):
+    """Independent anchor: for one response column the cooperative-lasso penalty
+    lambda * w_i * (||beta_i^+|| + ||beta_i^-||) is lambda * w_i * |beta_i|, i.e. a weighted lasso, whose optimum
+    scikit-learn's coordinate descent finds by a completely different route.  With the objective of
+    src/optim.cpp:134-176 (1/2 ||y - x beta||^2 + penalty) and columns rescaled by 1 / w_i:
+    Lasso(alpha = lambda / n) on x / w returns w * beta."""
+    from sklearn.linear_model import Lasso
+    n, p = 400, 30
+    x = rng.standard_normal((n, p)) / np.sqrt(n)
+    beta_true = np.zeros(p); beta_true[:6] = rng.standard_normal(6)
+    y = x @ beta_true + 0.3 * rng.standard_normal(n) / np.sqrt(n)
+    w = 0.5 + rng.random(p)
+    lam = 0.05
+    beta, it = orc.coop_lasso(y[:, None], x, lam, w, max_iter=100000, eps_rel=1e-12, eps_abs=1e-14)
+    sk = Lasso(alpha=lam / n, fit_intercept=False, tol=1e-14, max_iter=1000000).fit(x / w[None, :], y)
+    ref = sk.coef_ / w
+    assert it < 100000
+    assert np.max(np.abs(beta[:, 0] - ref)) < 1e-7 * max(1.0, np.max(np.abs(ref)))
+    assert np.array_equal(np.abs(beta[:, 0]) > 1e-6, np.abs(ref) > 1e-6) and 0 < np.sum(np.abs(ref) > 1e-6) < p
