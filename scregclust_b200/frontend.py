@@ -143,6 +143,7 @@ def scregclust(expression, genesymbols, is_regulator, penalization, n_modules, i
                prior_indicator=None, prior_genesymbols=None, prior_baseline=1e-6, prior_weight=0.5, min_module_size=0,
                noise_threshold=0.025, n_cycles=50, n_initializations=50, max_optim_iter=10000, tol_coop_rel=1e-8,
                tol_coop_abs=1e-12, tol_nnls=1e-4, compute_predictive_r2=True, compute_silhouette=False,
+               allocate_per_obs=True, use_kmeanspp_init=True, quick_mode=False, quick_mode_percent=0.1,
                update_orders=None, seed=None, device=0, session_factory=None):
     """``scregclust(expression, genesymbols, is_regulator, penalization, n_modules, ...)`` of the reference.
 
@@ -157,6 +158,15 @@ def scregclust(expression, genesymbols, is_regulator, penalization, n_modules, i
     ex, isr, pen = _validate(expression, genesymbols, is_regulator, penalization, n_modules, initial_target_modules,
                              sample_assignment, split1_proportion, total_proportion, split_indices, noise_threshold,
                              n_cycles, min_module_size, prior_weight)
+    if not isinstance(quick_mode, (bool, np.bool_)):
+        _abort("quick_mode needs to be TRUE or FALSE.")                                  # R/scregclust.R:796-806
+    if quick_mode and not allocate_per_obs:
+        _abort("quick_mode only available when allocate_per_obs is TRUE.")               # :809-817
+    if quick_mode and not (0 <= float(quick_mode_percent) < 1):
+        _abort("quick_mode_percent needs to be numeric in [0, 1).")                      # :819-831
+    if quick_mode or not allocate_per_obs:
+        # the session path implements allocate_per_obs = TRUE, quick_mode = FALSE (DESIGN.md sections 7-8)
+        raise NotImplementedError("quick_mode = TRUE and allocate_per_obs = FALSE are not built in this library")
     rng = np.random.default_rng(seed)
     p, n = ex.shape
     genesymbols = np.asarray(genesymbols)

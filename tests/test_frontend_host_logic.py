@@ -166,3 +166,18 @@ def test_frontend_accepts_the_prior_matrix_form():
     out = fit["results"][0]["output"][0]
     assert out["silhouette"].shape == (len(fit["initial_target_modules"]),)
     assert out["r2_cross_module_per_target"] is out["r2"]
+
+
+def test_unsupported_modes_fail_loudly():
+    from scregclust_b200.frontend import ScregclustError, scregclust
+    expression, genesymbols, is_regulator, split = _constant_genes_case()
+    args = dict(expression=expression, genesymbols=genesymbols, is_regulator=is_regulator, penalization=0.1,
+                n_modules=2, split_indices=split, session_factory=OracleExpressionSession)
+    with pytest.raises(NotImplementedError):
+        scregclust(quick_mode=True, **args)
+    with pytest.raises(NotImplementedError):
+        scregclust(allocate_per_obs=False, **args)
+    with pytest.raises(ScregclustError, match="quick_mode only available"):
+        scregclust(quick_mode=True, allocate_per_obs=False, **args)
+    with pytest.raises(ScregclustError, match="quick_mode_percent"):
+        scregclust(quick_mode=True, quick_mode_percent=1.5, **args)
