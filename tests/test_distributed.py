@@ -87,3 +87,43 @@ def test_dynamic_counter_and_merge_world2(tmp_path):
     assert np.array_equal(a, np.repeat(np.arange(1, 8, dtype=np.int32)[:, None], 5, axis=1))   # every value fitted once
     m0 = set(np.load(tmp_path / "mine0.npy").tolist()); m1 = set(np.load(tmp_path / "mine1.npy").tolist())
     assert not (m0 & m1) and (m0 | m1) == set(range(7))
+
+
+def _worker_driver(rank, world, port, out):
+    """The multi-rank flow of bench.py on CPU: each rank runs the REAL driver loop (scregclust_fit with a shared
+    atomic counter and 1 value in flight), with the device session replaced by the oracle-backed one."""
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    from scregclust_b200 import parallel
+    from scregclust_b200.driver import scregclust_fit
+    from scregclust_b200.synthetic import make_workload
+    from test_driver_host_logic import OracleSession
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    store = dist.TCPStore("127.0.0.1", port + 23, world, rank == 0, wait_for_workers=True)
+    w = make_workload("tiny", seed=3, penalization=[0.1, 0.15, 0.2, 0.3])
+    counter = parallel.GridCounter(len(w.penalization), store, key="scrc_next_1")
+    res = scregclust_fit(penalization=w.penalization, n_modules=w.n_modules, initial_target_modules=w.k_init,
+                         session=OracleSession(w), claim=counter, concurrency=1, min_module_size=2)
+    mine = {i: r.k_final[0] for i, r in enumerate(res) if r is not None}
+    table = parallel.merge_assignments(mine, len(w.penalization), w.z1_target.shape[1], world)
+    np.save(os.path.join(out, f"drv{rank}.npy"), table)
+    np.save(os.path.join(out, f"drvmine{rank}.npy"), np.array(sorted(mine), dtype=np.int64))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_driver_with_dynamic_claiming_world2(tmp_path):
+    import torch.multiprocessing as mp
+    from oracle import scregclust_oracle as orc
+    from scregclust_b200.synthetic import make_workload
+    port = _free_port()
+    mp.spawn(_worker_driver, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    a = np.load(tmp_path / "drv0.npy"); b = np.load(tmp_path / "drv1.npy")
+    assert np.array_equal(a, b)                                   # every rank ends with the whole table
+    m0 = set(np.load(tmp_path / "drvmine0.npy").tolist()); m1 = set(np.load(tmp_path / "drvmine1.npy").tolist())
+    assert not (m0 & m1) and (m0 | m1) == set(range(4))           # every value fitted exactly once
+    w = make_workload("tiny", seed=3, penalization=[0.1, 0.15, 0.2, 0.3])
+    ref = orc.scregclust_fit(w.z1_reg, w.z2_reg, w.z1_target, w.z2_target, w.z1_target_sds, w.penalization,
+                             w.n_modules, w.k_init, min_module_size=2)
+    assert np.array_equal(a, np.stack([r.k_final[0] for r in ref]))   # and the fits do not depend on who ran them
