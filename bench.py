@@ -256,6 +256,9 @@ def main():
                           f"{n_modules} modules, {len(pens)}-value penalty grid (seed {args.seed})",
               "n1": n_cells // 2, "n2": n_cells - n_cells // 2, "targets": n_targets, "regulators": n_reg,
               "modules": n_modules, "penalties": [float(p) for p in pens],
+              "baseline_config": {"config1": "BASELINE.json configs[0] (synthetic stand-in of the same shape)",
+                                  "config2": "BASELINE.json configs[1]", "config3": "BASELINE.json configs[2]",
+                                  "config4": "BASELINE.json configs[3]"}.get(args.workload, "test-sized workload"),
               "parallelism": (f"penalization values claimed dynamically from a shared counter by {world} GPUs, "
                                f"{in_flight(len(pens), world)} in flight per GPU"
                               if world > 1 else "whole penalty grid advanced in lock-step on 1 GPU"),
