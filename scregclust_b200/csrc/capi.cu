@@ -67,7 +67,7 @@ extern "C" {
 
 int scrc_version(void) { return 100; }
 const char* scrc_last_error(void) { return g_err.c_str(); }
-unsigned long long scrc_launch_count(void) { return scrc::g_launch_count; }
+unsigned long long scrc_launch_count(void) { return scrc::g_launch_count.load(); }
 int scrc_set_device(int device) {
     if (device < 0) return fail(SCRC_ERR_ARG, "scrc_set_device: negative device index");
     g_dev_id = device;

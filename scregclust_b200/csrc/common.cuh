@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -33,8 +34,8 @@ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // Count of kernels of this library launched by the calling thread's process
 // (reported as `gpu_launches` by bench.py).
-extern unsigned long long g_launch_count;
-#define SCRC_LAUNCHED() (++::scrc::g_launch_count)
+extern std::atomic<unsigned long long> g_launch_count;
+#define SCRC_LAUNCHED() (::scrc::g_launch_count.fetch_add(1ull, std::memory_order_relaxed))
 
 // ----------------------------------------------------------------------------
 // Device buffer (RAII)

@@ -7,7 +7,7 @@
 
 namespace scrc {
 
-unsigned long long g_launch_count = 0;
+std::atomic<unsigned long long> g_launch_count{0ull};
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                     const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,

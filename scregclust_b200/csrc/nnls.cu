@@ -45,11 +45,13 @@ __global__ void __launch_bounds__(256) nnls_setup_q_kernel(NnlsDev d, const doub
 // grad0 = (-(S X'Y colscale)) * d   (optim.cpp:421)
 __global__ void __launch_bounds__(256) nnls_setup_grad_kernel(NnlsDev d, const double* __restrict__ xty,
                                                               int64_t ldy, const double* __restrict__ colscale) {
-    const NnlsProblem pr = d.prob[blockIdx.y];
+    // 1-D grid (problem-major): gridDim.y is capped at 65535, the importance step can exceed that
+    const int chunks = (d.m + 31) / 32;
+    const NnlsProblem pr = d.prob[blockIdx.x / chunks];
     const int s = pr.s;
     const int* sel = d.sel + pr.sel_off;
     const double* sg = d.sign + pr.sel_off;
-    const int col0 = blockIdx.x * 32;
+    const int col0 = (blockIdx.x % chunks) * 32;
     const int ncols = pr.ncols < 0 ? d.m : pr.ncols;
     for (int e = threadIdx.x; e < s * 32; e += blockDim.x) {
         const int a = e % s, col = col0 + e / s;
@@ -68,8 +70,9 @@ void nnls_setup(NnlsBatch& b, const double* xtx, int64_t ldx, const double* xty,
               b.beta.data(), b.beta.ld, b.iters.p, b.m};
     nnls_setup_q_kernel<<<b.nprob, 256, 0, st>>>(d, xtx, ldx);
     SCRC_LAUNCHED();
-    dim3 grid((unsigned)ceil_div(b.m, 32), b.nprob);
-    nnls_setup_grad_kernel<<<grid, 256, 0, st>>>(d, xty, ldy, colscale);
+    const int64_t gblocks = ceil_div(b.m, 32) * (int64_t)b.nprob;
+    if (gblocks > 0x7fffffffLL) throw Error(-72, "NNLS: too many (problem, column chunk) pairs in one batch");
+    nnls_setup_grad_kernel<<<(unsigned)gblocks, 256, 0, st>>>(d, xty, ldy, colscale);
     SCRC_LAUNCHED();
     SCRC_CUDA(cudaGetLastError());
 }
@@ -141,10 +144,12 @@ __device__ __forceinline__ bool alpha_ok(double a) {
 }
 
 template <bool QSMEM>
-__global__ void nnls_kernel(NnlsDev d, const int* __restrict__ prob_ids, int cols_per_cta, double eps,
+__global__ void nnls_kernel(NnlsDev d, const int* __restrict__ prob_ids, int cols_per_cta, int chunks, double eps,
                             int max_iter, const double* __restrict__ out_scale, int n_out_scale) {
     extern __shared__ double sm[];
-    const int pid = prob_ids[blockIdx.y];
+    // 1-D grid (problem-major) -- gridDim.y would cap the batch at 65535 problems
+    const int pid = prob_ids[blockIdx.x / chunks];
+    const int chunk = blockIdx.x % chunks;
     const NnlsProblem pr = d.prob[pid];
     const int s = pr.s;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -159,12 +164,12 @@ __global__ void nnls_kernel(NnlsDev d, const int* __restrict__ prob_ids, int col
            *tmp = vec + 5 * s;
     const double* sg = d.sign + pr.sel_off;
     const int ncols = pr.ncols < 0 ? d.m : pr.ncols;
-    const int col_end = min((int)((blockIdx.x + 1) * cols_per_cta), ncols);
+    const int col_end = min((chunk + 1) * cols_per_cta, ncols);
     const double* oscale = out_scale ? out_scale + pr.scale_off : nullptr;
     const int oscale_len = pr.scale_len > 0 ? pr.scale_len : n_out_scale;
     const int* opos = pr.pos_off < 0 ? nullptr : d.pos + pr.pos_off;
 
-    for (int col = blockIdx.x * cols_per_cta + warp; col < col_end; col += nwarps) {
+    for (int col = chunk * cols_per_cta + warp; col < col_end; col += nwarps) {
         const double* g0 = d.grad0 + pr.row_off + (int64_t)col * d.ldg;
         for (int a = lane; a < s; a += 32) {
             const double g = g0[a];
@@ -271,14 +276,19 @@ void nnls_solve(NnlsBatch& b, double eps, int max_iter, const double* out_scale,
                                   cudaMemcpyHostToDevice, st));
     const int cols_per_cta = 64;
     const unsigned chunks = (unsigned)ceil_div(b.m, cols_per_cta);
+    auto grid1d = [&](size_t nids) {
+        const uint64_t g = (uint64_t)chunks * nids;
+        if (g > 0x7fffffffULL) throw Error(-72, "NNLS: too many (problem, column chunk) pairs in one batch");
+        return (unsigned)g;
+    };
     ProfScope pscope(PROF_NNLS, st);
     if (!small_ids.empty()) {
         const int warps = 8;
         const size_t smem = ((size_t)smax_small * smax_small + (size_t)warps * 6 * smax_small) * 8;
         static SmemAttr attr;
         attr.ensure(nnls_kernel<true>, smem);
-        nnls_kernel<true><<<dim3(chunks, (unsigned)small_ids.size()), warps * 32, smem, st>>>(
-            d, ids.p, cols_per_cta, eps, max_iter, out_scale, n_out_scale);
+        nnls_kernel<true><<<grid1d(small_ids.size()), warps * 32, smem, st>>>(
+            d, ids.p, cols_per_cta, (int)chunks, eps, max_iter, out_scale, n_out_scale);
         SCRC_LAUNCHED();
     }
     if (!large_ids.empty()) {
@@ -287,8 +297,8 @@ void nnls_solve(NnlsBatch& b, double eps, int max_iter, const double* out_scale,
         const size_t smem = (size_t)warps * 6 * smax_large * 8;
         static SmemAttr attr;
         attr.ensure(nnls_kernel<false>, smem);
-        nnls_kernel<false><<<dim3(chunks, (unsigned)large_ids.size()), warps * 32, smem, st>>>(
-            d, ids.p + small_ids.size(), cols_per_cta, eps, max_iter, out_scale, n_out_scale);
+        nnls_kernel<false><<<grid1d(large_ids.size()), warps * 32, smem, st>>>(
+            d, ids.p + small_ids.size(), cols_per_cta, (int)chunks, eps, max_iter, out_scale, n_out_scale);
         SCRC_LAUNCHED();
     }
     SCRC_CUDA(cudaGetLastError());

@@ -2,7 +2,7 @@
 
 namespace scrc {
 
-Profiler g_prof;
+thread_local Profiler g_prof;
 
 cudaEvent_t Profiler::get_event() {
     if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
@@ -13,14 +13,23 @@ cudaEvent_t Profiler::get_event() {
 void Profiler::begin(int cls, cudaStream_t s) {
     Rec r{cls, get_event(), get_event()};
     SCRC_CUDA(cudaEventRecord(r.e0, s));
+    if (pending.size() >= 4096) collect();
     pending.push_back(r);
     launches[cls] += 1;
 }
-void Profiler::end(cudaStream_t s) {
-    SCRC_CUDA(cudaEventRecord(pending.back().e1, s));
-    if (pending.size() >= 4096) collect();
+void Profiler::end(cudaStream_t s) noexcept {
+    // scopes are never nested: the record opened by the matching begin() is the last one
+    if (pending.empty()) return;
+    const cudaError_t e = cudaEventRecord(pending.back().e1, s);
+    if (e != cudaSuccess && deferred_error == cudaSuccess) deferred_error = e;
 }
 void Profiler::collect() {
+    if (deferred_error != cudaSuccess) {
+        const cudaError_t e = deferred_error;
+        deferred_error = cudaSuccess;
+        pending.clear();
+        SCRC_CUDA(e);
+    }
     for (Rec& r : pending) {
         SCRC_CUDA(cudaEventSynchronize(r.e1));
         float t = 0.f;

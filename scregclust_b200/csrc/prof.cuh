@@ -28,12 +28,14 @@ struct Profiler {
 
     cudaEvent_t get_event();
     void begin(int cls, cudaStream_t s);
-    void end(cudaStream_t s);
+    void end(cudaStream_t s) noexcept;        // called from ~ProfScope: records the error instead of throwing
+    cudaError_t deferred_error = cudaSuccess; // first failure seen by end(); rethrown by collect()
     void add_work(int cls, double w) { if (enabled) work[cls] += w; }
     void collect();                           // synchronises and folds pending records into ms[]
     void reset();
 };
-extern Profiler g_prof;
+// One profiler per host thread: in thread-per-device mode every worker times its own stream.
+extern thread_local Profiler g_prof;
 
 struct ProfScope {
     cudaStream_t s;
@@ -42,6 +44,8 @@ struct ProfScope {
         if (on) { g_prof.begin(cls, s); g_prof.work[cls] += w; }
     }
     ~ProfScope() { if (on) g_prof.end(s); }
+    ProfScope(const ProfScope&) = delete;
+    ProfScope& operator=(const ProfScope&) = delete;
 };
 
 }  // namespace scrc

@@ -14,8 +14,11 @@ void Device::init(int device) {
     SCRC_CUDA(cudaSetDevice(id));
     cudaDeviceProp prop;
     SCRC_CUDA(cudaGetDeviceProperties(&prop, id));
-    if (prop.major < 10)
-        throw Error(SCRC_ERR_UNSUPPORTED, "libscregclust_b200 requires an sm_100a (Blackwell B200) device");
+    // the library is built for sm_100a only (arch-specific code, not forward compatible to sm_103 / sm_110 / sm_12x)
+    if (!(prop.major == 10 && prop.minor == 0))
+        throw Error(SCRC_ERR_UNSUPPORTED, std::string("libscregclust_b200 is built for sm_100a (B200) only; device ") +
+                                              std::to_string(device) + " is sm_" + std::to_string(prop.major) +
+                                              std::to_string(prop.minor));
     num_sms = prop.multiProcessorCount;
     if (!stream) SCRC_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     if (!h_pinned) SCRC_CUDA(cudaMallocHost(&h_pinned, 64 * sizeof(int)));
@@ -242,6 +245,30 @@ __global__ void fill_nan_kernel(double* x, int64_t n) {
     if (i < n) x[i] = nan("");
 }
 
+// The reference documents these as assumptions (allocation.cpp:4-6); on a public C ABI they are checked,
+// because the sequential sweep indexes shared and global memory with them.
+void validate_prior_inputs(const char* who, const int* k, int64_t T, int K, const int* prior_off, const int* prior_idx,
+                           const int* order) {
+    auto bad = [&](const std::string& what) { throw Error(SCRC_ERR_ARG, std::string(who) + ": " + what); };
+    for (int64_t t = 0; t < T; ++t)
+        if (!(k[t] == -1 || (k[t] >= 1 && k[t] <= K))) bad("module ids must be -1 (noise) or in 1..K");
+    if (order) {
+        std::vector<unsigned char> seen(T, 0);
+        for (int64_t t = 0; t < T; ++t) {
+            if (order[t] < 0 || order[t] >= T || seen[order[t]]) bad("update_order must be a permutation of 0..T-1");
+            seen[order[t]] = 1;
+        }
+    }
+    if (prior_off) {
+        if (prior_off[0] != 0) bad("prior_off[0] must be 0");
+        for (int64_t t = 0; t < T; ++t)
+            if (prior_off[t + 1] < prior_off[t]) bad("prior_off must be non-decreasing");
+        if (prior_off[T] > 0 && !prior_idx) bad("prior_idx is missing");
+        for (int e = 0; e < prior_off[T]; ++e)
+            if (prior_idx[e] < 0 || prior_idx[e] >= T) bad("prior_idx entries must be in 0..T-1");
+    }
+}
+
 // ============================================================================ one batched cycle
 void Ctx::fit_cycle(int F, const double* lambda, const int* k_in, const scrc_options& opt, bool skip_alloc,
                     scrc_cycle_out* out, const scrc_prior* prior) {
@@ -249,6 +276,11 @@ void Ctx::fit_cycle(int F, const double* lambda, const int* k_in, const scrc_opt
     if (use_prior && (!prior->update_order || !prior->prior_off))
         throw Error(SCRC_ERR_ARG, "scrc_fit_cycle_prior: prior_off and update_order are required when prior_weight != 0");
     if (F <= 0) throw Error(SCRC_ERR_ARG, "scrc_fit_cycle: F must be positive");
+    if ((int64_t)F * K > 65535) throw Error(SCRC_ERR_UNSUPPORTED, "scrc_fit_cycle: more than 65535 (fit, module) pairs in one call");
+    if (use_prior)
+        for (int f = 0; f < F; ++f)
+            validate_prior_inputs("scrc_fit_cycle_prior", k_in + (int64_t)f * T, T, K, f == 0 ? prior->prior_off : nullptr,
+                                  prior->prior_idx, prior->update_order + (int64_t)f * T);
     SCRC_CUDA(cudaSetDevice(dev.id));
     cudaStream_t st = dev.stream;
     const int64_t FK = (int64_t)F * K;
@@ -834,6 +866,7 @@ void dropin_allocate(Device& dev, const double* sq_resid, int K, int64_t n2, int
                      double weight, int* k_out, int* votes_out) {
     cudaStream_t st = dev.stream;
     if (K > RV_MAX_K) throw Error(SCRC_ERR_UNSUPPORTED, "allocate_into_modules: at most 64 modules are supported");
+    if (weight != 0.0) validate_prior_inputs("allocate_into_modules", k_in, T, K, prior_off, prior_idx, order);
     DevBuf<double> d_var((size_t)T * K);
     SCRC_CUDA(cudaMemcpyAsync(d_var.p, resid_var, (size_t)T * K * 8, cudaMemcpyHostToDevice, st));
     DevBuf<int> d_k(T), d_votes(votes_out ? (size_t)T * K : 0);

@@ -85,6 +85,10 @@ struct Ctx {
     ~Ctx() { dev.destroy(); }
 };
 
+// O(T + nnz) host checks of caller data that index device memory in the network-prior sweep; throws SCRC_ERR_ARG.
+void validate_prior_inputs(const char* who, const int* k, int64_t T, int K, const int* prior_off, const int* prior_idx,
+                           const int* order);
+
 // drop-in helpers (session.cu)
 void dropin_coop_lasso(Device& dev, const double* y, int64_t n, int64_t m, const double* x, int64_t p, double lambda,
                        const double* weights, const double* beta0, const AdmmOpts& o, double* beta_out, int* iters);
