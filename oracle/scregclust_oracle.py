@@ -410,6 +410,14 @@ def reset_array(arr: np.ndarray, inp: np.ndarray) -> None:
 # --------------------------------------------------------------------------- #
 # src/allocation.cpp:8-100
 # --------------------------------------------------------------------------- #
+# Relative score gap below which a cell's argmax over two structurally distinct modules counts as
+# decided by rounding noise.  Calibrated on what was measured, not on convenience: predictions of the
+# CUDA path agree with this oracle to 3e-15 relative and the Gram-form training SSE (hence sigma^2, which
+# scales the whole score) to 1e-14, so score differences between implementations stay below ~1e-13;
+# 1e-12 leaves one order of magnitude and is three orders tighter than round 1's 1e-9.
+AMBIGUITY_REL = 1e-12
+
+
 def allocate_into_modules(resid_array, resid_var, prior_indicator, k_, update_order,
                           prior_baseline, prior_weight, return_votes=False, ambiguity=None,
                           distinct=None):
@@ -421,7 +429,7 @@ def allocate_into_modules(resid_array, resid_var, prior_indicator, k_, update_or
     ``ambiguity`` (optional int array of length T, filled in place) receives, per gene, the
     number of cells whose two best scores -- over structurally distinct modules, ``distinct`` being
     a boolean mask that keeps one representative of every group of modules with identical
-    regulator sets and signs -- agree to 1e-9 relative, i.e. cells whose vote is decided by
+    regulator sets and signs -- agree to ``AMBIGUITY_REL`` relative, i.e. cells whose vote is decided by
     rounding noise.  (Modules with different regulator sets can predict a gene identically when
     its coefficients live on the shared regulators; whether such a tie is exact or off by one ulp
     depends on the summation order of the BLAS / tensor-core kernel.  Structurally identical
@@ -455,7 +463,7 @@ def allocate_into_modules(resid_array, resid_var, prior_indicator, k_, update_or
             if nd > 1:
                 part = np.partition(sc, nd - 2, axis=0)
                 top1 = part[nd - 1]; top2 = part[nd - 2]
-                ambiguity[j] = int(np.sum((top1 - top2) <= 1e-9 * np.maximum(1.0, np.abs(top1))))
+                ambiguity[j] = int(np.sum((top1 - top2) <= AMBIGUITY_REL * np.maximum(1.0, np.abs(top1))))
         votes = np.bincount(best_per_cell, minlength=n_modules).astype(np.int32)
         best = int(np.argmax(votes))                        # first max
         if return_votes:

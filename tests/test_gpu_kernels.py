@@ -64,7 +64,7 @@ def test_coef_ols_ridge(api, rng):
     assert rel_err(api.coef_ridge(y, x, 3.5), orc.coef_ridge(y, x, 3.5)) < 1e-9
     # n < p: Moore-Penrose branch (R/utils.R:20-30)
     x2 = rng.standard_normal((30, 50)); y2 = rng.standard_normal((30, 4))
-    assert rel_err(api.coef_ols(y2, x2), orc.coef_ols(y2, x2)) < 1e-7
+    assert rel_err(api.coef_ols(y2, x2), orc.coef_ols(y2, x2)) < 1e-8
 
 
 def _coop_case(rng, n, p, m, lam):

@@ -7,7 +7,8 @@ first cycles, where modules still share their regulators), the per-cell argmax o
 allocation.cpp:80-85 is decided by rounding noise of whatever BLAS computed the residuals --
 in the reference as much as here -- and different hosts give different votes for those cells.
 The oracle therefore reports, per gene, how many cells had a non-zero top-2 score gap below
-1e-9 relative (``ambiguity``).  Votes must agree exactly up to that many cells, and module
+``orc.AMBIGUITY_REL`` = 1e-12 relative (``ambiguity``; calibrated on the measured 3e-15 / 1e-14 agreement of
+predictions / variances, see oracle/scregclust_oracle.py).  Votes must agree exactly up to that many cells, and module
 assignments must agree exactly whenever the vote margin exceeds it.  Exact ties (identical
 models) are resolved by first index on both sides and are compared bit-exactly.
 """
@@ -20,7 +21,20 @@ from scregclust_b200.synthetic import make_workload
 
 pytestmark = pytest.mark.gpu
 
-CASES = [("tiny", 0, 0.0), ("tiny", 1, 0.5), ("tiny", 3, 0.0), ("small", 0, 0.0), ("small", 2, 0.5), ("small", 3, 0.0)]
+CASES = [("tiny", 0, 0.0), ("tiny", 1, 0.5), ("tiny", 3, 0.0), ("small", 0, 0.0), ("small", 2, 0.5), ("small", 3, 0.0),
+         ("small", 4, 0.9)]   # ar1 = 0.9: ill-conditioned Gram (eigenbasis solve vs the oracle's LDL^T)
+
+
+def _record(kind, entry):
+    """Appends one line to gpurun_out/parity_report.jsonl (brought back from the GPU box; summarised in profiles/)."""
+    import json, os
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    try:
+        os.makedirs(d, exist_ok=True)
+        with open(os.path.join(d, "parity_report.jsonl"), "a") as fh:
+            fh.write(json.dumps(dict(kind=kind, **entry)) + "\n")
+    except OSError:
+        pass
 
 
 def _check_votes(tag, vg, vr, amb, k_new_gpu):
@@ -70,6 +84,8 @@ def test_cycle_parity_teacher_forced(name, seed, ar1):
                         assert cg.shape == cr.shape and np.max(np.abs(cg - cr)) < 1e-8 * max(1.0, np.max(np.abs(cr))), tag
                 moved_total += _check_votes(tag, res["votes"][f], r.votes[c], r.ambiguity[c], res["k_new"][f])
     print(f"{name}/{seed}: cells whose vote was decided by rounding noise and differed: {moved_total}")
+    _record("teacher_forced", dict(case=f"{name}/{seed}/ar1={ar1}", cycles=int(max_cycles), cells_moved=int(moved_total),
+                                   noise_decided_cells=int(sum(int(a.sum()) for r in ref for a in r.ambiguity))))
 
 
 def _first_divergence(g, r):
@@ -93,6 +109,14 @@ def test_loop_free_running(name, seed, ar1):
                          w.n_modules, w.k_init, min_module_size=2, keep_diagnostics=True)
     tol = 1e-8
     identical = 0
+    # penalties whose oracle trajectory contains at least one gene whose assignment rounding noise could decide
+    decidable = 0
+    for r in ref:
+        flag = False
+        for v, a in zip(r.votes, r.ambiguity):
+            sv = np.sort(v, axis=1)
+            flag |= bool(np.any((a > 0) & (sv[:, -1] - sv[:, -2] <= 2 * a)))
+        decidable += int(flag)
     for g, r in zip(got, ref):
         c, genes = _first_divergence(g, r)
         if c is not None:
@@ -130,8 +154,13 @@ def test_loop_free_running(name, seed, ar1):
                 assert (cg is None) == (cr is None)
                 if cg is not None:
                     assert cg.shape == cr.shape and np.max(np.abs(cg - cr)) < tol * max(1.0, np.max(np.abs(cr)))
-    print(f"{name}/{seed}: {identical}/{len(ref)} penalties with trajectories identical to the oracle")
-    assert identical >= 1
+    amb_cells = int(sum(int(a.sum()) for r in ref for a in r.ambiguity))
+    print(f"{name}/{seed}: {identical}/{len(ref)} penalties with trajectories identical to the oracle; "
+          f"{decidable} penalties contain a gene rounding noise could decide ({amb_cells} noise-decided cells in all)")
+    _record("loop_free_running", dict(case=f"{name}/{seed}/ar1={ar1}", penalties=len(ref), identical=identical,
+                                      noise_decidable_penalties=decidable, noise_decided_cells=amb_cells))
+    # every penalty the oracle does not flag must be identical (a divergence anywhere else already failed above)
+    assert identical >= len(ref) - decidable
 
 
 def test_session_precompute():
@@ -158,8 +187,8 @@ def test_session_ridge_init_when_few_cells():
     with Session(w.z1_reg, w.z2_reg, w.z1_target, w.z2_target, w.z1_target_sds, w.n_modules) as s:
         init = s.initial_fit()
         assert abs(init["init_df"] - pre["init_df"]) < 1e-8 * pre["init_df"]
-        assert rel_err(init["beta_init"], pre["beta_init"]) < 1e-7
-        assert rel_err(init["res_sds"], pre["res_sds"]) < 1e-7
+        assert rel_err(init["beta_init"], pre["beta_init"]) < 1e-8
+        assert rel_err(init["res_sds"], pre["res_sds"]) < 1e-8
 
 
 def test_empty_and_noise_modules():
@@ -265,7 +294,7 @@ def test_importance_matches_oracle(name, seed):
         assert np.array_equal(np.isnan(r2m[f]), np.isnan(r.r2_module[0]))
         assert np.allclose(r2m[f], r.r2_module[0], rtol=1e-8, atol=1e-10, equal_nan=True)
         assert np.array_equal(np.isnan(imp[f].T), np.isnan(r.importance[0]))
-        assert np.allclose(imp[f].T, r.importance[0], rtol=1e-7, atol=1e-9, equal_nan=True)
+        assert np.allclose(imp[f].T, r.importance[0], rtol=1e-8, atol=1e-9, equal_nan=True)
         # per-target matrices incl. the reference's recycling of the column sums (scregclust.R:1890-1896)
         for j in range(K):
             a, b = removed[f][j], r.r2_removed[0][j]
@@ -285,7 +314,7 @@ def test_driver_importance_end_to_end():
                          w.n_modules, w.k_init, compute_predictive_r2=True)
     for g, r in zip(got, ref):
         assert np.allclose(g.r2_module[0], r.r2_module[0], rtol=1e-8, atol=1e-10, equal_nan=True)
-        assert np.allclose(g.importance[0], r.importance[0], rtol=1e-7, atol=1e-9, equal_nan=True)
+        assert np.allclose(g.importance[0], r.importance[0], rtol=1e-8, atol=1e-9, equal_nan=True)
         for a, b in zip(g.r2_removed[0], r.r2_removed[0]):
             assert (a is None) == (b is None)
             if a is not None:
@@ -390,4 +419,4 @@ def test_loop_matches_golden_trajectory():
         assert np.array_equal(r.models[0], g[f"models_{i}"])
         assert rel_err(r.r2[0], g[f"r2_{i}"]) < 1e-8
         assert rel_err(r.sigmas[0], g[f"sigmas_{i}"]) < 1e-8
-        assert np.allclose(r.importance[0], g[f"importance_{i}"], rtol=1e-7, atol=1e-9, equal_nan=True)
+        assert np.allclose(r.importance[0], g[f"importance_{i}"], rtol=1e-8, atol=1e-9, equal_nan=True)
