@@ -11,6 +11,7 @@ struct RvParams {
     CUtensorMap ta, tb;
     const double* Z; int64_t ldz;
     int ncells, T, K, L;
+    int t_begin, t_end;  // target slice of this rank (tiles are counted from t_begin)
     const int* row_off;
     const int* kpad;
     const int* nsel;     // optional: rows of each block that are not zero padding
@@ -62,8 +63,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) resid_vote_kernel(const __gri
     const int w = blockIdx.x;
     const int tn = w % p.tiles_n, cr = (w / p.tiles_n) % p.CR, l = w / (p.tiles_n * p.CR);
     const int ct0 = cr * ct_per, ct1 = min(ct0 + ct_per, p.ctiles);
-    const int ncol = p.col_cnt ? p.col_cnt[l] : p.T;      // columns of this fit
-    if (tn * RV_BN >= ncol) return;                       // whole CTA: nothing to do for this tile
+    const int ncol = p.col_cnt ? p.col_cnt[l] : p.t_end;  // one past the last column of this fit (slice)
+    if (p.t_begin + tn * RV_BN >= ncol) return;           // whole CTA: nothing to do for this tile
     const int* cidx = p.col_index ? p.col_index + p.col_off[l] : nullptr;
     PipeState ps;
 
@@ -81,7 +82,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) resid_vote_kernel(const __gri
                             uint8_t* sa = smem + ps.stage * RV_STAGE_BYTES;
                             mbar_expect_tx(&full[ps.stage], RV_STAGE_BYTES);
                             tma_load_2d(sa, &p.ta, ro + kk, ct * RV_BM, &full[ps.stage]);
-                            tma_load_2d(sa + RV_A_BYTES, &p.tb, rob + kk, tn * RV_BN, &full[ps.stage]);
+                            tma_load_2d(sa + RV_A_BYTES, &p.tb, rob + kk, p.t_begin + tn * RV_BN, &full[ps.stage]);
                             ps.advance<RV_STAGES>();
                         }
                     }
@@ -102,7 +103,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) resid_vote_kernel(const __gri
     const int r = lane >> 2, q = lane & 3;
 
     {
-        const int t0 = tn * RV_BN;
+        const int t0 = p.t_begin + tn * RV_BN;
         // zero the per-work-item accumulators (each SSE entry is owned by exactly one thread)
         if (r == 0) {
             for (int j = 0; j < K1; ++j)
@@ -321,7 +322,10 @@ void resid_vote(const ResidVoteArgs& a, int mode, int num_sms, cudaStream_t st) 
     p.sq_out = a.sq_out;
     if (mode == 1 && !a.inv_two_var) throw Error(-63, "resid_vote: vote mode needs the reciprocal table");
     if (mode == 2 && (a.L != 1 || !a.sq_out)) throw Error(-62, "resid_vote: store mode handles one fit per launch");
-    p.tiles_n = (int)ceil_div(a.T, RV_BN); p.ctiles = (int)ceil_div(a.ncells, RV_BM);
+    p.t_begin = a.t_begin; p.t_end = a.t_end < 0 ? a.T : a.t_end;
+    if (p.t_begin < 0 || p.t_end > a.T || p.t_begin > p.t_end) throw Error(-64, "resid_vote: target slice out of range");
+    if (p.t_begin == p.t_end) return;
+    p.tiles_n = (int)ceil_div(p.t_end - p.t_begin, RV_BN); p.ctiles = (int)ceil_div(a.ncells, RV_BM);
 
     const int smem = RV_STAGES * RV_STAGE_BYTES + 2 * RV_STAGES * 8 + 2 * (a.K + 1) * RV_BN * 8 +
                      RV_BN * a.K * 4;
@@ -336,7 +340,8 @@ void resid_vote(const ResidVoteArgs& a, int mode, int num_sms, cudaStream_t st) 
     {
         // algorithmic bytes: the target tile is read once per (fit, target tile, cell tile); the
         // gathered regulators and coefficients once per module slice
-        const double bytes = 8.0 * (double)a.L * a.ncells * a.T + 8.0 * (double)a.rows_total * (a.ncells * (double)p.tiles_n + (double)a.T * p.ctiles);
+        const double Ts = (double)(p.t_end - p.t_begin);
+        const double bytes = 8.0 * (double)a.L * a.ncells * Ts + 8.0 * (double)a.rows_total * (a.ncells * (double)p.tiles_n + Ts * p.ctiles);
         ProfScope ps(PROF_RESID_VOTE, st, bytes);
         if (mode == 1) resid_vote_kernel<1><<<grid, GEMM_THREADS, smem, st>>>(p);
         else if (mode == 2) resid_vote_kernel<2><<<grid, GEMM_THREADS, smem, st>>>(p);
@@ -347,19 +352,22 @@ void resid_vote(const ResidVoteArgs& a, int mode, int num_sms, cudaStream_t st) 
 }
 
 // ---------------------------------------------------------------- reductions / finishing kernels
-__global__ void reduce_sse_kernel(const double* __restrict__ partial, int T, int K1, int L, int CR, double* sse) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // over L*K1*T
-    if (i >= (int64_t)L * K1 * T) return;
-    const int t = (int)(i % T);
-    const int j = (int)((i / T) % K1);
-    const int l = (int)(i / ((int64_t)T * K1));
+__global__ void reduce_sse_kernel(const double* __restrict__ partial, int T, int K1, int L, int CR, double* sse, int t0,
+                                  int Ts) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // over L*K1*Ts
+    if (i >= (int64_t)L * K1 * Ts) return;
+    const int t = t0 + (int)(i % Ts);
+    const int j = (int)((i / Ts) % K1);
+    const int l = (int)(i / ((int64_t)Ts * K1));
     double s = 0.0;
     for (int c = 0; c < CR * 2; ++c) s += partial[(((int64_t)l * CR * 2 + c) * K1 + j) * T + t];
-    sse[i] = s;
+    sse[((int64_t)l * K1 + j) * T + t] = s;
 }
-void reduce_sse(const double* partial, int T, int K, int L, int CR, double* sse, cudaStream_t st) {
-    const int64_t n = (int64_t)L * (K + 1) * T;
-    reduce_sse_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(partial, T, K + 1, L, CR, sse);
+void reduce_sse(const double* partial, int T, int K, int L, int CR, double* sse, cudaStream_t st, int t0, int t1) {
+    if (t1 < 0) t1 = T;
+    const int64_t n = (int64_t)L * (K + 1) * (t1 - t0);
+    if (n == 0) return;
+    reduce_sse_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(partial, T, K + 1, L, CR, sse, t0, t1 - t0);
     SCRC_CUDA(cudaGetLastError());
     SCRC_LAUNCHED();
 }
@@ -371,14 +379,15 @@ __global__ void __launch_bounds__(128) sse_train_gram_kernel(const double* __res
                                                              const double* __restrict__ gtt,
                                                              const double* __restrict__ beta, int64_t ldb,
                                                              const int* __restrict__ sel, const int* __restrict__ row_off,
-                                                             const int* __restrict__ nsel, int T, int K, double* sse) {
+                                                             const int* __restrict__ nsel, int T, int K, double* sse,
+                                                             int t0, int t1) {
     __shared__ double s_g[SSG_MAX_S * SSG_MAX_S];
     __shared__ int s_sel[SSG_MAX_S];
     const int fk = blockIdx.y;
     const int l = fk / K, j = fk % K;
     const int s = nsel[fk];
     const int ro = row_off[fk];
-    const int t = blockIdx.x * 128 + threadIdx.x;
+    const int t = t0 + blockIdx.x * 128 + threadIdx.x;
     const bool in_smem = s <= SSG_MAX_S;
     if (in_smem) {
         for (int a = threadIdx.x; a < s; a += 128) s_sel[a] = sel[ro + a];
@@ -386,7 +395,7 @@ __global__ void __launch_bounds__(128) sse_train_gram_kernel(const double* __res
         for (int e = threadIdx.x; e < s * s; e += 128) s_g[e] = G_rr[s_sel[e % s] + (int64_t)s_sel[e / s] * ldrr];
         __syncthreads();
     }
-    if (t >= T) return;
+    if (t >= t1) return;
     double acc = gtt[t];
     if (s > 0) {
         const double* b = beta + ro + (int64_t)t * ldb;
@@ -408,42 +417,49 @@ __global__ void __launch_bounds__(128) sse_train_gram_kernel(const double* __res
 }
 void sse_train_gram(const double* G_rr, int64_t ldrr, const double* G_rt, int64_t ldrt, const double* gtt,
                     const double* beta, int64_t ldb, const int* sel, const int* row_off, const int* nsel, int T, int K,
-                    int L, double* sse, cudaStream_t st) {
-    dim3 grid((unsigned)ceil_div(T, 128), (unsigned)(L * K));
+                    int L, double* sse, cudaStream_t st, int t0, int t1) {
+    if (t1 < 0) t1 = T;
+    if (t1 == t0) return;
+    dim3 grid((unsigned)ceil_div(t1 - t0, 128), (unsigned)(L * K));
     ProfScope ps(PROF_RESID_VOTE, st, 0.0);
-    sse_train_gram_kernel<<<grid, 128, 0, st>>>(G_rr, ldrr, G_rt, ldrt, gtt, beta, ldb, sel, row_off, nsel, T, K, sse);
+    sse_train_gram_kernel<<<grid, 128, 0, st>>>(G_rr, ldrr, G_rt, ldrt, gtt, beta, ldb, sel, row_off, nsel, T, K, sse, t0, t1);
     SCRC_CUDA(cudaGetLastError());
     SCRC_LAUNCHED();
 }
 
 __global__ void resid_var_kernel(const double* __restrict__ sse_train, const int* __restrict__ nsel, int n1, int T,
-                                 int K, int L, double* var, double* two_var, double* inv_two_var, double* half_log) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // over L*K*T
-    if (i >= (int64_t)L * K * T) return;
-    const int t = (int)(i % T);
-    const int j = (int)((i / T) % K);
-    const int l = (int)(i / ((int64_t)T * K));
+                                 int K, int L, double* var, double* two_var, double* inv_two_var, double* half_log, int t0,
+                                 int Ts) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // over L*K*Ts
+    if (i >= (int64_t)L * K * Ts) return;
+    const int t = t0 + (int)(i % Ts);
+    const int j = (int)((i / Ts) % K);
+    const int l = (int)(i / ((int64_t)Ts * K));
     const double sse = sse_train[((int64_t)l * (K + 1) + j) * T + t];
     const double v = sse / (double)(n1 - nsel[l * K + j]);             // scregclust.R:1636-1638
-    var[i] = v;
-    two_var[i] = 2.0 * v;                                               // allocation.cpp:60
-    if (inv_two_var) inv_two_var[i] = 1.0 / (2.0 * v);                  // correctly rounded (IEEE division)
-    half_log[i] = 0.5 * log((2.0 * M_PI) * v);                          // allocation.cpp:62
+    const int64_t o = ((int64_t)l * K + j) * T + t;
+    var[o] = v;
+    two_var[o] = 2.0 * v;                                               // allocation.cpp:60
+    if (inv_two_var) inv_two_var[o] = 1.0 / (2.0 * v);                  // correctly rounded (IEEE division)
+    half_log[o] = 0.5 * log((2.0 * M_PI) * v);                          // allocation.cpp:62
 }
 void make_resid_var(const double* sse_train, const int* nsel, int n1, int T, int K, int L, double* var,
-                    double* two_var, double* inv_two_var, double* half_log, cudaStream_t st) {
-    const int64_t n = (int64_t)L * K * T;
+                    double* two_var, double* inv_two_var, double* half_log, cudaStream_t st, int t0, int t1) {
+    if (t1 < 0) t1 = T;
+    const int64_t n = (int64_t)L * K * (t1 - t0);
+    if (n == 0) return;
     resid_var_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(sse_train, nsel, n1, T, K, L, var, two_var,
-                                                                 inv_two_var, half_log);
+                                                                 inv_two_var, half_log, t0, t1 - t0);
     SCRC_CUDA(cudaGetLastError());
     SCRC_LAUNCHED();
 }
 
 __global__ void finish_alloc_kernel(const double* __restrict__ sse_test, const int* __restrict__ votes, int T, int K,
-                                    int L, double* r2, double* best_r2, int* best_idx, int* k_new) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // over L*T
-    if (i >= (int64_t)L * T) return;
-    const int t = (int)(i % T), l = (int)(i / T);
+                                    int L, double* r2, double* best_r2, int* best_idx, int* k_new, int t0, int Ts) {
+    const int64_t ii = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // over L*Ts
+    if (ii >= (int64_t)L * Ts) return;
+    const int t = t0 + (int)(ii % Ts), l = (int)(ii / Ts);
+    const int64_t i = (int64_t)l * T + t;
     const double ss0 = sse_test[((int64_t)l * (K + 1) + K) * T + t];
     double br = -INFINITY; int bi = 0;
     int bv = -1, bk = 0;
@@ -461,9 +477,12 @@ __global__ void finish_alloc_kernel(const double* __restrict__ sse_test, const i
     if (votes) k_new[i] = bk + 1;
 }
 void finish_alloc(const double* sse_test, const int* votes, int T, int K, int L, double* r2, double* best_r2,
-                  int* best_idx, int* k_new, cudaStream_t st) {
-    const int64_t n = (int64_t)L * T;
-    finish_alloc_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(sse_test, votes, T, K, L, r2, best_r2, best_idx, k_new);
+                  int* best_idx, int* k_new, cudaStream_t st, int t0, int t1) {
+    if (t1 < 0) t1 = T;
+    const int64_t n = (int64_t)L * (t1 - t0);
+    if (n == 0) return;
+    finish_alloc_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(sse_test, votes, T, K, L, r2, best_r2, best_idx, k_new,
+                                                                    t0, t1 - t0);
     SCRC_CUDA(cudaGetLastError());
     SCRC_LAUNCHED();
 }

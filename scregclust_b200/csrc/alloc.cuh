@@ -35,6 +35,7 @@ struct ResidVoteArgs {
     const int* col_off = nullptr;        // device [L]: start of fit l's list in col_index
     const int* col_cnt = nullptr;        // device [L]: number of columns of fit l (<= T = columns of beta)
     double* sq_out = nullptr;            // mode 2: K x ncells x T squared residuals (module fastest, one fit)
+    int t_begin = 0, t_end = -1;         // target slice [t_begin, t_end) handled by this launch (-1: T)
 };
 int resid_vote_pick_cr(int ncells, int T, int L, int num_sms);
 size_t resid_vote_partial_elems(int T, int K, int L, int CR);
@@ -42,7 +43,7 @@ size_t resid_vote_partial_elems(int T, int K, int L, int CR);
 void resid_vote(const ResidVoteArgs& a, int mode, int num_sms, cudaStream_t s);
 
 // sse[l][j][t] (j = 0..K, the last one is the "no model" pseudo module) = fixed-order sum of partials
-void reduce_sse(const double* partial, int T, int K, int L, int CR, double* sse, cudaStream_t s);
+void reduce_sse(const double* partial, int T, int K, int L, int CR, double* sse, cudaStream_t s, int t0 = 0, int t1 = -1);
 
 // Training SSE of every (fit, module, target) from the Gram matrices instead of the n1 cells:
 //   ||y_t - X_sel b||^2 = y_t'y_t - 2 b'(X_sel'y_t) + b'(X_sel'X_sel) b
@@ -51,17 +52,18 @@ void reduce_sse(const double* partial, int T, int K, int L, int CR, double* sse,
 // Modules without a model get gtt[t] exactly.  Output layout = sse[l][j][t] with K+1 module slots.
 void sse_train_gram(const double* G_rr, int64_t ldrr, const double* G_rt, int64_t ldrt, const double* gtt,
                     const double* beta, int64_t ldb, const int* sel /* per stacked row: regulator or -1 */,
-                    const int* row_off, const int* nsel, int T, int K, int L, double* sse, cudaStream_t s);
+                    const int* row_off, const int* nsel, int T, int K, int L, double* sse, cudaStream_t s, int t0 = 0,
+                    int t1 = -1);
 
 // resid_var = SSE_train / (n1 - s_j); two_var = 2 var; inv_two_var = RN(1 / two_var); half_log = 0.5 log(2 pi var)
 // (R/scregclust.R:1635-1638, allocation.cpp:59-62).  nsel: device [L*K].
 void make_resid_var(const double* sse_train, const int* nsel, int n1, int T, int K, int L, double* var,
-                    double* two_var, double* inv_two_var, double* half_log, cudaStream_t s);
+                    double* two_var, double* inv_two_var, double* half_log, cudaStream_t s, int t0 = 0, int t1 = -1);
 
 // r2[l][t][j] = 1 - SSE_test / SS0 ; best_r2 = row max ; best_idx = first argmax (1-based)
 // (R/scregclust.R:1628-1632, 1646).  k_new = first argmax of votes (1-based, allocation.cpp:88-94).
 void finish_alloc(const double* sse_test, const int* votes, int T, int K, int L, double* r2, double* best_r2,
-                  int* best_idx, int* k_new, cudaStream_t s);
+                  int* best_idx, int* k_new, cudaStream_t s, int t0 = 0, int t1 = -1);
 
 // out[r, c] = row_src[r] >= 0 ? Zr[c, row_src[r]] : 0   (out: rows x ncells, k contiguous)
 void gather_transpose(const double* Zr, int64_t ldz, int ncells, const int* row_src, int64_t rows,
