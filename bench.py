@@ -7,10 +7,10 @@ A *step* is one complete penalization-grid fit of the alternating loop (R/scregc
 Gram / eigenbasis / initial fit, then Step 1 + 2a + 2b cycles until every penalty has converged,
 its final configurations are re-fitted and their leave-one-regulator-out importances computed,
 i.e. the default compute_predictive_r2 = TRUE) on one seeded synthetic workload of a BASELINE.json
-shape.  With N > 1 (torchrun, one rank per GPU) the penalty grid is sharded round-robin over the
-ranks -- the fits are independent (R/scregclust.R:1223,1245) -- and the per-penalty module
-assignments are all-gathered over NCCL at the end of the step ("scaling": "strong": the grid is
-fixed, the wall time per grid falls with N).
+shape.  With N > 1 (torchrun, one rank per GPU) every cycle of the grid is spread over the ranks inside
+the library -- Step-1 problems by (penalization value, module), Step 2 by target-gene slice, module
+summaries and assignment vectors merged with NCCL all-reduces (csrc/session.cu) -- "scaling": "strong":
+the grid is fixed, the wall time per grid falls with N.
 
 Printed JSON (rank 0, one line):
   value        device-resident step time [s] (inputs already in HBM when the clock starts)
@@ -20,7 +20,9 @@ Printed JSON (rank 0, one line):
                flops / CUDA-event time on the launching stream, against cuBLAS DGEMM measured in
                this run (MEASURED_PEAKS.json has no FP64 entry)
   cpu_baseline reference-faithful C++ twin (oracle/_ref/liboracle_ref.so) timed on a bounded sample
-               of the same workload and extrapolated to the grid (N=1, rank 0 only)
+               of the same workload and extrapolated to the grid on the exact per-problem iteration
+               counts of the GPU run (N=1, rank 0 only; "extrapolated": true)
+  parity_spot  the modules the CPU leg solved, compared with the GPU's results for the same modules
   --impl reference prints only that CPU arm.
 """
 from __future__ import annotations
@@ -111,11 +113,21 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------
 # CPU arm: reference-faithful C++ twin on a bounded sample
 # --------------------------------------------------------------------------------------------
-def cpu_sample(w, budget_s, total_fit_cycles, total_last_cycles, lam):
-    """Times one cycle (Step 1 + 2a + 2b) of one penalization value with the cost structure of the
-    reference (oracle/ref_cpu.cpp) on as many modules / genes as fit the budget, and extrapolates
-    to the whole grid.  Returns (estimated seconds per grid, description, threads)."""
-    from oracle import ref_cpu
+def cpu_sample(w, budget_s, lam, totals, gpu_first_cycle=None):
+    """Times the first cycle (Step 1 + 2a + 2b) of one penalization value with the cost structure of the
+    reference (oracle/ref_cpu.cpp through oracle/twin_cycle.py) on as many modules / genes as fit the
+    budget, and extrapolates to the whole grid on the work counters of the GPU run:
+
+      Step 1   seconds per ADMM problem-iteration (measured) x problem-iterations of the grid (exact: the GPU's
+               per-problem iteration counts are bit-equal to the twin's, tests/test_gpu_baseline_scale.py)
+      Step 2a  seconds per (module with a model) x such modules over all cycles of the grid
+      Step 2b  seconds per gene of reset + allocation x T x fit cycles
+      importance  seconds per module x modules of the final configurations
+
+    `totals`: dict(problem_iterations, modules_with_model, fit_cycles, final_modules) of the grid.
+    `gpu_first_cycle` (optional): dict(admm_iterations[K], models[P, K]) of the GPU for the same penalization
+    value and configuration -> parity_spot.  Returns (seconds per grid, description, threads, details)."""
+    from oracle import ref_cpu, twin_cycle
     from oracle import scregclust_oracle as orc
 
     threads = ref_cpu.set_threads(os.cpu_count() or 1)
@@ -125,49 +137,30 @@ def cpu_sample(w, budget_s, total_fit_cycles, total_last_cycles, lam):
     t_pre0 = time.perf_counter()
     pre = orc.precompute(w.z1_reg, w.z1_target)               # R BLAS path of R/scregclust.R:1049-1113
     t_pre = time.perf_counter() - t_pre0
-    res_sds, bas = pre["res_sds"], pre["beta_adapt_sq"]
-    x = np.asfortranarray(w.z1_reg / np.sqrt(n1))
     k = w.k_init
-    # ---- Step 1: coop_lasso per module (Gram recomputed, LDL^T per iteration) ----
-    t1, done1, models, signs, admm_it = 0.0, 0, {}, {}, 0
+    # ---- Step 1 + 2a, module by module until the budget is used
+    t1 = t2 = 0.0
+    its = cols = 0
+    done, done2 = [], 0
+    spot = dict(modules=[], iterations_equal=True, sets_equal=True, max_rel=0.0)
+    sample = {}
     for j in range(1, K + 1):
-        cl = np.flatnonzero(k == j)
-        if cl.size == 0:
+        if not np.any(k == j):
             continue
-        if t1 > budget_s * 0.6 and done1 >= 1:
+        if (t1 + t2) > budget_s * 0.8 and len(done) >= 1:
             break
-        t0 = time.perf_counter()
-        y = np.asfortranarray((w.z1_target[:, cl] / res_sds[cl][None, :]) / np.sqrt(n1))
-        ws = np.sqrt(cl.size) / np.sqrt(np.sqrt(np.sum(bas[:, cl], axis=1)))
-        beta, it, nf = ref_cpu.coop_lasso(y, x, lam, ws, max_iter=10000)
-        beta = beta * res_sds[cl][None, :]
-        beta[np.abs(beta) < 1e-6] = 0.0
-        t1 += time.perf_counter() - t0
-        models[j] = np.flatnonzero(np.sum(np.abs(beta) > 0, axis=1) > 0)
-        signs[j] = np.sign(beta.sum(axis=1))[models[j]]
-        admm_it += it
-        done1 += 1
-    nonempty = int(sum(1 for j in range(1, K + 1) if np.any(k == j)))
-    step1_est = t1 * nonempty / max(done1, 1)
-    # ---- Step 2a for the modules fitted above: NNLS on all T targets + residual GEMMs ----
-    t2, done2 = 0.0, 0
-    y_nn = np.asfortranarray(w.z1_target / w.z1_target_sds[None, :])
-    for j, reg in models.items():
-        if reg.size == 0:
-            continue
-        if t2 > budget_s * 0.25 and done2 >= 1:
-            break
-        t0 = time.perf_counter()
-        xs = np.asfortranarray(w.z1_reg[:, reg] * signs[j][None, :])
-        b, _ = ref_cpu.coef_nnls(xs, y_nn, eps=1e-4, max_iter=10000)
-        bh = b * signs[j][:, None] * orc._recycle(w.z1_target_sds, b.shape)
-        r_tr = w.z1_target - w.z1_reg[:, reg] @ bh
-        r_te = w.z2_target - w.z2_reg[:, reg] @ bh
-        _ = (r_tr * r_tr).sum(axis=0), (r_te * r_te).sum(axis=0)
-        t2 += time.perf_counter() - t0
-        done2 += 1
-    step2a_est = t2 * nonempty / max(done2, 1)
-    # ---- array reset + allocation on a gene subset (the full K x n2 x T array is 8 GB at config 3) ----
+        c = twin_cycle.cycle(w, lam, k, pre=pre, modules=[j])
+        t1 += c["step1_seconds"]; t2 += c["step2a_seconds"]
+        its += int(c["admm_iterations"][j - 1]); cols += int(np.count_nonzero(k == j))
+        done.append(j); done2 += int(c["coeffs"][j - 1] is not None)
+        sample[j] = c
+        if gpu_first_cycle is not None:
+            spot["modules"].append(j)
+            spot["iterations_equal"] &= bool(gpu_first_cycle["admm_iterations"][j - 1] == c["admm_iterations"][j - 1])
+            spot["sets_equal"] &= bool(np.array_equal(gpu_first_cycle["models"][:, j - 1], c["models"][:, j - 1]))
+    sec_per_iter = t1 / max(its, 1)
+    sec_per_model = t2 / max(done2, 1)
+    # ---- array reset + allocation on a gene subset (the full K x n2 x T array is 8 GB at config 3)
     g = int(max(8, min(T, 2.5e8 // (K * n2 * 8))))
     z2sq = np.asfortranarray(w.z2_target[:, :g] ** 2)
     arr = np.empty((K, n2, g), order="F")
@@ -179,47 +172,75 @@ def cpu_sample(w, budget_s, total_fit_cycles, total_last_cycles, lam):
     t0 = time.perf_counter()
     ref_cpu.allocate_into_modules(arr, rv, None, None, np.ones(g, dtype=np.int32), np.arange(g, dtype=np.int32), 1e-6, 0.0)
     t_alloc = time.perf_counter() - t0
-    step2b_est = (t_fill * (1 + (nonempty - 1) * 0.5) + t_alloc) * T / g
-    # ---- post-processing: leave-one-regulator-out NNLS importance (R/scregclust.R:1823-1912) on one module ----
+    nonempty = int(sum(1 for j in range(1, K + 1) if np.any(k == j)))
+    sec_per_gene_cycle = (t_fill * (1 + (nonempty - 1) * 0.5) + t_alloc) / g
+    # ---- post-processing: leave-one-regulator-out NNLS importance (R/scregclust.R:1823-1912) on one module
     t_imp, imp_mods = 0.0, 0
-    for j, reg in models.items():
+    for j, c in sample.items():
+        reg = np.flatnonzero(c["models"][:, j - 1])
         cl = np.flatnonzero(k == j)
         if reg.size < 2 or cl.size == 0:
             continue
+        sg = c["signs"][reg, j - 1]
         t0 = time.perf_counter()
         y_cl = np.asfortranarray(w.z1_target[:, cl] / w.z1_target_sds[cl][None, :])
         for r in range(reg.size + 1):
             keep = np.ones(reg.size, dtype=bool)
             if r > 0:
                 keep[r - 1] = False
-            xs = np.asfortranarray(w.z1_reg[:, reg[keep]] * signs[j][keep][None, :])
+            xs = np.asfortranarray(w.z1_reg[:, reg[keep]] * sg[keep][None, :])
             b, _ = ref_cpu.coef_nnls(xs, y_cl, eps=1e-4, max_iter=10000)
-            bh = b * signs[j][keep][:, None] * orc._recycle(w.z1_target_sds[cl], b.shape)
+            bh = b * sg[keep][:, None] * orc._recycle(w.z1_target_sds[cl], b.shape)
             rt = w.z2_target[:, cl] - w.z2_reg[:, reg[keep]] @ bh
             _ = (rt * rt).sum(axis=0)
         t_imp += time.perf_counter() - t0
         imp_mods += 1
         break
-    imp_est = t_imp * nonempty / max(imp_mods, 1)
-    cycle_est = step1_est + step2a_est + step2b_est
-    last_est = step1_est + step2a_est + imp_est
-    total = t_pre + cycle_est * total_fit_cycles + last_est * total_last_cycles
+    sec_per_final_module = t_imp / max(imp_mods, 1)
+    parts = dict(precompute=t_pre, step1=sec_per_iter * totals["problem_iterations"],
+                 step2a=sec_per_model * totals["modules_with_model"],
+                 step2b=sec_per_gene_cycle * T * totals["fit_cycles"],
+                 importance=sec_per_final_module * totals["final_modules"])
+    total = float(sum(parts.values()))
+    measured = t_pre + t1 + t2 + t_fill + t_alloc + t_imp
     desc = (f"reference-faithful C++ twin (oracle/ref_cpu.cpp: Gram per call, LDL^T per iteration, K x n2 x T array), "
-            f"lambda={lam:.3g}, first cycle from the initial configuration: Step 1 on {done1}/{nonempty} modules "
-            f"({admm_it} ADMM iterations, {t1:.1f} s), Step 2a on {done2} modules ({t2:.1f} s), reset+allocate on {g}/{T} genes "
-            f"({t_fill + t_alloc:.2f} s), importance refits of {imp_mods} module ({t_imp:.1f} s), precompute {t_pre:.1f} s; extrapolated to {total_fit_cycles} fit cycles + "
-            f"{total_last_cycles} final re-fits of the grid")
-    return total, desc, threads
+            f"lambda={lam:.3g}, first cycle from the initial configuration: Step 1 + 2a on modules {done} of {nonempty} "
+            f"({its} ADMM iterations over {cols} columns, {t1:.1f} s + {t2:.1f} s), reset+allocate on {g}/{T} genes "
+            f"({t_fill + t_alloc:.2f} s), importance refits of {imp_mods} module ({t_imp:.1f} s), precompute {t_pre:.1f} s; "
+            f"extrapolated on the grid's work counters: {totals['problem_iterations']} ADMM problem-iterations, "
+            f"{totals['modules_with_model']} module refits, {totals['fit_cycles']} allocation sweeps, "
+            f"{totals['final_modules']} final modules")
+    details = dict(extrapolated=True, measured_seconds=measured, scale_factor=total / max(measured, 1e-9),
+                   seconds_per_problem_iteration=sec_per_iter, parts=parts,
+                   model_check="profiles/r02_cpu_full_config2.json: the same model against a fully measured config-2 grid")
+    if gpu_first_cycle is not None:
+        details["parity_spot"] = spot
+    return total, desc, threads, details
 
 
-def load_cycles(name, seed, n_pen):
-    """(fit cycles, final re-fit cycles) summed over the grid, from the last GPU run of this workload."""
+def load_totals(name, seed, n_pen, K):
+    """Work counters of the grid (and the GPU's first-cycle results of the sampled penalization value) from the
+    last GPU run of this seeded workload -- written by the GPU arm, read by `--impl reference`."""
     try:
-        tab = json.load(open(CYCLES_TABLE))
-        e = tab[f"{name}/seed{seed}"]
-        return int(e["fit_cycles"]), int(e["last_cycles"]), "profiles/bench_cycles.json"
+        e = json.load(open(CYCLES_TABLE))[f"{name}/seed{seed}"]
+        return e["totals"], e.get("first_cycle"), "profiles/bench_cycles.json"
     except Exception:
-        return 6 * n_pen, n_pen, "assumed 6 cycles per penalization value (no cycle table for this workload)"
+        return ({"problem_iterations": 25 * K * 7 * n_pen, "modules_with_model": K * 7 * n_pen, "fit_cycles": 6 * n_pen,
+                 "final_modules": K * n_pen}, None,
+                "assumed 6 cycles and 25 ADMM iterations per problem (no table for this workload)")
+
+
+def grid_totals(res, K):
+    """Exact work counters of a finished grid from its per-cycle records."""
+    tot = dict(problem_iterations=0, modules_with_model=0, fit_cycles=0, final_modules=0)
+    for r in res:
+        tot["fit_cycles"] += r.n_cycles_run - 1
+        for it, md in zip(r.admm_iterations, r.models_history):
+            tot["problem_iterations"] += int(np.sum(it))
+            tot["modules_with_model"] += int(np.count_nonzero(md.sum(axis=0)))
+        for kf in r.k_final:
+            tot["final_modules"] += int(len(set(kf[kf > 0].tolist())))
+    return tot
 
 
 # --------------------------------------------------------------------------------------------
@@ -229,13 +250,6 @@ _REAL_STDOUT = None
 def emit(line):
     """The one JSON line goes to the process's original stdout."""
     os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (json.dumps(line) + "\n").encode())
-
-
-def in_flight(n_pens, world):
-    """Penalization values a rank advances together when the grid is shared dynamically."""
-    if os.environ.get("SCRC_BENCH_CONCURRENCY"):
-        return max(1, int(os.environ["SCRC_BENCH_CONCURRENCY"]))
-    return max(1, n_pens // (2 * world))
 
 
 def main():
@@ -252,6 +266,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     n_cells, n_targets, n_reg, n_modules, pens = CONFIGS[args.workload]
+    i_med = len(pens) // 2                                     # the penalization value the CPU leg samples
     config = {"workload": f"{args.workload}: synthetic {n_cells} cells x {n_targets} targets x {n_reg} regulators, "
                           f"{n_modules} modules, {len(pens)}-value penalty grid (seed {args.seed})",
               "n1": n_cells // 2, "n2": n_cells - n_cells // 2, "targets": n_targets, "regulators": n_reg,
@@ -259,8 +274,8 @@ def main():
               "baseline_config": {"config1": "BASELINE.json configs[0] (synthetic stand-in of the same shape)",
                                   "config2": "BASELINE.json configs[1]", "config3": "BASELINE.json configs[2]",
                                   "config4": "BASELINE.json configs[3]"}.get(args.workload, "test-sized workload"),
-              "parallelism": (f"penalization values claimed dynamically from a shared counter by {world} GPUs, "
-                               f"{in_flight(len(pens), world)} in flight per GPU"
+              "parallelism": (f"every cycle of the whole grid spread over {world} GPUs inside the library: Step-1 problems by "
+                              f"(penalization value, module), Step 2 by target-gene slice, NCCL all-reduce merges"
                               if world > 1 else "whole penalty grid advanced in lock-step on 1 GPU"),
               "l2": "working set (FP64 state of all problems) exceeds the 126 MB L2; no flush between steps"}
 
@@ -268,18 +283,23 @@ def main():
         if rank != 0:
             return 0
         w = make_workload(args.workload, seed=args.seed)
-        fit_c, last_c, src = load_cycles(args.workload, args.seed, len(pens))
-        vals = []
-        desc, threads = "", 1
+        totals, first, src = load_totals(args.workload, args.seed, len(pens), n_modules)
+        gfc = None
+        if first is not None:
+            md = np.zeros((n_reg, n_modules), dtype=bool)
+            for j, sel in enumerate(first["selected"]):
+                md[sel, j] = True
+            gfc = {"admm_iterations": np.array(first["admm_iterations"]), "models": md}
+        vals, desc, threads, details = [], "", 1, {}
         for _ in range(max(1, min(args.steps, 2))):            # each step = one bounded sample
-            v, desc, threads = cpu_sample(w, args.cpu_budget, fit_c, last_c, float(np.median(pens)))
+            v, desc, threads, details = cpu_sample(w, args.cpu_budget, float(pens[i_med]), totals, gfc)
             vals.append(v)
         v = float(np.mean(vals))
         line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": v * 1e3, "higher_is_better": False,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": v, "unit": "s", "cores": threads, "kind": "port",
-                                 "sample": desc + f" [cycle counts: {src}]"},
+                                 "sample": desc + f" [work counters: {src}]", **details},
                 "e2e": {"value": v, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         emit(line)
         return 0
@@ -287,7 +307,7 @@ def main():
     import torch
     import torch.distributed as dist
 
-    from scregclust_b200 import _capi, api
+    from scregclust_b200 import _capi, api, parallel
     from scregclust_b200.driver import Session, scregclust_fit
 
     torch.cuda.set_device(local_rank)
@@ -296,16 +316,10 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     lib = _capi.load()
     api.set_device(local_rank)
+    comm = parallel.comm_from_torch(local_rank) if world > 1 else None    # the library's own NCCL communicator
 
     w = make_workload(args.workload, seed=args.seed)
-    from scregclust_b200 import parallel
     all_pens = [float(p) for p in pens]
-    store = None
-    if world > 1:   # shared counter for dynamic claiming of penalization values (host side)
-        store = dist.TCPStore("127.0.0.1", int(os.environ.get("MASTER_PORT", "29500")) + 17, world, rank == 0,
-                              wait_for_workers=True)
-    counter = parallel.GridCounter(len(all_pens), store)
-    step_no = [0]
     T = n_targets
     host = [np.asfortranarray(a) for a in (w.z1_reg, w.z2_reg, w.z1_target, w.z2_target)]
     pinned = []
@@ -324,43 +338,30 @@ def main():
 
     def run_step(resident: bool):
         t_a = time.perf_counter()
-        if resident:
-            ses = Session.from_pointers(dev[0].data_ptr(), dev[1].data_ptr(), dev[2].data_ptr(), dev[3].data_ptr(),
-                                        sds_dev.data_ptr(), n1, n2, P, T, n_modules, device=local_rank)
-        else:
-            ses = Session.from_pointers(pinned[0].data_ptr(), pinned[1].data_ptr(), pinned[2].data_ptr(),
-                                        pinned[3].data_ptr(), sds_pinned.data_ptr(), n1, n2, P, T, n_modules,
-                                        device=local_rank)
+        src = dev if resident else pinned
+        sd = sds_dev if resident else sds_pinned
+        ses = Session.from_pointers(src[0].data_ptr(), src[1].data_ptr(), src[2].data_ptr(), src[3].data_ptr(),
+                                    sd.data_ptr(), n1, n2, P, T, n_modules, device=local_rank, comm=comm)
+        if not resident:
             ses.h2d_bytes = sum(t.numel() * 8 for t in pinned) + sds_pinned.numel() * 8
         try:
             t_b = time.perf_counter()
-            step_no[0] += 1
-            counter.reset(f"scrc_next_{step_no[0]}")
-            # one GPU: the whole grid advances in lock-step; several GPUs: each rank keeps
-            # L / (2 N) penalization values in flight and claims the next one from the shared counter
-            # (most expensive first) whenever one of them finishes -- the longest fit (about twice
-            # the average number of cycles) then still fits inside a rank's share of the work
-            allres = scregclust_fit(penalization=all_pens, n_modules=n_modules, initial_target_modules=w.k_init,
-                                    session=ses, return_coeffs=not resident, compute_predictive_r2=True,
-                                    claim=counter if world > 1 else None,
-                                    concurrency=in_flight(len(all_pens), world) if world > 1 else None)
-            res = [r for r in allres if r is not None]
-            local_k = {i: r.k_final[0] for i, r in enumerate(allres) if r is not None}
-            stats = dict(h2d=ses.h2d_bytes, d2h=ses.d2h_bytes, sweeps=ses.admm_sweeps,
-                         admm_iters=ses.admm_problem_iterations,
-                         fit_cycles=sum(r.n_cycles_run - 1 for r in res),
-                         last_cycles=sum(r.final_cycle_length for r in res))
+            # one call: the whole alternating loop of the grid runs inside the library (scrc_grid_fit); with
+            # N > 1 it is collective -- every rank passes the same arguments and gets the complete result
+            res = scregclust_fit(penalization=all_pens, n_modules=n_modules, initial_target_modules=w.k_init,
+                                 session=ses, return_coeffs=not resident, compute_predictive_r2=True)
+            gi = ses.last_grid_info
+            stats = dict(h2d=ses.h2d_bytes, d2h=ses.d2h_bytes, sweeps=gi["admm_sweeps"],
+                         admm_iters=gi["admm_problem_iterations"], fit_cycles=gi["fit_cycles"],
+                         last_cycles=gi["final_refits"], device_calls=gi["device_calls"])
             t_c = time.perf_counter()
         finally:
             ses.close()
-        t_d = time.perf_counter()
-        # exchange step: every rank learns every penalty's final module assignment (int32 x T)
-        allk = parallel.merge_assignments(local_k, len(pens), T, world, device="cuda")
-        assert allk.min() >= -1, "a penalization value was not fitted by any rank"
+        allk = np.stack([r.k_final[0] for r in res])
         checksum = int(np.clip(allk, 0, None).sum())
         if dbg:
-            print(f"[bench step {step_no[0]} resident={resident}] create {t_b - t_a:.3f} s, fit {t_c - t_b:.3f} s, "
-                  f"close {t_d - t_c:.3f} s, merge {time.perf_counter() - t_d:.3f} s", file=sys.stderr, flush=True)
+            print(f"[bench rank {rank} resident={resident}] create {t_b - t_a:.3f} s, fit {t_c - t_b:.3f} s, "
+                  f"close {time.perf_counter() - t_c:.3f} s", file=sys.stderr, flush=True)
         return res, stats, checksum
 
     def timed(resident: bool, steps: int):
@@ -412,10 +413,15 @@ def main():
                 for i, n in enumerate(names)}
         adm = prof["gemm_admm"]
         achieved = adm["work_per_step"] / (adm["ms_per_step"] * 1e-3) / 1e12 if adm["ms_per_step"] > 0 else 0.0
-        sweeps = max(stats["sweeps"], 1)
+        kernel_ms = sum(v["ms_per_step"] for v in prof.values())
         traffic = None
         try:   # DRAM bytes of one (all-columns-active) launch of the dominant kernel from the committed ncu capture
             traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[args.workload]
+        except Exception:
+            pass
+        hbm = None
+        try:
+            hbm = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
         except Exception:
             pass
         line = {
@@ -425,9 +431,10 @@ def main():
             "e2e": {"value": e2e_dev * 1e-3, "unit": "s", "h2d_bytes_per_step": int(e2e_stats["h2d"]),
                     "d2h_bytes_per_step": int(e2e_stats["d2h"]), "host_wall_s": e2e_wall * 1e-3},
             "gpu_launches": int(launches),
-            "admm_iters_per_s": stats["admm_iters"] / (prof["gemm_admm"]["ms_per_step"] + prof["admm_elementwise"]["ms_per_step"] + 1e-9) * 1e3,
-            "admm": {"problem_iterations_rank0": int(stats["admm_iters"]), "batched_sweeps_rank0": int(stats["sweeps"]),
-                     "fit_cycles_rank0": int(stats["fit_cycles"]), "final_refits_rank0": int(stats["last_cycles"])},
+            "admm_iters_per_s": stats["admm_iters"] / (ms_dev * 1e-3),
+            "admm": {"problem_iterations": int(stats["admm_iters"]), "batched_sweeps_rank0": int(stats["sweeps"]),
+                     "fit_cycles": int(stats["fit_cycles"]), "final_refits": int(stats["last_cycles"]),
+                     "device_calls_per_step": int(stats["device_calls"])},
             "roofline": {"kernel": "gemm_tn_kernel<AdmmGemmPolicy> (two eigenbasis GEMMs per ADMM sweep)",
                          "bound": "tensor", "achieved": achieved, "peak": dgemm_tf, "unit": "TFLOP/s",
                          "frac": achieved / dgemm_tf if dgemm_tf > 0 else None,
@@ -435,44 +442,65 @@ def main():
                          "traffic_note": (f"ncu dram bytes of a launch with every column active; algorithmic "
                                           f"{traffic['algorithmic_bytes_per_launch']} B for that launch") if traffic else None,
                          "share_of_step": adm["ms_per_step"] / ms_dev if ms_dev > 0 else None,
-                         "launches_per_step": 2 * sweeps / max(args.steps, 1),
+                         "launches_per_step": adm["timed_groups"] / max(args.steps, 1),
                          "peak_source": "cuBLAS DGEMM 8192^3 (torch.matmul float64) measured in this run; "
                                         "MEASURED_PEAKS.json has no FP64 figure"},
-            "kernel_classes_rank0": prof, "clocks": clocks, "host_wall_ms_per_step": ms_wall,
-            "assignment_checksum": checksum,
+            "kernel_classes_rank0": prof, "kernel_share_of_step": kernel_ms / ms_dev if ms_dev > 0 else None,
+            "clocks": clocks, "host_wall_ms_per_step": ms_wall, "assignment_checksum": checksum,
         }
-        try:   # second-largest HBM-bound class against the driver-measured copy bandwidth
+        sec = []
+        if hbm:
             el = prof["admm_elementwise"]
-            hbm = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
-            gbs = el["work_per_step"] / (el["ms_per_step"] * 1e-3) / 1e9
-            line["roofline_secondary"] = [{
-                "kernel": "admm_rhs_kernel / admm_update_kernel (ADMM elementwise sweep)", "bound": "hbm",
-                "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
-                "share_of_step": el["ms_per_step"] / ms_dev,
-                "bytes_note": "algorithmic 80 B per active matrix element and sweep (DESIGN.md section 4)",
-                "peak_source": "MEASURED_PEAKS.json hbm_gbs (copy-measured)"}]
-        except Exception:
-            pass
+            if el["ms_per_step"] > 0:
+                gbs = el["work_per_step"] / (el["ms_per_step"] * 1e-3) / 1e9
+                sec.append({"kernel": "admm_rhs_kernel / admm_update_kernel / admm_finalize_kernel (ADMM elementwise sweep)",
+                            "bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
+                            "share_of_step": el["ms_per_step"] / ms_dev,
+                            "bytes_note": "algorithmic bytes per active column: 56 P on plain sweeps, 136 P on rho-adaptation "
+                                          "sweeps (DESIGN.md section 4; counted per sweep on the device)",
+                            "peak_source": "MEASURED_PEAKS.json hbm_gbs (copy-measured)"})
+            rv = prof["resid_vote"]
+            if rv["ms_per_step"] > 0:
+                gbs = rv["work_per_step"] / (rv["ms_per_step"] * 1e-3) / 1e9
+                sec.append({"kernel": "resid_vote_kernel (+ sse_train_gram_kernel): fused predict / residual / SSE / vote",
+                            "bound": "latency (DMMA chain + FP64 score chain per warp); HBM figure for reference",
+                            "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
+                            "share_of_step": rv["ms_per_step"] / ms_dev,
+                            "bytes_note": "algorithmic: 8 n2 T per fit + the gathered regulators / coefficients per tile",
+                            "peak_source": "MEASURED_PEAKS.json hbm_gbs (copy-measured)"})
+        nn = prof["nnls"]
+        if nn["ms_per_step"] > 0:
+            sec.append({"kernel": "nnls_kernel (one warp per (module, target) column)", "bound": "latency / issue",
+                        "share_of_step": nn["ms_per_step"] / ms_dev, "ms_per_step": nn["ms_per_step"]})
+        line["roofline_secondary"] = sec
         os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
+        totals = grid_totals(res, n_modules)
+        r_med = res[i_med]
+        first = {"lambda": float(pens[i_med]), "admm_iterations": [int(v) for v in r_med.admm_iterations[0]],
+                 "selected": [np.flatnonzero(r_med.models_history[0][:, j]).tolist() for j in range(n_modules)]}
         if world == 1:
             try:
                 tab = json.load(open(CYCLES_TABLE)) if os.path.exists(CYCLES_TABLE) else {}
-                tab[f"{args.workload}/seed{args.seed}"] = {"fit_cycles": int(stats["fit_cycles"]), "last_cycles": int(stats["last_cycles"]),
+                tab[f"{args.workload}/seed{args.seed}"] = {"totals": totals, "first_cycle": first,
                                                            "cycles_per_penalty": [int(r.n_cycles_run) for r in res]}
                 json.dump(tab, open(CYCLES_TABLE, "w"), indent=1, sort_keys=True)
             except Exception:
                 pass
             if not args.no_cpu_baseline:
                 try:
-                    v, desc, threads = cpu_sample(w, args.cpu_budget, stats["fit_cycles"], stats["last_cycles"],
-                                                  float(np.median(pens)))
-                    line["cpu_baseline"] = {"value": v, "unit": "s", "cores": threads, "kind": "port", "sample": desc}
+                    gfc = {"admm_iterations": r_med.admm_iterations[0], "models": r_med.models_history[0]}
+                    v, desc, threads, details = cpu_sample(w, args.cpu_budget, float(pens[i_med]), totals, gfc)
+                    line["parity_spot"] = details.pop("parity_spot", None)
+                    line["cpu_baseline"] = {"value": v, "unit": "s", "cores": threads, "kind": "port", "sample": desc, **details}
                 except Exception as exc:   # the checker library is optional for the GPU arm
                     line["cpu_baseline"] = {"value": None, "unit": "s", "cores": 0, "kind": "port",
                                             "sample": f"unavailable: {exc}"}
         emit(line)
     if world > 1:
         dist.barrier()
+    if comm is not None:
+        comm.close()
+    if world > 1:
         dist.destroy_process_group()
     return 0
 

@@ -38,6 +38,8 @@ extern "C" {
 #define SCRC_ERR_RESET_DIMS (-8)     /* "reset_array: input has wrong dimensions"                      utils.cpp:52 */
 #define SCRC_ERR_ARG (-20)           /* any other invalid argument */
 #define SCRC_ERR_UNSUPPORTED (-21)
+#define SCRC_ERR_COMM (-30)          /* NCCL unavailable or a collective failed */
+#define SCRC_ERR_INTERRUPTED (-31)   /* scrc_ctx_request_cancel(): the bridge raises R's interrupt condition */
 #define SCRC_ERR_INTERNAL (-50)
 #define SCRC_ERR_CUDA (-100)         /* CUDA failures: -100 - cudaError_t */
 
@@ -236,6 +238,141 @@ int scrc_ctx_get_coeffs(scrc_ctx* ctx, int f, int k, double* coeffs_out, int* se
  * column-major each) packed one after the other in coeffs_out (sum_k n_selected_k * T doubles) and
  * the regulator indices in sel_out (sum_k n_selected_k); n_selected as returned by the cycle. */
 int scrc_ctx_get_coeffs_fit(scrc_ctx* ctx, int f, double* coeffs_out, int* sel_out);
+
+/* ------------------------------------------------------------------ cancellation
+ * The reference polls Rcpp::checkUserInterrupt() every ADMM iteration, NNLS outer iteration and allocated gene
+ * (src/optim.cpp:307,536, src/allocation.cpp:96).  The library never calls the R API; instead the bridge (or any
+ * other thread / signal handler) sets this flag, which is polled at the ADMM host polls (every second sweep)
+ * and between the phases of a cycle.  The running call then returns SCRC_ERR_INTERRUPTED; in a multi-GPU job
+ * the ranks agree on the interrupt at the next merge point, so a flag set on one rank stops all of them. */
+int scrc_ctx_request_cancel(scrc_ctx* ctx);
+int scrc_ctx_clear_cancel(scrc_ctx* ctx);
+
+/* ------------------------------------------------------------------ multi-GPU
+ * One rank per GPU.  Ranks are processes (torchrun / mpirun: rank 0 calls scrc_comm_unique_id and hands the 128
+ * bytes to the others by whatever means the launcher offers) or the host threads scrc_grid_fit_multi starts.
+ * A session created with a communicator is COLLECTIVE: every rank calls scrc_fit_cycle / scrc_importance /
+ * scrc_grid_fit with identical arguments (and the same set of non-NULL output pointers) and every rank gets
+ * the complete result.  Inside a cycle the Step-1 problems ((fit, module) pairs, R/scregclust.R:1332-1388) are
+ * spread over the ranks and Step 2 (NNLS columns, residuals, votes; R/scregclust.R:1533-1615,
+ * src/allocation.cpp:59-94) runs on contiguous target-gene slices; the module summaries and the per-gene
+ * assignment vectors are merged with NCCL collectives over NVLink.  Results are bit-identical to one GPU.
+ * NCCL is resolved at run time (libnccl.so.2); single-GPU sessions do not need it. */
+typedef struct scrc_comm scrc_comm;
+int scrc_comm_unique_id(char id_out[128]);
+int scrc_comm_create(scrc_comm** out, const char id[128], int world, int rank, int device);
+void scrc_comm_destroy(scrc_comm* comm);
+/* scrc_ctx_create on comm's device; rank 0 computes Gram / eigenbasis / initial fit once and broadcasts them. */
+int scrc_ctx_create_sharded(scrc_ctx** out, scrc_comm* comm, const double* z1_reg, const double* z2_reg,
+                            const double* z1_target, const double* z2_target, const double* z1_target_sds,
+                            int64_t n1, int64_t n2, int64_t P, int64_t T, int K);
+/* Predicted ADMM iterations per (fit, module) (F x K, 0 = unknown) of the NEXT scrc_fit_cycle call; used only
+ * to balance the Step-1 problems over the ranks (typically last cycle's counts); never changes a result. */
+int scrc_ctx_set_cost_hint(scrc_ctx* ctx, const int* iterations, int n);
+/* The partition rules themselves (host only, deterministic; every rank evaluates them identically):
+ * longest-processing-time-first assignment of n problems to `world` ranks, and the contiguous slice of n
+ * items (in units of `align`) owned by `rank`. */
+int scrc_shard_assign(const double* cost, int n, int world, int* owner_out);
+int scrc_shard_slice(int64_t n, int64_t align, int rank, int world, int64_t* begin_out, int64_t* end_out);
+
+/* ------------------------------------------------------------------ whole-grid fit
+ * The alternating loop of scregclust() for a penalization grid in ONE call (R/scregclust.R:1222-1912 for
+ * allocate_per_obs = TRUE): cycle counter and forced last cycle (:1269-1284),
+ * Step 1 / 2a / 2b of every penalization value that is still iterating in one batched device call per cycle,
+ * noise threshold and minimum module size (:1731-1739), history match / limit cycles (:1763-1802), the re-fit
+ * of every final configuration (:1307-1311) and -- compute_predictive_r2 -- the leave-one-regulator-out
+ * importances (:1823-1912).  The R driver calls this once instead of ~10^3 .Call()s per grid; with a sharded
+ * session (or scrc_grid_fit_multi) it uses every GPU of the box. */
+typedef struct scrc_grid_params {
+    int n_penalties;
+    const double* penalization;             /* n_penalties */
+    const int* initial_target_modules;      /* T, 1-based, -1 noise (k_start_cl, R/scregclust.R:1127-1147) */
+    int n_cycles;                           /* 50    */
+    double noise_threshold;                 /* 0.025 */
+    int min_module_size;                    /* 0     */
+    scrc_options opt;
+    int compute_predictive_r2;              /* 1: importance step (the reference's default) */
+    int keep_coeffs;                        /* 1: keep the NNLS coefficient matrices of the final configurations */
+    int keep_diagnostics;                   /* 1: votes and NNLS iteration counts of every cycle are recorded */
+    /* network prior (R/scregclust.R:584-615, src/allocation.cpp:39-56): CSR over the T targets, or NULL */
+    const int* prior_off;
+    const int* prior_idx;
+    double prior_baseline;                  /* 1e-6 */
+    double prior_weight;                    /* 0 = no prior */
+    /* update_order(user, penalty index, cycle) -> the 0-based permutation R's sample() draws at
+     * R/scregclust.R:1666 (NULL: identity; only matters with a prior).  Must be thread-safe and return the
+     * same permutation on every rank. */
+    const int* (*update_order)(void* user, int penalty, int cycle);
+    void* update_order_user;
+} scrc_grid_params;
+void scrc_grid_default_params(scrc_grid_params* p);
+
+typedef struct scrc_grid_result scrc_grid_result;
+int scrc_grid_fit(scrc_ctx* ctx, const scrc_grid_params* p, scrc_grid_result** out);
+/* The same on n_devices GPUs of this process: one host thread per device, each with its own session and
+ * NCCL rank; inputs are read by every thread (host or device pointers).  Returns rank 0's result. */
+int scrc_grid_fit_multi(const int* devices, int n_devices, const double* z1_reg, const double* z2_reg,
+                        const double* z1_target, const double* z2_target, const double* z1_target_sds,
+                        int64_t n1, int64_t n2, int64_t P, int64_t T, int K, const scrc_grid_params* p,
+                        scrc_grid_result** out);
+/* The same loop over caller-supplied compute (used by the CPU tests of the host logic, which answer the
+ * callbacks from the oracle; a product caller has no reason to use it).  Callbacks return 0 or an error code. */
+typedef struct scrc_grid_backend {
+    void* user;
+    int64_t P, T;
+    int K;
+    int (*fit_cycle)(void* user, int F, const double* lambda, const int* k_in, const scrc_options* opt,
+                     int skip_allocation, const int* iterations_hint, const scrc_prior* prior, scrc_cycle_out* out);
+    int (*importance)(void* user, int F, const int* k_final, const unsigned char* models, const double* signs,
+                      const scrc_options* opt, double* r2_module, double* importance, double* r2_removed,
+                      int64_t r2_removed_capacity);
+    int (*coeffs_fit)(void* user, int f, double* coeffs_out, int* sel_out);
+} scrc_grid_backend;
+int scrc_grid_fit_custom(const scrc_grid_backend* backend, const scrc_grid_params* p, scrc_grid_result** out);
+
+typedef struct scrc_grid_info {
+    int n_penalties;
+    int64_t P, T;
+    int K;
+    long long admm_sweeps;              /* batched ADMM sweeps executed by this rank */
+    long long admm_problem_iterations;  /* sum of the per-problem iteration counts of the whole job */
+    int fit_cycles, final_refits, device_calls;
+} scrc_grid_info;
+int scrc_grid_result_info(const scrc_grid_result* r, scrc_grid_info* info);
+typedef struct scrc_grid_penalty_info {
+    double penalization;
+    int converged, n_cycles_run, final_cycle_length;
+    int n_history;    /* entries of k_history (initial configuration first) */
+    int n_records;    /* per-cycle records: the fit cycles in order, then one per final re-fit */
+} scrc_grid_penalty_info;
+int scrc_grid_result_penalty(const scrc_grid_result* r, int i, scrc_grid_penalty_info* info);
+int scrc_grid_result_history(const scrc_grid_result* r, int i, int* k_history /* n_history x T */);
+/* record `rec` of penalty i; votes (T x K, [t][k]) / nnls_iterations (K x T) only with keep_diagnostics */
+int scrc_grid_result_record(const scrc_grid_result* r, int i, int rec, int* admm_iterations /* K */,
+                            int* n_selected /* K */, unsigned char* models /* K x P */, int* votes,
+                            int* nnls_iterations);
+/* Final configuration m (0 <= m < final_cycle_length; m = 0 is the last entry of the history) in R's layouts
+ * ([k][p] = P x K, [k][t] = T x K column-major).  Every pointer may be NULL. */
+typedef struct scrc_grid_final {
+    int* k_final;              /* T */
+    unsigned char* models;     /* K x P */
+    double* weights;           /* K x P */
+    double* signs;             /* K x P, NaN where unselected */
+    double* r2_test;           /* K x T */
+    double* resid_var;         /* K x T  (sigmas = sqrt) */
+    double* best_r2;           /* T */
+    int* best_r2_idx;          /* T */
+    int* n_selected;           /* K */
+    double* r2_module;         /* K, NaN = NA (compute_predictive_r2) */
+    double* importance;        /* K x P, NaN = NA */
+} scrc_grid_final;
+int scrc_grid_result_final(const scrc_grid_result* r, int i, int m, scrc_grid_final* out);
+/* the K coefficient matrices (n_selected_k x T each, packed) and regulator indices, as scrc_ctx_get_coeffs_fit */
+int scrc_grid_result_coeffs(const scrc_grid_result* r, int i, int m, double* coeffs_out, int* sel_out);
+/* packed r2_removed blocks of configuration (i, m), as scrc_importance_ex; size in doubles first */
+int64_t scrc_grid_result_r2_removed_size(const scrc_grid_result* r, int i, int m);
+int scrc_grid_result_r2_removed(const scrc_grid_result* r, int i, int m, double* out);
+void scrc_grid_result_free(scrc_grid_result* r);
 
 #ifdef __cplusplus
 }

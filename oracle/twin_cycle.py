@@ -93,3 +93,56 @@ def cycle(w, lam, k, pre=None, modules=None, tol_rel=1e-8, tol_abs=1e-12, tol_nn
     out["r2"] = 1.0 - ss_test / ss_test0[:, None]                                  # scregclust.R:1629-1631
     out["resid_var"] = ss_train / (n1 - np.sum(out["models"], axis=0))[None, :]     # scregclust.R:1636-1638
     return out
+
+
+def full_fit(w, lam, n_cycles=50, noise_threshold=0.025, min_module_size=0, pre=None, log=None):
+    """The whole alternating loop of ONE penalization value on the C++ twin with the reference's cost structure:
+    Step 1 + 2a per module through :func:`cycle`, the K x n2 x T array reset and strided writes
+    (src/utils.cpp:43-63, R/scregclust.R:1599) and ``allocate_into_modules`` (src/allocation.cpp).  Returns
+    dict(k_history, admm_iterations (per cycle), seconds, step seconds).  Used to measure the CPU baseline of a
+    whole grid (profiles/) and to validate the extrapolation model of bench.py."""
+    K = w.n_modules
+    n2, T = w.z2_target.shape
+    if pre is None:
+        pre = orc.precompute(w.z1_reg, w.z1_target)
+    z2sq = np.asfortranarray(w.z2_target ** 2)
+    arr = np.empty((K, n2, T), order="F")
+    k = np.asarray(w.k_init, dtype=np.int32).copy()
+    hist = [k.copy()]
+    its_hist, t_all = [], dict(step1=0.0, step2a=0.0, step2b=0.0)
+    t_start = time.perf_counter()
+    last_cycle, fcl, n_k = False, 1, 2
+    for cyc in range(1, n_cycles + 2):
+        if cyc == n_cycles + 1:
+            last_cycle = True
+        for m in range(1, fcl + 1):
+            kk = hist[len(hist) - m]
+            c = cycle(w, lam, kk, pre=pre)
+            its_hist.append(c["admm_iterations"].copy())
+            t_all["step1"] += c["step1_seconds"]; t_all["step2a"] += c["step2a_seconds"]
+        if last_cycle:
+            break
+        t0 = time.perf_counter()
+        ref_cpu.fill_array(arr, z2sq)                                        # reset_array
+        for j in range(K):
+            if c["coeffs"][j] is not None:
+                sel = np.flatnonzero(c["models"][:, j])
+                r = w.z2_target - w.z2_reg[:, sel] @ c["coeffs"][j]
+                arr[j, :, :] = r * r                                          # sq_residuals_test[j, , ] <- ...
+        idx = ref_cpu.allocate_into_modules(arr, np.asfortranarray(c["resid_var"]), None, None, kk,
+                                            np.arange(T, dtype=np.int32), 1e-6, 0.0).copy()
+        t_all["step2b"] += time.perf_counter() - t0
+        idx[c["r2"].max(axis=1) < noise_threshold] = -1
+        sizes = np.array([np.sum(idx == i) for i in range(1, K + 1)])
+        idx[np.isin(idx, np.flatnonzero(sizes < min_module_size) + 1)] = -1
+        k = idx.astype(np.int32)
+        match = [i for i, kh in enumerate(hist, start=1) if np.array_equal(kh, k)]
+        hist.append(k.copy())
+        if match:
+            if n_k - match[0] != 1:
+                fcl = n_k - match[0]
+            last_cycle = True
+        n_k += 1
+        if log:
+            log(f"lambda={lam:.4g} cycle {cyc}: {time.perf_counter() - t_start:.1f} s so far, iterations {its_hist[-1].tolist()}")
+    return dict(k_history=hist, admm_iterations=its_hist, seconds=time.perf_counter() - t_start, **t_all)

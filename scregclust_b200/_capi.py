@@ -45,6 +45,48 @@ class Prior(C.Structure):
                 ("update_order", c_int_p)]
 
 
+UPDATE_ORDER_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_int, C.c_int)   # returns the address of T ints
+
+
+class GridParams(C.Structure):
+    _fields_ = [("n_penalties", C.c_int), ("penalization", c_double_p), ("initial_target_modules", c_int_p),
+                ("n_cycles", C.c_int), ("noise_threshold", C.c_double), ("min_module_size", C.c_int),
+                ("opt", Options), ("compute_predictive_r2", C.c_int), ("keep_coeffs", C.c_int),
+                ("keep_diagnostics", C.c_int), ("prior_off", c_int_p), ("prior_idx", c_int_p),
+                ("prior_baseline", C.c_double), ("prior_weight", C.c_double), ("update_order", UPDATE_ORDER_FN),
+                ("update_order_user", C.c_void_p)]
+
+
+class GridInfo(C.Structure):
+    _fields_ = [("n_penalties", C.c_int), ("P", C.c_int64), ("T", C.c_int64), ("K", C.c_int),
+                ("admm_sweeps", C.c_longlong), ("admm_problem_iterations", C.c_longlong), ("fit_cycles", C.c_int),
+                ("final_refits", C.c_int), ("device_calls", C.c_int)]
+
+
+class GridPenaltyInfo(C.Structure):
+    _fields_ = [("penalization", C.c_double), ("converged", C.c_int), ("n_cycles_run", C.c_int),
+                ("final_cycle_length", C.c_int), ("n_history", C.c_int), ("n_records", C.c_int)]
+
+
+class GridFinal(C.Structure):
+    _fields_ = [("k_final", c_int_p), ("models", c_ubyte_p), ("weights", c_double_p), ("signs", c_double_p),
+                ("r2_test", c_double_p), ("resid_var", c_double_p), ("best_r2", c_double_p), ("best_r2_idx", c_int_p),
+                ("n_selected", c_int_p), ("r2_module", c_double_p), ("importance", c_double_p)]
+
+
+BACKEND_FIT_CYCLE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, c_double_p, c_int_p, C.POINTER(Options), C.c_int, c_int_p,
+                                   C.POINTER(Prior), C.POINTER(CycleOut))
+BACKEND_IMPORTANCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, c_int_p, c_ubyte_p, c_double_p, C.POINTER(Options),
+                                    c_double_p, c_double_p, c_double_p, C.c_int64)
+BACKEND_COEFFS_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, c_double_p, c_int_p)
+
+
+class GridBackend(C.Structure):
+    _fields_ = [("user", C.c_void_p), ("P", C.c_int64), ("T", C.c_int64), ("K", C.c_int),
+                ("fit_cycle", BACKEND_FIT_CYCLE_FN), ("importance", BACKEND_IMPORTANCE_FN),
+                ("coeffs_fit", BACKEND_COEFFS_FN)]
+
+
 # name -> (restype, argtypes); also the list of symbols the header declares
 SIGNATURES = {
     "scrc_version": (C.c_int, []),
@@ -90,6 +132,31 @@ SIGNATURES = {
                                      c_double_p, c_double_p, C.c_int64]),
     "scrc_ctx_get_coeffs": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_double_p, c_int_p]),
     "scrc_ctx_get_coeffs_fit": (C.c_int, [C.c_void_p, C.c_int, c_double_p, c_int_p]),
+    "scrc_ctx_request_cancel": (C.c_int, [C.c_void_p]),
+    "scrc_ctx_clear_cancel": (C.c_int, [C.c_void_p]),
+    "scrc_comm_unique_id": (C.c_int, [C.c_char_p]),
+    "scrc_comm_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_char_p, C.c_int, C.c_int, C.c_int]),
+    "scrc_comm_destroy": (None, [C.c_void_p]),
+    "scrc_ctx_create_sharded": (C.c_int, [C.POINTER(C.c_void_p), C.c_void_p, c_double_p, c_double_p, c_double_p,
+                                          c_double_p, c_double_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int]),
+    "scrc_ctx_set_cost_hint": (C.c_int, [C.c_void_p, c_int_p, C.c_int]),
+    "scrc_shard_assign": (C.c_int, [c_double_p, C.c_int, C.c_int, c_int_p]),
+    "scrc_shard_slice": (C.c_int, [C.c_int64, C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "scrc_grid_default_params": (None, [C.POINTER(GridParams)]),
+    "scrc_grid_fit": (C.c_int, [C.c_void_p, C.POINTER(GridParams), C.POINTER(C.c_void_p)]),
+    "scrc_grid_fit_multi": (C.c_int, [c_int_p, C.c_int, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p,
+                                      C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.POINTER(GridParams),
+                                      C.POINTER(C.c_void_p)]),
+    "scrc_grid_fit_custom": (C.c_int, [C.POINTER(GridBackend), C.POINTER(GridParams), C.POINTER(C.c_void_p)]),
+    "scrc_grid_result_info": (C.c_int, [C.c_void_p, C.POINTER(GridInfo)]),
+    "scrc_grid_result_penalty": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(GridPenaltyInfo)]),
+    "scrc_grid_result_history": (C.c_int, [C.c_void_p, C.c_int, c_int_p]),
+    "scrc_grid_result_record": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_int_p, c_int_p, c_ubyte_p, c_int_p, c_int_p]),
+    "scrc_grid_result_final": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(GridFinal)]),
+    "scrc_grid_result_coeffs": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_double_p, c_int_p]),
+    "scrc_grid_result_r2_removed_size": (C.c_int64, [C.c_void_p, C.c_int, C.c_int]),
+    "scrc_grid_result_r2_removed": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_double_p]),
+    "scrc_grid_result_free": (None, [C.c_void_p]),
 }
 
 _lib = None

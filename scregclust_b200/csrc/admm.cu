@@ -21,7 +21,7 @@ struct AdmmDev {
     int* active;
     int* iters;
     int* n_active;
-    unsigned long long* col_iters;   // sum over sweeps of the number of active columns
+    unsigned long long* col_iters;   // [0] sum over sweeps of the number of active columns, [1] the same over update sweeps only
     const double* w;
     const double* xty;
     double *R, *W, *beta, *zeta, *mult, *beta_old, *zeta_old, *mult_old, *mult_hat_old;
@@ -36,7 +36,7 @@ void AdmmBatch::resize(int P_, int C_, int nprob_) {
     col_prob.ensure(C); prob_c0.ensure(nprob); prob_c1.ensure(nprob);
     prob_lambda.ensure(nprob); prob_rho.ensure(nprob); prob_alpha.ensure(nprob);
     prob_active.ensure(nprob); prob_iters.ensure(nprob);
-    n_active.ensure(2); col_iters.ensure(1);   // n_active[0] = active problems, [1] = their columns
+    n_active.ensure(2); col_iters.ensure(2);   // n_active[0] = active problems, [1] = their columns
     w.reshape(P, nprob);
     DMat* mats[] = {&xty, &R, &W, &beta, &zeta, &mult, &beta_old, &zeta_old, &mult_old, &mult_hat_old};
     for (DMat* m : mats) m->reshape(P, C);
@@ -69,7 +69,7 @@ __global__ void admm_init_prob_kernel(AdmmDev d, double rho0, double alpha0) {
         d.active[p] = (d.c1[p] > d.c0[p]) ? 1 : 0;
         d.iters[p] = 0;
     }
-    if (p == 0) { d.n_active[0] = d.nprob; d.n_active[1] = d.C; *d.col_iters = 0ull; }
+    if (p == 0) { d.n_active[0] = d.nprob; d.n_active[1] = d.C; d.col_iters[0] = 0ull; d.col_iters[1] = 0ull; }
 }
 
 // ------------------------------------------------------------------ rhs = xty + rho*zeta + mult   (optim.cpp:143)
@@ -415,12 +415,17 @@ __global__ void __launch_bounds__(1024) admm_finalize_kernel(AdmmDev d, AdmmOpts
         atomicAdd(&s_act_cols, d.c1[p] - d.c0[p]);
     }
     __syncthreads();
-    if (threadIdx.x == 0) { d.n_active[0] = s_cnt; d.n_active[1] = s_act_cols; *d.col_iters += s_cols; }
+    if (threadIdx.x == 0) {
+        d.n_active[0] = s_cnt; d.n_active[1] = s_act_cols;
+        d.col_iters[0] += s_cols;
+        if (is_update) d.col_iters[1] += s_cols;
+    }
 }
 
 // ------------------------------------------------------------------ driver
 int admm_solve(AdmmBatch& b, const EigBasis& eig, const AdmmOpts& o, bool cold, int num_sms,
-               cudaStream_t stream, int* h_scratch) {
+               cudaStream_t stream, int* h_scratch, const std::atomic<int>* cancel) {
+    b.aborted = false;
     if (b.nprob == 0 || b.C == 0) return 0;
     AdmmDev d = make_dev(b);
     if (cold) {
@@ -523,18 +528,23 @@ int admm_solve(AdmmBatch& b, const EigBasis& eig, const AdmmOpts& o, bool cold, 
             SCRC_CUDA(cudaStreamSynchronize(stream));
             if (h_scratch[0] == 0) break;
             active_cols = h_scratch[1];
+            // cooperative cancellation (optim.cpp:307 polls the interrupt flag every iteration)
+            if (cancel && cancel->load(std::memory_order_relaxed)) { b.aborted = true; break; }
         }
         ++it;
         if (it > o.max_iter + 1) break;  // safety net; finalize retires every problem at max_iter
     }
     {   // column-iterations actually executed -> algorithmic flops of the 2 GEMMs per sweep
-        unsigned long long ci = 0;
-        SCRC_CUDA(cudaMemcpyAsync(&ci, d.col_iters, sizeof(ci), cudaMemcpyDeviceToHost, stream));
+        unsigned long long ci[2] = {0ull, 0ull};
+        SCRC_CUDA(cudaMemcpyAsync(ci, d.col_iters, sizeof(ci), cudaMemcpyDeviceToHost, stream));
         SCRC_CUDA(cudaStreamSynchronize(stream));
-        b.last_col_iters = ci;
-        g_prof.add_work(PROF_GEMM_ADMM, 4.0 * (double)b.P * (double)b.P * (double)ci);
-        // elementwise sweep: ~10 matrix passes of 8 bytes per active element
-        g_prof.add_work(PROF_ADMM_ELEM, 80.0 * (double)b.P * (double)ci);
+        b.last_col_iters = ci[0];
+        g_prof.add_work(PROF_GEMM_ADMM, 4.0 * (double)b.P * (double)b.P * (double)ci[0]);
+        // elementwise sweep, algorithmic bytes per active column: plain sweeps read beta, zeta,
+        // mult, X'y and write zeta, mult, rhs = 7 x 8 = 56 P; rho-adaptation sweeps read beta, zeta, mult + 4 snapshots
+        // and write zeta, mult + 4 snapshots (104 P), and the rhs needs its own pass once rho is known (3 reads +
+        // 1 write, 32 P) = 136 P
+        g_prof.add_work(PROF_ADMM_ELEM, (56.0 * (double)(ci[0] - ci[1]) + 136.0 * (double)ci[1]) * (double)b.P);
     }
     return sweeps;
 }

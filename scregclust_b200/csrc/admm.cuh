@@ -11,6 +11,7 @@
 // refactorisation is ever needed when rho changes (the reference refactors a
 // P x P LDL^T per problem per rho change).
 #pragma once
+#include <atomic>
 #include <vector>
 
 #include "dmat.cuh"
@@ -57,6 +58,7 @@ struct AdmmBatch {
     DevBuf<int> prob_R;        // rows per update slab (32 / 16 / 8), chosen from the column count
     DevBuf<int> class_ids;     // problem ids grouped by slab height
     std::vector<int> h_cols;   // host copy of the column count of every problem (set by the caller)
+    bool aborted = false;      // set by admm_solve when the cancel flag stopped it early
 
     void resize(int P_, int C_, int nprob_);
 };
@@ -65,7 +67,8 @@ struct AdmmBatch {
 // max_iter.  Expects xty, w, prob_* descriptors and (optionally warm-started)
 // beta/zeta to be set up; zeroes the remaining state itself when `cold`.
 // Returns the number of batched sweeps executed.
+// `cancel` (optional) is polled with the device counters; when set the solve stops early and b.aborted is true.
 int admm_solve(AdmmBatch& b, const EigBasis& eig, const AdmmOpts& o, bool cold, int num_sms,
-               cudaStream_t stream, int* h_pinned_scratch);
+               cudaStream_t stream, int* h_pinned_scratch, const std::atomic<int>* cancel = nullptr);
 
 }  // namespace scrc

@@ -353,21 +353,23 @@ void resid_vote(const ResidVoteArgs& a, int mode, int num_sms, cudaStream_t st) 
 
 // ---------------------------------------------------------------- reductions / finishing kernels
 __global__ void reduce_sse_kernel(const double* __restrict__ partial, int T, int K1, int L, int CR, double* sse, int t0,
-                                  int Ts) {
+                                  int Ts, const int* __restrict__ skip_cnt) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // over L*K1*Ts
     if (i >= (int64_t)L * K1 * Ts) return;
     const int t = t0 + (int)(i % Ts);
     const int j = (int)((i / Ts) % K1);
     const int l = (int)(i / ((int64_t)Ts * K1));
+    if (skip_cnt && skip_cnt[l] == 0) return;      // fit not computed on this rank: leave its entries alone
     double s = 0.0;
     for (int c = 0; c < CR * 2; ++c) s += partial[(((int64_t)l * CR * 2 + c) * K1 + j) * T + t];
     sse[((int64_t)l * K1 + j) * T + t] = s;
 }
-void reduce_sse(const double* partial, int T, int K, int L, int CR, double* sse, cudaStream_t st, int t0, int t1) {
+void reduce_sse(const double* partial, int T, int K, int L, int CR, double* sse, cudaStream_t st, int t0, int t1,
+                const int* skip_cnt) {
     if (t1 < 0) t1 = T;
     const int64_t n = (int64_t)L * (K + 1) * (t1 - t0);
     if (n == 0) return;
-    reduce_sse_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(partial, T, K + 1, L, CR, sse, t0, t1 - t0);
+    reduce_sse_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(partial, T, K + 1, L, CR, sse, t0, t1 - t0, skip_cnt);
     SCRC_CUDA(cudaGetLastError());
     SCRC_LAUNCHED();
 }

@@ -43,7 +43,9 @@ size_t resid_vote_partial_elems(int T, int K, int L, int CR);
 void resid_vote(const ResidVoteArgs& a, int mode, int num_sms, cudaStream_t s);
 
 // sse[l][j][t] (j = 0..K, the last one is the "no model" pseudo module) = fixed-order sum of partials
-void reduce_sse(const double* partial, int T, int K, int L, int CR, double* sse, cudaStream_t s, int t0 = 0, int t1 = -1);
+// skip_cnt (optional, device [L]): fits with a zero entry are left untouched
+void reduce_sse(const double* partial, int T, int K, int L, int CR, double* sse, cudaStream_t s, int t0 = 0, int t1 = -1,
+                const int* skip_cnt = nullptr);
 
 // Training SSE of every (fit, module, target) from the Gram matrices instead of the n1 cells:
 //   ||y_t - X_sel b||^2 = y_t'y_t - 2 b'(X_sel'y_t) + b'(X_sel'X_sel) b

@@ -4,12 +4,9 @@
 
 #include "prof.cuh"
 #include "session.cuh"
+#include "shard.hpp"
 
 using namespace scrc;
-
-struct scrc_ctx {
-    Ctx impl;
-};
 
 namespace {
 thread_local std::string g_err;
@@ -50,22 +47,12 @@ int guarded(F&& f) {
 }
 }  // namespace
 
-namespace {
-// out[base[r] + a[r] + s[r] * t] = beta[src[r] + ld * t]: drops the 16-row padding of the stacked layout and
-// lays every module's s x T block out contiguously, so that one linear copy brings a whole fit to the host.
-__global__ void coeff_pack_kernel(const double* __restrict__ beta, int64_t ld, int T, int nrows,
-                                  const int* __restrict__ src, const int* __restrict__ s_of, const int* __restrict__ a_of,
-                                  const long long* __restrict__ base, double* out) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    const int t = blockIdx.y;
-    if (r >= nrows || t >= T) return;
-    out[base[r] + a_of[r] + (long long)s_of[r] * t] = beta[src[r] + ld * t];
-}
-}  // namespace
 
 extern "C" {
 
-int scrc_version(void) { return 100; }
+void scrc_set_last_error_(const char* msg) { g_err = msg ? msg : ""; }
+
+int scrc_version(void) { return 200; }
 const char* scrc_last_error(void) { return g_err.c_str(); }
 unsigned long long scrc_launch_count(void) { return scrc::g_launch_count.load(); }
 int scrc_set_device(int device) {
@@ -366,53 +353,74 @@ int scrc_ctx_get_coeffs(scrc_ctx* ctx, int f, int k, double* coeffs_out, int* se
         if (f < 0 || f >= c.last_F || k < 0 || k >= c.K) throw Error(SCRC_ERR_ARG, "scrc_ctx_get_coeffs: index out of range");
         SCRC_CUDA(cudaSetDevice(c.dev.id));
         const FitSlot& sl = c.slots[(size_t)f * c.K + k];
-        if (sel_out) for (int a = 0; a < sl.s; ++a) sel_out[a] = sl.sel[a];
+        if (sel_out && sl.s > 0)
+            SCRC_CUDA(cudaMemcpyAsync(sel_out, c.nnls.sel.p + sl.sel_off, (size_t)sl.s * 4, cudaMemcpyDeviceToHost, c.dev.stream));
         if (coeffs_out && sl.s > 0) {
             // compact on the device first: a strided device-to-host copy of T rows of s doubles is slow
             DevBuf<double> packed((size_t)sl.s * c.T);
             SCRC_CUDA(cudaMemcpy2DAsync(packed.p, (size_t)sl.s * 8, c.nnls.beta.data() + sl.row_off, c.nnls.beta.ld * 8,
                                         (size_t)sl.s * 8, c.T, cudaMemcpyDeviceToDevice, c.dev.stream));
             SCRC_CUDA(cudaMemcpyAsync(coeffs_out, packed.p, (size_t)sl.s * c.T * 8, cudaMemcpyDeviceToHost, c.dev.stream));
-            SCRC_CUDA(cudaStreamSynchronize(c.dev.stream));
         }
+        SCRC_CUDA(cudaStreamSynchronize(c.dev.stream));
     });
 }
 
 int scrc_ctx_get_coeffs_fit(scrc_ctx* ctx, int f, double* coeffs_out, int* sel_out) {
     if (!ctx) return fail(SCRC_ERR_ARG, "null context");
+    return guarded([&] { ctx->impl.get_coeffs_fit(f, coeffs_out, sel_out); });
+}
+
+int scrc_ctx_request_cancel(scrc_ctx* ctx) {
+    if (!ctx) return SCRC_ERR_ARG;          // no allocation, no locks: callable from a signal handler
+    ctx->impl.cancel.store(1, std::memory_order_relaxed);
+    return SCRC_OK;
+}
+int scrc_ctx_clear_cancel(scrc_ctx* ctx) {
+    if (!ctx) return SCRC_ERR_ARG;
+    ctx->impl.cancel.store(0, std::memory_order_relaxed);
+    return SCRC_OK;
+}
+
+int scrc_comm_unique_id(char id_out[128]) {
+    if (!id_out) return fail(SCRC_ERR_ARG, "scrc_comm_unique_id: null pointer");
+    return guarded([&] { comm_unique_id(id_out); });
+}
+int scrc_comm_create(scrc_comm** out, const char id[128], int world, int rank, int device) {
+    if (!out || !id) return fail(SCRC_ERR_ARG, "scrc_comm_create: null pointer");
+    *out = nullptr;
     return guarded([&] {
-        Ctx& c = ctx->impl;
-        if (f < 0 || f >= c.last_F) throw Error(SCRC_ERR_ARG, "scrc_ctx_get_coeffs_fit: index out of range");
-        SCRC_CUDA(cudaSetDevice(c.dev.id));
-        cudaStream_t st = c.dev.stream;
-        std::vector<int> src, s_of, a_of;
-        std::vector<long long> base;
-        long long off = 0;
-        size_t nsel = 0;
-        for (int k = 0; k < c.K; ++k) {
-            const FitSlot& sl = c.slots[(size_t)f * c.K + k];
-            for (int a = 0; a < sl.s; ++a) {
-                src.push_back(sl.row_off + a); s_of.push_back(sl.s); a_of.push_back(a); base.push_back(off);
-                if (sel_out) sel_out[nsel] = sl.sel[a];
-                ++nsel;
-            }
-            off += (long long)sl.s * c.T;
-        }
-        if (!coeffs_out || src.empty()) return;
-        const int nrows = (int)src.size();
-        DevBuf<int> d_src(nrows), d_s(nrows), d_a(nrows);
-        DevBuf<long long> d_base(nrows);
-        DevBuf<double> packed((size_t)off);
-        SCRC_CUDA(cudaMemcpyAsync(d_src.p, src.data(), nrows * 4, cudaMemcpyHostToDevice, st));
-        SCRC_CUDA(cudaMemcpyAsync(d_s.p, s_of.data(), nrows * 4, cudaMemcpyHostToDevice, st));
-        SCRC_CUDA(cudaMemcpyAsync(d_a.p, a_of.data(), nrows * 4, cudaMemcpyHostToDevice, st));
-        SCRC_CUDA(cudaMemcpyAsync(d_base.p, base.data(), nrows * 8, cudaMemcpyHostToDevice, st));
-        coeff_pack_kernel<<<dim3((unsigned)ceil_div(nrows, 128), (unsigned)c.T), 128, 0, st>>>(
-            c.nnls.beta.data(), c.nnls.beta.ld, (int)c.T, nrows, d_src.p, d_s.p, d_a.p, d_base.p, packed.p);
-        SCRC_LAUNCHED();
-        SCRC_CUDA(cudaMemcpyAsync(coeffs_out, packed.p, (size_t)off * 8, cudaMemcpyDeviceToHost, st));
-        SCRC_CUDA(cudaStreamSynchronize(st));
+        std::unique_ptr<scrc_comm> c(new scrc_comm());
+        c->impl.init(id, world, rank, device);
+        *out = c.release();
     });
+}
+void scrc_comm_destroy(scrc_comm* comm) { delete comm; }
+int scrc_ctx_create_sharded(scrc_ctx** out, scrc_comm* comm, const double* z1_reg, const double* z2_reg,
+                            const double* z1_target, const double* z2_target, const double* z1_target_sds, int64_t n1,
+                            int64_t n2, int64_t P, int64_t T, int K) {
+    if (!out || !comm || !z1_reg || !z2_reg || !z1_target || !z2_target || !z1_target_sds)
+        return fail(SCRC_ERR_ARG, "scrc_ctx_create_sharded: null pointer");
+    *out = nullptr;
+    return guarded([&] {
+        std::unique_ptr<scrc_ctx> c(new scrc_ctx());
+        c->impl.create(comm->impl.device, z1_reg, z2_reg, z1_target, z2_target, z1_target_sds, n1, n2, P, T, K, &comm->impl);
+        *out = c.release();
+    });
+}
+int scrc_ctx_set_cost_hint(scrc_ctx* ctx, const int* iterations, int n) {
+    if (!ctx || (n > 0 && !iterations) || n < 0) return fail(SCRC_ERR_ARG, "scrc_ctx_set_cost_hint: invalid argument");
+    return guarded([&] { ctx->impl.cost_hint.assign(iterations, iterations + n); });
+}
+int scrc_shard_assign(const double* cost, int n, int world, int* owner_out) {
+    if (n < 0 || world < 1 || (n > 0 && (!cost || !owner_out))) return fail(SCRC_ERR_ARG, "scrc_shard_assign: invalid argument");
+    return guarded([&] { shard_assign(cost, n, world, owner_out); });
+}
+int scrc_shard_slice(int64_t n, int64_t align, int rank, int world, int64_t* begin_out, int64_t* end_out) {
+    if (n < 0 || align < 1 || world < 1 || rank < 0 || rank >= world || !begin_out || !end_out)
+        return fail(SCRC_ERR_ARG, "scrc_shard_slice: invalid argument");
+    shard_slice(n, align, rank, world, begin_out, end_out);
+    return SCRC_OK;
 }
 
 /* debug accessor (not part of the public header): stacked selection matrix of the last cycle

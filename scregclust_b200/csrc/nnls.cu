@@ -20,11 +20,19 @@ struct NnlsDev {
     double* beta; int64_t ldb;
     int* iters;
     int m;
+    int col0, col1;          // column slice [col0, col1) processed by this launch
+    const int* ids;          // problems processed by this launch (nullptr: all, in order)
 };
+
+static NnlsDev make_dev(NnlsBatch& b) {
+    NnlsDev d{b.prob.p, b.sel.p, b.pos.p, b.cols.p, b.sign.p, b.Q.p, b.dvec.p, b.grad0.data(), b.grad0.ld,
+              b.beta.data(), b.beta.ld, b.iters.p, b.m, b.col0, b.col1 < 0 ? b.m : b.col1, nullptr};
+    return d;
+}
 
 // ---------------------------------------------------------------- setup: Q = (S G S) o (d d'),  d = 1/sqrt(diag)
 __global__ void __launch_bounds__(256) nnls_setup_q_kernel(NnlsDev d, const double* __restrict__ xtx, int64_t ldx) {
-    const NnlsProblem pr = d.prob[blockIdx.x];
+    const NnlsProblem pr = d.prob[d.ids ? d.ids[blockIdx.x] : blockIdx.x];
     const int s = pr.s;
     const int* sel = d.sel + pr.sel_off;
     const double* sg = d.sign + pr.sel_off;
@@ -46,13 +54,14 @@ __global__ void __launch_bounds__(256) nnls_setup_q_kernel(NnlsDev d, const doub
 __global__ void __launch_bounds__(256) nnls_setup_grad_kernel(NnlsDev d, const double* __restrict__ xty,
                                                               int64_t ldy, const double* __restrict__ colscale) {
     // 1-D grid (problem-major): gridDim.y is capped at 65535, the importance step can exceed that
-    const int chunks = (d.m + 31) / 32;
-    const NnlsProblem pr = d.prob[blockIdx.x / chunks];
+    const int chunks = (d.col1 - d.col0 + 31) / 32;
+    const int pi = blockIdx.x / chunks;
+    const NnlsProblem pr = d.prob[d.ids ? d.ids[pi] : pi];
     const int s = pr.s;
     const int* sel = d.sel + pr.sel_off;
     const double* sg = d.sign + pr.sel_off;
-    const int col0 = (blockIdx.x % chunks) * 32;
-    const int ncols = pr.ncols < 0 ? d.m : pr.ncols;
+    const int col0 = d.col0 + (blockIdx.x % chunks) * 32;
+    const int ncols = min(pr.ncols < 0 ? d.m : pr.ncols, d.col1);
     for (int e = threadIdx.x; e < s * 32; e += blockDim.x) {
         const int a = e % s, col = col0 + e / s;
         if (col >= ncols) break;
@@ -66,11 +75,21 @@ __global__ void __launch_bounds__(256) nnls_setup_grad_kernel(NnlsDev d, const d
 void nnls_setup(NnlsBatch& b, const double* xtx, int64_t ldx, const double* xty, int64_t ldy,
                 const double* colscale, cudaStream_t st) {
     if (b.nprob == 0) return;
-    NnlsDev d{b.prob.p, b.sel.p, b.pos.p, b.cols.p, b.sign.p, b.Q.p, b.dvec.p, b.grad0.data(), b.grad0.ld,
-              b.beta.data(), b.beta.ld, b.iters.p, b.m};
-    nnls_setup_q_kernel<<<b.nprob, 256, 0, st>>>(d, xtx, ldx);
+    if ((int)b.h_prob.size() != b.nprob) throw Error(-73, "nnls_setup: host problem descriptors missing");
+    NnlsDev d = make_dev(b);
+    if (d.col1 <= d.col0) return;
+    // problems handled by this rank / launch: b.active (ids into prob), or all of them
+    int nact = b.nprob;
+    if (b.use_active) {
+        nact = (int)b.active.size();
+        if (nact == 0) return;
+        b.ids.ensure(2 * (size_t)b.nprob + 2);
+        SCRC_CUDA(cudaMemcpyAsync(b.ids.p + b.nprob, b.active.data(), (size_t)nact * 4, cudaMemcpyHostToDevice, st));
+        d.ids = b.ids.p + b.nprob;
+    }
+    nnls_setup_q_kernel<<<nact, 256, 0, st>>>(d, xtx, ldx);
     SCRC_LAUNCHED();
-    const int64_t gblocks = ceil_div(b.m, 32) * (int64_t)b.nprob;
+    const int64_t gblocks = ceil_div(d.col1 - d.col0, 32) * (int64_t)nact;
     if (gblocks > 0x7fffffffLL) throw Error(-72, "NNLS: too many (problem, column chunk) pairs in one batch");
     nnls_setup_grad_kernel<<<(unsigned)gblocks, 256, 0, st>>>(d, xty, ldy, colscale);
     SCRC_LAUNCHED();
@@ -163,13 +182,13 @@ __global__ void nnls_kernel(NnlsDev d, const int* __restrict__ prob_ids, int col
     double *beta = vec, *grad = vec + s, *gb = vec + 2 * s, *bsave = vec + 3 * s, *db = vec + 4 * s,
            *tmp = vec + 5 * s;
     const double* sg = d.sign + pr.sel_off;
-    const int ncols = pr.ncols < 0 ? d.m : pr.ncols;
-    const int col_end = min((chunk + 1) * cols_per_cta, ncols);
+    const int ncols = min(pr.ncols < 0 ? d.m : pr.ncols, d.col1);
+    const int col_end = min(d.col0 + (chunk + 1) * cols_per_cta, ncols);
     const double* oscale = out_scale ? out_scale + pr.scale_off : nullptr;
     const int oscale_len = pr.scale_len > 0 ? pr.scale_len : n_out_scale;
     const int* opos = pr.pos_off < 0 ? nullptr : d.pos + pr.pos_off;
 
-    for (int col = chunk * cols_per_cta + warp; col < col_end; col += nwarps) {
+    for (int col = d.col0 + chunk * cols_per_cta + warp; col < col_end; col += nwarps) {
         const double* g0 = d.grad0 + pr.row_off + (int64_t)col * d.ldg;
         for (int a = lane; a < s; a += 32) {
             const double g = g0[a];
@@ -246,6 +265,8 @@ __global__ void nnls_kernel(NnlsDev d, const int* __restrict__ prob_ids, int col
             if (oscale) v = v * oscale[((int64_t)a + (int64_t)col * s) % oscale_len];
             out[opos ? opos[a] : a] = v;
         }
+        // rows up to the 16-row box of the stacked layout are exact zeros (the prediction kernel contracts over them)
+        if (!opos) for (int a = s + lane; a < ((s + 15) & ~15); a += 32) out[a] = 0.0;
         if (lane == 0) d.iters[(int64_t)pid * d.m + col] = iters;
         __syncwarp();
     }
@@ -253,29 +274,30 @@ __global__ void nnls_kernel(NnlsDev d, const int* __restrict__ prob_ids, int col
 
 void nnls_solve(NnlsBatch& b, double eps, int max_iter, const double* out_scale, int n_out_scale,
                 int num_sms, cudaStream_t st) {
+    (void)num_sms;
     if (b.nprob == 0 || b.m == 0) return;
-    NnlsDev d{b.prob.p, b.sel.p, b.pos.p, b.cols.p, b.sign.p, b.Q.p, b.dvec.p, b.grad0.data(), b.grad0.ld,
-              b.beta.data(), b.beta.ld, b.iters.p, b.m};
-    SCRC_CUDA(cudaMemsetAsync(b.beta.data(), 0, b.beta.bytes(), st));
-    // classify problems by size (host copy of the descriptors is cheap: nprob <= K*L)
-    std::vector<NnlsProblem> hp(b.nprob);
-    SCRC_CUDA(cudaMemcpyAsync(hp.data(), b.prob.p, sizeof(NnlsProblem) * b.nprob, cudaMemcpyDeviceToHost, st));
-    SCRC_CUDA(cudaStreamSynchronize(st));
+    if ((int)b.h_prob.size() != b.nprob) throw Error(-73, "nnls_solve: host problem descriptors missing");
+    NnlsDev d = make_dev(b);
+    if (d.col1 <= d.col0) return;
+    // classify the problems by size from the host copy of the descriptors (no device round trip)
     std::vector<int> small_ids, large_ids;
     int smax_small = 0, smax_large = 0;
-    for (int i = 0; i < b.nprob; ++i) {
-        if (hp[i].s <= 0) continue;
-        if (hp[i].s <= 112) { small_ids.push_back(i); smax_small = std::max(smax_small, hp[i].s); }
-        else { large_ids.push_back(i); smax_large = std::max(smax_large, hp[i].s); }
-    }
-    DevBuf<int> ids(small_ids.size() + large_ids.size() + 1);
-    if (!small_ids.empty())
-        SCRC_CUDA(cudaMemcpyAsync(ids.p, small_ids.data(), small_ids.size() * 4, cudaMemcpyHostToDevice, st));
-    if (!large_ids.empty())
-        SCRC_CUDA(cudaMemcpyAsync(ids.p + small_ids.size(), large_ids.data(), large_ids.size() * 4,
-                                  cudaMemcpyHostToDevice, st));
+    auto classify = [&](int i) {
+        const int s = b.h_prob[i].s;
+        if (s <= 0) return;
+        if (s <= 112) { small_ids.push_back(i); smax_small = std::max(smax_small, s); }
+        else { large_ids.push_back(i); smax_large = std::max(smax_large, s); }
+    };
+    if (b.use_active) for (int i : b.active) classify(i);
+    else for (int i = 0; i < b.nprob; ++i) classify(i);
+    if (small_ids.empty() && large_ids.empty()) return;
+    b.ids.ensure(2 * (size_t)b.nprob + 2);
+    b.h_ids.clear();
+    b.h_ids.insert(b.h_ids.end(), small_ids.begin(), small_ids.end());
+    b.h_ids.insert(b.h_ids.end(), large_ids.begin(), large_ids.end());
+    SCRC_CUDA(cudaMemcpyAsync(b.ids.p, b.h_ids.data(), b.h_ids.size() * 4, cudaMemcpyHostToDevice, st));
     const int cols_per_cta = 64;
-    const unsigned chunks = (unsigned)ceil_div(b.m, cols_per_cta);
+    const unsigned chunks = (unsigned)ceil_div(d.col1 - d.col0, cols_per_cta);
     auto grid1d = [&](size_t nids) {
         const uint64_t g = (uint64_t)chunks * nids;
         if (g > 0x7fffffffULL) throw Error(-72, "NNLS: too many (problem, column chunk) pairs in one batch");
@@ -288,7 +310,7 @@ void nnls_solve(NnlsBatch& b, double eps, int max_iter, const double* out_scale,
         static SmemAttr attr;
         attr.ensure(nnls_kernel<true>, smem);
         nnls_kernel<true><<<grid1d(small_ids.size()), warps * 32, smem, st>>>(
-            d, ids.p, cols_per_cta, (int)chunks, eps, max_iter, out_scale, n_out_scale);
+            d, b.ids.p, cols_per_cta, (int)chunks, eps, max_iter, out_scale, n_out_scale);
         SCRC_LAUNCHED();
     }
     if (!large_ids.empty()) {
@@ -298,11 +320,10 @@ void nnls_solve(NnlsBatch& b, double eps, int max_iter, const double* out_scale,
         static SmemAttr attr;
         attr.ensure(nnls_kernel<false>, smem);
         nnls_kernel<false><<<grid1d(large_ids.size()), warps * 32, smem, st>>>(
-            d, ids.p + small_ids.size(), cols_per_cta, (int)chunks, eps, max_iter, out_scale, n_out_scale);
+            d, b.ids.p + small_ids.size(), cols_per_cta, (int)chunks, eps, max_iter, out_scale, n_out_scale);
         SCRC_LAUNCHED();
     }
     SCRC_CUDA(cudaGetLastError());
-    SCRC_CUDA(cudaStreamSynchronize(st));   // `ids` is freed on return
 }
 
 }  // namespace scrc

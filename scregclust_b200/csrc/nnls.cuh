@@ -5,6 +5,8 @@
 // depend on the other columns.  One warp owns one column;
 // the CTA's warps share the module's Q matrix in shared memory.
 #pragma once
+#include <vector>
+
 #include "dmat.cuh"
 
 namespace scrc {
@@ -44,6 +46,13 @@ struct NnlsBatch {
     DMat grad0;                    // rows x m : initial gradient
     DMat beta;                     // rows x m : output (rescaled; padding rows = 0)
     DevBuf<int> iters;             // nprob x m
+    // host side
+    std::vector<NnlsProblem> h_prob;   // host copy of `prob` (size nprob), set by the caller
+    int col0 = 0, col1 = -1;           // column slice [col0, col1) to set up / solve (-1: m)
+    bool use_active = false;           // true: only the problems listed in `active` are set up / solved
+    std::vector<int> active;
+    DevBuf<int> ids;                   // device scratch for the launch lists (kept across calls)
+    std::vector<int> h_ids;            // pinned lifetime of the async upload of `ids`
 };
 
 // Builds Q, dvec and grad0 for every problem from the full Gram matrices:

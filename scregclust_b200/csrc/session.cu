@@ -1,4 +1,5 @@
 #include "session.cuh"
+#include "shard.hpp"
 
 #include <algorithm>
 #include <cmath>
@@ -98,83 +99,113 @@ void Ctx::begin(int64_t n1_, int64_t n2_, int64_t P_, int64_t T_, int K_) {
 }
 
 void Ctx::create(int device, const double* z1r, const double* z2r, const double* z1t, const double* z2t,
-                 const double* sds, int64_t n1_, int64_t n2_, int64_t P_, int64_t T_, int K_) {
+                 const double* sds, int64_t n1_, int64_t n2_, int64_t P_, int64_t T_, int K_, Comm* comm_) {
     if (n1_ <= 1 || n2_ <= 0 || P_ <= 0 || T_ <= 0 || K_ <= 0) throw Error(SCRC_ERR_ARG, "scrc_ctx_create: non-positive dimension");
-    dev.init(device);
+    comm = comm_;
+    dev.init(comm ? comm->device : device);
     begin(n1_, n2_, P_, T_, K_);
     cudaStream_t st = dev.stream;
-    Z1r.upload(z1r, n1, st); Z2r.upload(z2r, n2, st); Z1t.upload(z1t, n1, st); Z2t.upload(z2t, n2, st);
+    // the regulators of the first split go first: the Gram matrix and its eigenbasis only need them
+    Z1r.upload(z1r, n1, st); Z1t.upload(z1t, n1, st); Z2r.upload(z2r, n2, st); Z2t.upload(z2t, n2, st);
     SCRC_CUDA(cudaMemcpyAsync(sds_t.p, sds, T * 8, cudaMemcpyDefault, st));
     finish();
 }
 
-// Everything after the four scaled matrices and z1_target_sds are resident.
+// Everything after the four scaled matrices and z1_target_sds are resident.  In a multi-GPU job rank 0
+// computes the precompute once and broadcasts it (0.25 GB at config 3, < 1 ms over NVLink): the
+// eigen-decomposition is latency-bound and gains nothing from being repeated, and every rank then works
+// from bit-identical Gram matrices and eigenvectors by construction.
 void Ctx::finish() {
     cudaStream_t st = dev.stream;
     const bool dbg = getenv("SCRC_DEBUG_TIMING") != nullptr;
+    const bool root = rank() == 0;
     auto tick = [&](const char* what) {
-        static double t_prev = 0.0;
+        static thread_local double t_prev = 0.0;
         if (!dbg) return;
         cudaStreamSynchronize(st);
         timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);
         const double t = ts.tv_sec + 1e-9 * ts.tv_nsec;
-        if (what) fprintf(stderr, "[scrc create] %-28s %8.2f ms\n", what, (t - t_prev) * 1e3);
+        if (what) fprintf(stderr, "[scrc create rank %d] %-28s %8.2f ms\n", rank(), what, (t - t_prev) * 1e3);
         t_prev = t;
     };
     tick(nullptr);
     vec_recip_kernel<<<(unsigned)ceil_div(T, 256), 256, 0, st>>>(sds_t.p, inv_sds_t.p, (int)T);
     SCRC_LAUNCHED();
     tick("inputs resident");
+    DevBuf<double> df_d(1);
+    if (root) {
+        // Gram matrices (optim.cpp:17-27,99,414,421) -- computed once, the reference redoes them per call
+        gram(Z1r, Z1r, G_rr, true, dev);
+        gram(Z1r, Z1t, G_rt, false, dev);
+        tick("gram");
+        build_eig(G_rr, 1.0 / (double)n1, eig, dev);   // eigenbasis of X'X with X = Z1r / sqrt(n1)
+        tick("eigen-decomposition");
+        gtt.alloc(T);
+        col_sumsq(Z1t.data(), Z1t.ld, n1, T, gtt.p, st);
 
-    // Gram matrices (optim.cpp:17-27,99,414,421) -- computed once, the reference redoes them per call
-    gram(Z1r, Z1r, G_rr, true, dev);
-    gram(Z1r, Z1t, G_rt, false, dev);
-    tick("gram");
-    build_eig(G_rr, 1.0 / (double)n1, eig, dev);   // eigenbasis of X'X with X = Z1r / sqrt(n1)
-    tick("eigen-decomposition");
-    gtt.alloc(T);
-    col_sumsq(Z1t.data(), Z1t.ld, n1, T, gtt.p, st);
-
-    // Initial fit (scregclust.R:1049-1101): OLS when n1 >= P, ridge with the df search otherwise.
-    DMat tmp;
-    std::vector<double> lam(P);
-    SCRC_CUDA(cudaMemcpyAsync(lam.data(), eig.lam.p, P * 8, cudaMemcpyDeviceToHost, st));
-    SCRC_CUDA(cudaStreamSynchronize(st));
-    double ridge = 0.0;
-    if (n1 >= P) {
-        init_df = (double)P;
-    } else {
-        // es = eigenvalues of Z'Z, decreasing; lambda_minimal = es[n1 - 1] + 1e-4 (1-based)
-        std::vector<double> es(P);
-        for (int64_t i = 0; i < P; ++i) es[i] = lam[P - 1 - i] * (double)n1;
-        ridge = es[n1 - 2] + 1e-4;
-        auto df = [&](double l) { double s = 0.0; for (double e : es) s += e / (e + l); return s; };
-        init_df = df(ridge);
-        while (init_df >= (double)n1) { ridge *= 2.0; init_df = df(ridge); }
-    }
-    eig_solve(eig, (double)n1, ridge, 0.0, G_rt, beta_init, tmp, dev);
-    tick("initial fit solve");
-
-    // res_sds = sqrt(colSums((Y - X beta)^2) / (n1 - df))  -- explicit residuals (scregclust.R:1104-1107)
-    {
-        DMat Z1rT(P, n1), resid(n1, T);
-        if (Z1rT.ld != P) SCRC_CUDA(cudaMemsetAsync(Z1rT.data(), 0, Z1rT.bytes(), st));
-        transpose(Z1r.data(), Z1r.ld, n1, P, Z1rT.data(), Z1rT.ld, st);
-        DenseArgs a{Z1rT.data(), Z1rT.ld, beta_init.data(), beta_init.ld, resid.data(), resid.ld, (int)n1, (int)T, (int)P};
-        a.D = Z1t.data(); a.ldd = Z1t.ld;
-        gemm_tn_dense(EPI_SUBFROM, a, dev.num_sms, st);
-        DevBuf<double> ss(T);
-        col_sumsq(resid.data(), resid.ld, n1, T, ss.p, st);
-        res_sds.alloc(T);
-        res_sds_kernel<<<(unsigned)ceil_div(T, 256), 256, 0, st>>>(ss.p, (double)n1 - init_df, res_sds.p, (int)T);
-        SCRC_LAUNCHED();
+        // Initial fit (scregclust.R:1049-1101): OLS when n1 >= P, ridge with the df search otherwise.
+        DMat tmp;
+        std::vector<double> lam(P);
+        SCRC_CUDA(cudaMemcpyAsync(lam.data(), eig.lam.p, P * 8, cudaMemcpyDeviceToHost, st));
         SCRC_CUDA(cudaStreamSynchronize(st));
+        double ridge = 0.0;
+        if (n1 >= P) {
+            init_df = (double)P;
+        } else {
+            // es = eigenvalues of Z'Z, decreasing; lambda_minimal = es[n1 - 1] + 1e-4 (1-based)
+            std::vector<double> es(P);
+            for (int64_t i = 0; i < P; ++i) es[i] = lam[P - 1 - i] * (double)n1;
+            ridge = es[n1 - 2] + 1e-4;
+            auto df = [&](double l) { double s = 0.0; for (double e : es) s += e / (e + l); return s; };
+            init_df = df(ridge);
+            while (init_df >= (double)n1) { ridge *= 2.0; init_df = df(ridge); }
+        }
+        eig_solve(eig, (double)n1, ridge, 0.0, G_rt, beta_init, tmp, dev);
+        tick("initial fit solve");
+
+        // res_sds = sqrt(colSums((Y - X beta)^2) / (n1 - df))  -- explicit residuals (scregclust.R:1104-1107)
+        {
+            DMat Z1rT(P, n1), resid(n1, T);
+            if (Z1rT.ld != P) SCRC_CUDA(cudaMemsetAsync(Z1rT.data(), 0, Z1rT.bytes(), st));
+            transpose(Z1r.data(), Z1r.ld, n1, P, Z1rT.data(), Z1rT.ld, st);
+            DenseArgs a{Z1rT.data(), Z1rT.ld, beta_init.data(), beta_init.ld, resid.data(), resid.ld, (int)n1, (int)T, (int)P};
+            a.D = Z1t.data(); a.ldd = Z1t.ld;
+            gemm_tn_dense(EPI_SUBFROM, a, dev.num_sms, st);
+            DevBuf<double> ss(T);
+            col_sumsq(resid.data(), resid.ld, n1, T, ss.p, st);
+            res_sds.alloc(T);
+            res_sds_kernel<<<(unsigned)ceil_div(T, 256), 256, 0, st>>>(ss.p, (double)n1 - init_df, res_sds.p, (int)T);
+            SCRC_LAUNCHED();
+            SCRC_CUDA(cudaStreamSynchronize(st));
+        }
+        bas.alloc(P, T);
+        bas_kernel<<<(unsigned)ceil_div(P * T, 256), 256, 0, st>>>(beta_init.data(), beta_init.ld, res_sds.p, bas.data(), bas.ld, P, T);
+        SCRC_LAUNCHED();
+        SCRC_CUDA(cudaMemcpyAsync(df_d.p, &init_df, 8, cudaMemcpyHostToDevice, st));
+        SCRC_CUDA(cudaStreamSynchronize(st));
+        tick("residual sds + weights");
+    } else {
+        G_rr.alloc(P, P); G_rt.alloc(P, T);
+        eig.P = (int)P; eig.V.alloc(P, P); eig.Vt.alloc(P, P); eig.lam.alloc(P);
+        gtt.alloc(T); beta_init.alloc(P, T); res_sds.alloc(T); bas.alloc(P, T);
     }
-    bas.alloc(P, T);
-    bas_kernel<<<(unsigned)ceil_div(P * T, 256), 256, 0, st>>>(beta_init.data(), beta_init.ld, res_sds.p, bas.data(), bas.ld, P, T);
-    SCRC_LAUNCHED();
-    SCRC_CUDA(cudaStreamSynchronize(st));
-    tick("residual sds + weights");
+    if (world() > 1) {
+        comm->group_begin();
+        comm->broadcast_bytes(G_rr.data(), G_rr.bytes(), 0, st);
+        comm->broadcast_bytes(G_rt.data(), G_rt.bytes(), 0, st);
+        comm->broadcast_bytes(eig.V.data(), eig.V.bytes(), 0, st);
+        comm->broadcast_bytes(eig.Vt.data(), eig.Vt.bytes(), 0, st);
+        comm->broadcast_bytes(eig.lam.p, (size_t)P * 8, 0, st);
+        comm->broadcast_bytes(gtt.p, (size_t)T * 8, 0, st);
+        comm->broadcast_bytes(beta_init.data(), beta_init.bytes(), 0, st);
+        comm->broadcast_bytes(res_sds.p, (size_t)T * 8, 0, st);
+        comm->broadcast_bytes(bas.data(), bas.bytes(), 0, st);
+        comm->broadcast_bytes(df_d.p, 8, 0, st);
+        comm->group_end();
+        SCRC_CUDA(cudaMemcpyAsync(&init_df, df_d.p, 8, cudaMemcpyDeviceToHost, st));
+        SCRC_CUDA(cudaStreamSynchronize(st));
+        tick("precompute broadcast");
+    }
 }
 
 // ============================================================================ Step 1 helper kernels
@@ -200,13 +231,14 @@ __global__ void __launch_bounds__(256) admm_weights_kernel(const double* __restr
     for (int c = c0; c < c1; ++c) s += bas[i + (int64_t)col_target[c] * ldb];
     w[i + (int64_t)p * ldw] = sqrt((double)(c1 - c0)) / sqrt(sqrt(s));
 }
-// beta * res_sds, threshold 1e-6, models / weights / signs   (scregclust.R:1372-1386)
+// beta * res_sds, threshold 1e-6, models / weights of the problems solved on THIS rank (scregclust.R:1372-1385);
+// the iteration count of problem p goes to the (fit, module) table that the ranks merge afterwards.
 __global__ void __launch_bounds__(256) admm_extract_kernel(const double* __restrict__ beta, int64_t ld,
                                                            const int* __restrict__ col_target,
                                                            const double* __restrict__ res_sds, const int* c0s,
                                                            const int* c1s, const int* prob_fit, const int* prob_mod,
-                                                           int P, int K, unsigned char* models, double* weights,
-                                                           double* signs) {
+                                                           const int* __restrict__ prob_iters, int P, int K,
+                                                           unsigned char* models, double* weights, int* iters_fk) {
     __shared__ double s_sum[8][32];
     __shared__ int s_any[8][32];
     const int p = blockIdx.y;
@@ -226,23 +258,80 @@ __global__ void __launch_bounds__(256) admm_extract_kernel(const double* __restr
     s_sum[warp][lane] = sum;
     s_any[warp][lane] = any;
     __syncthreads();
+    const int64_t fk = (int64_t)prob_fit[p] * K + prob_mod[p];
     if (warp == 0 && row < P) {
         double t = 0.0; int a = 0;
         for (int w = 0; w < 8; ++w) { t += s_sum[w][lane]; a |= s_any[w][lane]; }
-        const double wt = t / (double)(c1 - c0);
-        const int64_t o = ((int64_t)prob_fit[p] * K + prob_mod[p]) * P + row;
-        models[o] = (unsigned char)a;
-        weights[o] = wt;
-        signs[o] = a ? (double)((wt > 0.0) - (wt < 0.0)) : nan("");
+        models[fk * P + row] = (unsigned char)a;
+        weights[fk * P + row] = t / (double)(c1 - c0);
     }
+    if (blockIdx.x == 0 && threadIdx.x == 0) iters_fk[fk] = prob_iters[p];
+}
+// signs = sign(weights) where selected, NA elsewhere (scregclust.R:1386); nsel[fk] = #selected regulators.
+// Runs on every rank over the merged tables, so every rank derives identical signs.
+__global__ void __launch_bounds__(256) signs_nsel_kernel(const unsigned char* __restrict__ models,
+                                                         const double* __restrict__ weights, int P, double* signs,
+                                                         int* nsel) {
+    __shared__ int s_c[8];
+    const int64_t fk = blockIdx.x;
+    int cnt = 0;
+    for (int i = threadIdx.x; i < P; i += 256) {
+        const int64_t o = fk * P + i;
+        const int a = models[o];
+        const double wt = weights[o];
+        signs[o] = a ? (double)((wt > 0.0) - (wt < 0.0)) : nan("");
+        cnt += a;
+    }
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if ((threadIdx.x & 31) == 0) s_c[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < 8; ++w) t += s_c[w];
+        nsel[fk] = t;
+    }
+}
+// Stacked selection tables of Step 2a from the model indicator, regulators in increasing index per
+// (fit, module) as which() returns them (scregclust.R:1541-1547): sel / sign per selected regulator and
+// row_src per stacked, 16-row padded row (-1 = padding).
+__global__ void __launch_bounds__(256) nnls_fill_kernel(const unsigned char* __restrict__ models,
+                                                        const double* __restrict__ signs, int P,
+                                                        const int* __restrict__ sel_off, const int* __restrict__ row_off,
+                                                        const int* __restrict__ kpad, int* sel, double* sign,
+                                                        int* row_src) {
+    __shared__ int s_warp[8];
+    __shared__ int s_base;
+    const int64_t fk = blockIdx.x;
+    const int kp = kpad[fk];
+    if (kp == 0) return;
+    const int so = sel_off[fk], ro = row_off[fk];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < P; i0 += 256) {
+        const int i = i0 + threadIdx.x;
+        const bool a = (i < P) && models[fk * P + i];
+        const unsigned bal = __ballot_sync(0xffffffffu, a);
+        if (lane == 0) s_warp[warp] = __popc(bal);
+        __syncthreads();
+        int woff = 0, tot = 0;
+        for (int w = 0; w < 8; ++w) { if (w < warp) woff += s_warp[w]; tot += s_warp[w]; }
+        const int base = s_base;
+        if (a) {
+            const int r = base + woff + __popc(bal & ((1u << lane) - 1u));
+            sel[so + r] = i;
+            sign[so + r] = signs[fk * P + i];
+            row_src[ro + r] = i;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_base = base + tot;
+        __syncthreads();
+    }
+    for (int r = s_base + threadIdx.x; r < kp; r += 256) row_src[ro + r] = -1;
 }
 __global__ void add_one_kernel(int* x, int64_t n) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) x[i] += 1;
-}
-__global__ void fill_nan_kernel(double* x, int64_t n) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) x[i] = nan("");
 }
 
 // The reference documents these as assumptions (allocation.cpp:4-6); on a public C ABI they are checked,
@@ -270,6 +359,18 @@ void validate_prior_inputs(const char* who, const int* k, int64_t T, int K, cons
 }
 
 // ============================================================================ one batched cycle
+// Multi-GPU layout of a cycle (world > 1; every rank executes this function with the same arguments):
+//   Step 1   the non-empty (fit, module) problems are dealt to the ranks by predicted cost (shard.hpp);
+//            each rank runs the lock-step ADMM on its problems only;
+//   merge 1  all-reduce(SUM) of the module summaries -- selection indicator (1 B), mean coefficient (8 B)
+//            per (fit, module, regulator), iteration counts -- every entry written by its owner, 0 elsewhere;
+//   Step 2   every rank rebuilds the (tiny) selection tables and runs NNLS, train / test SSE and the votes
+//            for ITS slice of the target genes (all fits, all modules);
+//   merge 2  all-reduce(SUM) of k_new, best_r2 (and whichever further outputs the caller asked for), slice
+//            entries written by their owner, 0 elsewhere; after a skip_allocation cycle the coefficient
+//            columns are exchanged as well, so that every rank can return them.
+// With a network prior Step 2b is sequential over the genes (allocation.cpp:33-97): Step 1 is still
+// spread over the ranks, Step 2 is then replicated on every rank.
 void Ctx::fit_cycle(int F, const double* lambda, const int* k_in, const scrc_options& opt, bool skip_alloc,
                     scrc_cycle_out* out, const scrc_prior* prior) {
     const bool use_prior = prior && prior->weight != 0.0 && !skip_alloc;
@@ -284,37 +385,67 @@ void Ctx::fit_cycle(int F, const double* lambda, const int* k_in, const scrc_opt
     SCRC_CUDA(cudaSetDevice(dev.id));
     cudaStream_t st = dev.stream;
     const int64_t FK = (int64_t)F * K;
+    const int W = world(), R = rank();
+    if (W == 1) check_cancel();   // (collective runs agree on an interrupt at merge 1)
 
     // ---------------- Step 1: problem table (one problem per non-empty (fit, module)) ----------------
-    std::vector<int> h_col_target, h_col_prob, h_c0, h_c1, h_fit, h_mod;
-    std::vector<double> h_lambda;
+    std::vector<int> cnt(FK, 0);
     for (int f = 0; f < F; ++f) {
         const int* k = k_in + (int64_t)f * T;
-        for (int j = 1; j <= K; ++j) {
-            const int c0 = (int)h_col_target.size();
-            for (int64_t t = 0; t < T; ++t)
-                if (k[t] == j) { h_col_target.push_back((int)t); h_col_prob.push_back((int)h_c0.size()); }
-            const int c1 = (int)h_col_target.size();
-            if (c1 > c0) { h_c0.push_back(c0); h_c1.push_back(c1); h_fit.push_back(f); h_mod.push_back(j - 1); h_lambda.push_back(lambda[f]); }
+        int* c = cnt.data() + (int64_t)f * K;
+        for (int64_t t = 0; t < T; ++t) { const int j = k[t]; if (j >= 1 && j <= K) ++c[j - 1]; }
+    }
+    std::vector<int> g_fk;
+    std::vector<double> g_cost;
+    const bool have_hint = (int64_t)cost_hint.size() == FK;
+    for (int64_t fk = 0; fk < FK; ++fk)
+        if (cnt[fk] > 0) {
+            g_fk.push_back((int)fk);
+            g_cost.push_back((double)cnt[fk] * (double)((have_hint && cost_hint[fk] > 0) ? cost_hint[fk] : 25));
+        }
+    cost_hint.clear();
+    std::vector<int> owner(g_fk.size());
+    shard_assign(g_cost.data(), (int)g_fk.size(), W, owner.data());
+    std::vector<int> prob_of_fk(FK, -1), h_c0, h_c1, h_fit, h_mod;
+    std::vector<double> h_lambda;
+    int C = 0;
+    for (size_t gi = 0; gi < g_fk.size(); ++gi) {
+        if (owner[gi] != R) continue;
+        const int fk = g_fk[gi];
+        prob_of_fk[fk] = (int)h_c0.size();
+        h_c0.push_back(C); C += cnt[fk]; h_c1.push_back(C);
+        h_fit.push_back(fk / K); h_mod.push_back(fk % K); h_lambda.push_back(lambda[fk / K]);
+    }
+    const int nprob = (int)h_c0.size();
+    std::vector<int> h_col_target(C), h_col_prob(C), fillpos(h_c0);
+    for (int f = 0; f < F; ++f) {
+        const int* k = k_in + (int64_t)f * T;
+        const int* pf = prob_of_fk.data() + (int64_t)f * K;
+        for (int64_t t = 0; t < T; ++t) {
+            const int j = k[t];
+            if (j < 1 || j > K) continue;
+            const int p = pf[j - 1];
+            if (p < 0) continue;
+            const int pos = fillpos[p]++;
+            h_col_target[pos] = (int)t; h_col_prob[pos] = p;
         }
     }
-    const int C = (int)h_col_target.size(), nprob = (int)h_c0.size();
 
     models_d.ensure(FK * P); weights_d.ensure(FK * P); signs_d.ensure(FK * P);
+    iters_fk_d.ensure(FK + 1); nsel_d.ensure(FK);
     SCRC_CUDA(cudaMemsetAsync(models_d.p, 0, FK * P, st));
     SCRC_CUDA(cudaMemsetAsync(weights_d.p, 0, FK * P * 8, st));
-    fill_nan_kernel<<<(unsigned)ceil_div(FK * P, 256), 256, 0, st>>>(signs_d.p, FK * P);
-    SCRC_LAUNCHED();
+    SCRC_CUDA(cudaMemsetAsync(iters_fk_d.p, 0, (FK + 1) * 4, st));
 
-    std::vector<int> h_admm_it(FK, 0);
     long long sweeps = 0;
+    bool aborted = false;
     if (nprob > 0) {
         admm.resize((int)P, C, nprob);
         admm.h_cols.resize(nprob);
         for (int p = 0; p < nprob; ++p) admm.h_cols[p] = h_c1[p] - h_c0[p];
         col_target.ensure(C); prob_fit.ensure(nprob); prob_mod.ensure(nprob);
-        SCRC_CUDA(cudaMemcpyAsync(col_target.p, h_col_target.data(), C * 4, cudaMemcpyHostToDevice, st));
-        SCRC_CUDA(cudaMemcpyAsync(admm.col_prob.p, h_col_prob.data(), C * 4, cudaMemcpyHostToDevice, st));
+        SCRC_CUDA(cudaMemcpyAsync(col_target.p, h_col_target.data(), (size_t)C * 4, cudaMemcpyHostToDevice, st));
+        SCRC_CUDA(cudaMemcpyAsync(admm.col_prob.p, h_col_prob.data(), (size_t)C * 4, cudaMemcpyHostToDevice, st));
         SCRC_CUDA(cudaMemcpyAsync(admm.prob_c0.p, h_c0.data(), nprob * 4, cudaMemcpyHostToDevice, st));
         SCRC_CUDA(cudaMemcpyAsync(admm.prob_c1.p, h_c1.data(), nprob * 4, cudaMemcpyHostToDevice, st));
         SCRC_CUDA(cudaMemcpyAsync(admm.prob_lambda.p, h_lambda.data(), nprob * 8, cudaMemcpyHostToDevice, st));
@@ -327,65 +458,85 @@ void Ctx::fit_cycle(int F, const double* lambda, const int* k_in, const scrc_opt
         AdmmOpts ao;
         ao.rho0 = opt.rho0; ao.alpha0 = opt.alpha0; ao.eps_corr = opt.eps_corr; ao.n_update = opt.n_update;
         ao.max_iter = opt.max_optim_iter; ao.eps_rel = opt.tol_coop_rel; ao.eps_abs = opt.tol_coop_abs;
-        sweeps = admm_solve(admm, eig, ao, true, dev.num_sms, st, dev.h_pinned);
+        sweeps = admm_solve(admm, eig, ao, true, dev.num_sms, st, dev.h_pinned, &cancel);
+        aborted = admm.aborted;
         admm_extract_kernel<<<dim3((unsigned)ceil_div(P, 32), nprob), 256, 0, st>>>(
             admm.beta.data(), admm.beta.ld, col_target.p, res_sds.p, admm.prob_c0.p, admm.prob_c1.p, prob_fit.p,
-            prob_mod.p, (int)P, K, models_d.p, weights_d.p, signs_d.p);
+            prob_mod.p, admm.prob_iters.p, (int)P, K, models_d.p, weights_d.p, iters_fk_d.p);
         SCRC_LAUNCHED();
-        std::vector<int> h_it(nprob);
-        SCRC_CUDA(cudaMemcpyAsync(h_it.data(), admm.prob_iters.p, nprob * 4, cudaMemcpyDeviceToHost, st));
-        SCRC_CUDA(cudaStreamSynchronize(st));
-        for (int p = 0; p < nprob; ++p) h_admm_it[(int64_t)h_fit[p] * K + h_mod[p]] = h_it[p];
     }
-    std::vector<unsigned char> h_models(FK * P);
-    std::vector<double> h_signs(FK * P);
-    SCRC_CUDA(cudaMemcpyAsync(h_models.data(), models_d.p, FK * P, cudaMemcpyDeviceToHost, st));
-    SCRC_CUDA(cudaMemcpyAsync(h_signs.data(), signs_d.p, FK * P * 8, cudaMemcpyDeviceToHost, st));
+    if (aborted || cancel.load(std::memory_order_relaxed)) {
+        const int one = 1;
+        SCRC_CUDA(cudaMemcpyAsync(iters_fk_d.p + FK, &one, 4, cudaMemcpyHostToDevice, st));
+    }
+    // ---------------- merge 1: module summaries ----------------
+    if (W > 1) {
+        comm->group_begin();
+        comm->allreduce_sum_u8(models_d.p, (size_t)(FK * P), st);
+        comm->allreduce_sum_f64(weights_d.p, (size_t)(FK * P), st);
+        comm->allreduce_sum_i32(iters_fk_d.p, (size_t)(FK + 1), st);
+        comm->group_end();
+    }
+    signs_nsel_kernel<<<(unsigned)FK, 256, 0, st>>>(models_d.p, weights_d.p, (int)P, signs_d.p, nsel_d.p);
+    SCRC_LAUNCHED();
+    if (h_fk_cap < (size_t)(2 * FK + 1)) {
+        if (h_fk) cudaFreeHost(h_fk);
+        h_fk_cap = (size_t)(2 * FK + 1) * 2;
+        SCRC_CUDA(cudaMallocHost(&h_fk, h_fk_cap * sizeof(int)));
+    }
+    SCRC_CUDA(cudaMemcpyAsync(h_fk, iters_fk_d.p, (FK + 1) * 4, cudaMemcpyDeviceToHost, st));
+    SCRC_CUDA(cudaMemcpyAsync(h_fk + FK + 1, nsel_d.p, FK * 4, cudaMemcpyDeviceToHost, st));
     SCRC_CUDA(cudaStreamSynchronize(st));
+    if (h_fk[FK] > 0) throw Error(SCRC_ERR_INTERRUPTED, "interrupted by scrc_ctx_request_cancel");
+    const int* h_admm_it = h_fk;
+    const int* h_nsel = h_fk + FK + 1;
 
     // ---------------- Step 2a: NNLS problem table ----------------
     slots.assign(FK, FitSlot());
     last_F = F;
-    std::vector<NnlsProblem> h_np;
-    std::vector<int> h_np_slot;
-    std::vector<int> h_sel, h_row_src, h_row_off(FK, 0), h_kpad(FK, 0), h_nsel(FK, 0);
-    std::vector<double> h_sign;
-    int64_t rows_total = 0, q_total = 0;
+    std::vector<NnlsProblem>& h_np = nnls.h_prob;
+    h_np.clear();
+    std::vector<int> h_np_slot, h_row_off(FK, 0), h_kpad(FK, 0), h_sel_off(FK, 0);
+    int64_t rows_total = 0, q_total = 0, sel_total = 0;
     for (int64_t fk = 0; fk < FK; ++fk) {
         FitSlot& sl = slots[fk];
-        const unsigned char* mk = h_models.data() + fk * P;
-        for (int64_t i = 0; i < P; ++i) if (mk[i]) sl.sel.push_back((int)i);
-        sl.s = (int)sl.sel.size();
-        h_nsel[fk] = sl.s;
+        sl.s = h_nsel[fk];
         if (sl.s == 0) continue;
         const int kp = (int)round_up(sl.s, 16);
-        sl.row_off = (int)rows_total;
-        h_row_off[fk] = sl.row_off; h_kpad[fk] = kp;
-        NnlsProblem np = make_nnls_problem(sl.s, (int)h_sel.size(), q_total, rows_total);
-        for (int a = 0; a < sl.s; ++a) { h_sel.push_back(sl.sel[a]); h_sign.push_back(h_signs[fk * P + sl.sel[a]]); h_row_src.push_back(sl.sel[a]); }
-        for (int a = sl.s; a < kp; ++a) h_row_src.push_back(-1);
-        h_np.push_back(np); h_np_slot.push_back((int)fk);
-        rows_total += kp; q_total += (int64_t)sl.s * sl.s;
+        sl.row_off = (int)rows_total; sl.sel_off = (int)sel_total;
+        h_row_off[fk] = sl.row_off; h_kpad[fk] = kp; h_sel_off[fk] = sl.sel_off;
+        h_np.push_back(make_nnls_problem(sl.s, (int)sel_total, q_total, rows_total));
+        h_np_slot.push_back((int)fk);
+        rows_total += kp; q_total += (int64_t)sl.s * sl.s; sel_total += sl.s;
     }
     if (rows_total > 0x7fffff00LL) throw Error(SCRC_ERR_UNSUPPORTED, "scrc_fit_cycle: too many selected regulators in one batch");
     const int nnp = (int)h_np.size();
     const int64_t rows_alloc = std::max<int64_t>(rows_total, 16);
     nnls.nprob = nnp; nnls.m = (int)T; nnls.rows = rows_total;
-    nnls.prob.ensure(std::max(nnp, 1)); nnls.sel.ensure(std::max<size_t>(h_sel.size(), 1)); nnls.sign.ensure(std::max<size_t>(h_sign.size(), 1));
+    nnls.prob.ensure(std::max(nnp, 1)); nnls.sel.ensure(std::max<int64_t>(sel_total, 1)); nnls.sign.ensure(std::max<int64_t>(sel_total, 1));
     nnls.Q.ensure(std::max<int64_t>(q_total, 1)); nnls.dvec.ensure(rows_alloc);
     nnls.grad0.reshape(rows_alloc, T); nnls.beta.reshape(rows_alloc, T);
     nnls.iters.ensure(std::max<int64_t>((int64_t)nnp * T, 1));
-    row_src.ensure(rows_alloc); row_off_d.ensure(FK); kpad_d.ensure(FK); nsel_d.ensure(FK);
-    if (nnp > 0) {
-        SCRC_CUDA(cudaMemcpyAsync(nnls.prob.p, h_np.data(), nnp * sizeof(NnlsProblem), cudaMemcpyHostToDevice, st));
-        SCRC_CUDA(cudaMemcpyAsync(nnls.sel.p, h_sel.data(), h_sel.size() * 4, cudaMemcpyHostToDevice, st));
-        SCRC_CUDA(cudaMemcpyAsync(nnls.sign.p, h_sign.data(), h_sign.size() * 8, cudaMemcpyHostToDevice, st));
-        SCRC_CUDA(cudaMemcpyAsync(row_src.p, h_row_src.data(), h_row_src.size() * 4, cudaMemcpyHostToDevice, st));
-    }
+    row_src.ensure(rows_alloc); row_off_d.ensure(FK); kpad_d.ensure(FK); sel_off_d.ensure(FK);
+    if (nnp > 0) SCRC_CUDA(cudaMemcpyAsync(nnls.prob.p, h_np.data(), nnp * sizeof(NnlsProblem), cudaMemcpyHostToDevice, st));
     SCRC_CUDA(cudaMemcpyAsync(row_off_d.p, h_row_off.data(), FK * 4, cudaMemcpyHostToDevice, st));
     SCRC_CUDA(cudaMemcpyAsync(kpad_d.p, h_kpad.data(), FK * 4, cudaMemcpyHostToDevice, st));
-    SCRC_CUDA(cudaMemcpyAsync(nsel_d.p, h_nsel.data(), FK * 4, cudaMemcpyHostToDevice, st));
-    SCRC_CUDA(cudaMemsetAsync(nnls.beta.data(), 0, nnls.beta.bytes(), st));
+    SCRC_CUDA(cudaMemcpyAsync(sel_off_d.p, h_sel_off.data(), FK * 4, cudaMemcpyHostToDevice, st));
+    if (nnp > 0) {
+        nnls_fill_kernel<<<(unsigned)FK, 256, 0, st>>>(models_d.p, signs_d.p, (int)P, sel_off_d.p, row_off_d.p, kpad_d.p,
+                                                       nnls.sel.p, nnls.sign.p, row_src.p);
+        SCRC_LAUNCHED();
+    }
+
+    // target slice of this rank (whole range with a prior: the sweep is sequential)
+    int64_t ts0 = 0, ts1 = T;
+    const bool sliced = (W > 1) && !use_prior;
+    if (sliced) shard_slice(T, RV_BN, R, W, &ts0, &ts1);
+    const int t0 = (int)ts0, t1 = (int)ts1;
+    const bool want_nnls_it = out && out->nnls_iterations;
+    nnls.col0 = t0; nnls.col1 = t1; nnls.use_active = false;
+    if (rows_total == 0) SCRC_CUDA(cudaMemsetAsync(nnls.beta.data(), 0, nnls.beta.bytes(), st));
+    if (sliced && want_nnls_it) SCRC_CUDA(cudaMemsetAsync(nnls.iters.p, 0, (size_t)std::max<int64_t>((int64_t)nnp * T, 1) * 4, st));
     if (nnp > 0) {
         nnls_setup(nnls, G_rr.data(), G_rr.ld, G_rt.data(), G_rt.ld, inv_sds_t.p, st);
         nnls_solve(nnls, opt.tol_nnls, opt.max_optim_iter, sds_t.p, (int)T, dev.num_sms, st);
@@ -394,30 +545,38 @@ void Ctx::fit_cycle(int F, const double* lambda, const int* k_in, const scrc_opt
     // ---------------- Step 2a/2b: residuals, SSE, variances, votes ----------------
     const int CRte = resid_vote_pick_cr((int)n2, (int)T, F, dev.num_sms);
     partial.ensure(resid_vote_partial_elems((int)T, K, F, CRte));
-    const size_t fkt = (size_t)F * K * T, fk1t = (size_t)F * (K + 1) * T;
+    const size_t fkt = (size_t)F * K * T, fk1t = (size_t)F * (K + 1) * T, ft = (size_t)F * T;
     sse_train.ensure(fk1t); sse_test.ensure(fk1t); var.ensure(fkt); two_var.ensure(fkt); inv_two_var.ensure(fkt); half_log.ensure(fkt);
-    r2.ensure(fkt); best_r2.ensure((size_t)F * T); best_idx.ensure((size_t)F * T); k_new.ensure((size_t)F * T);
+    r2.ensure(fkt); best_r2.ensure(ft); best_idx.ensure(ft); k_new.ensure(ft);
     votes.ensure(fkt);
+    const bool vote = !skip_alloc;
+    if (sliced) {   // merged outputs: zero outside the slice
+        SCRC_CUDA(cudaMemsetAsync(best_r2.p, 0, ft * 8, st));
+        if (vote) SCRC_CUDA(cudaMemsetAsync(k_new.p, 0, ft * 4, st));
+        if (out && out->r2_test) SCRC_CUDA(cudaMemsetAsync(r2.p, 0, fkt * 8, st));
+        if (out && out->resid_var) SCRC_CUDA(cudaMemsetAsync(var.p, 0, fkt * 8, st));
+        if (out && out->best_r2_idx) SCRC_CUDA(cudaMemsetAsync(best_idx.p, 0, ft * 4, st));
+    }
 
     ResidVoteArgs ra;
     ra.beta = nnls.beta.data(); ra.ldb = nnls.beta.ld; ra.rows_total = rows_total;
     ra.T = (int)T; ra.K = K; ra.L = F; ra.row_off = row_off_d.p; ra.kpad = kpad_d.p; ra.nsel = nsel_d.p;
     ra.two_var = two_var.p; ra.inv_two_var = inv_two_var.p; ra.half_log = half_log.p; ra.partial = partial.p; ra.votes = votes.p;
+    ra.t_begin = t0; ra.t_end = t1;
     // train split: SSE from the Gram matrices (no pass over the n1 cells), then the variances
     sse_train_gram(G_rr.data(), G_rr.ld, G_rt.data(), G_rt.ld, gtt.p, nnls.beta.data(), nnls.beta.ld, row_src.p,
-                   row_off_d.p, nsel_d.p, (int)T, K, F, sse_train.p, st);
-    make_resid_var(sse_train.p, nsel_d.p, (int)n1, (int)T, K, F, var.p, two_var.p, inv_two_var.p, half_log.p, st);
+                   row_off_d.p, nsel_d.p, (int)T, K, F, sse_train.p, st, t0, t1);
+    make_resid_var(sse_train.p, nsel_d.p, (int)n1, (int)T, K, F, var.p, two_var.p, inv_two_var.p, half_log.p, st, t0, t1);
     // test split
     ZselT.reshape(rows_alloc, n2);
     if (rows_total == 0) SCRC_CUDA(cudaMemsetAsync(ZselT.data(), 0, ZselT.bytes(), st));
     gather_transpose(Z2r.data(), Z2r.ld, (int)n2, row_src.p, rows_total, ZselT.data(), ZselT.ld, st);
     ra.ZselT = ZselT.data(); ra.ldzs = ZselT.ld; ra.Z = Z2t.data(); ra.ldz = Z2t.ld; ra.ncells = (int)n2; ra.CR = CRte;
-    const bool vote = !skip_alloc;
     if (!use_prior) {
         if (vote) SCRC_CUDA(cudaMemsetAsync(votes.p, 0, fkt * 4, st));
         resid_vote(ra, vote ? 1 : 0, dev.num_sms, st);
-        reduce_sse(partial.p, (int)T, K, F, CRte, sse_test.p, st);
-        finish_alloc(sse_test.p, vote ? votes.p : nullptr, (int)T, K, F, r2.p, best_r2.p, best_idx.p, k_new.p, st);
+        reduce_sse(partial.p, (int)T, K, F, CRte, sse_test.p, st, t0, t1);
+        finish_alloc(sse_test.p, vote ? votes.p : nullptr, (int)T, K, F, r2.p, best_r2.p, best_idx.p, k_new.p, st, t0, t1);
     } else {
         // Network prior (allocation.cpp:39-56,74-77): the sweep is sequential in update_order because every
         // reassignment changes the prior of the genes that follow, so each fit materialises its K x n2 x T
@@ -447,6 +606,7 @@ void Ctx::fit_cycle(int F, const double* lambda, const int* k_in, const scrc_opt
                                     prior->baseline, prior->weight, votes.p + (size_t)f * T * K, st);
             SCRC_CUDA(cudaMemcpyAsync(k_new.p + (size_t)f * T, d_k.p, T * 4, cudaMemcpyDeviceToDevice, st));
             SCRC_CUDA(cudaStreamSynchronize(st));   // k0 is reused by the next fit
+            check_cancel();                          // allocation.cpp:96 polls per gene; here per fit
         }
         reduce_sse(partial.p, (int)T, K, F, CRte, sse_test.p, st);
         // r2 / best_r2 from the SSEs; k_new (0-based from the sweep) is shifted to 1-based below
@@ -455,27 +615,104 @@ void Ctx::fit_cycle(int F, const double* lambda, const int* k_in, const scrc_opt
         SCRC_LAUNCHED();
     }
 
+    // ---------------- merge 2: per-gene results of the target slices ----------------
+    if (sliced) {
+        comm->group_begin();
+        comm->allreduce_sum_f64(best_r2.p, ft, st);
+        if (vote) comm->allreduce_sum_i32(k_new.p, ft, st);
+        if (out && out->r2_test) comm->allreduce_sum_f64(r2.p, fkt, st);
+        if (out && out->resid_var) comm->allreduce_sum_f64(var.p, fkt, st);
+        if (out && out->best_r2_idx) comm->allreduce_sum_i32(best_idx.p, ft, st);
+        if (vote && out && out->votes) comm->allreduce_sum_i32(votes.p, fkt, st);
+        if (want_nnls_it && nnp > 0) comm->allreduce_sum_i32(nnls.iters.p, (size_t)nnp * T, st);
+        if (skip_alloc && rows_total > 0)   // coefficient columns: every rank sends its slice (ragged all-gather)
+            for (int r = 0; r < W; ++r) {
+                int64_t a = 0, b = 0;
+                shard_slice(T, RV_BN, r, W, &a, &b);
+                comm->broadcast_bytes(nnls.beta.data() + nnls.beta.ld * a, (size_t)(nnls.beta.ld * (b - a)) * 8, r, st);
+            }
+        comm->group_end();
+    }
+
     // ---------------- outputs ----------------
     if (out) {
         auto d2h = [&](void* dst, const void* src, size_t bytes) {
             if (dst && bytes) SCRC_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));
         };
-        if (vote) { d2h(out->k_new, k_new.p, (size_t)F * T * 4); d2h(out->votes, votes.p, fkt * 4); }
+        if (vote) { d2h(out->k_new, k_new.p, ft * 4); d2h(out->votes, votes.p, fkt * 4); }
+        d2h(out->models, models_d.p, FK * P);
         d2h(out->weights, weights_d.p, FK * P * 8);
+        d2h(out->signs, signs_d.p, FK * P * 8);
         d2h(out->r2_test, r2.p, fkt * 8);
         d2h(out->resid_var, var.p, fkt * 8);
-        d2h(out->best_r2, best_r2.p, (size_t)F * T * 8);
-        d2h(out->best_r2_idx, best_idx.p, (size_t)F * T * 4);
-        if (out->models) std::memcpy(out->models, h_models.data(), FK * P);
-        if (out->signs) std::memcpy(out->signs, h_signs.data(), FK * P * 8);
-        if (out->admm_iterations) std::memcpy(out->admm_iterations, h_admm_it.data(), FK * 4);
-        if (out->n_selected) std::memcpy(out->n_selected, h_nsel.data(), FK * 4);
+        d2h(out->best_r2, best_r2.p, ft * 8);
+        d2h(out->best_r2_idx, best_idx.p, ft * 4);
+        if (out->admm_iterations) std::memcpy(out->admm_iterations, h_admm_it, FK * 4);
+        if (out->n_selected) std::memcpy(out->n_selected, h_nsel, FK * 4);
         if (out->admm_sweeps) *out->admm_sweeps = sweeps;
         if (out->nnls_iterations) {
             std::memset(out->nnls_iterations, 0, fkt * 4);
             for (int q = 0; q < nnp; ++q)
                 d2h(out->nnls_iterations + (size_t)h_np_slot[q] * T, nnls.iters.p + (size_t)q * T, (size_t)T * 4);
         }
+    }
+    SCRC_CUDA(cudaStreamSynchronize(st));
+}
+
+// out[base[r] + a[r] + s[r] * t] = beta[src[r] + ld * t]: drops the 16-row padding of the stacked layout and
+// lays every module's s x T block out contiguously, so that one linear copy brings a whole fit to the host.
+__global__ void coeff_pack_kernel(const double* __restrict__ beta, int64_t ld, int T, int nrows,
+                                  const int* __restrict__ src, const int* __restrict__ s_of, const int* __restrict__ a_of,
+                                  const long long* __restrict__ base, double* out) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    const int t = blockIdx.y;
+    if (r >= nrows || t >= T) return;
+    out[base[r] + a_of[r] + (long long)s_of[r] * t] = beta[src[r] + ld * t];
+}
+
+// Packs the K coefficient matrices of fit f (s_k x T each, one after the other) into `out_dev` on the device.
+void Ctx::pack_coeffs_fit(int f, double* out_dev) {
+    if (f < 0 || f >= last_F) throw Error(SCRC_ERR_ARG, "scrc_ctx_get_coeffs_fit: index out of range");
+    SCRC_CUDA(cudaSetDevice(dev.id));
+    cudaStream_t st = dev.stream;
+    std::vector<int> src, s_of, a_of;
+    std::vector<long long> base;
+    long long off = 0;
+    for (int k = 0; k < K; ++k) {
+        const FitSlot& sl = slots[(size_t)f * K + k];
+        for (int a = 0; a < sl.s; ++a) { src.push_back(sl.row_off + a); s_of.push_back(sl.s); a_of.push_back(a); base.push_back(off); }
+        off += (long long)sl.s * T;
+    }
+    if (src.empty()) return;
+    const int nrows = (int)src.size();
+    pack_src.ensure(nrows); pack_s.ensure(nrows); pack_a.ensure(nrows); pack_base.ensure(nrows);
+    SCRC_CUDA(cudaMemcpyAsync(pack_src.p, src.data(), nrows * 4, cudaMemcpyHostToDevice, st));
+    SCRC_CUDA(cudaMemcpyAsync(pack_s.p, s_of.data(), nrows * 4, cudaMemcpyHostToDevice, st));
+    SCRC_CUDA(cudaMemcpyAsync(pack_a.p, a_of.data(), nrows * 4, cudaMemcpyHostToDevice, st));
+    SCRC_CUDA(cudaMemcpyAsync(pack_base.p, base.data(), nrows * 8, cudaMemcpyHostToDevice, st));
+    coeff_pack_kernel<<<dim3((unsigned)ceil_div(nrows, 128), (unsigned)T), 128, 0, st>>>(
+        nnls.beta.data(), nnls.beta.ld, (int)T, nrows, pack_src.p, pack_s.p, pack_a.p, pack_base.p, out_dev);
+    SCRC_LAUNCHED();
+    SCRC_CUDA(cudaStreamSynchronize(st));
+}
+
+void Ctx::get_coeffs_fit(int f, double* coeffs_out, int* sel_out) {
+    if (f < 0 || f >= last_F) throw Error(SCRC_ERR_ARG, "scrc_ctx_get_coeffs_fit: index out of range");
+    SCRC_CUDA(cudaSetDevice(dev.id));
+    cudaStream_t st = dev.stream;
+    int nsel_fit = 0, first = -1;
+    for (int k = 0; k < K; ++k) {
+        const FitSlot& sl = slots[(size_t)f * K + k];
+        if (sl.s > 0 && first < 0) first = sl.sel_off;
+        nsel_fit += sl.s;
+    }
+    if (nsel_fit == 0) return;
+    // the selections of a fit are contiguous in the stacked list (fits and modules in order)
+    if (sel_out) SCRC_CUDA(cudaMemcpyAsync(sel_out, nnls.sel.p + first, (size_t)nsel_fit * 4, cudaMemcpyDeviceToHost, st));
+    if (coeffs_out) {
+        pack_out.ensure((size_t)nsel_fit * T);
+        pack_coeffs_fit(f, pack_out.p);
+        SCRC_CUDA(cudaMemcpyAsync(coeffs_out, pack_out.p, (size_t)nsel_fit * T * 8, cudaMemcpyDeviceToHost, st));
     }
     SCRC_CUDA(cudaStreamSynchronize(st));
 }
@@ -489,6 +726,8 @@ void Ctx::fit_cycle(int F, const double* lambda, const int* k_in, const scrc_opt
 // All (f, j, r) problems run in one batched NNLS launch and one batched residual launch; the s + 1
 // problems of a module share one gathered regulator block (the removed regulator's coefficient row
 // is kept as an exact zero row) and differ only in their coefficient rows.
+// Multi-GPU: every rank builds the same tables, solves the problems of the modules dealt to it
+// (shard.hpp) and the per-target SSE table is merged with one all-reduce(SUM).
 void Ctx::importance(int F, const int* k_final, const unsigned char* models, const double* signs,
                      const scrc_options& opt, double* r2_module, double* importance_out, double* r2_removed,
                      int64_t r2_removed_capacity) {
@@ -496,29 +735,36 @@ void Ctx::importance(int F, const int* k_final, const unsigned char* models, con
     SCRC_CUDA(cudaSetDevice(dev.id));
     cudaStream_t st = dev.stream;
     const int64_t FK = (int64_t)F * K;
+    const int W = world(), R = rank();
+    if (W == 1) check_cancel();
     const double nan_v = std::nan("");
     for (int64_t i = 0; i < FK; ++i) r2_module[i] = nan_v;
     for (int64_t i = 0; i < FK * P; ++i) importance_out[i] = nan_v;
 
     struct Group { int f, j, s, spad, m; int arow; int col_off; std::vector<int> regs; int first_prob; };
     std::vector<Group> groups;
-    std::vector<NnlsProblem> h_np;
+    NnlsBatch& nb = imp_nb;
+    std::vector<NnlsProblem>& h_np = nb.h_prob;
+    h_np.clear();
     std::vector<int> h_sel, h_pos, h_cols, h_row_src, h_arow, h_brow, h_kpad, h_coff, h_ccnt;
-    std::vector<double> h_sign;
+    std::vector<double> h_sign, g_cost;
     int64_t rows_a = 0, rows_b = 0, q_total = 0;
     int Tmax = 0;
     for (int f = 0; f < F; ++f) {
         const int* k = k_final + (int64_t)f * T;
+        // targets of every module in increasing index (one pass over the configuration)
+        std::vector<std::vector<int>> cols_of(K);
+        for (int64_t t = 0; t < T; ++t) { const int j = k[t]; if (j >= 1 && j <= K) cols_of[j - 1].push_back((int)t); }
         for (int j = 0; j < K; ++j) {
             Group g;
             g.f = f; g.j = j;
             const unsigned char* mk = models + ((int64_t)f * K + j) * P;
             for (int64_t i = 0; i < P; ++i) if (mk[i]) g.regs.push_back((int)i);
             g.s = (int)g.regs.size();
+            g.m = (int)cols_of[j].size();
+            if (!(g.m > 0 && g.s > 1)) continue;                                    // scregclust.R:1839
             g.col_off = (int)h_cols.size();
-            for (int64_t t = 0; t < T; ++t) if (k[t] == j + 1) h_cols.push_back((int)t);
-            g.m = (int)h_cols.size() - g.col_off;
-            if (!(g.m > 0 && g.s > 1)) { h_cols.resize(g.col_off); continue; }      // scregclust.R:1839
+            h_cols.insert(h_cols.end(), cols_of[j].begin(), cols_of[j].end());
             g.spad = (int)round_up(g.s, 16);
             g.arow = (int)rows_a;
             g.first_prob = (int)h_np.size();
@@ -541,59 +787,81 @@ void Ctx::importance(int F, const int* k_final, const unsigned char* models, con
                 h_coff.push_back(g.col_off); h_ccnt.push_back(g.m);
                 rows_b += g.spad; q_total += (int64_t)sp * sp;
             }
+            g_cost.push_back((double)g.m * (g.s + 1.0) * g.s * (g.s + 16.0));
             groups.push_back(std::move(g));
         }
     }
     if (groups.empty()) return;
     if (rows_b > 0x7fffff00LL) throw Error(SCRC_ERR_UNSUPPORTED, "scrc_importance: batch too large; pass fewer configurations per call");
     const int nprob = (int)h_np.size();
+    // modules dealt to the ranks; the problems of the others are skipped here (zero columns / not in `active`)
+    std::vector<int> owner(groups.size());
+    shard_assign(g_cost.data(), (int)groups.size(), W, owner.data());
+    nb.use_active = (W > 1);
+    nb.active.clear();
+    if (W > 1)
+        for (size_t gi = 0; gi < groups.size(); ++gi) {
+            const Group& g = groups[gi];
+            for (int r = 0; r <= g.s; ++r) {
+                if (owner[gi] == R) nb.active.push_back(g.first_prob + r);
+                else h_ccnt[g.first_prob + r] = 0;
+            }
+        }
 
-    // gathered per-group scale vector z1_target_sds[target_cl] shares the layout of h_cols
-    NnlsBatch nb;
-    nb.nprob = nprob; nb.m = Tmax; nb.rows = rows_b;
-    nb.prob.alloc(nprob); nb.sel.alloc(h_sel.size()); nb.sign.alloc(h_sign.size()); nb.pos.alloc(h_pos.size());
-    nb.cols.alloc(h_cols.size()); nb.Q.alloc(q_total); nb.dvec.alloc(rows_b);
-    nb.grad0.alloc(rows_b, Tmax); nb.beta.alloc(rows_b, Tmax); nb.iters.alloc((size_t)nprob * Tmax);
-    DevBuf<double> scale_vals(h_cols.size());
-    std::vector<double> h_sds(T), h_scale(h_cols.size());
-    SCRC_CUDA(cudaMemcpyAsync(h_sds.data(), sds_t.p, T * 8, cudaMemcpyDeviceToHost, st));
-    SCRC_CUDA(cudaStreamSynchronize(st));
+    nb.nprob = nprob; nb.m = Tmax; nb.rows = rows_b; nb.col0 = 0; nb.col1 = -1;
+    nb.prob.ensure(nprob); nb.sel.ensure(h_sel.size()); nb.sign.ensure(h_sign.size()); nb.pos.ensure(h_pos.size());
+    nb.cols.ensure(h_cols.size()); nb.Q.ensure(q_total); nb.dvec.ensure(rows_b);
+    nb.grad0.reshape(rows_b, Tmax); nb.beta.reshape(rows_b, Tmax); nb.iters.ensure((size_t)nprob * Tmax);
+    imp_scale.ensure(h_cols.size());
+    if (h_sds.empty()) {
+        h_sds.resize(T);
+        SCRC_CUDA(cudaMemcpyAsync(h_sds.data(), sds_t.p, T * 8, cudaMemcpyDeviceToHost, st));
+        SCRC_CUDA(cudaStreamSynchronize(st));
+    }
+    std::vector<double> h_scale(h_cols.size());
     for (size_t i = 0; i < h_cols.size(); ++i) h_scale[i] = h_sds[h_cols[i]];
     SCRC_CUDA(cudaMemcpyAsync(nb.prob.p, h_np.data(), nprob * sizeof(NnlsProblem), cudaMemcpyHostToDevice, st));
     SCRC_CUDA(cudaMemcpyAsync(nb.sel.p, h_sel.data(), h_sel.size() * 4, cudaMemcpyHostToDevice, st));
     SCRC_CUDA(cudaMemcpyAsync(nb.sign.p, h_sign.data(), h_sign.size() * 8, cudaMemcpyHostToDevice, st));
     SCRC_CUDA(cudaMemcpyAsync(nb.pos.p, h_pos.data(), h_pos.size() * 4, cudaMemcpyHostToDevice, st));
     SCRC_CUDA(cudaMemcpyAsync(nb.cols.p, h_cols.data(), h_cols.size() * 4, cudaMemcpyHostToDevice, st));
-    SCRC_CUDA(cudaMemcpyAsync(scale_vals.p, h_scale.data(), h_scale.size() * 8, cudaMemcpyHostToDevice, st));
+    SCRC_CUDA(cudaMemcpyAsync(imp_scale.p, h_scale.data(), h_scale.size() * 8, cudaMemcpyHostToDevice, st));
     SCRC_CUDA(cudaMemsetAsync(nb.grad0.data(), 0, nb.grad0.bytes(), st));
+    SCRC_CUDA(cudaMemsetAsync(nb.beta.data(), 0, nb.beta.bytes(), st));   // left-out rows and padding stay exact zeros
     nnls_setup(nb, G_rr.data(), G_rr.ld, G_rt.data(), G_rt.ld, inv_sds_t.p, st);
-    nnls_solve(nb, opt.tol_nnls, opt.max_optim_iter, scale_vals.p, 1, dev.num_sms, st);   // scregclust.R:1865-1873
+    nnls_solve(nb, opt.tol_nnls, opt.max_optim_iter, imp_scale.p, 1, dev.num_sms, st);   // scregclust.R:1865-1873
 
     // test residuals: SSE per (problem, target of the module)                          scregclust.R:1875-1878
-    DevBuf<int> d_row_src(rows_a), d_arow(nprob), d_brow(nprob), d_kpad(nprob), d_coff(nprob), d_ccnt(nprob);
-    SCRC_CUDA(cudaMemcpyAsync(d_row_src.p, h_row_src.data(), rows_a * 4, cudaMemcpyHostToDevice, st));
-    SCRC_CUDA(cudaMemcpyAsync(d_arow.p, h_arow.data(), nprob * 4, cudaMemcpyHostToDevice, st));
-    SCRC_CUDA(cudaMemcpyAsync(d_brow.p, h_brow.data(), nprob * 4, cudaMemcpyHostToDevice, st));
-    SCRC_CUDA(cudaMemcpyAsync(d_kpad.p, h_kpad.data(), nprob * 4, cudaMemcpyHostToDevice, st));
-    SCRC_CUDA(cudaMemcpyAsync(d_coff.p, h_coff.data(), nprob * 4, cudaMemcpyHostToDevice, st));
-    SCRC_CUDA(cudaMemcpyAsync(d_ccnt.p, h_ccnt.data(), nprob * 4, cudaMemcpyHostToDevice, st));
-    DMat Zs(rows_a, n2);
-    gather_transpose(Z2r.data(), Z2r.ld, (int)n2, d_row_src.p, rows_a, Zs.data(), Zs.ld, st);
+    imp_row_src.ensure(rows_a); imp_arow.ensure(nprob); imp_brow.ensure(nprob); imp_kpad.ensure(nprob);
+    imp_coff.ensure(nprob); imp_ccnt.ensure(nprob);
+    SCRC_CUDA(cudaMemcpyAsync(imp_row_src.p, h_row_src.data(), rows_a * 4, cudaMemcpyHostToDevice, st));
+    SCRC_CUDA(cudaMemcpyAsync(imp_arow.p, h_arow.data(), nprob * 4, cudaMemcpyHostToDevice, st));
+    SCRC_CUDA(cudaMemcpyAsync(imp_brow.p, h_brow.data(), nprob * 4, cudaMemcpyHostToDevice, st));
+    SCRC_CUDA(cudaMemcpyAsync(imp_kpad.p, h_kpad.data(), nprob * 4, cudaMemcpyHostToDevice, st));
+    SCRC_CUDA(cudaMemcpyAsync(imp_coff.p, h_coff.data(), nprob * 4, cudaMemcpyHostToDevice, st));
+    SCRC_CUDA(cudaMemcpyAsync(imp_ccnt.p, h_ccnt.data(), nprob * 4, cudaMemcpyHostToDevice, st));
+    imp_Zs.reshape(rows_a, n2);
+    gather_transpose(Z2r.data(), Z2r.ld, (int)n2, imp_row_src.p, rows_a, imp_Zs.data(), imp_Zs.ld, st);
     const int CR = resid_vote_pick_cr((int)n2, Tmax, nprob, dev.num_sms);
-    DevBuf<double> part(resid_vote_partial_elems(Tmax, 1, nprob, CR)), sse((size_t)nprob * 2 * Tmax);
+    imp_part.ensure(resid_vote_partial_elems(Tmax, 1, nprob, CR));
+    imp_sse.ensure((size_t)nprob * 2 * Tmax);
+    if (W > 1) SCRC_CUDA(cudaMemsetAsync(imp_sse.p, 0, (size_t)nprob * 2 * Tmax * 8, st));
     ResidVoteArgs ra;
-    ra.ZselT = Zs.data(); ra.ldzs = Zs.ld; ra.beta = nb.beta.data(); ra.ldb = nb.beta.ld; ra.rows_total = rows_b;
+    ra.ZselT = imp_Zs.data(); ra.ldzs = imp_Zs.ld; ra.beta = nb.beta.data(); ra.ldb = nb.beta.ld; ra.rows_total = rows_b;
     ra.Z = Z2t.data(); ra.ldz = Z2t.ld; ra.ncells = (int)n2; ra.T = Tmax; ra.K = 1; ra.L = nprob;
-    ra.row_off = d_arow.p; ra.kpad = d_kpad.p; ra.two_var = nullptr; ra.half_log = nullptr;
-    ra.partial = part.p; ra.votes = nullptr; ra.CR = CR;
-    ra.row_off_b = d_brow.p; ra.col_index = nb.cols.p; ra.col_off = d_coff.p; ra.col_cnt = d_ccnt.p;
+    ra.row_off = imp_arow.p; ra.kpad = imp_kpad.p; ra.two_var = nullptr; ra.half_log = nullptr;
+    ra.partial = imp_part.p; ra.votes = nullptr; ra.CR = CR;
+    ra.row_off_b = imp_brow.p; ra.col_index = nb.cols.p; ra.col_off = imp_coff.p; ra.col_cnt = imp_ccnt.p;
     // the A operand (rows_a rows) and the B operand (rows_b rows) need tensor maps of their own extent
     ra.rows_total_a = rows_a;
     resid_vote(ra, 0, dev.num_sms, st);
-    reduce_sse(part.p, Tmax, 1, nprob, CR, sse.p, st);
+    reduce_sse(imp_part.p, Tmax, 1, nprob, CR, imp_sse.p, st, 0, -1, W > 1 ? imp_ccnt.p : nullptr);
+    if (W > 1) comm->allreduce_sum_f64(imp_sse.p, (size_t)nprob * 2 * Tmax, st);
     if (z2t_css.n == 0) { z2t_css.alloc(T); col_centered_ss(Z2t.data(), Z2t.ld, n2, T, z2t_css.p, st); }
-    std::vector<double> h_sse((size_t)nprob * 2 * Tmax), h_css(T);
-    SCRC_CUDA(cudaMemcpyAsync(h_sse.data(), sse.p, h_sse.size() * 8, cudaMemcpyDeviceToHost, st));
+    std::vector<double>& h_sse = imp_h_sse;
+    h_sse.resize((size_t)nprob * 2 * Tmax);
+    std::vector<double> h_css(T);
+    SCRC_CUDA(cudaMemcpyAsync(h_sse.data(), imp_sse.p, h_sse.size() * 8, cudaMemcpyDeviceToHost, st));
     SCRC_CUDA(cudaMemcpyAsync(h_css.data(), z2t_css.p, T * 8, cudaMemcpyDeviceToHost, st));
     SCRC_CUDA(cudaStreamSynchronize(st));
 

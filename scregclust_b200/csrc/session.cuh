@@ -4,8 +4,11 @@
 #include <vector>
 
 #include "../../include/scregclust_b200.h"
+#include <atomic>
+
 #include "admm.cuh"
 #include "alloc.cuh"
+#include "comm.cuh"
 #include "misc.cuh"
 #include "nnls.cuh"
 
@@ -30,13 +33,25 @@ void eig_solve(const EigBasis& eig, double mult, double shift, double cut, const
 struct FitSlot {        // bookkeeping of one (fit, module) after Step 1
     int s = 0;          // selected regulators
     int row_off = 0;    // first stacked row
-    std::vector<int> sel;
+    int sel_off = 0;    // first entry in the stacked selection list (nnls.sel)
 };
 
 struct Ctx {
     Device dev;
     int64_t n1 = 0, n2 = 0, P = 0, T = 0;
     int K = 0;
+    // Multi-GPU: with a communicator every call below is COLLECTIVE -- all ranks call it with
+    // the same arguments; Step-1 problems are spread over the ranks, Step 2 runs on target slices, and the
+    // outputs are merged so that every rank returns the complete result.  Not owned.
+    Comm* comm = nullptr;
+    int rank() const { return comm ? comm->rank : 0; }
+    int world() const { return comm ? comm->world : 1; }
+    // Cooperative cancellation (the reference polls Rcpp::checkUserInterrupt() in its loops,
+    // optim.cpp:307,536, allocation.cpp:96): set from any thread / signal handler, polled at the ADMM
+    // host polls and between the phases of a cycle; the call then fails with SCRC_ERR_INTERRUPTED.
+    std::atomic<int> cancel{0};
+    // predicted ADMM iterations per (fit, module) of the NEXT fit_cycle call (balances the ranks); consumed
+    std::vector<int> cost_hint;
     DMat Z1r, Z2r, Z1t, Z2t;
     DevBuf<double> sds_t;        // z1_target_sds
     DevBuf<double> inv_sds_t;    // 1 / z1_target_sds
@@ -52,7 +67,9 @@ struct Ctx {
     DevBuf<int> col_target;
     DevBuf<int> prob_fit, prob_mod;
     NnlsBatch nnls;
-    DevBuf<int> row_src, row_off_d, kpad_d, nsel_d;
+    DevBuf<int> row_src, row_off_d, kpad_d, nsel_d, sel_off_d, iters_fk_d;
+    int* h_fk = nullptr;          // pinned: [FK admm iterations | abort flag | FK selected counts]
+    size_t h_fk_cap = 0;
     DMat ZselT;
     DevBuf<double> partial, sse_train, sse_test, var, two_var, inv_two_var, half_log, r2, best_r2;
     DevBuf<int> votes, best_idx, k_new;
@@ -62,7 +79,7 @@ struct Ctx {
     int last_F = 0;
 
     void create(int device, const double* z1r, const double* z2r, const double* z1t, const double* z2t,
-                const double* sds, int64_t n1, int64_t n2, int64_t P, int64_t T, int K);
+                const double* sds, int64_t n1, int64_t n2, int64_t P, int64_t T, int K, Comm* comm = nullptr);
     // Raw p x n expression matrix in; split, per-stratum centring, constant-gene filter and scaling on
     // the device (stage.cu).  keep_gene[p] (may be null) marks the genes that survive the filter;
     // dims_out[4] = n1, n2, P, T after filtering.
@@ -80,9 +97,25 @@ struct Ctx {
     void importance(int F, const int* k_final, const unsigned char* models, const double* signs,
                     const scrc_options& opt, double* r2_module, double* importance_out,
                     double* r2_removed = nullptr, int64_t r2_removed_capacity = 0);
+    // scratch of the post-processing and of the coefficient packing, kept across calls (cudaMalloc / cudaFree
+    // synchronise the device and cost more than the kernels they serve)
+    NnlsBatch imp_nb;
+    DevBuf<double> imp_scale, imp_part, imp_sse;
+    DevBuf<int> imp_row_src, imp_arow, imp_brow, imp_kpad, imp_coff, imp_ccnt;
+    DMat imp_Zs;
+    std::vector<double> imp_h_sse, h_sds;
+    DevBuf<int> pack_src, pack_s, pack_a;
+    DevBuf<long long> pack_base;
+    DevBuf<double> pack_out;
     DevBuf<double> z2t_css;      // centred sums of squares of the test targets (lazy)
     DevBuf<double> gtt;          // colSums(z1_target_centered^2)
-    ~Ctx() { dev.destroy(); }
+    // All K coefficient matrices of fit f of the last (skip_allocation) cycle, packed; see scrc_ctx_get_coeffs_fit.
+    void get_coeffs_fit(int f, double* coeffs_out, int* sel_out);
+    void pack_coeffs_fit(int f, double* out_dev);     // the same, packed into a device buffer
+    void check_cancel() const {
+        if (cancel.load(std::memory_order_relaxed)) throw Error(SCRC_ERR_INTERRUPTED, "interrupted by scrc_ctx_request_cancel");
+    }
+    ~Ctx() { if (h_fk) cudaFreeHost(h_fk); dev.destroy(); }
 };
 
 // O(T + nnz) host checks of caller data that index device memory in the network-prior sweep; throws SCRC_ERR_ARG.
@@ -107,3 +140,12 @@ void dropin_allocate(Device& dev, const double* sq_resid, int K, int64_t n2, int
                      double weight, int* k_out, int* votes_out);
 
 }  // namespace scrc
+
+// the opaque handle of the public header
+struct scrc_ctx {
+    scrc::Ctx impl;
+};
+struct scrc_comm {
+    scrc::Comm impl;
+};
+extern "C" void scrc_set_last_error_(const char* msg);   // capi.cu: message returned by scrc_last_error()

@@ -1,12 +1,11 @@
-"""Host driver of the alternating fit / reallocate loop on top of the session API.
+"""Python caller of the session and whole-grid entry points of ``libscregclust_b200.so``.
 
-Mirrors the control flow of ``scregclust()`` (R/scregclust.R:1222-1803) for
-``allocate_per_obs = TRUE``, ``quick_mode = FALSE`` and no network prior: module
-history, noise threshold, minimum module size, convergence / limit-cycle
-detection and the final re-fit of every configuration of a limit cycle.  All
-numerics run in ``libscregclust_b200.so``; every penalization value that is still
-iterating is advanced by the same batched device call (the fits are independent,
-R/scregclust.R:1223,1245).
+The alternating loop of ``scregclust()`` (R/scregclust.R:1222-1912: module history, noise
+threshold, minimum module size, convergence / limit-cycle detection, the re-fit of every final
+configuration and the importance step) runs inside the library (``scrc_grid_fit``,
+csrc/grid.cu); :func:`scregclust_fit` marshals its arguments and unpacks the result handle into
+:class:`FitResult` objects.  :class:`Session` exposes the per-cycle entry points the parity tests
+drive directly, and :class:`Comm` the NCCL communicator of a multi-GPU job.
 """
 from __future__ import annotations
 
@@ -17,6 +16,34 @@ import numpy as np
 
 from . import _capi
 from ._capi import CycleOut, Options, Prior, check, dptr, f64, iptr
+
+
+class Comm:
+    """One rank of a multi-GPU job (one rank per GPU; NCCL over NVLink).  ``unique_id`` is the
+    128-byte token rank 0 obtains from :meth:`new_unique_id` and hands to the other ranks."""
+
+    def __init__(self, unique_id: bytes, world: int, rank: int, device: int):
+        self._lib = _capi.load()
+        self._h = C.c_void_p()
+        self.world, self.rank, self.device = int(world), int(rank), int(device)
+        check(self._lib.scrc_comm_create(C.byref(self._h), C.c_char_p(bytes(unique_id)), self.world, self.rank, self.device))
+
+    @staticmethod
+    def new_unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        check(_capi.load().scrc_comm_unique_id(buf))
+        return buf.raw
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.scrc_comm_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 @dataclass
@@ -49,8 +76,9 @@ class Session:
     """Owns a ``scrc_ctx``: data splits, Gram matrices, eigenbasis and initial fit on one GPU."""
 
     def __init__(self, z1_reg_scaled, z2_reg_scaled, z1_target_centered, z2_target_centered, z1_target_sds,
-                 n_modules, device=0):
+                 n_modules, device=0, comm=None):
         self._lib = _capi.load()
+        self._comm = comm
         z1r, z2r = f64(z1_reg_scaled), f64(z2_reg_scaled)
         z1t, z2t = f64(z1_target_centered), f64(z2_target_centered)
         sds = np.ascontiguousarray(z1_target_sds, dtype=np.float64)
@@ -59,18 +87,20 @@ class Session:
         if z2r.shape != (n2, P) or z1t.shape != (n1, T) or sds.size != T:
             raise ValueError("inconsistent split dimensions")
         self._create(device, z1r.ctypes.data, z2r.ctypes.data, z1t.ctypes.data, z2t.ctypes.data, sds.ctypes.data,
-                     n1, n2, P, T, n_modules)
+                     n1, n2, P, T, n_modules, comm)
         self.h2d_bytes = z1r.nbytes + z2r.nbytes + z1t.nbytes + z2t.nbytes + sds.nbytes
 
     @classmethod
-    def from_pointers(cls, z1_reg, z2_reg, z1_target, z2_target, z1_target_sds, n1, n2, P, T, n_modules, device=0):
+    def from_pointers(cls, z1_reg, z2_reg, z1_target, z2_target, z1_target_sds, n1, n2, P, T, n_modules, device=0,
+                      comm=None):
         """Create a session from raw addresses of column-major FP64 buffers.  The buffers may live in
         host memory or already in device memory (e.g. ``tensor.data_ptr()`` of a CUDA tensor); the
         library copies them into its own padded layout either way."""
         self = cls.__new__(cls)
         self._lib = _capi.load()
+        self._comm = comm
         self._create(device, int(z1_reg), int(z2_reg), int(z1_target), int(z2_target), int(z1_target_sds),
-                     int(n1), int(n2), int(P), int(T), n_modules)
+                     int(n1), int(n2), int(P), int(T), n_modules, comm)
         self.h2d_bytes = 0
         return self
 
@@ -103,6 +133,7 @@ class Session:
                                             1 if center else 0, int(n_modules),
                                             keep.ctypes.data_as(_capi.c_ubyte_p), dims))
         self.n1, self.n2, self.P, self.T, self.K = int(dims[0]), int(dims[1]), int(dims[2]), int(dims[3]), int(n_modules)
+        self._comm = None
         self.keep_gene = keep.astype(bool)
         self.h2d_bytes = ex.nbytes + isr.nbytes + si.nbytes + (st.nbytes if st is not None else 0)
         self.d2h_bytes = keep.nbytes
@@ -119,12 +150,16 @@ class Session:
         check(self._lib.scrc_ctx_get_inputs(self._h, dptr(z1r), dptr(z2r), dptr(z1t), dptr(z2t), dptr(sds)))
         return z1r, z2r, z1t, z2t, sds
 
-    def _create(self, device, p1r, p2r, p1t, p2t, psd, n1, n2, P, T, n_modules):
+    def _create(self, device, p1r, p2r, p1t, p2t, psd, n1, n2, P, T, n_modules, comm=None):
         self.n1, self.n2, self.P, self.T, self.K = int(n1), int(n2), int(P), int(T), int(n_modules)
         self._h = C.c_void_p()
         cast = lambda a: C.cast(C.c_void_p(a), _capi.c_double_p)
-        check(self._lib.scrc_ctx_create(C.byref(self._h), int(device), cast(p1r), cast(p2r), cast(p1t), cast(p2t),
-                                        cast(psd), self.n1, self.n2, self.P, self.T, self.K))
+        if comm is not None:      # collective: rank 0 builds the precompute and broadcasts it
+            check(self._lib.scrc_ctx_create_sharded(C.byref(self._h), comm._h, cast(p1r), cast(p2r), cast(p1t), cast(p2t),
+                                                    cast(psd), self.n1, self.n2, self.P, self.T, self.K))
+        else:
+            check(self._lib.scrc_ctx_create(C.byref(self._h), int(device), cast(p1r), cast(p2r), cast(p1t), cast(p2t),
+                                            cast(psd), self.n1, self.n2, self.P, self.T, self.K))
         self.d2h_bytes = 0
         self.admm_sweeps = 0
         self.admm_problem_iterations = 0
@@ -133,6 +168,14 @@ class Session:
         if getattr(self, "_h", None) is not None and self._h.value:
             self._lib.scrc_ctx_destroy(self._h)
             self._h = C.c_void_p()
+
+    def request_cancel(self):
+        """Cooperative interrupt (the reference polls Rcpp::checkUserInterrupt()): the running / next
+        device call of this session fails with SCRC_ERR_INTERRUPTED.  Safe from another thread."""
+        check(self._lib.scrc_ctx_request_cancel(self._h))
+
+    def clear_cancel(self):
+        check(self._lib.scrc_ctx_clear_cancel(self._h))
 
     def __del__(self):
         try:
@@ -294,172 +337,235 @@ def default_options(**kw) -> Options:
     return o
 
 
-@dataclass
-class _PenState:
-    k: np.ndarray
-    k_history: list
-    n_k: int = 2
-    last_cycle: bool = False
-    final_cycle_length: int = 1
-    converged: bool = False
-    cycle: int = 0
-    done: bool = False
+def _csr_lists(off, idx, T):
+    return [list(idx[off[t]:off[t + 1]]) for t in range(T)]
 
 
-def _unpack(fr, res, f, K, keep_diag):
-    fr.admm_iterations.append(res["admm_iterations"][f].copy())
-    fr.models_history.append(res["models"][f].T.astype(bool))
-    if keep_diag and res["nnls_iterations"] is not None:
-        fr.nnls_iterations.append(res["nnls_iterations"][f].copy())
+class _PyBackend:
+    """Adapts a duck-typed session (``fit_cycle`` / ``importance`` / ``coeffs_fit`` returning the
+    dictionaries of :class:`Session`) to the callback table of ``scrc_grid_fit_custom``.  Used by the
+    CPU tests, which answer the cycles from the oracle."""
+
+    def __init__(self, ses, keep_diag):
+        self.ses, self.keep_diag = ses, keep_diag
+        self.error = None
+        K, P, T = ses.K, ses.P, ses.T
+        self._keep = []
+
+        def fill(ptr, arr, dtype):
+            if ptr and arr is not None:
+                a = np.ascontiguousarray(arr, dtype=dtype)
+                C.memmove(ptr, a.ctypes.data, a.nbytes)
+
+        def fit_cycle(user, F, lam, k_in, opt, skip, hint, prior, out):
+            try:
+                lams = np.ctypeslib.as_array(lam, shape=(F,)).copy()
+                ks = np.ctypeslib.as_array(k_in, shape=(F, T)).copy()
+                o = out.contents
+                pr = None
+                if prior:
+                    pc = prior.contents
+                    off = np.ctypeslib.as_array(pc.prior_off, shape=(T + 1,)).copy()
+                    idx = np.ctypeslib.as_array(pc.prior_idx, shape=(max(int(off[T]), 1),)).copy()
+                    orders = np.ctypeslib.as_array(pc.update_order, shape=(F, T)).copy()
+                    pr = (_csr_lists(off, idx, T), pc.baseline, pc.weight, orders)
+                kw = {}
+                if getattr(ses, "accepts_hint", False) and hint:
+                    kw["hint"] = np.ctypeslib.as_array(hint, shape=(F, K)).copy()
+                res = ses.fit_cycle(lams, ks, opt.contents, skip_allocation=bool(skip), want_votes=bool(o.votes),
+                                    want_nnls_iters=bool(o.nnls_iterations), prior=pr, light=False, **kw)
+                if not skip:
+                    fill(o.k_new, res["k_new"], np.int32); fill(o.votes, res.get("votes"), np.int32)
+                fill(o.models, res["models"], np.uint8); fill(o.weights, res.get("weights"), np.float64)
+                fill(o.signs, res.get("signs"), np.float64); fill(o.r2_test, res.get("r2_test"), np.float64)
+                fill(o.resid_var, res.get("resid_var"), np.float64); fill(o.best_r2, res["best_r2"], np.float64)
+                fill(o.best_r2_idx, res.get("best_r2_idx"), np.int32); fill(o.admm_iterations, res["admm_iterations"], np.int32)
+                fill(o.nnls_iterations, res.get("nnls_iterations"), np.int32); fill(o.n_selected, res["n_selected"], np.int32)
+                if o.admm_sweeps:
+                    o.admm_sweeps[0] = int(res.get("admm_sweeps", 0))
+                return 0
+            except Exception as exc:                     # never unwind through the C frames
+                self.error = exc
+                return -50
+
+        def importance(user, F, k_final, models, signs, opt, r2m, imp, rem, cap):
+            try:
+                kf = np.ctypeslib.as_array(k_final, shape=(F, T)).copy()
+                md = np.ctypeslib.as_array(models, shape=(F, K, P)).copy()
+                sg = np.ctypeslib.as_array(signs, shape=(F, K, P)).copy()
+                r2, im, removed = ses.importance(kf, md, sg, opt.contents, want_r2_removed=True)
+                fill(r2m, r2, np.float64); fill(imp, im, np.float64)
+                flat = [np.asarray(b, dtype=np.float64).ravel(order="F") for f in range(F) for b in removed[f] if b is not None]
+                if flat:
+                    buf = np.concatenate(flat)
+                    if buf.size > cap:
+                        raise ValueError("r2_removed does not fit the buffer")
+                    fill(rem, buf, np.float64)
+                return 0
+            except Exception as exc:
+                self.error = exc
+                return -50
+
+        def coeffs_fit(user, f, coeffs_out, sel_out):
+            try:
+                cos, sels = ses.coeffs_fit(f)
+                flat = [np.asarray(c, dtype=np.float64).ravel(order="F") for c in cos if c is not None]
+                if flat:
+                    fill(coeffs_out, np.concatenate(flat), np.float64)
+                if sels is not None:
+                    sl = [np.asarray(x, dtype=np.int32) for x in sels if x is not None and len(x)]
+                    if sl:
+                        fill(sel_out, np.concatenate(sl), np.int32)
+                return 0
+            except Exception as exc:
+                self.error = exc
+                return -50
+
+        self.table = _capi.GridBackend(None, P, T, K, _capi.BACKEND_FIT_CYCLE_FN(fit_cycle),
+                                       _capi.BACKEND_IMPORTANCE_FN(importance), _capi.BACKEND_COEFFS_FN(coeffs_fit))
+
+
+def _unpack_grid(lib, handle, K, P, T, keep_diag, return_coeffs, compute_r2):
+    """scrc_grid_result -> list of FitResult (R's layouts: P x K, T x K)."""
+    info = _capi.GridInfo()
+    check(lib.scrc_grid_result_info(handle, C.byref(info)))
+    out = []
+    d2h = 0
+    for i in range(info.n_penalties):
+        pi = _capi.GridPenaltyInfo()
+        check(lib.scrc_grid_result_penalty(handle, i, C.byref(pi)))
+        fr = FitResult(penalization=pi.penalization, converged=bool(pi.converged), n_cycles_run=pi.n_cycles_run,
+                       final_cycle_length=pi.final_cycle_length)
+        hist = np.zeros((pi.n_history, T), dtype=np.int32)
+        check(lib.scrc_grid_result_history(handle, i, iptr(hist)))
+        fr.k_history = [hist[h].copy() for h in range(pi.n_history)]
+        n_fit_records = pi.n_records - pi.final_cycle_length
+        for rec in range(pi.n_records):
+            ai = np.zeros(K, dtype=np.int32); ns = np.zeros(K, dtype=np.int32); md = np.zeros((K, P), dtype=np.uint8)
+            vt = np.zeros((T, K), dtype=np.int32) if (keep_diag and rec < n_fit_records) else None
+            ni = np.zeros((K, T), dtype=np.int32) if keep_diag else None
+            check(lib.scrc_grid_result_record(handle, i, rec, iptr(ai), iptr(ns), md.ctypes.data_as(_capi.c_ubyte_p),
+                                              iptr(vt), iptr(ni)))
+            fr.admm_iterations.append(ai)
+            fr.models_history.append(md.T.astype(bool))
+            if ni is not None:
+                fr.nnls_iterations.append(ni)
+            if vt is not None:
+                fr.votes.append(vt)
+        for m in range(pi.final_cycle_length):
+            kf = np.zeros(T, dtype=np.int32); md = np.zeros((K, P), dtype=np.uint8)
+            wt = np.zeros((K, P)); sg = np.zeros((K, P)); r2 = np.zeros((K, T)); rv = np.zeros((K, T))
+            br = np.zeros(T); bi = np.zeros(T, dtype=np.int32); ns = np.zeros(K, dtype=np.int32)
+            r2m = np.zeros(K) if compute_r2 else None
+            imp = np.zeros((K, P)) if compute_r2 else None
+            gf = _capi.GridFinal(iptr(kf), md.ctypes.data_as(_capi.c_ubyte_p), dptr(wt), dptr(sg), dptr(r2), dptr(rv),
+                                 dptr(br), iptr(bi), iptr(ns), dptr(r2m), dptr(imp))
+            check(lib.scrc_grid_result_final(handle, i, m, C.byref(gf)))
+            d2h += sum(a.nbytes for a in (kf, md, wt, sg, r2, rv, br, bi, ns))
+            fr.k_final.append(kf); fr.models.append(md.T.astype(bool)); fr.signs.append(sg.T.copy())
+            fr.weights.append(wt.T.copy()); fr.sigmas.append(np.sqrt(rv.T)); fr.r2.append(r2.T.copy())
+            fr.best_r2.append(br); fr.best_r2_idx.append(bi)
+            if return_coeffs:
+                tot = int(ns.sum())
+                buf = np.zeros(max(tot, 1) * T); sel = np.zeros(max(tot, 1), dtype=np.int32)
+                check(lib.scrc_grid_result_coeffs(handle, i, m, dptr(buf), iptr(sel)))
+                d2h += tot * T * 8 + tot * 4
+                cos, o = [], 0
+                for s_ in (int(v) for v in ns):
+                    cos.append(buf[o:o + s_ * T].reshape((s_, T), order="F") if s_ else None)
+                    o += s_ * T
+                fr.coeffs.append(cos)
+            if compute_r2:
+                fr.r2_module.append(r2m); fr.importance.append(imp.T.copy())
+                n = int(lib.scrc_grid_result_r2_removed_size(handle, i, m))
+                buf = np.zeros(max(n, 1))
+                check(lib.scrc_grid_result_r2_removed(handle, i, m, dptr(buf)))
+                d2h += r2m.nbytes + imp.nbytes + n * 8
+                removed, o = [None] * K, 0
+                for j in range(K):
+                    m_j, s_j = int(np.count_nonzero(kf == j + 1)), int(ns[j])
+                    if m_j > 0 and s_j > 1:
+                        removed[j] = buf[o:o + m_j * (s_j + 1)].reshape((m_j, s_j + 1), order="F")
+                        o += m_j * (s_j + 1)
+                fr.r2_removed.append(removed)
+        out.append(fr)
+    return out, info, d2h
 
 
 def scregclust_fit(z1_reg_scaled=None, z2_reg_scaled=None, z1_target_centered=None, z2_target_centered=None,
                    z1_target_sds=None, penalization=(), n_modules=1, initial_target_modules=None,
                    min_module_size=0, noise_threshold=0.025, n_cycles=50, max_optim_iter=10000,
                    tol_coop_rel=1e-8, tol_coop_abs=1e-12, tol_nnls=1e-4, device=0, session=None,
-                   keep_diagnostics=False, return_coeffs=True, claim=None, concurrency=None,
-                   compute_predictive_r2=False, prior_indicator=None, prior_baseline=1e-6, prior_weight=0.0,
-                   update_orders=None):
-    """The alternating loop of ``scregclust()`` (R/scregclust.R:1222-1803) for all penalization values.
+                   keep_diagnostics=False, return_coeffs=True, compute_predictive_r2=False, prior_indicator=None,
+                   prior_baseline=1e-6, prior_weight=0.0, update_orders=None, comm=None):
+    """The alternating loop of ``scregclust()`` (R/scregclust.R:1222-1912) for all penalization values,
+    one ``scrc_grid_fit`` call.  Returns one :class:`FitResult` per penalization value, in order.
 
-    Returns one :class:`FitResult` per penalization value, in order.  ``session`` may be passed to
-    reuse the device-resident precompute (R/scregclust.R:996-1183) across calls.
-
-    Network prior (R/scregclust.R:584-615): ``prior_indicator`` is a list of T lists of 0-based
-    neighbour targets, ``update_orders(penalty_index, cycle)`` returns the permutation R's
+    ``session`` may be passed to reuse the device-resident precompute (R/scregclust.R:996-1183) across
+    calls; any object with the ``fit_cycle`` / ``importance`` / ``coeffs_fit`` methods of
+    :class:`Session` is accepted and then driven through ``scrc_grid_fit_custom`` (the CPU tests pass an
+    oracle-backed one).  Network prior (R/scregclust.R:584-615): ``prior_indicator`` is a list of T lists of
+    0-based neighbour targets, ``update_orders(penalty_index, cycle)`` returns the permutation R's
     ``sample()`` would draw (R/scregclust.R:1666; identity when omitted).
 
-    Multi-GPU work sharing: the fits of different penalization values are independent
-    (R/scregclust.R:1223,1245), so ``claim`` may be a callable returning the index of the next
-    penalization value this process should fit (or ``None`` when the grid is exhausted) --
-    e.g. an atomic counter shared by all ranks -- and ``concurrency`` bounds how many claimed
-    values are advanced together by one batched device call.  Values never claimed here come
-    back as ``None``.  A fit's result does not depend on what it is batched with.
+    Multi-GPU: with ``comm`` (or a session created with one) the call is collective -- every rank calls
+    it with the same arguments and every rank gets the complete result.
     """
+    lib = _capi.load()
     own = session is None
     ses = session or Session(z1_reg_scaled, z2_reg_scaled, z1_target_centered, z2_target_centered, z1_target_sds,
-                             n_modules, device=device)
+                             n_modules, device=device, comm=comm)
     try:
-        K, T = ses.K, ses.T
-        opt = default_options(max_optim_iter=int(max_optim_iter), tol_coop_rel=float(tol_coop_rel),
-                              tol_coop_abs=float(tol_coop_abs), tol_nnls=float(tol_nnls))
-        pens = [float(p) for p in penalization]
-        k_start = np.asarray(initial_target_modules, dtype=np.int32)
+        K, T, P = ses.K, ses.T, ses.P
+        pens = np.ascontiguousarray([float(p) for p in penalization], dtype=np.float64)
+        k_start = np.ascontiguousarray(initial_target_modules, dtype=np.int32)
         if k_start.size != T:
             raise ValueError("initial_target_modules needs one entry per target gene")
-        if claim is None:
-            queue = iter(range(len(pens)))
-            claim = lambda: next(queue, None)
-        concurrency = len(pens) if concurrency is None else max(1, int(concurrency))
-        states, results = {}, [None] * len(pens)
-        active, pending_final = [], []
-
-        while True:
-            while len(active) < concurrency:
-                i = claim()
-                if i is None:
-                    break
-                states[i] = _PenState(k=k_start.copy(), k_history=[k_start.copy()])
-                results[i] = FitResult(penalization=pens[i])
-                results[i].k_history = states[i].k_history
-                active.append(i)
-            if not active:
-                break
-            # R/scregclust.R:1269-1284: cycle counter, forced last cycle after n_cycles
-            for i in active:
-                s = states[i]
-                s.cycle += 1
-                if s.cycle == n_cycles + 1:
-                    s.last_cycle = True
-            run = [i for i in active if not states[i].last_cycle]
-            fin = [i for i in active if states[i].last_cycle]
-
-            if run:
-                prior = None
-                if prior_indicator is not None and len(prior_indicator) > 0 and prior_weight != 0.0:
-                    orders = np.stack([np.asarray(update_orders(i, states[i].cycle), dtype=np.int32)
-                                       if update_orders is not None else np.arange(T, dtype=np.int32) for i in run])
-                    prior = (prior_indicator, prior_baseline, prior_weight, orders)
-                res = ses.fit_cycle([pens[i] for i in run], np.stack([states[i].k for i in run]), opt,
-                                    skip_allocation=False, want_votes=keep_diagnostics,
-                                    want_nnls_iters=keep_diagnostics, prior=prior, light=True)
-                for f, i in enumerate(run):
-                    s, fr = states[i], results[i]
-                    _unpack(fr, res, f, K, keep_diagnostics)
-                    if keep_diagnostics:
-                        fr.votes.append(res["votes"][f].copy())
-                    idx = res["k_new"][f].copy()
-                    # noise module and minimum module size (R/scregclust.R:1731-1739)
-                    idx[res["best_r2"][f] < noise_threshold] = -1
-                    sizes = np.bincount(idx[idx > 0], minlength=K + 1)[1:]
-                    small = np.flatnonzero(sizes < min_module_size) + 1
-                    if small.size:
-                        idx[np.isin(idx, small)] = -1
-                    k = idx.astype(np.int32)
-                    # convergence / limit cycle (R/scregclust.R:1763-1802)
-                    matching = [j for j, kh in enumerate(s.k_history, start=1) if np.array_equal(kh, k)]
-                    s.k_history.append(k.copy())
-                    if matching:
-                        s.converged = True
-                        if s.n_k - matching[0] != 1:
-                            s.final_cycle_length = s.n_k - matching[0]
-                        s.last_cycle = True
-                    s.n_k += 1
-                    s.k = k
-                    fr.n_cycles_run = s.cycle
-
-            # Penalization values entering their last cycle only need the re-fit of their final
-            # configuration(s) (R/scregclust.R:1307-1311, Step 2b skipped) and the post-processing.
-            # Nothing depends on those results, so they are deferred and batched into as few device
-            # calls as possible instead of one small call whenever a value happens to finish.
-            pending_final.extend(fin)
-            active = [i for i in active if i not in fin]
-
-        def finalize(batch):
-            lam_f, k_f, owner = [], [], []
-            for i in batch:
-                s = states[i]
-                for m in range(1, s.final_cycle_length + 1):     # R/scregclust.R:1307-1311
-                    lam_f.append(pens[i]); k_f.append(s.k_history[len(s.k_history) - m]); owner.append(i)
-            res = ses.fit_cycle(lam_f, np.stack(k_f), opt, skip_allocation=True,
-                                want_nnls_iters=keep_diagnostics)
-            ses._last_nsel = res["n_selected"]
-            for f, i in enumerate(owner):
-                s, fr = states[i], results[i]
-                _unpack(fr, res, f, K, keep_diagnostics)
-                fr.k_final.append(np.asarray(k_f[f]).copy())
-                fr.models.append(res["models"][f].T.astype(bool))
-                fr.signs.append(res["signs"][f].T.copy())
-                fr.weights.append(res["weights"][f].T.copy())
-                fr.sigmas.append(np.sqrt(res["resid_var"][f].T))
-                fr.r2.append(res["r2_test"][f].T.copy())
-                fr.best_r2.append(res["best_r2"][f].copy())
-                fr.best_r2_idx.append(res["best_r2_idx"][f].copy())
-                if return_coeffs:
-                    fr.coeffs.append(ses.coeffs_fit(f)[0])
-            if compute_predictive_r2:                             # R/scregclust.R:1823-1912
-                r2m, imp, rem = ses.importance(np.stack(k_f), res["models"], res["signs"], opt, want_r2_removed=True)
-                for f, i in enumerate(owner):
-                    results[i].r2_module.append(r2m[f].copy())
-                    results[i].importance.append(imp[f].T.copy())
-                    results[i].r2_removed.append(rem[f])
-            for i in batch:
-                s, fr = states[i], results[i]
-                s.done = True
-                fr.converged = s.converged
-                fr.final_cycle_length = s.final_cycle_length
-                fr.n_cycles_run = s.cycle
-
-        # at most ~2x the regular batch width per call (bounds the state matrices of the re-fit)
-        batch, width = [], 0
-        for i in pending_final:
-            w_i = states[i].final_cycle_length
-            if batch and width + w_i > 2 * concurrency:
-                finalize(batch)
-                batch, width = [], 0
-            batch.append(i); width += w_i
-        if batch:
-            finalize(batch)
+        gp = _capi.GridParams()
+        lib.scrc_grid_default_params(C.byref(gp))
+        gp.n_penalties = pens.size; gp.penalization = dptr(pens); gp.initial_target_modules = iptr(k_start)
+        gp.n_cycles = int(n_cycles); gp.noise_threshold = float(noise_threshold); gp.min_module_size = int(min_module_size)
+        gp.opt = default_options(max_optim_iter=int(max_optim_iter), tol_coop_rel=float(tol_coop_rel),
+                                 tol_coop_abs=float(tol_coop_abs), tol_nnls=float(tol_nnls))
+        gp.compute_predictive_r2 = 1 if compute_predictive_r2 else 0
+        gp.keep_coeffs = 1 if return_coeffs else 0
+        gp.keep_diagnostics = 1 if keep_diagnostics else 0
+        keep = []
+        if prior_indicator is not None and len(prior_indicator) > 0 and float(prior_weight) != 0.0:
+            from .api import _csr
+            off, idx = _csr(prior_indicator, T)
+            if off is None:
+                off = np.zeros(T + 1, dtype=np.int32); idx = np.zeros(1, dtype=np.int32)
+            gp.prior_off = iptr(off); gp.prior_idx = iptr(idx)
+            gp.prior_baseline = float(prior_baseline); gp.prior_weight = float(prior_weight)
+            keep += [off, idx]
+            if update_orders is not None:
+                def _order(user, penalty, cycle):
+                    o = np.ascontiguousarray(update_orders(int(penalty), int(cycle)), dtype=np.int32)
+                    keep.append(o)
+                    return o.ctypes.data
+                gp.update_order = _capi.UPDATE_ORDER_FN(_order)
+        handle = C.c_void_p()
+        if isinstance(ses, Session):
+            check(lib.scrc_grid_fit(ses._h, C.byref(gp), C.byref(handle)))
+        else:
+            be = _PyBackend(ses, keep_diagnostics)
+            rc = lib.scrc_grid_fit_custom(C.byref(be.table), C.byref(gp), C.byref(handle))
+            if be.error is not None:
+                raise be.error
+            check(rc)
+        try:
+            results, info, d2h = _unpack_grid(lib, handle, K, P, T, keep_diagnostics, return_coeffs, compute_predictive_r2)
+        finally:
+            lib.scrc_grid_result_free(handle)
+        if isinstance(ses, Session):
+            ses.h2d_bytes += pens.nbytes + k_start.nbytes
+            ses.d2h_bytes += d2h
+            ses.admm_sweeps += int(info.admm_sweeps)
+            ses.admm_problem_iterations += int(info.admm_problem_iterations)
+        ses.last_grid_info = {"fit_cycles": int(info.fit_cycles), "final_refits": int(info.final_refits),
+                              "device_calls": int(info.device_calls), "admm_sweeps": int(info.admm_sweeps),
+                              "admm_problem_iterations": int(info.admm_problem_iterations)}
         return results
     finally:
         if own:

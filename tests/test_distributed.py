@@ -1,4 +1,7 @@
-"""world_size-2 gloo test of the penalty-grid sharding and the assignment all-gather (CPU)."""
+"""Multi-rank paths on the CPU: the partition rules exported by the library, and a world_size-2 gloo run of
+the library's whole-grid loop (scrc_grid_fit_custom, csrc/grid.cu) on both ranks, each rank answering its cycles
+from the sharded oracle session (tests/_sharded_oracle.py) that follows the ownership / merge protocol of the
+CUDA session (csrc/session.cu) with gloo all-reduces in the place of NCCL."""
 import os
 import socket
 import sys
@@ -15,115 +18,101 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, out):
-    sys.path.insert(0, ROOT)
-    import torch.distributed as dist
-    from oracle import scregclust_oracle as orc
-    from scregclust_b200 import parallel
-    from scregclust_b200.synthetic import make_workload
-    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
-    dist.init_process_group("gloo", rank=rank, world_size=world)
-    w = make_workload("tiny", seed=3, penalization=[0.1, 0.15, 0.2])
-    idx = parallel.shard_penalties(len(w.penalization), rank, world)
-    res = orc.scregclust_fit(w.z1_reg, w.z2_reg, w.z1_target, w.z2_target, w.z1_target_sds,
-                             [w.penalization[i] for i in idx], w.n_modules, w.k_init)
-    allk = parallel.gather_assignments([r.k_final[0] for r in res], len(w.penalization), w.z1_target.shape[1], rank, world)
-    np.save(os.path.join(out, f"rank{rank}.npy"), allk)
-    dist.barrier()
-    dist.destroy_process_group()
+def test_shard_assign_is_a_balanced_partition():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from _sharded_oracle import shard_assign
+    rng = np.random.default_rng(5)
+    for n, world in [(1, 1), (7, 2), (400, 8), (3, 8), (40, 4)]:
+        cost = rng.integers(1, 1000, n).astype(np.float64)
+        owner = shard_assign(cost, world)
+        assert owner.min() >= 0 and owner.max() < world
+        loads = np.bincount(owner, weights=cost, minlength=world)
+        # longest-processing-time-first: no rank exceeds the mean by more than the largest single problem
+        assert loads.max() <= cost.sum() / world + cost.max() + 1e-9
+        assert np.array_equal(owner, shard_assign(cost, world))         # deterministic
+    # ties: equal costs are dealt round-robin in index order
+    assert shard_assign(np.ones(6), 3).tolist() == [0, 1, 2, 0, 1, 2]
 
 
-def test_shard_and_gather_world2(tmp_path):
-    import torch.multiprocessing as mp
-    from oracle import scregclust_oracle as orc
-    from scregclust_b200 import parallel
-    from scregclust_b200.synthetic import make_workload
-    assert parallel.shard_penalties(5, 0, 2) == [0, 2, 4] and parallel.shard_penalties(5, 1, 2) == [1, 3]
-    assert sorted(sum((parallel.shard_penalties(20, r, 8) for r in range(8)), [])) == list(range(20))
-    port = _free_port()
-    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
-    a = np.load(tmp_path / "rank0.npy"); b = np.load(tmp_path / "rank1.npy")
-    assert np.array_equal(a, b)
-    w = make_workload("tiny", seed=3, penalization=[0.1, 0.15, 0.2])
-    ref = orc.scregclust_fit(w.z1_reg, w.z2_reg, w.z1_target, w.z2_target, w.z1_target_sds, w.penalization,
-                             w.n_modules, w.k_init)
-    assert np.array_equal(a, np.stack([r.k_final[0] for r in ref]))
+def test_shard_slice_tiles_the_range():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from _sharded_oracle import shard_slice
+    for n, align, world in [(5000, 32, 8), (120, 32, 2), (31, 32, 4), (0, 32, 3), (10000, 32, 8), (65, 1, 64)]:
+        edges = [shard_slice(n, align, r, world) for r in range(world)]
+        assert edges[0][0] == 0 and edges[-1][1] == n
+        for (a0, a1), (b0, b1) in zip(edges[:-1], edges[1:]):
+            assert a1 == b0 and a0 <= a1
+            assert a1 % align == 0 or a1 == n
+        sizes = [b - a for a, b in edges]
+        assert max(sizes) - min(sizes) < 2 * align      # one unit, plus the ragged last unit
 
 
-def test_gather_single_rank():
-    from scregclust_b200 import parallel
-    k = [np.arange(5, dtype=np.int32), np.arange(5, dtype=np.int32) + 1]
-    out = parallel.gather_assignments(k, 2, 5, 0, 1)
-    assert np.array_equal(out, np.stack(k))
-
-
-def _worker_dynamic(rank, world, port, out):
-    sys.path.insert(0, ROOT)
-    import torch.distributed as dist
-    from scregclust_b200 import parallel
-    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
-    dist.init_process_group("gloo", rank=rank, world_size=world)
-    store = dist.TCPStore("127.0.0.1", port + 17, world, rank == 0, wait_for_workers=True)
-    counter = parallel.GridCounter(7, store, key="scrc_next_1")
-    mine = {}
-    while True:
-        i = counter()
-        if i is None:
-            break
-        mine[i] = np.full(5, i + 1, dtype=np.int32)          # stand-in for a fitted assignment vector
-    table = parallel.merge_assignments(mine, 7, 5, world)
-    np.save(os.path.join(out, f"dyn{rank}.npy"), table)
-    np.save(os.path.join(out, f"mine{rank}.npy"), np.array(sorted(mine), dtype=np.int64))
-    dist.barrier()
-    dist.destroy_process_group()
-
-
-def test_dynamic_counter_and_merge_world2(tmp_path):
-    import torch.multiprocessing as mp
-    port = _free_port()
-    mp.spawn(_worker_dynamic, args=(2, port, str(tmp_path)), nprocs=2, join=True)
-    a = np.load(tmp_path / "dyn0.npy"); b = np.load(tmp_path / "dyn1.npy")
-    assert np.array_equal(a, b)
-    assert np.array_equal(a, np.repeat(np.arange(1, 8, dtype=np.int32)[:, None], 5, axis=1))   # every value fitted once
-    m0 = set(np.load(tmp_path / "mine0.npy").tolist()); m1 = set(np.load(tmp_path / "mine1.npy").tolist())
-    assert not (m0 & m1) and (m0 | m1) == set(range(7))
-
-
-def _worker_driver(rank, world, port, out):
-    """The multi-rank flow of bench.py on CPU: each rank runs the REAL driver loop (scregclust_fit with a shared
-    atomic counter and 1 value in flight), with the device session replaced by the oracle-backed one."""
+def _worker_spmd(rank, world, port, out):
     sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch
     import torch.distributed as dist
-    from scregclust_b200 import parallel
+    from _sharded_oracle import ShardedOracleSession
     from scregclust_b200.driver import scregclust_fit
     from scregclust_b200.synthetic import make_workload
-    from test_driver_host_logic import OracleSession
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    store = dist.TCPStore("127.0.0.1", port + 23, world, rank == 0, wait_for_workers=True)
+
+    def allreduce(a):
+        t = torch.from_numpy(a)            # shares memory: the reduction lands in the caller's array
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return a
+
     w = make_workload("tiny", seed=3, penalization=[0.1, 0.15, 0.2, 0.3])
-    counter = parallel.GridCounter(len(w.penalization), store, key="scrc_next_1")
+    ses = ShardedOracleSession(w, rank, world, allreduce)
     res = scregclust_fit(penalization=w.penalization, n_modules=w.n_modules, initial_target_modules=w.k_init,
-                         session=OracleSession(w), claim=counter, concurrency=1, min_module_size=2)
-    mine = {i: r.k_final[0] for i, r in enumerate(res) if r is not None}
-    table = parallel.merge_assignments(mine, len(w.penalization), w.z1_target.shape[1], world)
-    np.save(os.path.join(out, f"drv{rank}.npy"), table)
-    np.save(os.path.join(out, f"drvmine{rank}.npy"), np.array(sorted(mine), dtype=np.int64))
+                         session=ses, min_module_size=2, keep_diagnostics=True)
+    np.savez(os.path.join(out, f"spmd{rank}.npz"), solved=ses.problems_solved,
+             hist=np.array([len(r.k_history) for r in res]),
+             **{f"k{i}": np.stack(r.k_history) for i, r in enumerate(res)},
+             **{f"r2_{i}": r.r2[0] for i, r in enumerate(res)},
+             **{f"sig_{i}": r.sigmas[0] for i, r in enumerate(res)},
+             **{f"it_{i}": np.stack(r.admm_iterations) for i, r in enumerate(res)},
+             **{f"co_{i}": np.concatenate([c.ravel() for c in r.coeffs[0] if c is not None] or [np.zeros(1)])
+                for i, r in enumerate(res)})
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_driver_with_dynamic_claiming_world2(tmp_path):
+def test_grid_loop_sharded_over_two_ranks_matches_the_oracle(tmp_path):
     import torch.multiprocessing as mp
     from oracle import scregclust_oracle as orc
     from scregclust_b200.synthetic import make_workload
     port = _free_port()
-    mp.spawn(_worker_driver, args=(2, port, str(tmp_path)), nprocs=2, join=True)
-    a = np.load(tmp_path / "drv0.npy"); b = np.load(tmp_path / "drv1.npy")
-    assert np.array_equal(a, b)                                   # every rank ends with the whole table
-    m0 = set(np.load(tmp_path / "drvmine0.npy").tolist()); m1 = set(np.load(tmp_path / "drvmine1.npy").tolist())
-    assert not (m0 & m1) and (m0 | m1) == set(range(4))           # every value fitted exactly once
+    mp.spawn(_worker_spmd, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    a = np.load(tmp_path / "spmd0.npz"); b = np.load(tmp_path / "spmd1.npz")
     w = make_workload("tiny", seed=3, penalization=[0.1, 0.15, 0.2, 0.3])
     ref = orc.scregclust_fit(w.z1_reg, w.z2_reg, w.z1_target, w.z2_target, w.z1_target_sds, w.penalization,
                              w.n_modules, w.k_init, min_module_size=2)
-    assert np.array_equal(a, np.stack([r.k_final[0] for r in ref]))   # and the fits do not depend on who ran them
+    # both ranks solved Step-1 problems, and between them every problem exactly once
+    total = sum(int(np.count_nonzero(np.stack(r.admm_iterations))) for r in ref)
+    assert int(a["solved"]) > 0 and int(b["solved"]) > 0 and int(a["solved"]) + int(b["solved"]) == total
+    for i, r in enumerate(ref):
+        for z in (a, b):                                             # every rank holds the complete result
+            assert np.array_equal(z[f"k{i}"], np.stack(r.k_history))
+            assert np.array_equal(z[f"it_{i}"], np.stack(r.admm_iterations))
+            assert np.allclose(z[f"r2_{i}"], r.r2[0], rtol=0, atol=1e-12)
+            assert np.allclose(z[f"sig_{i}"], r.sigmas[0], rtol=1e-12, atol=0)
+            co = np.concatenate([c.ravel() for c in r.coeffs[0] if c is not None] or [np.zeros(1)])
+            assert np.allclose(z[f"co_{i}"], co, rtol=1e-12, atol=1e-14)
+        assert np.array_equal(a[f"r2_{i}"], b[f"r2_{i}"])            # and the ranks agree bit for bit
+
+
+def test_sharded_session_single_rank_is_the_plain_loop():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from _sharded_oracle import ShardedOracleSession
+    from oracle import scregclust_oracle as orc
+    from scregclust_b200.driver import scregclust_fit
+    from scregclust_b200.synthetic import make_workload
+    w = make_workload("tiny", seed=3)
+    ref = orc.scregclust_fit(w.z1_reg, w.z2_reg, w.z1_target, w.z2_target, w.z1_target_sds, w.penalization,
+                             w.n_modules, w.k_init)
+    got = scregclust_fit(penalization=w.penalization, n_modules=w.n_modules, initial_target_modules=w.k_init,
+                         session=ShardedOracleSession(w))
+    for g, r in zip(got, ref):
+        assert all(np.array_equal(x, y) for x, y in zip(g.k_history, r.k_history))
+        assert np.array_equal(g.models[0], r.models[0]) and np.allclose(g.r2[0], r.r2[0], atol=1e-12)

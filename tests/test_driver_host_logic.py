@@ -117,17 +117,79 @@ def test_forced_last_cycle_after_n_cycles(case):
     assert all(g.n_cycles_run <= 3 for g in got)
 
 
-@pytest.mark.parametrize("concurrency", [1, 2])
-def test_claiming_with_bounded_concurrency_gives_the_same_fits(case, concurrency):
+class ScriptedSession:
+    """Answers the cycles from a script of configurations: exercises the history / limit-cycle logic of the
+    library's loop (csrc/grid.cu) without any numerics."""
+
+    def __init__(self, T, K, P, script):
+        self.T, self.K, self.P, self.script = T, K, P, script
+        self.step = 0
+        self.final_ks = []
+
+    def fit_cycle(self, lambdas, ks, options=None, skip_allocation=False, want_votes=False, want_nnls_iters=False,
+                  prior=None, light=False):
+        F, K, T, P = len(lambdas), self.K, self.T, self.P
+        ks = np.asarray(ks).reshape(F, T)
+        res = {"k_new": np.zeros((F, T), np.int32), "models": np.zeros((F, K, P), np.uint8),
+               "best_r2": np.ones((F, T)), "admm_iterations": np.full((F, K), 7, np.int32),
+               "n_selected": np.zeros((F, K), np.int32), "votes": None, "nnls_iterations": None,
+               "signs": np.full((F, K, P), np.nan), "weights": np.zeros((F, K, P)), "r2_test": np.zeros((F, K, T)),
+               "resid_var": np.ones((F, K, T)), "best_r2_idx": np.ones((F, T), np.int32)}
+        if skip_allocation:
+            self.final_ks = [k.copy() for k in ks]
+            # mark every final configuration so that the order of the re-fits can be checked
+            for f in range(F):
+                res["r2_test"][f] = float(ks[f][0])
+        else:
+            for f in range(F):
+                res["k_new"][f] = self.script[min(self.step, len(self.script) - 1)]
+            self.step += 1
+        return res
+
+    def coeffs_fit(self, f):
+        return [None] * self.K, None
+
+    def close(self):
+        pass
+
+
+def test_limit_cycle_yields_one_final_configuration_per_member():
+    """k_start -> A -> B -> C -> B: the new configuration equals history entry 3 while n_k = 5, so the limit cycle
+    has length 2 and the re-fit runs on the last two configurations, last one first (R/scregclust.R:1763-1800,
+    1307-1311)."""
     from scregclust_b200.driver import scregclust_fit
-    w, kw, ref = case
-    pens = list(w.penalization) + [0.3]
-    ref = ref + orc.scregclust_fit(w.z1_reg, w.z2_reg, w.z1_target, w.z2_target, w.z1_target_sds, [0.3],
-                                   w.n_modules, w.k_init, **kw)
-    order = iter([2, 0])                             # this "rank" is handed values 2 and 0, never 1
-    ses = OracleSession(w)
-    got = scregclust_fit(penalization=pens, n_modules=w.n_modules, initial_target_modules=w.k_init, session=ses,
-                         claim=lambda: next(order, None), concurrency=concurrency, **kw)
-    assert got[1] is None
-    _same([got[0], got[2]], [ref[0], ref[2]])
-    assert max(c[0] for c in ses.calls if not c[1]) <= concurrency
+    T, K, P = 6, 2, 3
+    A = np.array([1, 1, 2, 2, 1, 2], np.int32); B = np.array([2, 1, 2, 1, 1, 2], np.int32); Cc = np.array([2, 2, 2, 1, 1, 1], np.int32)
+    ses = ScriptedSession(T, K, P, [A, B, Cc, B])
+    got = scregclust_fit(penalization=[0.1], n_modules=K, initial_target_modules=np.array([1, 2, 1, 2, 1, 2], np.int32),
+                         session=ses, noise_threshold=0.0, return_coeffs=False)[0]
+    assert got.converged and got.final_cycle_length == 2 and got.n_cycles_run == 5
+    assert [k.tolist() for k in got.k_history] == [[1, 2, 1, 2, 1, 2], A.tolist(), B.tolist(), Cc.tolist(), B.tolist()]
+    assert [k.tolist() for k in got.k_final] == [B.tolist(), Cc.tolist()]
+    assert got.r2[0][0, 0] == float(B[0]) and got.r2[1][0, 0] == float(Cc[0])
+    assert len(got.admm_iterations) == 4 + 2            # four fit cycles, two final re-fits
+
+
+def test_fixed_point_and_noise_rules():
+    """A repeats immediately: converged with a single final configuration; genes below the noise threshold go to -1
+    and modules smaller than min_module_size are dissolved before the history comparison (R/scregclust.R:1731-1739)."""
+    from scregclust_b200.driver import scregclust_fit
+    T, K, P = 6, 3, 2
+    A = np.array([1, 1, 1, 2, 2, 3], np.int32)
+    ses = ScriptedSession(T, K, P, [A, A])
+    got = scregclust_fit(penalization=[0.2], n_modules=K, initial_target_modules=np.ones(T, np.int32), session=ses,
+                         noise_threshold=0.0, min_module_size=2, return_coeffs=False)[0]
+    want = np.array([1, 1, 1, 2, 2, -1], np.int32)      # module 3 has one member < min_module_size
+    assert got.converged and got.final_cycle_length == 1 and got.n_cycles_run == 3
+    assert np.array_equal(got.k_history[1], want) and np.array_equal(got.k_final[0], want)
+
+
+def test_cancel_and_errors_surface_as_exceptions():
+    from scregclust_b200.driver import scregclust_fit
+
+    class Failing(ScriptedSession):
+        def fit_cycle(self, *a, **k):
+            raise RuntimeError("backend failure")
+    with pytest.raises(RuntimeError, match="backend failure"):
+        scregclust_fit(penalization=[0.1], n_modules=2, initial_target_modules=np.ones(4, np.int32),
+                       session=Failing(4, 2, 2, []), return_coeffs=False)

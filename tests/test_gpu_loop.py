@@ -256,22 +256,80 @@ def test_fit_is_independent_of_batch_composition():
                     assert np.array_equal(v[0], together[key][f], equal_nan=True), f"{key} of fit {f} depends on the batch"
 
 
-def test_dynamic_claiming_matches_lockstep():
-    """concurrency=1 with a claim counter (the multi-GPU schedule) == the lock-step single-GPU run."""
+def test_fit_does_not_depend_on_the_rest_of_the_grid():
+    """A penalization value fitted alone == the same value inside the whole grid (the fits are independent,
+    R/scregclust.R:1223,1245; every reduction order is a function of the problem alone)."""
     from scregclust_b200.driver import Session, scregclust_fit
-    from scregclust_b200.parallel import GridCounter
     w = make_workload("small", seed=2)
     with Session(w.z1_reg, w.z2_reg, w.z1_target, w.z2_target, w.z1_target_sds, w.n_modules) as s:
         a = scregclust_fit(penalization=w.penalization, n_modules=w.n_modules, initial_target_modules=w.k_init, session=s)
-        b = scregclust_fit(penalization=w.penalization, n_modules=w.n_modules, initial_target_modules=w.k_init, session=s,
-                           claim=GridCounter(len(w.penalization)), concurrency=1)
-        c = scregclust_fit(penalization=w.penalization, n_modules=w.n_modules, initial_target_modules=w.k_init, session=s,
-                           claim=GridCounter(2), concurrency=2)       # this "rank" only gets the first two values
-    assert c[2] is None and c[0] is not None and c[1] is not None
-    for x, y in list(zip(a, b)) + list(zip(a[:2], c[:2])):
+        c = scregclust_fit(penalization=w.penalization[1:2], n_modules=w.n_modules, initial_target_modules=w.k_init, session=s)
+    x, y = a[1], c[0]
+    assert len(x.k_history) == len(y.k_history) and all(np.array_equal(p, q) for p, q in zip(x.k_history, y.k_history))
+    assert np.array_equal(x.models[0], y.models[0]) and np.array_equal(x.r2[0], y.r2[0])
+    assert all((p is None and q is None) or np.array_equal(p, q) for p, q in zip(x.coeffs[0], y.coeffs[0]))
+
+
+def test_cancel_flag_interrupts_and_clears():
+    """scrc_ctx_request_cancel (the bridge's stand-in for Rcpp::checkUserInterrupt, optim.cpp:307): the next device
+    call fails with SCRC_ERR_INTERRUPTED, clearing the flag restores the session."""
+    from scregclust_b200._capi import ScrcError
+    from scregclust_b200.driver import Session
+    w = make_workload("tiny", seed=0)
+    with Session(w.z1_reg, w.z2_reg, w.z1_target, w.z2_target, w.z1_target_sds, w.n_modules) as s:
+        ok = s.fit_cycle(w.penalization[:1], w.k_init[None, :])
+        s.request_cancel()
+        with pytest.raises(ScrcError) as e:
+            s.fit_cycle(w.penalization[:1], w.k_init[None, :])
+        assert e.value.code == -31
+        s.clear_cancel()
+        again = s.fit_cycle(w.penalization[:1], w.k_init[None, :])
+        assert np.array_equal(ok["k_new"], again["k_new"])
+
+
+def _multi_gpu_available():
+    try:
+        import torch
+        return torch.cuda.device_count() >= 2
+    except Exception:
+        return False
+
+
+@pytest.mark.skipif(not _multi_gpu_available(), reason="needs two GPUs (gpurun --gpus 2)")
+@pytest.mark.parametrize("name,seed", [("small", 2), ("tiny", 3)])
+def test_two_gpus_in_one_process_give_the_single_gpu_bits(name, seed):
+    """scrc_grid_fit_multi: one host thread per device, Step 1 spread over the ranks by (penalization value, module),
+    Step 2 on target-gene slices, NCCL merges.  Every number must equal the one-GPU run bit for bit."""
+    import ctypes as C
+    from scregclust_b200 import _capi
+    from scregclust_b200.driver import Session, _unpack_grid, default_options, scregclust_fit
+    w = make_workload(name, seed=seed)
+    one = scregclust_fit(w.z1_reg, w.z2_reg, w.z1_target, w.z2_target, w.z1_target_sds, w.penalization, w.n_modules,
+                         w.k_init, min_module_size=2, compute_predictive_r2=True, keep_diagnostics=True)
+    lib = _capi.load()
+    pens = np.ascontiguousarray(w.penalization, dtype=np.float64)
+    gp = _capi.GridParams()
+    lib.scrc_grid_default_params(C.byref(gp))
+    gp.n_penalties = pens.size; gp.penalization = _capi.dptr(pens); gp.initial_target_modules = _capi.iptr(w.k_init)
+    gp.min_module_size = 2; gp.keep_diagnostics = 1
+    devs = np.array([0, 1], dtype=np.int32)
+    n1, P = w.z1_reg.shape; n2, T = w.z2_target.shape
+    f = _capi.f64
+    handle = C.c_void_p()
+    sds = np.ascontiguousarray(w.z1_target_sds)
+    _capi.check(lib.scrc_grid_fit_multi(_capi.iptr(devs), 2, _capi.dptr(f(w.z1_reg)), _capi.dptr(f(w.z2_reg)),
+                                        _capi.dptr(f(w.z1_target)), _capi.dptr(f(w.z2_target)), _capi.dptr(sds),
+                                        n1, n2, P, T, w.n_modules, C.byref(gp), C.byref(handle)))
+    two, _, _ = _unpack_grid(lib, handle, w.n_modules, P, T, True, True, True)
+    lib.scrc_grid_result_free(handle)
+    for x, y in zip(one, two):
         assert len(x.k_history) == len(y.k_history) and all(np.array_equal(p, q) for p, q in zip(x.k_history, y.k_history))
-        assert np.array_equal(x.models[0], y.models[0]) and np.array_equal(x.r2[0], y.r2[0])
-        assert all((p is None and q is None) or np.array_equal(p, q) for p, q in zip(x.coeffs[0], y.coeffs[0]))
+        for key in ("admm_iterations", "nnls_iterations", "votes", "models_history", "models", "signs", "weights", "sigmas",
+                    "r2", "best_r2", "best_r2_idx", "r2_module", "importance"):
+            for p, q in zip(getattr(x, key), getattr(y, key)):
+                assert np.array_equal(p, q, equal_nan=True), f"{key} differs between one and two GPUs"
+        for cx, cy in zip(x.coeffs, y.coeffs):
+            assert all((p is None and q is None) or np.array_equal(p, q) for p, q in zip(cx, cy))
 
 
 @pytest.mark.parametrize("name,seed", [("tiny", 3), ("small", 1)])
