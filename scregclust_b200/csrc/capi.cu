@@ -158,6 +158,7 @@ int scrc_bench_gemm(int64_t k, int64_t m, int64_t n, int symmetric, int reps, do
     return guarded([&] {
         Device& dev = dropin_device();
         cudaStream_t st = dev.stream;
+        AllocScope as(st);
         DMat A(k, m), B(k, symmetric ? m : n), Cm(m, symmetric ? m : n);
         fill_pseudo_kernel<<<(unsigned)ceil_div((int64_t)A.buf.n, 256), 256, 0, st>>>(A.data(), (int64_t)A.buf.n, 1u);
         fill_pseudo_kernel<<<(unsigned)ceil_div((int64_t)B.buf.n, 256), 256, 0, st>>>(B.data(), (int64_t)B.buf.n, 2u);
@@ -290,6 +291,7 @@ int scrc_ctx_cross_corr(scrc_ctx* ctx, double* out) {
         Ctx& c = ctx->impl;
         SCRC_CUDA(cudaSetDevice(c.dev.id));
         cudaStream_t st = c.dev.stream;
+        AllocScope as(st);
         // fast_cor(z1_target_centered, z1_reg_scaled) on device copies (R/scregclust.R:1116)
         DMat X(c.n1, c.T), Y(c.n1, c.P), C(c.T, c.P);
         SCRC_CUDA(cudaMemcpyAsync(X.data(), c.Z1t.data(), c.Z1t.bytes(), cudaMemcpyDeviceToDevice, st));
@@ -352,6 +354,7 @@ int scrc_ctx_get_coeffs(scrc_ctx* ctx, int f, int k, double* coeffs_out, int* se
         Ctx& c = ctx->impl;
         if (f < 0 || f >= c.last_F || k < 0 || k >= c.K) throw Error(SCRC_ERR_ARG, "scrc_ctx_get_coeffs: index out of range");
         SCRC_CUDA(cudaSetDevice(c.dev.id));
+        AllocScope as(c.dev.stream);
         const FitSlot& sl = c.slots[(size_t)f * c.K + k];
         if (sel_out && sl.s > 0)
             SCRC_CUDA(cudaMemcpyAsync(sel_out, c.nnls.sel.p + sl.sel_off, (size_t)sl.s * 4, cudaMemcpyDeviceToHost, c.dev.stream));

@@ -39,7 +39,24 @@ extern std::atomic<unsigned long long> g_launch_count;
 
 // ----------------------------------------------------------------------------
 // Device buffer (RAII)
+//
+// Allocation is stream-ordered (cudaMallocAsync / cudaFreeAsync on the stream all of the calling session's work
+// runs on) whenever the public entry point has opened an AllocScope: the per-cycle work buffers change size from
+// cycle to cycle and from session to session, and synchronous cudaMalloc / cudaFree of multi-GB buffers cost
+// ~0.5 s per penalty grid.  The device's default memory pool keeps freed blocks (release threshold = unlimited,
+// Device::init), so steady-state allocation never reaches the driver.  Outside a scope (result handles, teardown)
+// plain cudaMalloc / cudaFree are used; cudaFree is valid for stream-ordered allocations too.
 // ----------------------------------------------------------------------------
+extern thread_local cudaStream_t g_alloc_stream;
+extern thread_local bool g_alloc_async;
+struct AllocScope {
+    cudaStream_t prev_s; bool prev_a;
+    explicit AllocScope(cudaStream_t s) : prev_s(g_alloc_stream), prev_a(g_alloc_async) { g_alloc_stream = s; g_alloc_async = true; }
+    ~AllocScope() { g_alloc_stream = prev_s; g_alloc_async = prev_a; }
+    AllocScope(const AllocScope&) = delete;
+    AllocScope& operator=(const AllocScope&) = delete;
+};
+
 template <class T>
 struct DevBuf {
     T* p = nullptr;
@@ -54,11 +71,16 @@ struct DevBuf {
         return *this;
     }
     ~DevBuf() { release(); }
-    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void release() {
+        if (p) { if (g_alloc_async) cudaFreeAsync(p, g_alloc_stream); else cudaFree(p); }
+        p = nullptr; n = 0;
+    }
     void alloc(size_t n_) {
         release();
         n = n_;
-        if (n) SCRC_CUDA(cudaMalloc(&p, n * sizeof(T)));
+        if (!n) return;
+        if (g_alloc_async) SCRC_CUDA(cudaMallocAsync((void**)&p, n * sizeof(T), g_alloc_stream));
+        else SCRC_CUDA(cudaMalloc((void**)&p, n * sizeof(T)));
     }
     void ensure(size_t n_) { if (n_ > n) alloc(n_); }
     void zero(cudaStream_t s) { if (n) SCRC_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }

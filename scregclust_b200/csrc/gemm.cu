@@ -8,6 +8,8 @@
 namespace scrc {
 
 std::atomic<unsigned long long> g_launch_count{0ull};
+thread_local cudaStream_t g_alloc_stream = nullptr;
+thread_local bool g_alloc_async = false;
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                     const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,

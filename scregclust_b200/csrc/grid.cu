@@ -7,7 +7,9 @@
 // ranks take identical decisions without exchanging anything here.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <memory>
 #include <thread>
 
@@ -116,7 +118,12 @@ struct PenState {
     std::vector<int> last_iters;     // ADMM iterations of the previous cycle per module (cost hint)
 };
 
+static double wall_now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
+
 static void grid_loop(GridBackend& be, const scrc_grid_params& gp, scrc_grid_result& res) {
+    const bool dbg_t = getenv("SCRC_DEBUG_TIMING") != nullptr;
+    const double t_loop0 = wall_now();
+    double t_cycle = 0.0, t_final = 0.0, t_imp = 0.0, t_coef = 0.0;
     const int L = gp.n_penalties, K = be.K;
     const int64_t P = be.P, T = be.T;
     if (L <= 0 || !gp.penalization || !gp.initial_target_modules) throw Error(SCRC_ERR_ARG, "scrc_grid_fit: empty grid or null pointer");
@@ -185,7 +192,9 @@ static void grid_loop(GridBackend& be, const scrc_grid_params& gp, scrc_grid_res
                 pr.weight = gp.prior_weight; pr.update_order = orders.data();
             }
             sweeps = 0;
+            const double tc0 = wall_now();
             be.fit_cycle(F, lam.data(), ks.data(), gp.opt, false, hint.data(), use_prior ? &pr : nullptr, &co);
+            t_cycle += wall_now() - tc0;
             res.info.admm_sweeps += sweeps; res.info.device_calls += 1;
             for (int f = 0; f < F; ++f) {
                 const int i = run[f];
@@ -262,7 +271,9 @@ static void grid_loop(GridBackend& be, const scrc_grid_params& gp, scrc_grid_res
         co.admm_sweeps = &sweeps;
         if (diag) { nnls_it.assign(fkt, 0); co.nnls_iterations = nnls_it.data(); }
         sweeps = 0;
+        const double tf0 = wall_now();
         be.fit_cycle(F, lam.data(), ks.data(), gp.opt, true, hint.data(), nullptr, &co);
+        t_final += wall_now() - tf0;
         res.info.admm_sweeps += sweeps; res.info.device_calls += 1;
         for (int f = 0; f < F; ++f) {
             PenaltyResult& pr_ = res.pens[owner[f]];
@@ -289,7 +300,9 @@ static void grid_loop(GridBackend& be, const scrc_grid_params& gp, scrc_grid_res
                 for (int j = 0; j < K; ++j) tot += fc.n_selected[j];
                 fc.coeffs_n = (int64_t)tot * T;
                 fc.have_coeffs = true;
+                const double tk0 = wall_now();
                 if (tot > 0) be.coeffs_fit(f, fc.coeffs_n, tot, fc.coeffs_host, fc.coeffs_dev, fc.sel);
+                t_coef += wall_now() - tk0;
             }
         }
         if (gp.compute_predictive_r2) {                                                   // R/scregclust.R:1823-1912
@@ -305,7 +318,9 @@ static void grid_loop(GridBackend& be, const scrc_grid_params& gp, scrc_grid_res
                 cap += block[f];
             }
             std::vector<double> rem((size_t)std::max<int64_t>(cap, 1));
+            const double ti0 = wall_now();
             be.importance(F, ks.data(), md.data(), sg.data(), gp.opt, r2m.data(), imp.data(), rem.data(), cap);
+            t_imp += wall_now() - ti0;
             res.info.device_calls += 1;
             int64_t off = 0;
             // finals were appended in the order of `owner`, so walk them in the same order
@@ -331,6 +346,12 @@ static void grid_loop(GridBackend& be, const scrc_grid_params& gp, scrc_grid_res
     }
     if (!batch.empty()) finalize(batch);
     for (int i = 0; i < L; ++i) res.info.fit_cycles += res.pens[i].n_cycles_run - 1;
+    if (dbg_t) {
+        const double tot = wall_now() - t_loop0;
+        fprintf(stderr, "[scrc grid] total %.1f ms: fit cycles %.1f, final re-fit %.1f, coefficient packing %.1f, importance %.1f, "
+                        "loop logic %.1f\n", tot * 1e3, t_cycle * 1e3, t_final * 1e3, t_coef * 1e3, t_imp * 1e3,
+                (tot - t_cycle - t_final - t_coef - t_imp) * 1e3);
+    }
 }
 
 }  // namespace scrc

@@ -9,6 +9,34 @@
 
 namespace scrc {
 
+// SCRC_DEBUG_TIMING=1: host wall time per phase of a cycle (with a stream synchronisation at every phase
+// boundary, so the phases do not overlap; totals are printed when the session is destroyed).
+struct PhaseTimer {
+    bool on;
+    cudaStream_t st;
+    double t_prev;
+    static double now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
+    PhaseTimer(cudaStream_t s) : on(getenv("SCRC_DEBUG_TIMING") != nullptr), st(s), t_prev(0.0) { if (on) t_prev = now(); }
+    void mark(double* acc, int idx) {
+        if (!on) return;
+        cudaStreamSynchronize(st);
+        const double t = now();
+        acc[idx] += t - t_prev;
+        t_prev = t;
+    }
+};
+static const char* kPhaseNames[] = {"tables(host)", "admm", "merge1+extract+sync", "nnls tables", "nnls", "resid/vote",
+                                    "merge2", "outputs", "importance tables", "importance nnls", "importance resid",
+                                    "importance host", "coeff pack"};
+void Ctx::print_phase_times() const {
+    if (getenv("SCRC_DEBUG_TIMING") == nullptr) return;
+    double tot = 0.0;
+    for (int i = 0; i < 13; ++i) tot += phase_s[i];
+    fprintf(stderr, "[scrc rank %d] host wall per phase (synchronised), total %.1f ms:", rank(), tot * 1e3);
+    for (int i = 0; i < 13; ++i) if (phase_s[i] > 0.0) fprintf(stderr, "  %s %.1f", kPhaseNames[i], phase_s[i] * 1e3);
+    fprintf(stderr, "\n");
+}
+
 // ============================================================================ device / helpers
 void Device::init(int device) {
     id = device;
@@ -22,6 +50,12 @@ void Device::init(int device) {
                                               std::to_string(prop.minor));
     num_sms = prop.multiProcessorCount;
     if (!stream) SCRC_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    {   // keep freed work buffers in the device's pool instead of returning them to the driver (common.cuh: DevBuf)
+        cudaMemPool_t pool;
+        SCRC_CUDA(cudaDeviceGetDefaultMemPool(&pool, id));
+        unsigned long long keep = ~0ull;
+        SCRC_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
     if (!h_pinned) SCRC_CUDA(cudaMallocHost(&h_pinned, 64 * sizeof(int)));
 }
 void Device::destroy() {
@@ -103,6 +137,7 @@ void Ctx::create(int device, const double* z1r, const double* z2r, const double*
     if (n1_ <= 1 || n2_ <= 0 || P_ <= 0 || T_ <= 0 || K_ <= 0) throw Error(SCRC_ERR_ARG, "scrc_ctx_create: non-positive dimension");
     comm = comm_;
     dev.init(comm ? comm->device : device);
+    AllocScope as(dev.stream);
     begin(n1_, n2_, P_, T_, K_);
     cudaStream_t st = dev.stream;
     // the regulators of the first split go first: the Gram matrix and its eigenbasis only need them
@@ -384,9 +419,11 @@ void Ctx::fit_cycle(int F, const double* lambda, const int* k_in, const scrc_opt
                                   prior->prior_idx, prior->update_order + (int64_t)f * T);
     SCRC_CUDA(cudaSetDevice(dev.id));
     cudaStream_t st = dev.stream;
+    AllocScope as(st);
     const int64_t FK = (int64_t)F * K;
     const int W = world(), R = rank();
     if (W == 1) check_cancel();   // (collective runs agree on an interrupt at merge 1)
+    PhaseTimer pt(st);
 
     // ---------------- Step 1: problem table (one problem per non-empty (fit, module)) ----------------
     std::vector<int> cnt(FK, 0);
@@ -439,6 +476,7 @@ void Ctx::fit_cycle(int F, const double* lambda, const int* k_in, const scrc_opt
 
     long long sweeps = 0;
     bool aborted = false;
+    pt.mark(phase_s, 0);
     if (nprob > 0) {
         admm.resize((int)P, C, nprob);
         admm.h_cols.resize(nprob);
@@ -469,6 +507,7 @@ void Ctx::fit_cycle(int F, const double* lambda, const int* k_in, const scrc_opt
         const int one = 1;
         SCRC_CUDA(cudaMemcpyAsync(iters_fk_d.p + FK, &one, 4, cudaMemcpyHostToDevice, st));
     }
+    pt.mark(phase_s, 1);
     // ---------------- merge 1: module summaries ----------------
     if (W > 1) {
         comm->group_begin();
@@ -490,6 +529,7 @@ void Ctx::fit_cycle(int F, const double* lambda, const int* k_in, const scrc_opt
     if (h_fk[FK] > 0) throw Error(SCRC_ERR_INTERRUPTED, "interrupted by scrc_ctx_request_cancel");
     const int* h_admm_it = h_fk;
     const int* h_nsel = h_fk + FK + 1;
+    pt.mark(phase_s, 2);
 
     // ---------------- Step 2a: NNLS problem table ----------------
     slots.assign(FK, FitSlot());
@@ -535,6 +575,7 @@ void Ctx::fit_cycle(int F, const double* lambda, const int* k_in, const scrc_opt
     const int t0 = (int)ts0, t1 = (int)ts1;
     const bool want_nnls_it = out && out->nnls_iterations;
     nnls.col0 = t0; nnls.col1 = t1; nnls.use_active = false;
+    pt.mark(phase_s, 3);
     if (rows_total == 0) SCRC_CUDA(cudaMemsetAsync(nnls.beta.data(), 0, nnls.beta.bytes(), st));
     if (sliced && want_nnls_it) SCRC_CUDA(cudaMemsetAsync(nnls.iters.p, 0, (size_t)std::max<int64_t>((int64_t)nnp * T, 1) * 4, st));
     if (nnp > 0) {
@@ -542,6 +583,7 @@ void Ctx::fit_cycle(int F, const double* lambda, const int* k_in, const scrc_opt
         nnls_solve(nnls, opt.tol_nnls, opt.max_optim_iter, sds_t.p, (int)T, dev.num_sms, st);
     }
 
+    pt.mark(phase_s, 4);
     // ---------------- Step 2a/2b: residuals, SSE, variances, votes ----------------
     const int CRte = resid_vote_pick_cr((int)n2, (int)T, F, dev.num_sms);
     partial.ensure(resid_vote_partial_elems((int)T, K, F, CRte));
@@ -615,6 +657,7 @@ void Ctx::fit_cycle(int F, const double* lambda, const int* k_in, const scrc_opt
         SCRC_LAUNCHED();
     }
 
+    pt.mark(phase_s, 5);
     // ---------------- merge 2: per-gene results of the target slices ----------------
     if (sliced) {
         comm->group_begin();
@@ -634,6 +677,7 @@ void Ctx::fit_cycle(int F, const double* lambda, const int* k_in, const scrc_opt
         comm->group_end();
     }
 
+    pt.mark(phase_s, 6);
     // ---------------- outputs ----------------
     if (out) {
         auto d2h = [&](void* dst, const void* src, size_t bytes) {
@@ -657,6 +701,7 @@ void Ctx::fit_cycle(int F, const double* lambda, const int* k_in, const scrc_opt
         }
     }
     SCRC_CUDA(cudaStreamSynchronize(st));
+    pt.mark(phase_s, 7);
 }
 
 // out[base[r] + a[r] + s[r] * t] = beta[src[r] + ld * t]: drops the 16-row padding of the stacked layout and
@@ -675,6 +720,8 @@ void Ctx::pack_coeffs_fit(int f, double* out_dev) {
     if (f < 0 || f >= last_F) throw Error(SCRC_ERR_ARG, "scrc_ctx_get_coeffs_fit: index out of range");
     SCRC_CUDA(cudaSetDevice(dev.id));
     cudaStream_t st = dev.stream;
+    AllocScope as(st);
+    PhaseTimer pt(st);
     std::vector<int> src, s_of, a_of;
     std::vector<long long> base;
     long long off = 0;
@@ -694,12 +741,14 @@ void Ctx::pack_coeffs_fit(int f, double* out_dev) {
         nnls.beta.data(), nnls.beta.ld, (int)T, nrows, pack_src.p, pack_s.p, pack_a.p, pack_base.p, out_dev);
     SCRC_LAUNCHED();
     SCRC_CUDA(cudaStreamSynchronize(st));
+    pt.mark(phase_s, 12);
 }
 
 void Ctx::get_coeffs_fit(int f, double* coeffs_out, int* sel_out) {
     if (f < 0 || f >= last_F) throw Error(SCRC_ERR_ARG, "scrc_ctx_get_coeffs_fit: index out of range");
     SCRC_CUDA(cudaSetDevice(dev.id));
     cudaStream_t st = dev.stream;
+    AllocScope as(st);
     int nsel_fit = 0, first = -1;
     for (int k = 0; k < K; ++k) {
         const FitSlot& sl = slots[(size_t)f * K + k];
@@ -734,9 +783,11 @@ void Ctx::importance(int F, const int* k_final, const unsigned char* models, con
     if (F <= 0) throw Error(SCRC_ERR_ARG, "scrc_importance: F must be positive");
     SCRC_CUDA(cudaSetDevice(dev.id));
     cudaStream_t st = dev.stream;
+    AllocScope as(st);
     const int64_t FK = (int64_t)F * K;
     const int W = world(), R = rank();
     if (W == 1) check_cancel();
+    PhaseTimer pt(st);
     const double nan_v = std::nan("");
     for (int64_t i = 0; i < FK; ++i) r2_module[i] = nan_v;
     for (int64_t i = 0; i < FK * P; ++i) importance_out[i] = nan_v;
@@ -828,9 +879,11 @@ void Ctx::importance(int F, const int* k_final, const unsigned char* models, con
     SCRC_CUDA(cudaMemcpyAsync(imp_scale.p, h_scale.data(), h_scale.size() * 8, cudaMemcpyHostToDevice, st));
     SCRC_CUDA(cudaMemsetAsync(nb.grad0.data(), 0, nb.grad0.bytes(), st));
     SCRC_CUDA(cudaMemsetAsync(nb.beta.data(), 0, nb.beta.bytes(), st));   // left-out rows and padding stay exact zeros
+    pt.mark(phase_s, 8);
     nnls_setup(nb, G_rr.data(), G_rr.ld, G_rt.data(), G_rt.ld, inv_sds_t.p, st);
     nnls_solve(nb, opt.tol_nnls, opt.max_optim_iter, imp_scale.p, 1, dev.num_sms, st);   // scregclust.R:1865-1873
 
+    pt.mark(phase_s, 9);
     // test residuals: SSE per (problem, target of the module)                          scregclust.R:1875-1878
     imp_row_src.ensure(rows_a); imp_arow.ensure(nprob); imp_brow.ensure(nprob); imp_kpad.ensure(nprob);
     imp_coff.ensure(nprob); imp_ccnt.ensure(nprob);
@@ -864,6 +917,7 @@ void Ctx::importance(int F, const int* k_final, const unsigned char* models, con
     SCRC_CUDA(cudaMemcpyAsync(h_sse.data(), imp_sse.p, h_sse.size() * 8, cudaMemcpyDeviceToHost, st));
     SCRC_CUDA(cudaMemcpyAsync(h_css.data(), z2t_css.p, T * 8, cudaMemcpyDeviceToHost, st));
     SCRC_CUDA(cudaStreamSynchronize(st));
+    pt.mark(phase_s, 10);
 
     int64_t rr_off = 0;
     for (const Group& g : groups) {
@@ -896,11 +950,13 @@ void Ctx::importance(int F, const int* k_final, const unsigned char* models, con
         for (int r = 1; r <= g.s; ++r)
             importance_out[((int64_t)g.f * K + g.j) * P + g.regs[r - 1]] = 1.0 - vec[r] / vec[0];   // scregclust.R:1904-1909
     }
+    pt.mark(phase_s, 11);
 }
 
 // ============================================================================ drop-ins
 void dropin_crossprod(Device& dev, const double* x, const double* y, int64_t n, int64_t px, int64_t py, double* out) {
     cudaStream_t st = dev.stream;
+    AllocScope as(st);
     DMat X(n, px), C;
     X.upload(x, n, st);
     if (y == x && px == py) {
@@ -919,6 +975,7 @@ void dropin_crossprod(Device& dev, const double* x, const double* y, int64_t n, 
 
 void dropin_fast_cor(Device& dev, const double* x, const double* y, int64_t n, int64_t px, int64_t py, double* out) {
     cudaStream_t st = dev.stream;
+    AllocScope as(st);
     DMat X(n, px), Y(n, py), C(px, py);
     X.upload(x, n, st); Y.upload(y, n, st);
     DevBuf<double> xss(px), yss(py);
@@ -934,6 +991,7 @@ void dropin_fast_cor(Device& dev, const double* x, const double* y, int64_t n, i
 void dropin_ols(Device& dev, const double* y, const double* x, int64_t n, int64_t p, int64_t m, double lambda, bool ridge,
                 double* beta_out) {
     cudaStream_t st = dev.stream;
+    AllocScope as(st);
     DMat X(n, p), Y(n, m), G, Gy, B, tmp;
     X.upload(x, n, st); Y.upload(y, n, st);
     gram(X, X, G, true, dev);
@@ -968,6 +1026,7 @@ __global__ void set_warm_start_kernel(const double* b0, int64_t ld0, double* bet
 void dropin_coop_lasso(Device& dev, const double* y, int64_t n, int64_t m, const double* x, int64_t p, double lambda,
                        const double* weights, const double* beta0, const AdmmOpts& o, double* beta_out, int* iters) {
     cudaStream_t st = dev.stream;
+    AllocScope as(st);
     DMat X(n, p), Y(n, m), G, Gy;
     X.upload(x, n, st); Y.upload(y, n, st);
     gram(X, X, G, true, dev);       // optim.cpp:97
@@ -1004,6 +1063,7 @@ void dropin_coop_lasso(Device& dev, const double* y, int64_t n, int64_t m, const
 void dropin_nnls(Device& dev, const double* x, int64_t nobs, int64_t nvar, const double* y, int64_t m, double eps,
                  int max_iter, double* beta_out, int* iters) {
     cudaStream_t st = dev.stream;
+    AllocScope as(st);
     DMat X(nobs, nvar), Y(nobs, m), G, Gy;
     X.upload(x, nobs, st); Y.upload(y, nobs, st);
     gram(X, X, G, true, dev);       // optim.cpp:414
@@ -1018,6 +1078,7 @@ void dropin_nnls(Device& dev, const double* x, int64_t nobs, int64_t nvar, const
     std::vector<double> sg(nvar, 1.0);
     b.prob.alloc(1); b.sel.alloc(nvar); b.sign.alloc(nvar); b.Q.alloc((size_t)nvar * nvar); b.dvec.alloc(rows);
     b.grad0.alloc(rows, m); b.beta.alloc(rows, m); b.iters.alloc(m);
+    b.h_prob.assign(1, np);
     SCRC_CUDA(cudaMemcpyAsync(b.prob.p, &np, sizeof(np), cudaMemcpyHostToDevice, st));
     SCRC_CUDA(cudaMemcpyAsync(b.sel.p, sel.data(), nvar * 4, cudaMemcpyHostToDevice, st));
     SCRC_CUDA(cudaMemcpyAsync(b.sign.p, sg.data(), nvar * 8, cudaMemcpyHostToDevice, st));
@@ -1133,6 +1194,7 @@ void dropin_allocate(Device& dev, const double* sq_resid, int K, int64_t n2, int
                      const int* prior_off, const int* prior_idx, const int* k_in, const int* order, double baseline,
                      double weight, int* k_out, int* votes_out) {
     cudaStream_t st = dev.stream;
+    AllocScope as(st);
     if (K > RV_MAX_K) throw Error(SCRC_ERR_UNSUPPORTED, "allocate_into_modules: at most 64 modules are supported");
     if (weight != 0.0) validate_prior_inputs("allocate_into_modules", k_in, T, K, prior_off, prior_idx, order);
     DevBuf<double> d_var((size_t)T * K);

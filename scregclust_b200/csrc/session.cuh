@@ -115,7 +115,9 @@ struct Ctx {
     void check_cancel() const {
         if (cancel.load(std::memory_order_relaxed)) throw Error(SCRC_ERR_INTERRUPTED, "interrupted by scrc_ctx_request_cancel");
     }
-    ~Ctx() { if (h_fk) cudaFreeHost(h_fk); dev.destroy(); }
+    double phase_s[16] = {0};     // SCRC_DEBUG_TIMING accumulators (session.cu: kPhaseNames)
+    void print_phase_times() const;
+    ~Ctx() { print_phase_times(); if (h_fk) cudaFreeHost(h_fk); dev.destroy(); }
 };
 
 // O(T + nnz) host checks of caller data that index device memory in the network-prior sweep; throws SCRC_ERR_ARG.

@@ -150,6 +150,7 @@ void Ctx::create_raw(int device, const double* expr, int64_t p, int64_t n, const
     if (p > 0x7fffffffLL || n > 0x7fffffffLL) throw Error(SCRC_ERR_UNSUPPORTED, "scrc_ctx_create_raw: more than 2^31 genes or cells");
     dev.init(device);
     cudaStream_t st = dev.stream;
+    AllocScope as(st);
 
     // ---- host-side index logic of split_sample (scregclust.R:2303-2323), explicit split_indices only
     std::vector<int> included;                       // cells that take part (split 1 or 2), original order
