@@ -28,6 +28,8 @@ struct AdmmDev {
     double* partial;
     const int* prob_R;     // rows per update slab of each problem (32 / 16 / 8)
     int max_nslab;
+    int* tiles;            // compact lists of column tiles that hold an active problem (see admm_tile_lists)
+    int n64, n128;         // number of 64- / 128-column tiles of the batch
 };
 
 void AdmmBatch::resize(int P_, int C_, int nprob_) {
@@ -42,6 +44,7 @@ void AdmmBatch::resize(int P_, int C_, int nprob_) {
     for (DMat* m : mats) m->reshape(P, C);
     partial.ensure((size_t)nprob * nslab * ADMM_NSUM);
     prob_R.ensure(nprob); class_ids.ensure(nprob);
+    tiles.ensure(2 + (size_t)ceil_div(C, 64) + (size_t)ceil_div(C, 128));
 }
 
 static AdmmDev make_dev(AdmmBatch& b) {
@@ -58,8 +61,46 @@ static AdmmDev make_dev(AdmmBatch& b) {
     d.mult_old = b.mult_old.data(); d.mult_hat_old = b.mult_hat_old.data();
     d.partial = b.partial.p;
     d.prob_R = b.prob_R.p; d.max_nslab = b.nslab;
+    d.tiles = b.tiles.p; d.n64 = (int)ceil_div(b.C, 64); d.n128 = (int)ceil_div(b.C, 128);
     return d;
 }
+
+// ------------------------------------------------------------------ compact lists of live column tiles
+// tiles[0] / tiles[1] = number of 64- / 128-column tiles that contain a column of an active problem, followed by
+// the two lists (increasing tile index).  The GEMM CTAs walk these lists round-robin, so the tiles of converged
+// problems cost nothing -- not even an imbalance between the CTAs that would have drawn them.  One CTA.
+__device__ void admm_tile_lists(const AdmmDev& d) {
+    __shared__ int s_wtot[32];
+    __shared__ int s_run;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int pass = 0; pass < 2; ++pass) {
+        const int bn = pass == 0 ? 64 : 128;
+        const int nt = pass == 0 ? d.n64 : d.n128;
+        int* list = d.tiles + 2 + (pass == 0 ? 0 : d.n64);
+        if (threadIdx.x == 0) s_run = 0;
+        __syncthreads();
+        for (int t0 = 0; t0 < nt; t0 += blockDim.x) {
+            const int t = t0 + threadIdx.x;
+            int live = 0;
+            if (t < nt) {
+                const int cf = t * bn, cl = min(cf + bn, d.C) - 1;
+                for (int q = d.col_prob[cf]; q <= d.col_prob[cl]; ++q) live |= d.active[q];
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, live);
+            if (lane == 0) s_wtot[warp] = __popc(bal);
+            __syncthreads();
+            int off = s_run, tot = 0;
+            for (int w = 0; w < nw; ++w) { if (w < warp) off += s_wtot[w]; tot += s_wtot[w]; }
+            if (live) list[off + __popc(bal & ((1u << lane) - 1u))] = t;
+            __syncthreads();
+            if (threadIdx.x == 0) s_run += tot;
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) d.tiles[pass] = s_run;
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(1024) admm_tiles_kernel(AdmmDev d) { admm_tile_lists(d); }
 
 // ------------------------------------------------------------------ init state
 __global__ void admm_init_prob_kernel(AdmmDev d, double rho0, double alpha0) {
@@ -99,19 +140,15 @@ struct AdmmGemmPolicy {
         const int* active;
         const double* rho;
         const double* lam;
+        const int* tile_count;   // live column tiles of this tile width ...
+        const int* tile_list;    // ... and their indices (admm_tile_lists)
     };
     __device__ static int tiles_m(const Params& p) { return (p.P + BM - 1) / BM; }
-    __device__ static int num_tiles(const Params& p) { return tiles_m(p) * ((p.C + BN - 1) / BN); }
+    __device__ static int num_tiles(const Params& p) { return tiles_m(p) * (*p.tile_count); }
     __device__ static bool tile(const Params& p, int t, TileInfo& ti) {
-        const int tm = t % tiles_m(p), tn = t / tiles_m(p);
-        const int n0 = tn * BN;
-        const int last = min(n0 + BN, p.C) - 1;
-        const int pf = p.col_prob[n0], pl = p.col_prob[last];
-        int any = 0;
-        for (int q = pf; q <= pl; ++q) any |= p.active[q];
-        if (!any) return false;
+        const int tm = t % tiles_m(p), tn = p.tile_list[t / tiles_m(p)];
         ti.ta = &p.ta; ti.tb = &p.tb;
-        ti.m0 = tm * BM; ti.n0 = n0; ti.k0 = 0; ti.k1 = p.P;
+        ti.m0 = tm * BM; ti.n0 = tn * BN; ti.k0 = 0; ti.k1 = p.P;
         return true;
     }
     template <int MT, int NT>
@@ -144,6 +181,9 @@ static void launch_admm_gemm(const AdmmDev& d, const DMat& A, const double* Bm, 
     p.tb = make_tmap_f64(Bm, d.P, d.C, d.ld, BN);
     p.out = out; p.ld = d.ld; p.P = d.P; p.C = d.C;
     p.col_prob = d.col_prob; p.active = d.active; p.rho = d.rho; p.lam = lam;
+    static_assert(BN == 64 || BN == 128, "tile lists exist for 64- and 128-column tiles");
+    p.tile_count = d.tiles + (BN == 64 ? 0 : 1);
+    p.tile_list = d.tiles + 2 + (BN == 64 ? 0 : d.n64);
     constexpr int smem = GemmSmem<BM, BN, STAGES>::TOTAL;
     static SmemAttr attr;
     attr.ensure(gemm_tn_kernel<Pol>, smem);
@@ -420,6 +460,8 @@ __global__ void __launch_bounds__(1024) admm_finalize_kernel(AdmmDev d, AdmmOpts
         d.col_iters[0] += s_cols;
         if (is_update) d.col_iters[1] += s_cols;
     }
+    __syncthreads();            // the new activity flags are visible to the whole CTA
+    admm_tile_lists(d);
 }
 
 // ------------------------------------------------------------------ driver
@@ -435,6 +477,8 @@ int admm_solve(AdmmBatch& b, const EigBasis& eig, const AdmmOpts& o, bool cold, 
     DMat* z2[] = {&b.mult, &b.mult_old, &b.mult_hat_old};
     for (DMat* m : z2) SCRC_CUDA(cudaMemsetAsync(m->data(), 0, m->bytes(), stream));
     admm_init_prob_kernel<<<(b.nprob + 127) / 128, 128, 0, stream>>>(d, o.rho0, o.alpha0);
+    SCRC_LAUNCHED();
+    admm_tiles_kernel<<<1, 1024, 0, stream>>>(d);
     SCRC_LAUNCHED();
 
     const bool big = ceil_div(b.P, 128) * ceil_div(b.C, 128) >= num_sms;

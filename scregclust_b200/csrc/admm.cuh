@@ -57,6 +57,7 @@ struct AdmmBatch {
     DevBuf<double> partial;    // nprob x nslab x ADMM_NSUM
     DevBuf<int> prob_R;        // rows per update slab (32 / 16 / 8), chosen from the column count
     DevBuf<int> class_ids;     // problem ids grouped by slab height
+    DevBuf<int> tiles;         // [n live 64-col tiles, n live 128-col tiles, list64..., list128...] (admm.cu)
     std::vector<int> h_cols;   // host copy of the column count of every problem (set by the caller)
     bool aborted = false;      // set by admm_solve when the cancel flag stopped it early
 

@@ -440,19 +440,24 @@ void Ctx::fit_cycle(int F, const double* lambda, const int* k_in, const scrc_opt
             g_fk.push_back((int)fk);
             g_cost.push_back((double)cnt[fk] * (double)((have_hint && cost_hint[fk] > 0) ? cost_hint[fk] : 25));
         }
-    cost_hint.clear();
     std::vector<int> owner(g_fk.size());
     shard_assign(g_cost.data(), (int)g_fk.size(), W, owner.data());
     std::vector<int> prob_of_fk(FK, -1), h_c0, h_c1, h_fit, h_mod;
     std::vector<double> h_lambda;
     int C = 0;
-    for (size_t gi = 0; gi < g_fk.size(); ++gi) {
-        if (owner[gi] != R) continue;
+    // Local problems in order of decreasing predicted iteration count (stable; plain (fit, module) order without a
+    // hint): problems that converge at about the same sweep sit next to each other, so the converged part of the
+    // column range is mostly whole tiles and few live tiles carry dead columns.  The order changes no number.
+    std::vector<int> mine;
+    for (size_t gi = 0; gi < g_fk.size(); ++gi) if (owner[gi] == R) mine.push_back((int)gi);
+    std::stable_sort(mine.begin(), mine.end(), [&](int a, int b) { return g_cost[a] / cnt[g_fk[a]] > g_cost[b] / cnt[g_fk[b]]; });
+    for (int gi : mine) {
         const int fk = g_fk[gi];
         prob_of_fk[fk] = (int)h_c0.size();
         h_c0.push_back(C); C += cnt[fk]; h_c1.push_back(C);
         h_fit.push_back(fk / K); h_mod.push_back(fk % K); h_lambda.push_back(lambda[fk / K]);
     }
+    cost_hint.clear();
     const int nprob = (int)h_c0.size();
     std::vector<int> h_col_target(C), h_col_prob(C), fillpos(h_c0);
     for (int f = 0; f < F; ++f) {
