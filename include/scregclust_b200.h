@@ -351,6 +351,9 @@ int scrc_grid_result_history(const scrc_grid_result* r, int i, int* k_history /*
 int scrc_grid_result_record(const scrc_grid_result* r, int i, int rec, int* admm_iterations /* K */,
                             int* n_selected /* K */, unsigned char* models /* K x P */, int* votes,
                             int* nnls_iterations);
+/* all records of penalty i at once: n_records x K, n_records x K, n_records x K x P (any may be NULL) */
+int scrc_grid_result_records(const scrc_grid_result* r, int i, int* admm_iterations, int* n_selected,
+                             unsigned char* models);
 /* Final configuration m (0 <= m < final_cycle_length; m = 0 is the last entry of the history) in R's layouts
  * ([k][p] = P x K, [k][t] = T x K column-major).  Every pointer may be NULL. */
 typedef struct scrc_grid_final {

@@ -152,6 +152,7 @@ SIGNATURES = {
     "scrc_grid_result_penalty": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(GridPenaltyInfo)]),
     "scrc_grid_result_history": (C.c_int, [C.c_void_p, C.c_int, c_int_p]),
     "scrc_grid_result_record": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_int_p, c_int_p, c_ubyte_p, c_int_p, c_int_p]),
+    "scrc_grid_result_records": (C.c_int, [C.c_void_p, C.c_int, c_int_p, c_int_p, c_ubyte_p]),
     "scrc_grid_result_final": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(GridFinal)]),
     "scrc_grid_result_coeffs": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_double_p, c_int_p]),
     "scrc_grid_result_r2_removed_size": (C.c_int64, [C.c_void_p, C.c_int, C.c_int]),

@@ -30,7 +30,11 @@ struct AdmmDev {
     int max_nslab;
     int* tiles;            // compact lists of column tiles that hold an active problem (see admm_tile_lists)
     int n64, n128;         // number of 64- / 128-column tiles of the batch
+    int nsm, bm_big;       // SMs of the device, row height of the large GEMM tile (160 or 128)
+    int force_small;       // batch too small for large tiles: always 64 x 64
+    double small_cost;     // time of a 64 x 64 tile relative to a large one (measured, see admm_solve)
 };
+constexpr int TILE_HDR = 4;   // tiles[0] = live 64-col tiles, [1] = live 128-col tiles, [2] = tile shape of the next sweep
 
 void AdmmBatch::resize(int P_, int C_, int nprob_) {
     P = P_; C = C_; nprob = nprob_;
@@ -44,7 +48,7 @@ void AdmmBatch::resize(int P_, int C_, int nprob_) {
     for (DMat* m : mats) m->reshape(P, C);
     partial.ensure((size_t)nprob * nslab * ADMM_NSUM);
     prob_R.ensure(nprob); class_ids.ensure(nprob);
-    tiles.ensure(2 + (size_t)ceil_div(C, 64) + (size_t)ceil_div(C, 128));
+    tiles.ensure(TILE_HDR + (size_t)ceil_div(C, 64) + (size_t)ceil_div(C, 128));
 }
 
 static AdmmDev make_dev(AdmmBatch& b) {
@@ -62,6 +66,7 @@ static AdmmDev make_dev(AdmmBatch& b) {
     d.partial = b.partial.p;
     d.prob_R = b.prob_R.p; d.max_nslab = b.nslab;
     d.tiles = b.tiles.p; d.n64 = (int)ceil_div(b.C, 64); d.n128 = (int)ceil_div(b.C, 128);
+    d.nsm = 148; d.bm_big = 128; d.force_small = 0; d.small_cost = 0.26;
     return d;
 }
 
@@ -76,7 +81,7 @@ __device__ void admm_tile_lists(const AdmmDev& d) {
     for (int pass = 0; pass < 2; ++pass) {
         const int bn = pass == 0 ? 64 : 128;
         const int nt = pass == 0 ? d.n64 : d.n128;
-        int* list = d.tiles + 2 + (pass == 0 ? 0 : d.n64);
+        int* list = d.tiles + TILE_HDR + (pass == 0 ? 0 : d.n64);
         if (threadIdx.x == 0) s_run = 0;
         __syncthreads();
         for (int t0 = 0; t0 < nt; t0 += blockDim.x) {
@@ -98,6 +103,15 @@ __device__ void admm_tile_lists(const AdmmDev& d) {
         }
         if (threadIdx.x == 0) d.tiles[pass] = s_run;
         __syncthreads();
+    }
+    // Tile shape of the next sweep, from the exact live-tile counts: whole waves of large tiles against whole waves
+    // of 64 x 64 tiles (4-5 x as many CTAs, each cheaper but less efficient).  Both shapes give the same bits: the
+    // accumulation order along k does not depend on the tile.
+    if (threadIdx.x == 0) {
+        const long long tb = (long long)((d.P + d.bm_big - 1) / d.bm_big) * d.tiles[1];
+        const long long ts = (long long)((d.P + 63) / 64) * d.tiles[0];
+        const double wb = (double)((tb + d.nsm - 1) / d.nsm), ws = (double)((ts + d.nsm - 1) / d.nsm) * d.small_cost;
+        d.tiles[2] = (d.force_small || ws < wb) ? 1 : 0;
     }
 }
 __global__ void __launch_bounds__(1024) admm_tiles_kernel(AdmmDev d) { admm_tile_lists(d); }
@@ -142,9 +156,11 @@ struct AdmmGemmPolicy {
         const double* lam;
         const int* tile_count;   // live column tiles of this tile width ...
         const int* tile_list;    // ... and their indices (admm_tile_lists)
+        const int* shape;        // tile shape chosen on the device for this sweep (0 large, 1 small)
     };
     __device__ static int tiles_m(const Params& p) { return (p.P + BM - 1) / BM; }
-    __device__ static int num_tiles(const Params& p) { return tiles_m(p) * (*p.tile_count); }
+    // both shapes are launched every sweep; the one that was not chosen finds no tiles and exits
+    __device__ static int num_tiles(const Params& p) { return (*p.shape == (BN == 64 ? 1 : 0)) ? tiles_m(p) * (*p.tile_count) : 0; }
     __device__ static bool tile(const Params& p, int t, TileInfo& ti) {
         const int tm = t % tiles_m(p), tn = p.tile_list[t / tiles_m(p)];
         ti.ta = &p.ta; ti.tb = &p.tb;
@@ -183,7 +199,8 @@ static void launch_admm_gemm(const AdmmDev& d, const DMat& A, const double* Bm, 
     p.col_prob = d.col_prob; p.active = d.active; p.rho = d.rho; p.lam = lam;
     static_assert(BN == 64 || BN == 128, "tile lists exist for 64- and 128-column tiles");
     p.tile_count = d.tiles + (BN == 64 ? 0 : 1);
-    p.tile_list = d.tiles + 2 + (BN == 64 ? 0 : d.n64);
+    p.tile_list = d.tiles + TILE_HDR + (BN == 64 ? 0 : d.n64);
+    p.shape = d.tiles + 2;
     constexpr int smem = GemmSmem<BM, BN, STAGES>::TOTAL;
     static SmemAttr attr;
     attr.ensure(gemm_tn_kernel<Pol>, smem);
@@ -470,6 +487,15 @@ int admm_solve(AdmmBatch& b, const EigBasis& eig, const AdmmOpts& o, bool cold, 
     b.aborted = false;
     if (b.nprob == 0 || b.C == 0) return 0;
     AdmmDev d = make_dev(b);
+    const bool big = ceil_div(b.P, 128) * ceil_div(b.C, 128) >= num_sms;
+    // 160-row tiles when they waste fewer padded rows than 128-row tiles (e.g. P = 1600: 0 % vs 4 %)
+    const bool tall = (getenv("SCRC_NO_TALL_TILES") == nullptr) &&
+                      (ceil_div(b.P, 160) * 160 < ceil_div(b.P, 128) * 128);
+    d.nsm = num_sms; d.bm_big = tall ? 160 : 128; d.force_small = big ? 0 : 1;
+    // time of one 64 x 64 tile relative to one large tile: MAC ratio / relative efficiency (0.75, measured with
+    // scrc_bench_gemm on B200); SCRC_SMALL_TILE_COST overrides for tuning
+    d.small_cost = (64.0 * 64.0) / ((double)d.bm_big * 128.0) / 0.75;
+    if (const char* e = getenv("SCRC_SMALL_TILE_COST")) d.small_cost = atof(e);
     if (cold) {
         DMat* z[] = {&b.beta, &b.zeta, &b.beta_old, &b.zeta_old};
         for (DMat* m : z) SCRC_CUDA(cudaMemsetAsync(m->data(), 0, m->bytes(), stream));
@@ -481,10 +507,6 @@ int admm_solve(AdmmBatch& b, const EigBasis& eig, const AdmmOpts& o, bool cold, 
     admm_tiles_kernel<<<1, 1024, 0, stream>>>(d);
     SCRC_LAUNCHED();
 
-    const bool big = ceil_div(b.P, 128) * ceil_div(b.C, 128) >= num_sms;
-    // 160-row tiles when they waste fewer padded rows than 128-row tiles (e.g. P = 1600: 0 % vs 4 %)
-    const bool tall = (getenv("SCRC_NO_TALL_TILES") == nullptr) &&
-                      (ceil_div(b.P, 160) * 160 < ceil_div(b.P, 128) * 128);
     // problems grouped by slab height (see admm_update_kernel); lists live in class_ids
     if ((int)b.h_cols.size() != b.nprob) throw Error(-71, "admm_solve: host column counts missing");
     std::vector<int> hR(b.nprob), ids[3];
@@ -546,16 +568,21 @@ int admm_solve(AdmmBatch& b, const EigBasis& eig, const AdmmOpts& o, bool cold, 
         // Tail of the solve: once the surviving problems fill less than about half of the SMs with
         // large tiles, 64 x 64 tiles give 4-5x the CTAs (the accumulation order along k does not depend
         // on the tile shape, so the bits are the same).
-        const bool small_tiles = !big || (int64_t)ceil_div(b.P, 128) * ceil_div((int64_t)active_cols, 128) * 20 < (int64_t)num_sms * 9;
-        if (small_tiles) {
-            launch_admm_gemm<64, 64, 8, 1>(d, eig.V, d.R, d.W, num_sms, eig.lam.p, stream);
-            launch_admm_gemm<64, 64, 8, 2>(d, eig.Vt, d.W, d.beta, num_sms, eig.lam.p, stream);
-        } else if (tall) {
-            launch_admm_gemm<160, 128, 5, 1>(d, eig.V, d.R, d.W, num_sms, eig.lam.p, stream);
-            launch_admm_gemm<160, 128, 5, 2>(d, eig.Vt, d.W, d.beta, num_sms, eig.lam.p, stream);
-        } else {
-            launch_admm_gemm<128, 128, 6, 1>(d, eig.V, d.R, d.W, num_sms, eig.lam.p, stream);
-            launch_admm_gemm<128, 128, 6, 2>(d, eig.Vt, d.W, d.beta, num_sms, eig.lam.p, stream);
+        // The tile shape of each sweep is chosen on the device from the exact live-tile counts (admm_tile_lists);
+        // both shapes are launched, the one not chosen exits at once.
+        for (int step = 1; step <= 2; ++step) {
+            const DMat& A = step == 1 ? eig.V : eig.Vt;
+            const double* Bm = step == 1 ? d.R : d.W;
+            double* out = step == 1 ? d.W : d.beta;
+            if (step == 1) {
+                if (big && tall) launch_admm_gemm<160, 128, 5, 1>(d, A, Bm, out, num_sms, eig.lam.p, stream);
+                else if (big) launch_admm_gemm<128, 128, 6, 1>(d, A, Bm, out, num_sms, eig.lam.p, stream);
+                launch_admm_gemm<64, 64, 8, 1>(d, A, Bm, out, num_sms, eig.lam.p, stream);
+            } else {
+                if (big && tall) launch_admm_gemm<160, 128, 5, 2>(d, A, Bm, out, num_sms, eig.lam.p, stream);
+                else if (big) launch_admm_gemm<128, 128, 6, 2>(d, A, Bm, out, num_sms, eig.lam.p, stream);
+                launch_admm_gemm<64, 64, 8, 2>(d, A, Bm, out, num_sms, eig.lam.p, stream);
+            }
         }
         const int is_update = (it % o.n_update == 0) ? 1 : 0;
         {

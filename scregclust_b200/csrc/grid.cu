@@ -49,6 +49,7 @@ struct CtxBackend : GridBackend {
         // stays on the device (packed) until the caller asks for it: no staging copy on the host
         sel.resize(nsel);
         c.get_coeffs_fit(f, nullptr, sel.data());
+        AllocScope as(c.dev.stream);           // pooled, stream-ordered allocation (freed with the result handle)
         dev.alloc((size_t)ndoubles);
         c.pack_coeffs_fit(f, dev.p);
     }
@@ -487,6 +488,18 @@ int scrc_grid_result_record(const scrc_grid_result* r, int i, int rec, int* admm
     if (nnls_iterations) {
         if (c.nnls_iterations.empty()) return SCRC_ERR_ARG;
         std::memcpy(nnls_iterations, c.nnls_iterations.data(), c.nnls_iterations.size() * 4);
+    }
+    return SCRC_OK;
+}
+int scrc_grid_result_records(const scrc_grid_result* r, int i, int* admm_iterations, int* n_selected, unsigned char* models) {
+    if (!r || i < 0 || i >= (int)r->pens.size()) return SCRC_ERR_ARG;
+    const PenaltyResult& p = r->pens[i];
+    const size_t K = (size_t)r->info.K, KP = K * (size_t)r->info.P;
+    for (size_t rec = 0; rec < p.records.size(); ++rec) {
+        const CycleRecord& c = p.records[rec];
+        if (admm_iterations) std::memcpy(admm_iterations + rec * K, c.admm_iterations.data(), K * 4);
+        if (n_selected) std::memcpy(n_selected + rec * K, c.n_selected.data(), K * 4);
+        if (models) std::memcpy(models + rec * KP, c.models.data(), KP);
     }
     return SCRC_OK;
 }

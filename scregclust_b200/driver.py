@@ -440,18 +440,20 @@ def _unpack_grid(lib, handle, K, P, T, keep_diag, return_coeffs, compute_r2):
         check(lib.scrc_grid_result_history(handle, i, iptr(hist)))
         fr.k_history = [hist[h].copy() for h in range(pi.n_history)]
         n_fit_records = pi.n_records - pi.final_cycle_length
-        for rec in range(pi.n_records):
-            ai = np.zeros(K, dtype=np.int32); ns = np.zeros(K, dtype=np.int32); md = np.zeros((K, P), dtype=np.uint8)
-            vt = np.zeros((T, K), dtype=np.int32) if (keep_diag and rec < n_fit_records) else None
-            ni = np.zeros((K, T), dtype=np.int32) if keep_diag else None
-            check(lib.scrc_grid_result_record(handle, i, rec, iptr(ai), iptr(ns), md.ctypes.data_as(_capi.c_ubyte_p),
-                                              iptr(vt), iptr(ni)))
-            fr.admm_iterations.append(ai)
-            fr.models_history.append(md.T.astype(bool))
-            if ni is not None:
+        ai = np.zeros((pi.n_records, K), dtype=np.int32)
+        md = np.zeros((pi.n_records, K, P), dtype=np.uint8)
+        check(lib.scrc_grid_result_records(handle, i, iptr(ai), None, md.ctypes.data_as(_capi.c_ubyte_p)))
+        mdb = md.astype(bool).transpose(0, 2, 1)             # views: P x K per record
+        fr.admm_iterations = [ai[rec] for rec in range(pi.n_records)]
+        fr.models_history = [mdb[rec] for rec in range(pi.n_records)]
+        if keep_diag:
+            for rec in range(pi.n_records):
+                vt = np.zeros((T, K), dtype=np.int32) if rec < n_fit_records else None
+                ni = np.zeros((K, T), dtype=np.int32)
+                check(lib.scrc_grid_result_record(handle, i, rec, None, None, None, iptr(vt), iptr(ni)))
                 fr.nnls_iterations.append(ni)
-            if vt is not None:
-                fr.votes.append(vt)
+                if vt is not None:
+                    fr.votes.append(vt)
         for m in range(pi.final_cycle_length):
             kf = np.zeros(T, dtype=np.int32); md = np.zeros((K, P), dtype=np.uint8)
             wt = np.zeros((K, P)); sg = np.zeros((K, P)); r2 = np.zeros((K, T)); rv = np.zeros((K, T))
