@@ -492,9 +492,10 @@ int admm_solve(AdmmBatch& b, const EigBasis& eig, const AdmmOpts& o, bool cold, 
     const bool tall = (getenv("SCRC_NO_TALL_TILES") == nullptr) &&
                       (ceil_div(b.P, 160) * 160 < ceil_div(b.P, 128) * 128);
     d.nsm = num_sms; d.bm_big = tall ? 160 : 128; d.force_small = big ? 0 : 1;
-    // time of one 64 x 64 tile relative to one large tile: MAC ratio / relative efficiency (0.75, measured with
-    // scrc_bench_gemm on B200); SCRC_SMALL_TILE_COST overrides for tuning
-    d.small_cost = (64.0 * 64.0) / ((double)d.bm_big * 128.0) / 0.75;
+    // time of one 64 x 64 tile relative to one large tile: MAC ratio / relative efficiency.  0.85 from a sweep on
+    // B200 (tools/tile_cost_sweep.py, profiles/r02_tile_cost_sweep.log: best for the 20-value grid and for a
+    // 3-value grid alike); SCRC_SMALL_TILE_COST overrides for tuning
+    d.small_cost = (64.0 * 64.0) / ((double)d.bm_big * 128.0) / 0.85;
     if (const char* e = getenv("SCRC_SMALL_TILE_COST")) d.small_cost = atof(e);
     if (cold) {
         DMat* z[] = {&b.beta, &b.zeta, &b.beta_old, &b.zeta_old};

@@ -142,18 +142,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) resid_vote_kernel(const __gri
 #pragma unroll
                     for (int jj = 0; jj < NT; ++jj) acc[i][jj][0] = acc[i][jj][1] = 0.0;
                 // score constants of this module's columns, requested before the mainloop hides their latency
-                double tv[NT][2], hl[NT][2], iv[NT][2];
+                double nhl[NT][2], iv[NT][2];
 #pragma unroll
                 for (int jj = 0; jj < NT; ++jj)
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
-                        tv[jj][e] = 1.0; hl[jj][e] = 0.0; iv[jj][e] = 1.0;
+                        nhl[jj][e] = 0.0; iv[jj][e] = 1.0;
                         const int col = t0 + b_col0 + jj * 8 + q * 2 + e;
                         if (VOTE && j < p.K && col < ncol) {
                             const int64_t vi = ((int64_t)l * p.K + j) * p.T + col;
-                            tv[jj][e] = p.two_var[vi];
                             iv[jj][e] = p.inv_two_var[vi];
-                            hl[jj][e] = p.half_log[vi];
+                            nhl[jj][e] = -p.half_log[vi];
                         }
                     }
                 if (j < p.K) {
@@ -172,12 +171,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) resid_vote_kernel(const __gri
                 }
                 // residual, squared residual, column sums (scregclust.R:1593-1599)
                 double csum[NT][2];
-                bool fast = true;
 #pragma unroll
                 for (int jj = 0; jj < NT; ++jj)
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
-                        if (VOTE) fast &= (((unsigned)__double2hiint(tv[jj][e]) >> 20) - 93u) < 1860u;
                         double cs = 0.0;
 #pragma unroll
                         for (int i = 0; i < MT; ++i) {
@@ -185,8 +182,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) resid_vote_kernel(const __gri
                             const double sq = res * res;
                             acc[i][jj][e] = sq;
                             cs += sq;
-                            // biased exponent in [93, 1953) <=> 2^-930 <= sq < 2^930 (integer pipe, not FP64)
-                            if (VOTE) fast &= (((unsigned)__double2hiint(sq) >> 20) - 93u) < 1860u;
                         }
                         csum[jj][e] = cs;
                     }
@@ -203,40 +198,24 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) resid_vote_kernel(const __gri
                                     p.sq_out[j + (int64_t)p.K * (row + (int64_t)p.ncells * col)] = acc[i][jj][e];
                             }
                 }
-                // per-cell score -sq / (2 var) - 0.5 log(2 pi var) and running first maximum (allocation.cpp:59-62,80-85).
-                // sq / tv goes through the correctly rounded reciprocal iv = RN(1 / tv): each step
-                // q <- q + RN(sq - tv q) iv is Markstein's quotient correction; after the first one q is a
-                // faithful quotient, so the second returns RN(sq / tv) -- the bits of the IEEE division at a
-                // quarter of its instructions and, unlike the division subroutine, as 16 independent
-                // straight-line chains per thread.  If any operand of the thread lies outside the range where
-                // the remainders are exact (zero residuals of padding rows, degenerate variances) the whole
-                // thread takes the division.
+                // per-cell score -sq / (2 var) - 0.5 log(2 pi var) and running first maximum (allocation.cpp:59-62,80-85),
+                // evaluated as one fused multiply-add with the correctly rounded reciprocal RN(1 / (2 var)) and
+                // -0.5 log(2 pi var) from make_resid_var.  It differs from the reference's quotient-then-subtract by
+                // at most ~1.5 ulp of the score -- four orders of magnitude below the rounding noise the squared
+                // residual itself carries (its bits depend on the summation order of whatever BLAS / tensor kernel
+                // produced the prediction) and below the 1e-12 band in which the oracle calls a cell's vote
+                // noise-decided.  Structurally identical modules still tie bit for bit (same inputs, same formula),
+                // so first-index tie breaking is preserved.
                 if (VOTE && j < p.K) {
-                    if (fast) {
 #pragma unroll
-                        for (int jj = 0; jj < NT; ++jj)
+                    for (int jj = 0; jj < NT; ++jj)
 #pragma unroll
-                            for (int e = 0; e < 2; ++e)
+                        for (int e = 0; e < 2; ++e)
 #pragma unroll
-                                for (int i = 0; i < MT; ++i) {
-                                    const double sq = acc[i][jj][e];
-                                    double qd = sq * iv[jj][e];
-                                    qd = fma(fma(-qd, tv[jj][e], sq), iv[jj][e], qd);
-                                    qd = fma(fma(-qd, tv[jj][e], sq), iv[jj][e], qd);
-                                    const double sc = -qd - hl[jj][e];
-                                    if (sc > best[i][jj][e]) { best[i][jj][e] = sc; bidx[i][jj][e] = j; }
-                                }
-                    } else {
-#pragma unroll
-                        for (int jj = 0; jj < NT; ++jj)
-#pragma unroll
-                            for (int e = 0; e < 2; ++e)
-#pragma unroll
-                                for (int i = 0; i < MT; ++i) {
-                                    const double sc = (-acc[i][jj][e]) / tv[jj][e] - hl[jj][e];
-                                    if (sc > best[i][jj][e]) { best[i][jj][e] = sc; bidx[i][jj][e] = j; }
-                                }
-                    }
+                            for (int i = 0; i < MT; ++i) {
+                                const double sc = fma(-acc[i][jj][e], iv[jj][e], nhl[jj][e]);
+                                if (sc > best[i][jj][e]) { best[i][jj][e] = sc; bidx[i][jj][e] = j; }
+                            }
                 }
 #pragma unroll
                 for (int jj = 0; jj < NT; ++jj)

@@ -97,10 +97,23 @@ void col_sumsq(const double* x, int64_t ld, int64_t rows, int64_t cols, double* 
     SCRC_LAUNCHED();
 }
 
+// One cuSOLVER handle per (host thread, device), created on first use and kept: creating one costs several
+// milliseconds (it brings up a cuBLAS handle with its workspace) and a session is created per scregclust() call.
+static cusolverDnHandle_t solver_handle() {
+    struct Cache { cusolverDnHandle_t h[64] = {}; };   // never destroyed: library teardown order at exit is not ours
+    static thread_local Cache cache;
+    int dev = 0;
+    SCRC_CUDA(cudaGetDevice(&dev));
+    dev &= 63;
+    if (!cache.h[dev] && cusolverDnCreate(&cache.h[dev]) != CUSOLVER_STATUS_SUCCESS) {
+        cache.h[dev] = nullptr;
+        throw Error(-80, "cusolverDnCreate failed");
+    }
+    return cache.h[dev];
+}
+
 void sym_eig(double* A, int64_t lda, int n, double* w, cudaStream_t s) {
-    cusolverDnHandle_t h = nullptr;
-    if (cusolverDnCreate(&h) != CUSOLVER_STATUS_SUCCESS) throw Error(-80, "cusolverDnCreate failed");
-    struct Guard { cusolverDnHandle_t h; ~Guard() { cusolverDnDestroy(h); } } guard{h};
+    cusolverDnHandle_t h = solver_handle();
     cusolverDnSetStream(h, s);
     int lwork = 0;
     if (cusolverDnDsyevd_bufferSize(h, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n, A, (int)lda, w,

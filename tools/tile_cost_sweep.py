@@ -22,7 +22,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
                       "checksum": int(sum(int(np.clip(r.k_final[0], 0, None).sum()) for r in res))}))
 else:
     for which in ("three", "all"):
-        for cost in ("0.15", "0.20", "0.267", "0.33", "0.45"):
+        for cost in ("0.20", "0.22", "0.235", "0.25", "0.267"):
             env = dict(os.environ, SCRC_SMALL_TILE_COST=cost)
             out = subprocess.run([sys.executable, __file__, "child", which], env=env, capture_output=True, text=True)
             print(which, "small_cost", cost, out.stdout.strip().splitlines()[-1] if out.stdout.strip() else out.stderr[-300:], flush=True)
