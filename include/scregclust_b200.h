@@ -231,6 +231,19 @@ typedef struct scrc_prior {
 int scrc_fit_cycle_prior(scrc_ctx* ctx, int F, const double* lambda, const int* k_in, const scrc_options* opt,
                          const scrc_prior* prior, scrc_cycle_out* out);
 
+/* Quick mode (R/scregclust.R:1435-1496, quick_mode = TRUE): from cycle two on, Step 2 of a fit only sees the targets
+ * currently in a module plus the `percent` share of the noise targets whose largest absolute correlation with an
+ * active regulator is highest (R's default quantile, type 7); in the last cycle (skip_allocation) the active targets
+ * only.  idx_latest: F x T, R's `idx` -- the LATEST allocation of each fit, which is k_in except while an older
+ * configuration of a limit cycle is re-fitted.  The skipped targets come back with the reference's values (r2 0,
+ * resid_var 1e6 -- 0 in the last cycle --, zero coefficients, k_new 1).  The caller passes NULL in cycle 1. */
+typedef struct scrc_quick {
+    const int* idx_latest;     /* F x T, 1-based, -1 noise */
+    double percent;            /* quick_mode_percent in [0, 1) */
+} scrc_quick;
+int scrc_fit_cycle_quick(scrc_ctx* ctx, int F, const double* lambda, const int* k_in, const scrc_options* opt,
+                         int skip_allocation, const scrc_quick* quick, scrc_cycle_out* out);
+
 /* NNLS coefficients of module k (0-based) of fit f from the last scrc_fit_cycle call:
  * n_selected x T (R/scregclust.R:1588); sel_out receives the 0-based regulator indices. */
 int scrc_ctx_get_coeffs(scrc_ctx* ctx, int f, int k, double* coeffs_out, int* sel_out);
@@ -304,6 +317,8 @@ typedef struct scrc_grid_params {
      * same permutation on every rank. */
     const int* (*update_order)(void* user, int penalty, int cycle);
     void* update_order_user;
+    int quick_mode;                         /* R/scregclust.R:201: 0 */
+    double quick_mode_percent;              /* 0.1 */
 } scrc_grid_params;
 void scrc_grid_default_params(scrc_grid_params* p);
 
@@ -322,7 +337,8 @@ typedef struct scrc_grid_backend {
     int64_t P, T;
     int K;
     int (*fit_cycle)(void* user, int F, const double* lambda, const int* k_in, const scrc_options* opt,
-                     int skip_allocation, const int* iterations_hint, const scrc_prior* prior, scrc_cycle_out* out);
+                     int skip_allocation, const int* iterations_hint, const scrc_prior* prior,
+                     const scrc_quick* quick, scrc_cycle_out* out);
     int (*importance)(void* user, int F, const int* k_final, const unsigned char* models, const double* signs,
                       const scrc_options* opt, double* r2_module, double* importance, double* r2_removed,
                       int64_t r2_removed_capacity);

@@ -692,7 +692,8 @@ def scregclust_fit(z1_reg_scaled, z2_reg_scaled, z1_target_centered, z2_target_c
                    min_module_size=0, noise_threshold=0.025, n_cycles=50,
                    max_optim_iter=10000, tol_coop_rel=1e-8, tol_coop_abs=1e-12,
                    tol_nnls=1e-4, update_orders=None, compute_predictive_r2=False,
-                   materialize_array=True, pre=None, keep_history=False):
+                   materialize_array=True, pre=None, keep_history=False, quick_mode=False,
+                   quick_mode_percent=0.1, quick_first_cycle_idx=None):
     """The alternating loop of ``scregclust()`` (R/scregclust.R:1222-1803) for
     ``allocate_per_obs = TRUE``, ``quick_mode = FALSE``.
 
@@ -701,6 +702,10 @@ def scregclust_fit(z1_reg_scaled, z2_reg_scaled, z1_target_centered, z2_target_c
     is result-neutral when ``prior_weight == 0`` (allocation.cpp:39-56).
     ``materialize_array=False`` skips the K x n2 x T array (scregclust.R:1177) and
     streams gene by gene with identical arithmetic.
+    ``quick_mode`` (scregclust.R:1435-1496): from cycle two on Step 2 only sees the targets currently in
+    a module plus the ``quick_mode_percent`` noise targets best correlated with an active regulator.
+    ``quick_first_cycle_idx`` (test hook): treat the first cycle of this call as a later cycle of a longer run whose
+    latest allocation (R's ``idx``) is the given vector -- lets a test replay single cycles of a quick-mode trajectory.
     """
     z1r, z2r = z1_reg_scaled, z2_reg_scaled
     z1t, z2t = z1_target_centered, z2_target_centered
@@ -724,6 +729,7 @@ def scregclust_fit(z1_reg_scaled, z2_reg_scaled, z1_target_centered, z2_target_c
     ss_test0 = np.sum(z2sq, axis=0)
 
     sq_arr = alloc_array(z2sq, n_modules) if materialize_array else None
+    abs_corr = np.abs(fast_cor(z1t, z1r)) if quick_mode else None          # scregclust.R:1116-1122
     results = []
     k_start = np.asarray(initial_target_modules, dtype=np.int32)
 
@@ -739,6 +745,9 @@ def scregclust_fit(z1_reg_scaled, z2_reg_scaled, z1_target_centered, z2_target_c
         fr = FitResult(penalization=float(lam), converged=False, n_cycles_run=0,
                        k_history=k_history, final_cycle_length=1)
         final_cycle_length = 1
+        idx_latest = None                                   # R's `idx`: the latest allocation (scregclust.R:1731-1739)
+        if quick_first_cycle_idx is not None:
+            idx_latest = np.asarray(quick_first_cycle_idx, dtype=np.int32)
         for cycle in range(1, n_cycles + 2):
             if cycle == n_cycles + 1:
                 last_cycle = True
@@ -750,9 +759,16 @@ def scregclust_fit(z1_reg_scaled, z2_reg_scaled, z1_target_centered, z2_target_c
                                                 max_optim_iter, admm_it)
                 fr.admm_iterations.append(admm_it)
                 fr.models_history.append(models.copy())
+                # ---- Step 1.5 (scregclust.R:1435-1496): quick-mode target subset ----
+                if quick_mode and (cycle != 1 or quick_first_cycle_idx is not None) and np.sum(models) != 0:
+                    filt = quick_mode_targets(abs_corr, models, idx_latest, quick_mode_percent, last_cycle)
+                else:
+                    filt = np.arange(n_target)
+                nt = filt.size
+                z1t_f, z2t_f, sds_f = z1t[:, filt], z2t[:, filt], z1_target_sds[filt]
                 # ---- Step 2a (scregclust.R:1505-1647) ----
-                ss_train = np.repeat(ss_train0[:, None], n_modules, axis=1)
-                ss_test = np.repeat(ss_test0[:, None], n_modules, axis=1)
+                ss_train = np.repeat(np.sum(z1t_f * z1t_f, axis=0)[:, None], n_modules, axis=1)
+                ss_test = np.repeat(np.sum(z2t_f * z2t_f, axis=0)[:, None], n_modules, axis=1)
                 if not last_cycle and materialize_array:
                     reset_array(sq_arr, z2sq)
                 nn_it = np.zeros((n_modules, n_target), dtype=np.int32)
@@ -763,21 +779,27 @@ def scregclust_fit(z1_reg_scaled, z2_reg_scaled, z1_target_centered, z2_target_c
                         continue
                     sg = signs[reg_cl, j]
                     xtx_j = G_rr[np.ix_(reg_cl, reg_cl)] * np.outer(sg, sg)
-                    xty_j = G_rt_nnls[reg_cl, :] * sg[:, None]
+                    xty_j = G_rt_nnls[np.ix_(reg_cl, filt)] * sg[:, None]
                     b_nn, its = coef_nnls(eps=tol_nnls, max_iter=max_optim_iter, xtx=xtx_j, xty=xty_j)
-                    nn_it[j] = its
-                    beta_hat = b_nn * sg[:, None] * _recycle(z1_target_sds, b_nn.shape)
-                    betas[j] = beta_hat
-                    r_train = z1t - z1r[:, reg_cl] @ beta_hat
-                    r_test = z2t - z2r[:, reg_cl] @ beta_hat
+                    nn_it[j, filt] = its
+                    beta_hat = b_nn * sg[:, None] * _recycle(sds_f, b_nn.shape)      # modulus = #filtered targets
+                    full = np.zeros((reg_cl.size, n_target)); full[:, filt] = beta_hat   # scregclust.R:1606-1610
+                    betas[j] = full
+                    r_train = z1t_f - z1r[:, reg_cl] @ beta_hat
+                    r_test = z2t_f - z2r[:, reg_cl] @ beta_hat
                     if not last_cycle and materialize_array:
-                        sq_arr[j, :, :] = r_test * r_test
+                        sq_arr[j][:, filt] = r_test * r_test
                     ss_test[:, j] = np.sum(r_test * r_test, axis=0)
                     ss_train[:, j] = np.sum(r_train * r_train, axis=0)
                 fr.nnls_iterations.append(nn_it)
-                r2_test = 1.0 - ss_test / ss_test0[:, None]
+                r2_test = np.zeros((n_target, n_modules))                              # scregclust.R:1628-1631
+                r2_test[filt] = 1.0 - ss_test / np.sum(z2t_f * z2t_f, axis=0)[:, None]
                 best_r2[cycle] = np.max(r2_test, axis=1)
-                resid_var = ss_train / (n1 - np.sum(models, axis=0))[None, :]
+                resid_var = np.full((n_target, n_modules), 1e6)                        # scregclust.R:1635-1638
+                resid_var[filt] = ss_train / (n1 - np.sum(models, axis=0))[None, :]
+                if last_cycle and nt < n_target:
+                    rest = np.setdiff1d(np.arange(n_target), filt)
+                    resid_var[rest] = 0.0                                              # scregclust.R:1642
                 if keep_history:
                     fr.resid_var_history.append(resid_var.copy()); fr.r2_history.append(r2_test.copy())
                     fr.coeffs_history.append(betas)
@@ -816,6 +838,7 @@ def scregclust_fit(z1_reg_scaled, z2_reg_scaled, z1_target_centered, z2_target_c
             small = np.flatnonzero(module_size < min_module_size) + 1
             idx[np.isin(idx, small)] = -1
             k = idx.astype(np.int32)
+            idx_latest = k.copy()
             matching = [i for i, kh in enumerate(k_history, start=1) if np.array_equal(kh, k)]
             k_history.append(k.copy())
             if matching:
@@ -834,6 +857,39 @@ def scregclust_fit(z1_reg_scaled, z2_reg_scaled, z1_target_centered, z2_target_c
                         tol_nnls, max_optim_iter)
         results.append(fr)
     return results
+
+
+def r_quantile7(x, prob):
+    """R's default quantile (type 7), with its back-compatible arithmetic (stats:::quantile.default):
+    index = 1 + (n-1) p; qs = x[lo]; where index > lo and x[hi] != qs: qs = (1-h) qs + h x[hi]."""
+    x = np.sort(np.asarray(x, dtype=np.float64))
+    n = x.size
+    if n == 0:
+        return float("nan")
+    index = 1.0 + max(n - 1, 0) * prob
+    lo = int(math.floor(index)); hi = int(math.ceil(index))
+    qs = x[lo - 1]
+    if index > lo and x[hi - 1] != qs:
+        h = index - lo
+        qs = (1.0 - h) * qs + h * x[hi - 1]
+    return float(qs)
+
+
+def quick_mode_targets(abs_corr, models, idx, percent, last_cycle):
+    """Step 1.5 (scregclust.R:1444-1477): targets currently in a module (``idx != -1``, increasing) followed by the
+    noise targets whose largest absolute correlation with an ACTIVE regulator reaches the (1 - percent) quantile of
+    those maxima (increasing).  ``idx`` is R's ``idx``: the latest allocation, also while an older configuration of a
+    limit cycle is re-fitted in the last cycle."""
+    active_reg = np.flatnonzero(models.sum(axis=1) >= 1)
+    active_t = np.flatnonzero(idx != -1)
+    if last_cycle:
+        return active_t
+    noise_t = np.setdiff1d(np.arange(abs_corr.shape[0]), active_t)
+    if noise_t.size == 0:
+        return active_t
+    mx = abs_corr[np.ix_(noise_t, active_reg)].max(axis=1)
+    thr = r_quantile7(mx, 1.0 - percent)
+    return np.concatenate([active_t, noise_t[mx >= thr]])
 
 
 def _allocate_streaming(z2t, z2r, models, betas, resid_var, prior_indicator, k_, order,

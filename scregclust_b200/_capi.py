@@ -45,6 +45,10 @@ class Prior(C.Structure):
                 ("update_order", c_int_p)]
 
 
+class Quick(C.Structure):
+    _fields_ = [("idx_latest", c_int_p), ("percent", C.c_double)]
+
+
 UPDATE_ORDER_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_int, C.c_int)   # returns the address of T ints
 
 
@@ -54,7 +58,7 @@ class GridParams(C.Structure):
                 ("opt", Options), ("compute_predictive_r2", C.c_int), ("keep_coeffs", C.c_int),
                 ("keep_diagnostics", C.c_int), ("prior_off", c_int_p), ("prior_idx", c_int_p),
                 ("prior_baseline", C.c_double), ("prior_weight", C.c_double), ("update_order", UPDATE_ORDER_FN),
-                ("update_order_user", C.c_void_p)]
+                ("update_order_user", C.c_void_p), ("quick_mode", C.c_int), ("quick_mode_percent", C.c_double)]
 
 
 class GridInfo(C.Structure):
@@ -75,7 +79,7 @@ class GridFinal(C.Structure):
 
 
 BACKEND_FIT_CYCLE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, c_double_p, c_int_p, C.POINTER(Options), C.c_int, c_int_p,
-                                   C.POINTER(Prior), C.POINTER(CycleOut))
+                                   C.POINTER(Prior), C.POINTER(Quick), C.POINTER(CycleOut))
 BACKEND_IMPORTANCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, c_int_p, c_ubyte_p, c_double_p, C.POINTER(Options),
                                     c_double_p, c_double_p, c_double_p, C.c_int64)
 BACKEND_COEFFS_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, c_double_p, c_int_p)
@@ -126,6 +130,8 @@ SIGNATURES = {
                                  C.POINTER(CycleOut)]),
     "scrc_fit_cycle_prior": (C.c_int, [C.c_void_p, C.c_int, c_double_p, c_int_p, C.POINTER(Options), C.POINTER(Prior),
                                        C.POINTER(CycleOut)]),
+    "scrc_fit_cycle_quick": (C.c_int, [C.c_void_p, C.c_int, c_double_p, c_int_p, C.POINTER(Options), C.c_int,
+                                       C.POINTER(Quick), C.POINTER(CycleOut)]),
     "scrc_importance": (C.c_int, [C.c_void_p, C.c_int, c_int_p, c_ubyte_p, c_double_p, C.POINTER(Options), c_double_p,
                                   c_double_p]),
     "scrc_importance_ex": (C.c_int, [C.c_void_p, C.c_int, c_int_p, c_ubyte_p, c_double_p, C.POINTER(Options), c_double_p,

@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) resid_vote_kernel(const __gri
     const int w = blockIdx.x;
     const int tn = w % p.tiles_n, cr = (w / p.tiles_n) % p.CR, l = w / (p.tiles_n * p.CR);
     const int ct0 = cr * ct_per, ct1 = min(ct0 + ct_per, p.ctiles);
-    const int ncol = p.col_cnt ? p.col_cnt[l] : p.t_end;  // one past the last column of this fit (slice)
+    const int ncol = p.col_cnt ? min(p.col_cnt[l], p.t_end) : p.t_end;  // one past the last column of this fit (slice)
     if (p.t_begin + tn * RV_BN >= ncol) return;           // whole CTA: nothing to do for this tile
     const int* cidx = p.col_index ? p.col_index + p.col_off[l] : nullptr;
     PipeState ps;
@@ -361,7 +361,9 @@ __global__ void __launch_bounds__(128) sse_train_gram_kernel(const double* __res
                                                              const double* __restrict__ beta, int64_t ldb,
                                                              const int* __restrict__ sel, const int* __restrict__ row_off,
                                                              const int* __restrict__ nsel, int T, int K, double* sse,
-                                                             int t0, int t1) {
+                                                             int t0, int t1, const int* __restrict__ col_index,
+                                                             const int* __restrict__ col_off,
+                                                             const int* __restrict__ col_cnt) {
     __shared__ double s_g[SSG_MAX_S * SSG_MAX_S];
     __shared__ int s_sel[SSG_MAX_S];
     const int fk = blockIdx.y;
@@ -377,14 +379,17 @@ __global__ void __launch_bounds__(128) sse_train_gram_kernel(const double* __res
         __syncthreads();
     }
     if (t >= t1) return;
-    double acc = gtt[t];
+    // quick mode: column t of this fit is target col_index[col_off[l] + t] (per-fit target subsets)
+    if (col_cnt && t >= col_cnt[l]) return;
+    const int tg = col_index ? col_index[col_off[l] + t] : t;
+    double acc = gtt[tg];
     if (s > 0) {
         const double* b = beta + ro + (int64_t)t * ldb;
         double cross = 0.0, quad = 0.0;
         for (int a = 0; a < s; ++a) {
             const double ba = b[a];
             const int ia = in_smem ? s_sel[a] : sel[ro + a];
-            cross += ba * G_rt[ia + (int64_t)t * ldrt];
+            cross += ba * G_rt[ia + (int64_t)tg * ldrt];
             double row = 0.0;
             for (int c = 0; c < s; ++c) {
                 const double g = in_smem ? s_g[a + c * s] : G_rr[ia + (int64_t)sel[ro + c] * ldrr];
@@ -398,12 +403,14 @@ __global__ void __launch_bounds__(128) sse_train_gram_kernel(const double* __res
 }
 void sse_train_gram(const double* G_rr, int64_t ldrr, const double* G_rt, int64_t ldrt, const double* gtt,
                     const double* beta, int64_t ldb, const int* sel, const int* row_off, const int* nsel, int T, int K,
-                    int L, double* sse, cudaStream_t st, int t0, int t1) {
+                    int L, double* sse, cudaStream_t st, int t0, int t1, const int* col_index, const int* col_off,
+                    const int* col_cnt) {
     if (t1 < 0) t1 = T;
     if (t1 == t0) return;
     dim3 grid((unsigned)ceil_div(t1 - t0, 128), (unsigned)(L * K));
     ProfScope ps(PROF_RESID_VOTE, st, 0.0);
-    sse_train_gram_kernel<<<grid, 128, 0, st>>>(G_rr, ldrr, G_rt, ldrt, gtt, beta, ldb, sel, row_off, nsel, T, K, sse, t0, t1);
+    sse_train_gram_kernel<<<grid, 128, 0, st>>>(G_rr, ldrr, G_rt, ldrt, gtt, beta, ldb, sel, row_off, nsel, T, K, sse, t0, t1,
+                                                col_index, col_off, col_cnt);
     SCRC_CUDA(cudaGetLastError());
     SCRC_LAUNCHED();
 }

@@ -55,7 +55,8 @@ void reduce_sse(const double* partial, int T, int K, int L, int CR, double* sse,
 void sse_train_gram(const double* G_rr, int64_t ldrr, const double* G_rt, int64_t ldrt, const double* gtt,
                     const double* beta, int64_t ldb, const int* sel /* per stacked row: regulator or -1 */,
                     const int* row_off, const int* nsel, int T, int K, int L, double* sse, cudaStream_t s, int t0 = 0,
-                    int t1 = -1);
+                    int t1 = -1, const int* col_index = nullptr, const int* col_off = nullptr,
+                    const int* col_cnt = nullptr);
 
 // resid_var = SSE_train / (n1 - s_j); two_var = 2 var; inv_two_var = RN(1 / two_var); half_log = 0.5 log(2 pi var)
 // (R/scregclust.R:1635-1638, allocation.cpp:59-62).  nsel: device [L*K].

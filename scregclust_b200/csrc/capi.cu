@@ -327,6 +327,16 @@ int scrc_fit_cycle_prior(scrc_ctx* ctx, int F, const double* lambda, const int* 
     return guarded([&] { ctx->impl.fit_cycle(F, lambda, k_in, o, false, out, prior); });
 }
 
+int scrc_fit_cycle_quick(scrc_ctx* ctx, int F, const double* lambda, const int* k_in, const scrc_options* opt,
+                         int skip_allocation, const scrc_quick* quick, scrc_cycle_out* out) {
+    if (!ctx || !lambda || !k_in) return fail(SCRC_ERR_ARG, "scrc_fit_cycle_quick: null pointer");
+    scrc_options o;
+    if (opt) o = *opt; else scrc_default_options(&o);
+    if (o.max_optim_iter <= 0 || o.n_update <= 0 || !(o.rho0 > 0.0) || o.alpha0 <= 0.0 || o.alpha0 > 2.0)
+        return fail(SCRC_ERR_ARG, "scrc_fit_cycle_quick: invalid options");
+    return guarded([&] { ctx->impl.fit_cycle(F, lambda, k_in, o, skip_allocation != 0, out, nullptr, quick); });
+}
+
 int scrc_importance(scrc_ctx* ctx, int F, const int* k_final, const unsigned char* models, const double* signs,
                     const scrc_options* opt, double* r2_module, double* importance) {
     if (!ctx || !k_final || !models || !signs || !r2_module || !importance)

@@ -23,7 +23,7 @@ struct GridBackend {
     int K = 0;
     virtual ~GridBackend() {}
     virtual void fit_cycle(int F, const double* lambda, const int* k_in, const scrc_options& opt, bool skip_alloc,
-                           const int* hint, const scrc_prior* prior, scrc_cycle_out* out) = 0;
+                           const int* hint, const scrc_prior* prior, const scrc_quick* quick, scrc_cycle_out* out) = 0;
     virtual void importance(int F, const int* k_final, const unsigned char* models, const double* signs,
                             const scrc_options& opt, double* r2_module, double* importance, double* r2_removed,
                             int64_t cap) = 0;
@@ -37,9 +37,9 @@ struct CtxBackend : GridBackend {
     Ctx& c;
     explicit CtxBackend(Ctx& ctx) : c(ctx) { P = c.P; T = c.T; K = c.K; }
     void fit_cycle(int F, const double* lambda, const int* k_in, const scrc_options& opt, bool skip_alloc, const int* hint,
-                   const scrc_prior* prior, scrc_cycle_out* out) override {
+                   const scrc_prior* prior, const scrc_quick* quick, scrc_cycle_out* out) override {
         if (hint) c.cost_hint.assign(hint, hint + (size_t)F * K);
-        c.fit_cycle(F, lambda, k_in, opt, skip_alloc, out, prior);
+        c.fit_cycle(F, lambda, k_in, opt, skip_alloc, out, prior, quick);
     }
     void importance(int F, const int* k_final, const unsigned char* models, const double* signs, const scrc_options& opt,
                     double* r2_module, double* imp, double* r2_removed, int64_t cap) override {
@@ -63,8 +63,8 @@ struct CallbackBackend : GridBackend {
         if (rc != 0) throw Error(rc, std::string("scrc_grid_fit_custom: the ") + what + " callback failed");
     }
     void fit_cycle(int F, const double* lambda, const int* k_in, const scrc_options& opt, bool skip_alloc, const int* hint,
-                   const scrc_prior* prior, scrc_cycle_out* out) override {
-        chk(cb.fit_cycle(cb.user, F, lambda, k_in, &opt, skip_alloc ? 1 : 0, hint, prior, out), "fit_cycle");
+                   const scrc_prior* prior, const scrc_quick* quick, scrc_cycle_out* out) override {
+        chk(cb.fit_cycle(cb.user, F, lambda, k_in, &opt, skip_alloc ? 1 : 0, hint, prior, quick, out), "fit_cycle");
     }
     void importance(int F, const int* k_final, const unsigned char* models, const double* signs, const scrc_options& opt,
                     double* r2_module, double* imp, double* r2_removed, int64_t cap) override {
@@ -129,6 +129,10 @@ static void grid_loop(GridBackend& be, const scrc_grid_params& gp, scrc_grid_res
     const int64_t P = be.P, T = be.T;
     if (L <= 0 || !gp.penalization || !gp.initial_target_modules) throw Error(SCRC_ERR_ARG, "scrc_grid_fit: empty grid or null pointer");
     if (gp.n_cycles < 0 || gp.min_module_size < 0) throw Error(SCRC_ERR_ARG, "scrc_grid_fit: negative n_cycles / min_module_size");
+    if (gp.quick_mode && !(gp.quick_mode_percent >= 0.0 && gp.quick_mode_percent < 1.0))
+        throw Error(SCRC_ERR_ARG, "quick_mode_percent needs to be numeric in [0, 1).");
+    if (gp.quick_mode && gp.prior_weight != 0.0 && gp.prior_off)
+        throw Error(SCRC_ERR_UNSUPPORTED, "scrc_grid_fit: quick mode together with a network prior is not supported");
     const bool use_prior = gp.prior_weight != 0.0 && gp.prior_off != nullptr;
     const bool diag = gp.keep_diagnostics != 0;
     res.pens.clear();
@@ -194,7 +198,11 @@ static void grid_loop(GridBackend& be, const scrc_grid_params& gp, scrc_grid_res
             }
             sweeps = 0;
             const double tc0 = wall_now();
-            be.fit_cycle(F, lam.data(), ks.data(), gp.opt, false, hint.data(), use_prior ? &pr : nullptr, &co);
+            // quick mode from cycle two on (R/scregclust.R:1444); in a fit cycle R's `idx` is the configuration itself
+            scrc_quick qk{ks.data(), gp.quick_mode_percent};
+            const bool quick_now = gp.quick_mode && st[run[0]].cycle != 1;
+            be.fit_cycle(F, lam.data(), ks.data(), gp.opt, false, hint.data(), use_prior ? &pr : nullptr,
+                         quick_now ? &qk : nullptr, &co);
             t_cycle += wall_now() - tc0;
             res.info.admm_sweeps += sweeps; res.info.device_calls += 1;
             for (int f = 0; f < F; ++f) {
@@ -257,9 +265,13 @@ static void grid_loop(GridBackend& be, const scrc_grid_params& gp, scrc_grid_res
         }
         const int F = (int)owner.size();
         lam.resize(F); ks.resize((size_t)F * T); hint.assign((size_t)F * K, 0);
+        std::vector<int> latest;
+        if (gp.quick_mode) latest.resize((size_t)F * T);
         for (int f = 0; f < F; ++f) {
             lam[f] = gp.penalization[owner[f]];
             std::copy(kf[f]->begin(), kf[f]->end(), ks.begin() + (size_t)f * T);
+            // R's `idx` stays the LATEST allocation while older configurations of a limit cycle are re-fitted
+            if (gp.quick_mode) std::copy(st[owner[f]].k.begin(), st[owner[f]].k.end(), latest.begin() + (size_t)f * T);
             std::copy(st[owner[f]].last_iters.begin(), st[owner[f]].last_iters.end(), hint.begin() + (size_t)f * K);
         }
         const size_t fkp = (size_t)F * K * P, fkt = (size_t)F * K * T, ft = (size_t)F * T;
@@ -273,7 +285,11 @@ static void grid_loop(GridBackend& be, const scrc_grid_params& gp, scrc_grid_res
         if (diag) { nnls_it.assign(fkt, 0); co.nnls_iterations = nnls_it.data(); }
         sweeps = 0;
         const double tf0 = wall_now();
-        be.fit_cycle(F, lam.data(), ks.data(), gp.opt, true, hint.data(), nullptr, &co);
+        scrc_quick qk{latest.data(), gp.quick_mode_percent};
+        // (a value that never ran a fit cycle -- n_cycles = 0 -- is still in "cycle 1": no subset)
+        bool quick_fin = gp.quick_mode != 0;
+        for (int i : batch) quick_fin &= st[i].cycle != 1;
+        be.fit_cycle(F, lam.data(), ks.data(), gp.opt, true, hint.data(), nullptr, quick_fin ? &qk : nullptr, &co);
         t_final += wall_now() - tf0;
         res.info.admm_sweeps += sweeps; res.info.device_calls += 1;
         for (int f = 0; f < F; ++f) {
@@ -387,6 +403,7 @@ void scrc_grid_default_params(scrc_grid_params* p) {
     scrc_default_options(&p->opt);
     p->compute_predictive_r2 = 1; p->keep_coeffs = 1; p->keep_diagnostics = 0;
     p->prior_baseline = 1e-6; p->prior_weight = 0.0;
+    p->quick_mode = 0; p->quick_mode_percent = 0.1;
 }
 
 int scrc_grid_fit(scrc_ctx* ctx, const scrc_grid_params* p, scrc_grid_result** out) {

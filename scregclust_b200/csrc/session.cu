@@ -369,6 +369,67 @@ __global__ void add_one_kernel(int* x, int64_t n) {
     if (i < n) x[i] += 1;
 }
 
+// ---------------------------------------------------------------- quick mode (scregclust.R:1435-1496)
+// areg[f][r] = regulator r is selected by some module of fit f (scregclust.R:1447)
+__global__ void quick_areg_kernel(const unsigned char* __restrict__ models, int K, int P, unsigned char* areg) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int f = blockIdx.y;
+    if (i >= P) return;
+    int a = 0;
+    for (int j = 0; j < K; ++j) a |= models[((int64_t)f * K + j) * P + i];
+    areg[(int64_t)f * P + i] = (unsigned char)a;
+}
+// mx[f][t] = max over the active regulators r of |cor(target t, regulator r)| for the noise targets of fit f
+// (scregclust.R:1455-1460); corr is cross_corr1 (T x P).  Consecutive threads read consecutive targets.
+__global__ void quick_max_kernel(const double* __restrict__ corr, int64_t ldc, const int* __restrict__ idx,
+                                 const unsigned char* __restrict__ areg, int T, int P, double* mx) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int f = blockIdx.y;
+    if (t >= T || idx[(int64_t)f * T + t] != -1) return;
+    const unsigned char* a = areg + (int64_t)f * P;
+    double m = -INFINITY;
+    for (int r = 0; r < P; ++r)
+        if (a[r]) m = fmax(m, fabs(corr[t + (int64_t)r * ldc]));
+    mx[(int64_t)f * T + t] = m;
+}
+// Local (subset) column space -> all T targets, with the reference's values for the targets Step 2 skipped:
+// r2 = 0, resid_var = 1e6 (0 in the last cycle), best_r2 = 0, which.max = 1, and -- all K scores being equal -- every
+// cell's vote and hence the gene itself going to module 1 (scregclust.R:1628-1642, allocation.cpp:80-94).
+__global__ void quick_scatter_kernel(int F, int K, int T, const int* __restrict__ inv, int n2, int last_cycle,
+                                     const double* r2_l, const double* var_l, const double* br_l, const int* bi_l,
+                                     const int* kn_l, const int* votes_l, double* r2_g, double* var_g, double* br_g,
+                                     int* bi_g, int* kn_g, int* votes_g) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)F * T) return;
+    const int f = (int)(i / T), t = (int)(i % T);
+    const int c = inv[i];
+    const int64_t lo = (int64_t)f * T + (c >= 0 ? c : 0);
+    if (br_g) br_g[i] = c >= 0 ? br_l[lo] : 0.0;
+    if (bi_g) bi_g[i] = c >= 0 ? bi_l[lo] : 1;
+    if (kn_g) kn_g[i] = c >= 0 ? kn_l[lo] : 1;
+    for (int j = 0; j < K; ++j) {
+        const int64_t g = ((int64_t)f * K + j) * T + t, l = ((int64_t)f * K + j) * T + (c >= 0 ? c : 0);
+        if (r2_g) r2_g[g] = c >= 0 ? r2_l[l] : 0.0;
+        if (var_g) var_g[g] = c >= 0 ? var_l[l] : (last_cycle ? 0.0 : 1e6);
+        if (votes_g) votes_g[i * K + j] = c >= 0 ? votes_l[lo * K + j] : (j == 0 ? n2 : 0);
+    }
+}
+// R's default quantile (type 7) with its own arithmetic (stats:::quantile.default): index = 1 + (n-1) p,
+// qs = x[lo]; where index > lo and x[hi] != qs: qs = (1-h) qs + h x[hi].
+static double r_quantile7(std::vector<double> x, double prob) {
+    const size_t n = x.size();
+    if (n == 0) return std::nan("");
+    std::sort(x.begin(), x.end());
+    const double index = 1.0 + (double)(n - 1) * prob;
+    const double lo = std::floor(index), hi = std::ceil(index);
+    double qs = x[(size_t)lo - 1];
+    if (index > lo && x[(size_t)hi - 1] != qs) {
+        const double h = index - lo;
+        qs = (1.0 - h) * qs + h * x[(size_t)hi - 1];
+    }
+    return qs;
+}
+
 // The reference documents these as assumptions (allocation.cpp:4-6); on a public C ABI they are checked,
 // because the sequential sweep indexes shared and global memory with them.
 void validate_prior_inputs(const char* who, const int* k, int64_t T, int K, const int* prior_off, const int* prior_idx,
@@ -407,8 +468,12 @@ void validate_prior_inputs(const char* who, const int* k, int64_t T, int K, cons
 // With a network prior Step 2b is sequential over the genes (allocation.cpp:33-97): Step 1 is still
 // spread over the ranks, Step 2 is then replicated on every rank.
 void Ctx::fit_cycle(int F, const double* lambda, const int* k_in, const scrc_options& opt, bool skip_alloc,
-                    scrc_cycle_out* out, const scrc_prior* prior) {
+                    scrc_cycle_out* out, const scrc_prior* prior, const scrc_quick* quick) {
     const bool use_prior = prior && prior->weight != 0.0 && !skip_alloc;
+    const bool use_quick = quick && quick->idx_latest;
+    if (use_quick && use_prior) throw Error(SCRC_ERR_UNSUPPORTED, "quick mode together with a network prior is not supported");
+    if (use_quick && !(quick->percent >= 0.0 && quick->percent < 1.0))
+        throw Error(SCRC_ERR_ARG, "quick_mode_percent needs to be numeric in [0, 1).");
     if (use_prior && (!prior->update_order || !prior->prior_off))
         throw Error(SCRC_ERR_ARG, "scrc_fit_cycle_prior: prior_off and update_order are required when prior_weight != 0");
     if (F <= 0) throw Error(SCRC_ERR_ARG, "scrc_fit_cycle: F must be positive");
@@ -536,6 +601,72 @@ void Ctx::fit_cycle(int F, const double* lambda, const int* k_in, const scrc_opt
     const int* h_nsel = h_fk + FK + 1;
     pt.mark(phase_s, 2);
 
+    // ---------------- Step 1.5 (quick mode): per-fit target subsets ----------------
+    std::vector<int> h_filt, h_foff, h_fcnt, h_finv;
+    if (use_quick) {
+        if (abs_corr.rows == 0) {     // cross_corr1 = fast_cor(z1_target_centered, z1_reg_scaled), once per session (:1116-1122)
+            DMat X(n1, T), Y(n1, P);
+            SCRC_CUDA(cudaMemcpyAsync(X.data(), Z1t.data(), Z1t.bytes(), cudaMemcpyDeviceToDevice, st));
+            SCRC_CUDA(cudaMemcpyAsync(Y.data(), Z1r.data(), Z1r.bytes(), cudaMemcpyDeviceToDevice, st));
+            DevBuf<double> xss(T), yss(P);
+            col_center_ss(X.data(), X.ld, n1, T, xss.p, st);
+            col_center_ss(Y.data(), Y.ld, n1, P, yss.p, st);
+            abs_corr.alloc(T, P);
+            DenseArgs a{X.data(), X.ld, Y.data(), Y.ld, abs_corr.data(), abs_corr.ld, (int)T, (int)P, (int)n1};
+            a.rvec = xss.p; a.cvec = yss.p;
+            gemm_tn_dense(EPI_COR, a, dev.num_sms, st);
+            SCRC_CUDA(cudaStreamSynchronize(st));
+        }
+        q_areg.ensure(FK / K * P); q_idx.ensure((size_t)F * T); q_mx.ensure((size_t)F * T);
+        SCRC_CUDA(cudaMemcpyAsync(q_idx.p, quick->idx_latest, (size_t)F * T * 4, cudaMemcpyHostToDevice, st));
+        quick_areg_kernel<<<dim3((unsigned)ceil_div(P, 256), F), 256, 0, st>>>(models_d.p, K, (int)P, q_areg.p);
+        SCRC_LAUNCHED();
+        quick_max_kernel<<<dim3((unsigned)ceil_div(T, 256), F), 256, 0, st>>>(abs_corr.data(), abs_corr.ld, q_idx.p, q_areg.p,
+                                                                              (int)T, (int)P, q_mx.p);
+        SCRC_LAUNCHED();
+        std::vector<double> h_mx((size_t)F * T);
+        SCRC_CUDA(cudaMemcpyAsync(h_mx.data(), q_mx.p, h_mx.size() * 8, cudaMemcpyDeviceToHost, st));
+        SCRC_CUDA(cudaStreamSynchronize(st));
+        h_foff.assign(F, 0); h_fcnt.assign(F, 0); h_finv.assign((size_t)F * T, -1);
+        for (int f = 0; f < F; ++f) {
+            const int* idx = quick->idx_latest + (int64_t)f * T;
+            h_foff[f] = (int)h_filt.size();
+            int nsel_fit = 0;
+            for (int j = 0; j < K; ++j) nsel_fit += h_nsel[(int64_t)f * K + j];
+            if (nsel_fit == 0) {                                       // sum(models) == 0: Step 2 sees every target (:1444)
+                for (int64_t t = 0; t < T; ++t) h_filt.push_back((int)t);
+            } else {
+                std::vector<int> noise;
+                for (int64_t t = 0; t < T; ++t) { if (idx[t] != -1) h_filt.push_back((int)t); else noise.push_back((int)t); }
+                if (!skip_alloc && !noise.empty()) {                   // the last cycle keeps the active targets only (:1451)
+                    std::vector<double> v(noise.size());
+                    for (size_t q = 0; q < noise.size(); ++q) v[q] = h_mx[(size_t)f * T + noise[q]];
+                    const double thr = r_quantile7(v, 1.0 - quick->percent);          // :1463
+                    for (size_t q = 0; q < noise.size(); ++q) if (v[q] >= thr) h_filt.push_back(noise[q]);
+                }
+            }
+            h_fcnt[f] = (int)h_filt.size() - h_foff[f];
+            for (int c = 0; c < h_fcnt[f]; ++c) h_finv[(size_t)f * T + h_filt[h_foff[f] + c]] = c;
+        }
+        std::vector<double> h_fsds(h_filt.size());
+        if (h_sds.empty()) {
+            h_sds.resize(T);
+            SCRC_CUDA(cudaMemcpyAsync(h_sds.data(), sds_t.p, T * 8, cudaMemcpyDeviceToHost, st));
+            SCRC_CUDA(cudaStreamSynchronize(st));
+        }
+        for (size_t q = 0; q < h_filt.size(); ++q) h_fsds[q] = h_sds[h_filt[q]];
+        nnls.cols.ensure(std::max<size_t>(h_filt.size(), 1)); q_off.ensure(F); q_cnt.ensure(F); q_inv.ensure((size_t)F * T);
+        q_sds.ensure(std::max<size_t>(h_filt.size(), 1));
+        if (!h_filt.empty()) {
+            SCRC_CUDA(cudaMemcpyAsync(nnls.cols.p, h_filt.data(), h_filt.size() * 4, cudaMemcpyHostToDevice, st));
+            SCRC_CUDA(cudaMemcpyAsync(q_sds.p, h_fsds.data(), h_fsds.size() * 8, cudaMemcpyHostToDevice, st));
+        }
+        SCRC_CUDA(cudaMemcpyAsync(q_off.p, h_foff.data(), F * 4, cudaMemcpyHostToDevice, st));
+        SCRC_CUDA(cudaMemcpyAsync(q_cnt.p, h_fcnt.data(), F * 4, cudaMemcpyHostToDevice, st));
+        SCRC_CUDA(cudaMemcpyAsync(q_inv.p, h_finv.data(), (size_t)F * T * 4, cudaMemcpyHostToDevice, st));
+    }
+    last_quick = use_quick;
+
     // ---------------- Step 2a: NNLS problem table ----------------
     slots.assign(FK, FitSlot());
     last_F = F;
@@ -551,6 +682,11 @@ void Ctx::fit_cycle(int F, const double* lambda, const int* k_in, const scrc_opt
         sl.row_off = (int)rows_total; sl.sel_off = (int)sel_total;
         h_row_off[fk] = sl.row_off; h_kpad[fk] = kp; h_sel_off[fk] = sl.sel_off;
         h_np.push_back(make_nnls_problem(sl.s, (int)sel_total, q_total, rows_total));
+        if (use_quick) {          // columns = the fit's target subset; R recycles z1_target_sds_tmp over ITS length (:1580-1588)
+            NnlsProblem& np = h_np.back();
+            const int f = (int)(fk / K);
+            np.ncols = h_fcnt[f]; np.xcol_off = h_foff[f]; np.scale_off = h_foff[f]; np.scale_len = h_fcnt[f];
+        }
         h_np_slot.push_back((int)fk);
         rows_total += kp; q_total += (int64_t)sl.s * sl.s; sel_total += sl.s;
     }
@@ -610,9 +746,10 @@ void Ctx::fit_cycle(int F, const double* lambda, const int* k_in, const scrc_opt
     ra.T = (int)T; ra.K = K; ra.L = F; ra.row_off = row_off_d.p; ra.kpad = kpad_d.p; ra.nsel = nsel_d.p;
     ra.two_var = two_var.p; ra.inv_two_var = inv_two_var.p; ra.half_log = half_log.p; ra.partial = partial.p; ra.votes = votes.p;
     ra.t_begin = t0; ra.t_end = t1;
+    if (use_quick) { ra.col_index = nnls.cols.p; ra.col_off = q_off.p; ra.col_cnt = q_cnt.p; }
     // train split: SSE from the Gram matrices (no pass over the n1 cells), then the variances
     sse_train_gram(G_rr.data(), G_rr.ld, G_rt.data(), G_rt.ld, gtt.p, nnls.beta.data(), nnls.beta.ld, row_src.p,
-                   row_off_d.p, nsel_d.p, (int)T, K, F, sse_train.p, st, t0, t1);
+                   row_off_d.p, nsel_d.p, (int)T, K, F, sse_train.p, st, t0, t1, ra.col_index, ra.col_off, ra.col_cnt);
     make_resid_var(sse_train.p, nsel_d.p, (int)n1, (int)T, K, F, var.p, two_var.p, inv_two_var.p, half_log.p, st, t0, t1);
     // test split
     ZselT.reshape(rows_alloc, n2);
@@ -682,27 +819,51 @@ void Ctx::fit_cycle(int F, const double* lambda, const int* k_in, const scrc_opt
         comm->group_end();
     }
 
+    // quick mode: subset column space -> all targets, with the reference's values for the skipped targets
+    double *o_r2 = r2.p, *o_var = var.p, *o_br = best_r2.p;
+    int *o_bi = best_idx.p, *o_kn = k_new.p, *o_votes = votes.p;
+    if (use_quick) {
+        q_r2.ensure(fkt); q_var.ensure(fkt); q_br.ensure(ft); q_bi.ensure(ft); q_kn.ensure(ft);
+        const bool wv = vote && out && out->votes;
+        if (wv) q_votes.ensure(fkt);
+        quick_scatter_kernel<<<(unsigned)ceil_div((int64_t)ft, 256), 256, 0, st>>>(
+            F, K, (int)T, q_inv.p, (int)n2, skip_alloc ? 1 : 0, r2.p, var.p, best_r2.p, best_idx.p, vote ? k_new.p : nullptr,
+            wv ? votes.p : nullptr, q_r2.p, q_var.p, q_br.p, q_bi.p, vote ? q_kn.p : nullptr, wv ? q_votes.p : nullptr);
+        SCRC_LAUNCHED();
+        o_r2 = q_r2.p; o_var = q_var.p; o_br = q_br.p; o_bi = q_bi.p; o_kn = q_kn.p; o_votes = q_votes.p;
+    }
     pt.mark(phase_s, 6);
     // ---------------- outputs ----------------
     if (out) {
         auto d2h = [&](void* dst, const void* src, size_t bytes) {
             if (dst && bytes) SCRC_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));
         };
-        if (vote) { d2h(out->k_new, k_new.p, ft * 4); d2h(out->votes, votes.p, fkt * 4); }
+        if (vote) { d2h(out->k_new, o_kn, ft * 4); d2h(out->votes, o_votes, fkt * 4); }
         d2h(out->models, models_d.p, FK * P);
         d2h(out->weights, weights_d.p, FK * P * 8);
         d2h(out->signs, signs_d.p, FK * P * 8);
-        d2h(out->r2_test, r2.p, fkt * 8);
-        d2h(out->resid_var, var.p, fkt * 8);
-        d2h(out->best_r2, best_r2.p, ft * 8);
-        d2h(out->best_r2_idx, best_idx.p, ft * 4);
+        d2h(out->r2_test, o_r2, fkt * 8);
+        d2h(out->resid_var, o_var, fkt * 8);
+        d2h(out->best_r2, o_br, ft * 8);
+        d2h(out->best_r2_idx, o_bi, ft * 4);
         if (out->admm_iterations) std::memcpy(out->admm_iterations, h_admm_it, FK * 4);
         if (out->n_selected) std::memcpy(out->n_selected, h_nsel, FK * 4);
         if (out->admm_sweeps) *out->admm_sweeps = sweeps;
         if (out->nnls_iterations) {
             std::memset(out->nnls_iterations, 0, fkt * 4);
-            for (int q = 0; q < nnp; ++q)
-                d2h(out->nnls_iterations + (size_t)h_np_slot[q] * T, nnls.iters.p + (size_t)q * T, (size_t)T * 4);
+            if (!use_quick) {
+                for (int q = 0; q < nnp; ++q)
+                    d2h(out->nnls_iterations + (size_t)h_np_slot[q] * T, nnls.iters.p + (size_t)q * T, (size_t)T * 4);
+            } else if (nnp > 0) {           // subset column space -> targets
+                std::vector<int> loc((size_t)nnp * T);
+                SCRC_CUDA(cudaMemcpyAsync(loc.data(), nnls.iters.p, loc.size() * 4, cudaMemcpyDeviceToHost, st));
+                SCRC_CUDA(cudaStreamSynchronize(st));
+                for (int q = 0; q < nnp; ++q) {
+                    const int f = h_np_slot[q] / K;
+                    for (int c = 0; c < h_fcnt[f]; ++c)
+                        out->nnls_iterations[(size_t)h_np_slot[q] * T + h_filt[h_foff[f] + c]] = loc[(size_t)q * T + c];
+                }
+            }
         }
     }
     SCRC_CUDA(cudaStreamSynchronize(st));
@@ -711,13 +872,16 @@ void Ctx::fit_cycle(int F, const double* lambda, const int* k_in, const scrc_opt
 
 // out[base[r] + a[r] + s[r] * t] = beta[src[r] + ld * t]: drops the 16-row padding of the stacked layout and
 // lays every module's s x T block out contiguously, so that one linear copy brings a whole fit to the host.
+// inv (optional, quick mode): column of `beta` that holds target t, or -1 -- the reference returns zero coefficients
+// for the targets Step 2 skipped (scregclust.R:1606-1610).
 __global__ void coeff_pack_kernel(const double* __restrict__ beta, int64_t ld, int T, int nrows,
                                   const int* __restrict__ src, const int* __restrict__ s_of, const int* __restrict__ a_of,
-                                  const long long* __restrict__ base, double* out) {
+                                  const long long* __restrict__ base, const int* __restrict__ inv, double* out) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     const int t = blockIdx.y;
     if (r >= nrows || t >= T) return;
-    out[base[r] + a_of[r] + (long long)s_of[r] * t] = beta[src[r] + ld * t];
+    const int c = inv ? inv[t] : t;
+    out[base[r] + a_of[r] + (long long)s_of[r] * t] = c >= 0 ? beta[src[r] + ld * c] : 0.0;
 }
 
 // Packs the K coefficient matrices of fit f (s_k x T each, one after the other) into `out_dev` on the device.
@@ -743,7 +907,8 @@ void Ctx::pack_coeffs_fit(int f, double* out_dev) {
     SCRC_CUDA(cudaMemcpyAsync(pack_a.p, a_of.data(), nrows * 4, cudaMemcpyHostToDevice, st));
     SCRC_CUDA(cudaMemcpyAsync(pack_base.p, base.data(), nrows * 8, cudaMemcpyHostToDevice, st));
     coeff_pack_kernel<<<dim3((unsigned)ceil_div(nrows, 128), (unsigned)T), 128, 0, st>>>(
-        nnls.beta.data(), nnls.beta.ld, (int)T, nrows, pack_src.p, pack_s.p, pack_a.p, pack_base.p, out_dev);
+        nnls.beta.data(), nnls.beta.ld, (int)T, nrows, pack_src.p, pack_s.p, pack_a.p, pack_base.p,
+        last_quick ? q_inv.p + (size_t)f * T : nullptr, out_dev);
     SCRC_LAUNCHED();
     SCRC_CUDA(cudaStreamSynchronize(st));
     pt.mark(phase_s, 12);

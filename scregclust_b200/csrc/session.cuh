@@ -89,7 +89,13 @@ struct Ctx {
     void begin(int64_t n1, int64_t n2, int64_t P, int64_t T, int K);   // dimensions + input buffers
     void finish();                                                      // Gram, eigenbasis, initial fit
     void fit_cycle(int F, const double* lambda, const int* k_in, const scrc_options& opt, bool skip_alloc,
-                   scrc_cycle_out* out, const scrc_prior* prior = nullptr);
+                   scrc_cycle_out* out, const scrc_prior* prior = nullptr, const scrc_quick* quick = nullptr);
+    // quick mode (scregclust.R:1435-1496): |cross_corr1| (lazy), per-fit target subsets of the last cycle
+    DMat abs_corr;
+    DevBuf<unsigned char> q_areg;
+    DevBuf<int> q_idx, q_off, q_cnt, q_inv, q_bi, q_kn, q_votes;
+    DevBuf<double> q_mx, q_sds, q_r2, q_var, q_br;
+    bool last_quick = false;
     DevBuf<double> sq_arr;       // K x n2 x T squared residuals, only with a network prior
     // Leave-one-regulator-out importance and module R2 (R/scregclust.R:1823-1912) for F final configurations.
     // r2_removed (optional): the per-target matrices of scregclust.R:1890-1898, packed in (fit, module) order --

@@ -15,7 +15,7 @@ from dataclasses import dataclass, field
 import numpy as np
 
 from . import _capi
-from ._capi import CycleOut, Options, Prior, check, dptr, f64, iptr
+from ._capi import CycleOut, Options, Prior, Quick, check, dptr, f64, iptr
 
 
 class Comm:
@@ -210,8 +210,10 @@ class Session:
 
     # ------------------------------------------------------------------ one batched cycle
     def fit_cycle(self, lambdas, ks, options=None, skip_allocation=False, want_votes=False, want_nnls_iters=False,
-                  prior=None, light=False):
+                  prior=None, light=False, quick=None):
         """Step 1 + 2a (+ 2b) for ``F`` (lambda, k) pairs; returns a dict of arrays in R's layouts.
+
+        ``quick``: optional ``(idx_latest[F, T], quick_mode_percent)`` -- quick mode (R/scregclust.R:1435-1496).
 
         ``prior``: optional ``(prior_indicator, prior_baseline, prior_weight, update_orders)`` with
         ``prior_indicator`` a list of T lists of 0-based neighbour targets and ``update_orders`` an
@@ -254,6 +256,11 @@ class Session:
             orders = np.ascontiguousarray(prior[3], dtype=np.int32).reshape(F, T)
             pr = Prior(iptr(off), iptr(idx), float(prior[1]), float(prior[2]), iptr(orders))
             check(self._lib.scrc_fit_cycle_prior(self._h, F, dptr(lam), iptr(k), C.byref(opt), C.byref(pr), C.byref(out)))
+        elif quick is not None:
+            idx = np.ascontiguousarray(quick[0], dtype=np.int32).reshape(F, self.T)
+            qk = Quick(iptr(idx), float(quick[1]))
+            check(self._lib.scrc_fit_cycle_quick(self._h, F, dptr(lam), iptr(k), C.byref(opt), 1 if skip_allocation else 0,
+                                                 C.byref(qk), C.byref(out)))
         else:
             check(self._lib.scrc_fit_cycle(self._h, F, dptr(lam), iptr(k), C.byref(opt), 1 if skip_allocation else 0,
                                            C.byref(out)))
@@ -357,7 +364,7 @@ class _PyBackend:
                 a = np.ascontiguousarray(arr, dtype=dtype)
                 C.memmove(ptr, a.ctypes.data, a.nbytes)
 
-        def fit_cycle(user, F, lam, k_in, opt, skip, hint, prior, out):
+        def fit_cycle(user, F, lam, k_in, opt, skip, hint, prior, quick, out):
             try:
                 lams = np.ctypeslib.as_array(lam, shape=(F,)).copy()
                 ks = np.ctypeslib.as_array(k_in, shape=(F, T)).copy()
@@ -370,6 +377,8 @@ class _PyBackend:
                     orders = np.ctypeslib.as_array(pc.update_order, shape=(F, T)).copy()
                     pr = (_csr_lists(off, idx, T), pc.baseline, pc.weight, orders)
                 kw = {}
+                if quick:
+                    kw["quick"] = (np.ctypeslib.as_array(quick.contents.idx_latest, shape=(F, T)).copy(), quick.contents.percent)
                 if getattr(ses, "accepts_hint", False) and hint:
                     kw["hint"] = np.ctypeslib.as_array(hint, shape=(F, K)).copy()
                 res = ses.fit_cycle(lams, ks, opt.contents, skip_allocation=bool(skip), want_votes=bool(o.votes),
@@ -499,7 +508,8 @@ def scregclust_fit(z1_reg_scaled=None, z2_reg_scaled=None, z1_target_centered=No
                    min_module_size=0, noise_threshold=0.025, n_cycles=50, max_optim_iter=10000,
                    tol_coop_rel=1e-8, tol_coop_abs=1e-12, tol_nnls=1e-4, device=0, session=None,
                    keep_diagnostics=False, return_coeffs=True, compute_predictive_r2=False, prior_indicator=None,
-                   prior_baseline=1e-6, prior_weight=0.0, update_orders=None, comm=None):
+                   prior_baseline=1e-6, prior_weight=0.0, update_orders=None, comm=None, quick_mode=False,
+                   quick_mode_percent=0.1):
     """The alternating loop of ``scregclust()`` (R/scregclust.R:1222-1912) for all penalization values,
     one ``scrc_grid_fit`` call.  Returns one :class:`FitResult` per penalization value, in order.
 
@@ -532,6 +542,8 @@ def scregclust_fit(z1_reg_scaled=None, z2_reg_scaled=None, z1_target_centered=No
         gp.compute_predictive_r2 = 1 if compute_predictive_r2 else 0
         gp.keep_coeffs = 1 if return_coeffs else 0
         gp.keep_diagnostics = 1 if keep_diagnostics else 0
+        gp.quick_mode = 1 if quick_mode else 0
+        gp.quick_mode_percent = float(quick_mode_percent)
         keep = []
         if prior_indicator is not None and len(prior_indicator) > 0 and float(prior_weight) != 0.0:
             from .api import _csr

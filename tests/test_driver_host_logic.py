@@ -22,18 +22,23 @@ class OracleSession:
         self.P = w.z1_reg.shape[1]
         self.pre = orc.precompute(w.z1_reg, w.z1_target)
         self.calls = []          # (n_fits, skip_allocation) per batched call
+        self.quick_calls = []    # idx_latest handed to each call (None: no quick-mode subset)
         self._last = None
 
-    def _one(self, lam, k, n_cycles):
+    def _one(self, lam, k, n_cycles, quick=None):
         w = self.w
+        kw = {}
+        if quick is not None:
+            kw = dict(quick_mode=True, quick_mode_percent=quick[1], quick_first_cycle_idx=quick[0])
         return orc.scregclust_fit(w.z1_reg, w.z2_reg, w.z1_target, w.z2_target, w.z1_target_sds, [lam], self.K, k,
-                                  n_cycles=n_cycles, pre=self.pre, keep_history=True, materialize_array=False)[0]
+                                  n_cycles=n_cycles, pre=self.pre, keep_history=True, materialize_array=False, **kw)[0]
 
     def fit_cycle(self, lambdas, ks, options=None, skip_allocation=False, want_votes=False, want_nnls_iters=False,
-                  prior=None, light=False):
+                  prior=None, light=False, quick=None):
         F, K, T, P = len(lambdas), self.K, self.T, self.P
         ks = np.asarray(ks).reshape(F, T)
         self.calls.append((F, bool(skip_allocation)))
+        self.quick_calls.append(None if quick is None else np.asarray(quick[0]).copy())
         res = {"k_new": np.zeros((F, T), np.int32), "models": np.zeros((F, K, P), np.uint8),
                "best_r2": np.zeros((F, T)), "admm_iterations": np.zeros((F, K), np.int32),
                "n_selected": np.zeros((F, K), np.int32), "votes": None, "nnls_iterations": None,
@@ -42,7 +47,7 @@ class OracleSession:
         self._last = []
         for f in range(F):
             if skip_allocation:                     # the forced last cycle of the reference: re-fit only
-                r = self._one(lambdas[f], ks[f], 0)
+                r = self._one(lambdas[f], ks[f], 0, None if quick is None else (quick[0][f], quick[1]))
                 res["models"][f] = r.models[0].T
                 res["signs"][f] = r.signs[0].T; res["weights"][f] = r.weights[0].T
                 res["r2_test"][f] = r.r2[0].T; res["resid_var"][f] = (r.sigmas[0] ** 2).T
@@ -51,7 +56,7 @@ class OracleSession:
                 res["n_selected"][f] = r.models[0].sum(axis=0)
                 self._last.append(r.coeffs[0])
             else:
-                r = self._one(lambdas[f], ks[f], 1)
+                r = self._one(lambdas[f], ks[f], 1, None if quick is None else (quick[0][f], quick[1]))
                 res["models"][f] = r.models_history[0].T
                 res["k_new"][f] = np.argmax(r.votes[0], axis=1) + 1
                 res["best_r2"][f] = r.r2_history[0].max(axis=1)
@@ -115,6 +120,21 @@ def test_forced_last_cycle_after_n_cycles(case):
                          session=OracleSession(w), n_cycles=2, **kw)
     _same(got, ref)
     assert all(g.n_cycles_run <= 3 for g in got)
+
+
+def test_quick_mode_bookkeeping_of_the_loop(case):
+    """quick mode (R/scregclust.R:1435-1496): no subset in cycle 1, afterwards R's `idx` (the latest allocation) goes
+    with every call -- also with the final re-fit -- and the trajectory equals the oracle's quick-mode run."""
+    from scregclust_b200.driver import scregclust_fit
+    w, kw, _ = case
+    ref = orc.scregclust_fit(w.z1_reg, w.z2_reg, w.z1_target, w.z2_target, w.z1_target_sds, w.penalization,
+                             w.n_modules, w.k_init, quick_mode=True, quick_mode_percent=0.3, **kw)
+    ses = OracleSession(w)
+    got = scregclust_fit(penalization=w.penalization, n_modules=w.n_modules, initial_target_modules=w.k_init,
+                         session=ses, quick_mode=True, quick_mode_percent=0.3, **kw)
+    _same(got, ref)
+    assert ses.quick_calls[0] is None and all(q is not None for q in ses.quick_calls[1:])
+    assert any(np.any(k == -1) for r in ref for k in r.k_history)        # the case does put targets into the noise module
 
 
 class ScriptedSession:

@@ -163,6 +163,58 @@ def test_loop_free_running(name, seed, ar1):
     assert identical >= len(ref) - decidable
 
 
+@pytest.mark.parametrize("name,seed,pct", [("tiny", 3, 0.3), ("small", 1, 0.1), ("small", 4, 0.5), ("small", 2, 0.0)])
+def test_quick_mode_matches_oracle(name, seed, pct):
+    """quick_mode = TRUE (R/scregclust.R:1435-1496): per-fit target subsets in Step 2 from cycle two on -- the
+    changed recycling modulus of z1_target_sds_tmp, r2 = 0 / resid_var = 1e6 outside the subset (0 in the last cycle),
+    zero coefficients there, and the skipped targets voted into module 1 before the noise rule.  Every cycle of the
+    oracle's trajectory is replayed on the GPU, then the library's loop runs freely."""
+    from scregclust_b200.driver import Session, scregclust_fit
+    w = make_workload(name, seed=seed)
+    K = w.n_modules
+    kw = dict(min_module_size=2, quick_mode=True, quick_mode_percent=pct)
+    ref = orc.scregclust_fit(w.z1_reg, w.z2_reg, w.z1_target, w.z2_target, w.z1_target_sds, w.penalization, K,
+                             w.k_init, keep_history=True, **kw)
+    skipped = 0
+    with Session(w.z1_reg, w.z2_reg, w.z1_target, w.z2_target, w.z1_target_sds, K) as s:
+        for c in range(max(len(r.votes) for r in ref)):
+            fits = [i for i, r in enumerate(ref) if c < len(r.votes)]
+            ks = np.stack([ref[i].k_history[c] for i in fits])
+            res = s.fit_cycle([ref[i].penalization for i in fits], ks, want_votes=True, want_nnls_iters=True,
+                              quick=None if c == 0 else (ks, pct))
+            for f, i in enumerate(fits):
+                r = ref[i]
+                tag = f"quick {name}/{seed} lambda={r.penalization} cycle={c + 1}"
+                assert np.array_equal(res["models"][f].T.astype(bool), r.models_history[c]), tag
+                assert np.array_equal(res["nnls_iterations"][f], r.nnls_iterations[c]), tag
+                assert np.array_equal(res["resid_var"][f].T == 1e6, r.resid_var_history[c] == 1e6), tag
+                assert rel_err(res["resid_var"][f].T, r.resid_var_history[c]) < 1e-8, tag
+                assert np.max(np.abs(res["r2_test"][f].T - r.r2_history[c])) < 1e-8, tag
+                skipped += int(np.count_nonzero(np.all(r.resid_var_history[c] == 1e6, axis=1)))
+                _check_votes(tag, res["votes"][f], r.votes[c], r.ambiguity[c], res["k_new"][f])
+    assert pct >= 0.99 or skipped > 0 or name == "tiny", "the case never exercised a target subset"
+    got = scregclust_fit(session=None, z1_reg_scaled=w.z1_reg, z2_reg_scaled=w.z2_reg, z1_target_centered=w.z1_target,
+                         z2_target_centered=w.z2_target, z1_target_sds=w.z1_target_sds, penalization=w.penalization,
+                         n_modules=K, initial_target_modules=w.k_init, keep_diagnostics=True, **kw)
+    for g, r in zip(got, ref):
+        c, genes = _first_divergence(g, r)
+        if c is not None:
+            amb = r.ambiguity[c - 1]
+            sv = np.sort(r.votes[c - 1], axis=1)
+            assert genes.size > 0 and np.all((sv[:, -1] - sv[:, -2])[genes] <= 2 * amb[genes]), f"quick: diverges at cycle {c}"
+            continue
+        assert g.final_cycle_length == r.final_cycle_length and g.n_cycles_run == r.n_cycles_run
+        for m in range(r.final_cycle_length):
+            assert np.array_equal(g.k_final[m], r.k_final[m]) and np.array_equal(g.models[m], r.models[m])
+            assert np.array_equal(g.sigmas[m] == 0.0, r.sigmas[m] == 0.0)           # skipped targets: sigma 0 (:1642)
+            assert rel_err(g.sigmas[m], r.sigmas[m]) < 1e-8 and np.max(np.abs(g.r2[m] - r.r2[m])) < 1e-8
+            for cg, cr in zip(g.coeffs[m], r.coeffs[m]):
+                assert (cg is None) == (cr is None)
+                if cg is not None:
+                    assert np.array_equal(cg == 0.0, cr == 0.0) and np.max(np.abs(cg - cr)) < 1e-8 * max(1.0, np.max(np.abs(cr)))
+    print(f"quick {name}/{seed}/{pct}: {skipped} (fit, cycle, target) triples skipped by Step 2")
+
+
 def test_session_precompute():
     from scregclust_b200.driver import Session
     w = make_workload("small", seed=3)
