@@ -319,6 +319,10 @@ typedef struct scrc_grid_params {
     void* update_order_user;
     int quick_mode;                         /* R/scregclust.R:201: 0 */
     double quick_mode_percent;              /* 0.1 */
+    /* Optional interrupt flag owned by the caller (NULL: none): polled before every device call of the loop; once
+     * it reads non-zero the fit stops with SCRC_ERR_INTERRUPTED on every rank (same mechanism as
+     * scrc_ctx_request_cancel).  The bridge sets it from the R thread while the fit runs on a worker thread. */
+    const volatile int* cancel;
 } scrc_grid_params;
 void scrc_grid_default_params(scrc_grid_params* p);
 

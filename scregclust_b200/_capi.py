@@ -58,7 +58,8 @@ class GridParams(C.Structure):
                 ("opt", Options), ("compute_predictive_r2", C.c_int), ("keep_coeffs", C.c_int),
                 ("keep_diagnostics", C.c_int), ("prior_off", c_int_p), ("prior_idx", c_int_p),
                 ("prior_baseline", C.c_double), ("prior_weight", C.c_double), ("update_order", UPDATE_ORDER_FN),
-                ("update_order_user", C.c_void_p), ("quick_mode", C.c_int), ("quick_mode_percent", C.c_double)]
+                ("update_order_user", C.c_void_p), ("quick_mode", C.c_int), ("quick_mode_percent", C.c_double),
+                ("cancel", C.POINTER(C.c_int))]
 
 
 class GridInfo(C.Structure):

@@ -31,6 +31,7 @@ struct GridBackend {
     virtual void coeffs_fit(int f, int64_t ndoubles, int nsel, std::vector<double>& host, DevBuf<double>& dev,
                             std::vector<int>& sel) = 0;
     virtual int device() const { return -1; }
+    virtual void request_cancel() {}
 };
 
 struct CtxBackend : GridBackend {
@@ -54,6 +55,7 @@ struct CtxBackend : GridBackend {
         c.pack_coeffs_fit(f, dev.p);
     }
     int device() const override { return c.dev.id; }
+    void request_cancel() override { c.cancel.store(1, std::memory_order_relaxed); }
 };
 
 struct CallbackBackend : GridBackend {
@@ -197,6 +199,7 @@ static void grid_loop(GridBackend& be, const scrc_grid_params& gp, scrc_grid_res
                 pr.weight = gp.prior_weight; pr.update_order = orders.data();
             }
             sweeps = 0;
+            if (gp.cancel && *gp.cancel) be.request_cancel();
             const double tc0 = wall_now();
             // quick mode from cycle two on (R/scregclust.R:1444); in a fit cycle R's `idx` is the configuration itself
             scrc_quick qk{ks.data(), gp.quick_mode_percent};
@@ -284,6 +287,7 @@ static void grid_loop(GridBackend& be, const scrc_grid_params& gp, scrc_grid_res
         co.admm_sweeps = &sweeps;
         if (diag) { nnls_it.assign(fkt, 0); co.nnls_iterations = nnls_it.data(); }
         sweeps = 0;
+        if (gp.cancel && *gp.cancel) be.request_cancel();
         const double tf0 = wall_now();
         scrc_quick qk{latest.data(), gp.quick_mode_percent};
         // (a value that never ran a fit cycle -- n_cycles = 0 -- is still in "cycle 1": no subset)
