@@ -721,7 +721,10 @@ void Ctx::fit_cycle(int F, const double* lambda, const int* k_in, const scrc_opt
     if (sliced && want_nnls_it) SCRC_CUDA(cudaMemsetAsync(nnls.iters.p, 0, (size_t)std::max<int64_t>((int64_t)nnp * T, 1) * 4, st));
     if (nnp > 0) {
         nnls_setup(nnls, G_rr.data(), G_rr.ld, G_rt.data(), G_rt.ld, inv_sds_t.p, st);
-        nnls_solve(nnls, opt.tol_nnls, opt.max_optim_iter, sds_t.p, (int)T, dev.num_sms, st);
+        // out scale: z1_target_sds recycled over T -- in quick mode the gathered z1_target_sds_tmp of each fit,
+        // recycled over the fit's own subset length (per-problem window, scregclust.R:1580-1588)
+        if (use_quick) nnls_solve(nnls, opt.tol_nnls, opt.max_optim_iter, q_sds.p, 1, dev.num_sms, st);
+        else nnls_solve(nnls, opt.tol_nnls, opt.max_optim_iter, sds_t.p, (int)T, dev.num_sms, st);
     }
 
     pt.mark(phase_s, 4);
