@@ -48,8 +48,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) resid_vote_kernel(const __gri
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + RV_STAGES * RV_STAGE_BYTES);
     uint64_t* empty = full + RV_STAGES;
     const int K1 = p.K + 1;
-    double* sse_s = reinterpret_cast<double*>(smem + RV_STAGES * RV_STAGE_BYTES + 2 * RV_STAGES * 8);  // [2][K1][64]
-    int* votes_s = reinterpret_cast<int*>(sse_s + 2 * K1 * RV_BN);                                     // [64][K]
+    double* sse_s = reinterpret_cast<double*>(smem + RV_STAGES * RV_STAGE_BYTES + 2 * RV_STAGES * 8);  // [2][K1][32]
+    // score constants of this CTA's 32 target columns for every module, loaded once: RN(1 / (2 var)) and
+    // -0.5 log(2 pi var); the slice counts of the modules (the per-module global loads they replace sat on the
+    // critical path of every (cell tile, module) step: each was an L2 round trip in front of a branch)
+    double* iv_s = sse_s + 2 * K1 * RV_BN;                                                             // [K][32]
+    double* nhl_s = iv_s + (VOTE ? p.K * RV_BN : 0);                                                   // [K][32]
+    int* votes_s = reinterpret_cast<int*>(nhl_s + (VOTE ? p.K * RV_BN : 0));                           // [32][K]
+    int* kp_s = votes_s + (VOTE ? RV_BN * p.K : 0);                                                    // [K] padded rows
+    int* s4_s = kp_s + p.K;                                                                            // [K] live rows, in 4s
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -113,10 +120,25 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) resid_vote_kernel(const __gri
                     for (int e = 0; e < 2; ++e)
                         sse_s[(warp_m * K1 + j) * RV_BN + b_col0 + jj * 8 + q * 2 + e] = 0.0;
         }
-        if (VOTE) {
-            for (int i = ctid; i < RV_BN * p.K; i += 256) votes_s[i] = 0;
-            consumer_bar();
+        for (int j = ctid; j < p.K; j += 256) {
+            const int kp = p.kpad[l * p.K + j];
+            kp_s[j] = kp;
+            s4_s[j] = p.nsel ? ((p.nsel[l * p.K + j] + 3) & ~3) : kp;
         }
+        if (VOTE) {
+            for (int i = ctid; i < RV_BN * p.K; i += 256) {
+                votes_s[i] = 0;
+                const int j = i / RV_BN, lc = i % RV_BN;
+                const int col = t0 + lc;
+                double a = 1.0, b = 0.0;
+                if (col < ncol) {
+                    const int64_t vi = ((int64_t)l * p.K + j) * p.T + col;
+                    a = p.inv_two_var[vi]; b = -p.half_log[vi];
+                }
+                iv_s[i] = a; nhl_s[i] = b;
+            }
+        }
+        consumer_bar();
         for (int ct = ct0; ct < ct1; ++ct) {
             const int c0 = ct * RV_BM;
             double z[MT][NT][2], best[MT][NT][2];
@@ -135,40 +157,48 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) resid_vote_kernel(const __gri
                         best[i][jj][e] = -INFINITY;
                         bidx[i][jj][e] = 0;
                     }
-            for (int j = 0; j <= p.K; ++j) {
-                double acc[MT][NT][2];
+            // Software pipeline over the modules: the DMMA mainloop of module j + 1 is issued BEFORE the FP64 epilogue
+            // of module j, so the tensor pipe works on the next prediction while this warp scores the previous one
+            // (the epilogue no longer waits at the end of its own accumulator chains).  Stages are consumed in the
+            // producer's order (module by module).
+            auto mainloop = [&](int j, double (&acc)[MT][NT][2]) {
 #pragma unroll
                 for (int i = 0; i < MT; ++i)
 #pragma unroll
                     for (int jj = 0; jj < NT; ++jj) acc[i][jj][0] = acc[i][jj][1] = 0.0;
-                // score constants of this module's columns, requested before the mainloop hides their latency
-                double nhl[NT][2], iv[NT][2];
+                if (j < p.K) {
+                    // rows beyond the selection are zero padding up to the 16-row box: their 4-deep slices
+                    // add exact zeros and are skipped
+                    const int kp = kp_s[j], s4 = s4_s[j];
+                    for (int kk = 0; kk < kp; kk += GEMM_BK) {
+                        mbar_wait_warp(&full[ps.stage], ps.phase, lane);
+                        const double* As = reinterpret_cast<const double*>(smem + ps.stage * RV_STAGE_BYTES);
+                        const double* Bs = reinterpret_cast<const double*>(smem + ps.stage * RV_STAGE_BYTES + RV_A_BYTES);
+                        // full stages take the branch-free path, which lets the fragment loads of the next 4-deep slice
+                        // be scheduled above the DMMAs of the current one
+                        const int ns = (s4 - kk) >> 2;
+                        if (ns >= 4) mma_kslice<MT, NT>(As, Bs, a_row0, b_col0, lane, acc);
+                        else mma_kslice_n<MT, NT>(As, Bs, a_row0, b_col0, lane, ns, acc);
+                        stage_release_warp(&empty[ps.stage], lane);
+                        ps.advance<RV_STAGES>();
+                    }
+                }
+            };
+            // score constants of a module's columns (requested before the next mainloop hides their latency)
+            auto load_consts = [&](int j, double (&iv)[NT][2], double (&nhl)[NT][2]) {
 #pragma unroll
                 for (int jj = 0; jj < NT; ++jj)
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
                         nhl[jj][e] = 0.0; iv[jj][e] = 1.0;
-                        const int col = t0 + b_col0 + jj * 8 + q * 2 + e;
-                        if (VOTE && j < p.K && col < ncol) {
-                            const int64_t vi = ((int64_t)l * p.K + j) * p.T + col;
-                            iv[jj][e] = p.inv_two_var[vi];
-                            nhl[jj][e] = -p.half_log[vi];
+                        if (VOTE && j < p.K) {
+                            const int lc = b_col0 + jj * 8 + q * 2 + e;
+                            iv[jj][e] = iv_s[j * RV_BN + lc];
+                            nhl[jj][e] = nhl_s[j * RV_BN + lc];
                         }
                     }
-                if (j < p.K) {
-                    const int kp = p.kpad[l * p.K + j];
-                    // rows beyond the selection are zero padding up to the 16-row box: their 4-deep slices
-                    // add exact zeros and are skipped
-                    const int s4 = p.nsel ? ((p.nsel[l * p.K + j] + 3) & ~3) : kp;
-                    for (int kk = 0; kk < kp; kk += GEMM_BK) {
-                        mbar_wait_warp(&full[ps.stage], ps.phase, lane);
-                        const double* As = reinterpret_cast<const double*>(smem + ps.stage * RV_STAGE_BYTES);
-                        const double* Bs = reinterpret_cast<const double*>(smem + ps.stage * RV_STAGE_BYTES + RV_A_BYTES);
-                        mma_kslice_n<MT, NT>(As, Bs, a_row0, b_col0, lane, min(4, (s4 - kk) >> 2), acc);
-                        stage_release_warp(&empty[ps.stage], lane);
-                        ps.advance<RV_STAGES>();
-                    }
-                }
+            };
+            auto epilogue = [&](int j, double (&acc)[MT][NT][2], const double (&iv)[NT][2], const double (&nhl)[NT][2]) {
                 // residual, squared residual, column sums (scregclust.R:1593-1599)
                 double csum[NT][2];
 #pragma unroll
@@ -227,6 +257,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) resid_vote_kernel(const __gri
                         cs += __shfl_xor_sync(0xffffffffu, cs, 16);
                         if (r == 0) sse_s[(warp_m * K1 + j) * RV_BN + b_col0 + jj * 8 + q * 2 + e] += cs;
                     }
+            };
+            {
+                double accA[MT][NT][2], accB[MT][NT][2];
+                double iv[NT][2], nhl[NT][2];
+                mainloop(0, accA);
+                for (int j = 0; j <= p.K; j += 2) {
+                    load_consts(j, iv, nhl);
+                    if (j + 1 <= p.K) mainloop(j + 1, accB);
+                    epilogue(j, accA, iv, nhl);
+                    if (j + 1 <= p.K) {
+                        load_consts(j + 1, iv, nhl);
+                        if (j + 2 <= p.K) mainloop(j + 2, accA);
+                        epilogue(j + 1, accB, iv, nhl);
+                    }
+                }
             }
             if (VOTE) {
                 // The 8 lanes that share a target column mostly vote for the same module: lanes with the
@@ -307,7 +352,7 @@ void resid_vote(const ResidVoteArgs& a, int mode, int num_sms, cudaStream_t st) 
     p.tiles_n = (int)ceil_div(p.t_end - p.t_begin, RV_BN); p.ctiles = (int)ceil_div(a.ncells, RV_BM);
 
     const int smem = RV_STAGES * RV_STAGE_BYTES + 2 * RV_STAGES * 8 + 2 * (a.K + 1) * RV_BN * 8 +
-                     RV_BN * a.K * 4;
+                     (mode == 1 ? 2 * a.K * RV_BN * 8 + RV_BN * a.K * 4 : 0) + 2 * a.K * 4;
     static SmemAttr attr[3];
     if (mode == 1) attr[1].ensure(resid_vote_kernel<1>, smem);
     else if (mode == 2) attr[2].ensure(resid_vote_kernel<2>, smem);

@@ -9,7 +9,7 @@ namespace scrc {
 
 constexpr int RV_BM = 64;   // cells per tile
 constexpr int RV_BN = 32;   // targets per tile
-constexpr int RV_STAGES = 6;
+constexpr int RV_STAGES = 4;   // the loads are never the limiter (profiles/): a short ring leaves shared memory for two CTAs per SM
 constexpr int RV_MAX_K = 64;  // modules (+1 pseudo module) kept in shared memory
 
 struct ResidVoteArgs {
