@@ -36,9 +36,10 @@ __device__ __forceinline__ void consumer_bar() {   // the 8 consumer warps only
     asm volatile("bar.sync 1, 256;" ::: "memory");
 }
 
-// MODE 0: SSE only; MODE 1: SSE + per-cell votes; MODE 2: SSE + squared residuals written out
-// (only used for the sequential network-prior sweep, which needs every gene's K x n2 slab).
-template <int MODE>
+// MODE 1: per-cell votes; MODE 2: squared residuals written out (only used for the sequential network-prior sweep,
+// which needs every gene's K x n2 slab).  The test-split sums of squares no longer come from this pass: like the
+// training ones they are evaluated from the split's Gram matrices (sse_train_gram), O(s^2) per (module, target).
+template <int MODE, bool PIPE>
 __global__ void __launch_bounds__(GEMM_THREADS, 2) resid_vote_kernel(const __grid_constant__ RvParams p) {
     constexpr bool VOTE = (MODE == 1);
     constexpr int MT = RV_BM / (GEMM_WARPS_M * 8);   // 4
@@ -47,12 +48,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) resid_vote_kernel(const __gri
     if ((smem_u32(smem) & 1023u) != 0) __trap();
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + RV_STAGES * RV_STAGE_BYTES);
     uint64_t* empty = full + RV_STAGES;
-    const int K1 = p.K + 1;
-    double* sse_s = reinterpret_cast<double*>(smem + RV_STAGES * RV_STAGE_BYTES + 2 * RV_STAGES * 8);  // [2][K1][32]
     // score constants of this CTA's 32 target columns for every module, loaded once: RN(1 / (2 var)) and
     // -0.5 log(2 pi var); the slice counts of the modules (the per-module global loads they replace sat on the
     // critical path of every (cell tile, module) step: each was an L2 round trip in front of a branch)
-    double* iv_s = sse_s + 2 * K1 * RV_BN;                                                             // [K][32]
+    double* iv_s = reinterpret_cast<double*>(smem + RV_STAGES * RV_STAGE_BYTES + 2 * RV_STAGES * 8);   // [K][32]
     double* nhl_s = iv_s + (VOTE ? p.K * RV_BN : 0);                                                   // [K][32]
     int* votes_s = reinterpret_cast<int*>(nhl_s + (VOTE ? p.K * RV_BN : 0));                           // [32][K]
     int* kp_s = votes_s + (VOTE ? RV_BN * p.K : 0);                                                    // [K] padded rows
@@ -111,15 +110,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) resid_vote_kernel(const __gri
 
     {
         const int t0 = p.t_begin + tn * RV_BN;
-        // zero the per-work-item accumulators (each SSE entry is owned by exactly one thread)
-        if (r == 0) {
-            for (int j = 0; j < K1; ++j)
-#pragma unroll
-                for (int jj = 0; jj < NT; ++jj)
-#pragma unroll
-                    for (int e = 0; e < 2; ++e)
-                        sse_s[(warp_m * K1 + j) * RV_BN + b_col0 + jj * 8 + q * 2 + e] = 0.0;
-        }
         for (int j = ctid; j < p.K; j += 256) {
             const int kp = p.kpad[l * p.K + j];
             kp_s[j] = kp;
@@ -199,22 +189,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) resid_vote_kernel(const __gri
                     }
             };
             auto epilogue = [&](int j, double (&acc)[MT][NT][2], const double (&iv)[NT][2], const double (&nhl)[NT][2]) {
-                // residual, squared residual, column sums (scregclust.R:1593-1599)
-                double csum[NT][2];
+                // residual and squared residual (scregclust.R:1593-1599)
 #pragma unroll
                 for (int jj = 0; jj < NT; ++jj)
 #pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        double cs = 0.0;
+                    for (int e = 0; e < 2; ++e)
 #pragma unroll
                         for (int i = 0; i < MT; ++i) {
                             const double res = z[i][jj][e] - acc[i][jj][e];
-                            const double sq = res * res;
-                            acc[i][jj][e] = sq;
-                            cs += sq;
+                            acc[i][jj][e] = res * res;
                         }
-                        csum[jj][e] = cs;
-                    }
                 if (MODE == 2 && j < p.K) {
 #pragma unroll
                     for (int jj = 0; jj < NT; ++jj)
@@ -247,30 +231,28 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) resid_vote_kernel(const __gri
                                 if (sc > best[i][jj][e]) { best[i][jj][e] = sc; bidx[i][jj][e] = j; }
                             }
                 }
-#pragma unroll
-                for (int jj = 0; jj < NT; ++jj)
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        double cs = csum[jj][e];
-                        cs += __shfl_xor_sync(0xffffffffu, cs, 4);
-                        cs += __shfl_xor_sync(0xffffffffu, cs, 8);
-                        cs += __shfl_xor_sync(0xffffffffu, cs, 16);
-                        if (r == 0) sse_s[(warp_m * K1 + j) * RV_BN + b_col0 + jj * 8 + q * 2 + e] += cs;
-                    }
             };
             {
                 double accA[MT][NT][2], accB[MT][NT][2];
                 double iv[NT][2], nhl[NT][2];
+                if (!PIPE) {
+                    for (int j = 0; j < p.K; ++j) {
+                        load_consts(j, iv, nhl);
+                        mainloop(j, accA);
+                        epilogue(j, accA, iv, nhl);
+                    }
+                } else {
                 mainloop(0, accA);
-                for (int j = 0; j <= p.K; j += 2) {
+                for (int j = 0; j < p.K; j += 2) {
                     load_consts(j, iv, nhl);
-                    if (j + 1 <= p.K) mainloop(j + 1, accB);
+                    if (j + 1 < p.K) mainloop(j + 1, accB);
                     epilogue(j, accA, iv, nhl);
-                    if (j + 1 <= p.K) {
+                    if (j + 1 < p.K) {
                         load_consts(j + 1, iv, nhl);
-                        if (j + 2 <= p.K) mainloop(j + 2, accA);
+                        if (j + 2 < p.K) mainloop(j + 2, accA);
                         epilogue(j + 1, accB, iv, nhl);
                     }
+                }
                 }
             }
             if (VOTE) {
@@ -295,19 +277,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) resid_vote_kernel(const __gri
                         if (lane == __ffs(peers) - 1 && total > 0) atomicAdd(&votes_s[lc * p.K + b0], total);
                     }
             }
-        }
-        // flush
-        if (r == 0) {
-            for (int j = 0; j < K1; ++j)
-#pragma unroll
-                for (int jj = 0; jj < NT; ++jj)
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const int lc = b_col0 + jj * 8 + q * 2 + e;
-                        if (t0 + lc < ncol)
-                            p.partial[((((int64_t)l * p.CR + cr) * 2 + warp_m) * K1 + j) * p.T + t0 + lc] =
-                                sse_s[(warp_m * K1 + j) * RV_BN + lc];
-                    }
         }
         if (VOTE) {
             consumer_bar();
@@ -351,12 +320,14 @@ void resid_vote(const ResidVoteArgs& a, int mode, int num_sms, cudaStream_t st) 
     if (p.t_begin == p.t_end) return;
     p.tiles_n = (int)ceil_div(p.t_end - p.t_begin, RV_BN); p.ctiles = (int)ceil_div(a.ncells, RV_BM);
 
-    const int smem = RV_STAGES * RV_STAGE_BYTES + 2 * RV_STAGES * 8 + 2 * (a.K + 1) * RV_BN * 8 +
+    const int smem = RV_STAGES * RV_STAGE_BYTES + 2 * RV_STAGES * 8 +
                      (mode == 1 ? 2 * a.K * RV_BN * 8 + RV_BN * a.K * 4 : 0) + 2 * a.K * 4;
+    if (mode != 1 && mode != 2) throw Error(-65, "resid_vote: mode must be 1 (votes) or 2 (store)");
     static SmemAttr attr[3];
-    if (mode == 1) attr[1].ensure(resid_vote_kernel<1>, smem);
-    else if (mode == 2) attr[2].ensure(resid_vote_kernel<2>, smem);
-    else attr[0].ensure(resid_vote_kernel<0>, smem);
+    static const bool pipe = getenv("SCRC_VOTE_PIPELINE") != nullptr;   // module software pipeline (experiment switch)
+    if (mode == 1 && pipe) attr[0].ensure(resid_vote_kernel<1, true>, smem);
+    else if (mode == 1) attr[1].ensure(resid_vote_kernel<1, false>, smem);
+    else attr[2].ensure(resid_vote_kernel<2, false>, smem);
     const int64_t nwork = (int64_t)a.L * a.CR * p.tiles_n;
     if (nwork > 0x7fffffffLL) throw Error(-61, "resid_vote: too many work items");
     const int grid = (int)nwork;
@@ -367,9 +338,9 @@ void resid_vote(const ResidVoteArgs& a, int mode, int num_sms, cudaStream_t st) 
         const double Ts = (double)(p.t_end - p.t_begin);
         const double bytes = 8.0 * (double)a.L * a.ncells * Ts + 8.0 * (double)a.rows_total * (a.ncells * (double)p.tiles_n + Ts * p.ctiles);
         ProfScope ps(PROF_RESID_VOTE, st, bytes);
-        if (mode == 1) resid_vote_kernel<1><<<grid, GEMM_THREADS, smem, st>>>(p);
-        else if (mode == 2) resid_vote_kernel<2><<<grid, GEMM_THREADS, smem, st>>>(p);
-        else resid_vote_kernel<0><<<grid, GEMM_THREADS, smem, st>>>(p);
+        if (mode == 1 && pipe) resid_vote_kernel<1, true><<<grid, GEMM_THREADS, smem, st>>>(p);
+        else if (mode == 1) resid_vote_kernel<1, false><<<grid, GEMM_THREADS, smem, st>>>(p);
+        else resid_vote_kernel<2, false><<<grid, GEMM_THREADS, smem, st>>>(p);
     }
     SCRC_CUDA(cudaGetLastError());
     SCRC_LAUNCHED();
@@ -408,17 +379,21 @@ __global__ void __launch_bounds__(128) sse_train_gram_kernel(const double* __res
                                                              const int* __restrict__ nsel, int T, int K, double* sse,
                                                              int t0, int t1, const int* __restrict__ col_index,
                                                              const int* __restrict__ col_off,
-                                                             const int* __restrict__ col_cnt) {
+                                                             const int* __restrict__ col_cnt, int pseudo,
+                                                             const int* __restrict__ sel_row_off) {
     __shared__ double s_g[SSG_MAX_S * SSG_MAX_S];
     __shared__ int s_sel[SSG_MAX_S];
-    const int fk = blockIdx.y;
-    const int l = fk / K, j = fk % K;
-    const int s = nsel[fk];
-    const int ro = row_off[fk];
+    // pseudo: one extra slot per fit (j == K) that holds y'y, the "no model" sum of squares (scregclust.R:1505-1515)
+    const int KK = K + (pseudo ? 1 : 0);
+    const int l = blockIdx.y / KK, j = blockIdx.y % KK;
+    const int fk = l * K + j;
+    const int s = j < K ? nsel[fk] : 0;
+    const int ro = j < K ? row_off[fk] : 0;
+    const int so = j < K ? (sel_row_off ? sel_row_off[fk] : ro) : 0;   // rows of `sel` (may differ from the rows of beta)
     const int t = t0 + blockIdx.x * 128 + threadIdx.x;
     const bool in_smem = s <= SSG_MAX_S;
     if (in_smem) {
-        for (int a = threadIdx.x; a < s; a += 128) s_sel[a] = sel[ro + a];
+        for (int a = threadIdx.x; a < s; a += 128) s_sel[a] = sel[so + a];
         __syncthreads();
         for (int e = threadIdx.x; e < s * s; e += 128) s_g[e] = G_rr[s_sel[e % s] + (int64_t)s_sel[e / s] * ldrr];
         __syncthreads();
@@ -433,11 +408,11 @@ __global__ void __launch_bounds__(128) sse_train_gram_kernel(const double* __res
         double cross = 0.0, quad = 0.0;
         for (int a = 0; a < s; ++a) {
             const double ba = b[a];
-            const int ia = in_smem ? s_sel[a] : sel[ro + a];
+            const int ia = in_smem ? s_sel[a] : sel[so + a];
             cross += ba * G_rt[ia + (int64_t)tg * ldrt];
             double row = 0.0;
             for (int c = 0; c < s; ++c) {
-                const double g = in_smem ? s_g[a + c * s] : G_rr[ia + (int64_t)sel[ro + c] * ldrr];
+                const double g = in_smem ? s_g[a + c * s] : G_rr[ia + (int64_t)sel[so + c] * ldrr];
                 row += g * b[c];
             }
             quad += ba * row;
@@ -449,13 +424,24 @@ __global__ void __launch_bounds__(128) sse_train_gram_kernel(const double* __res
 void sse_train_gram(const double* G_rr, int64_t ldrr, const double* G_rt, int64_t ldrt, const double* gtt,
                     const double* beta, int64_t ldb, const int* sel, const int* row_off, const int* nsel, int T, int K,
                     int L, double* sse, cudaStream_t st, int t0, int t1, const int* col_index, const int* col_off,
-                    const int* col_cnt) {
+                    const int* col_cnt, bool pseudo, const int* sel_row_off) {
     if (t1 < 0) t1 = T;
     if (t1 == t0) return;
-    dim3 grid((unsigned)ceil_div(t1 - t0, 128), (unsigned)(L * K));
+    const int64_t gy = (int64_t)L * (K + (pseudo ? 1 : 0));
+    if (gy > 65535) {      // gridDim.y limit: the leave-one-out batch of the importance step can exceed it
+        const int chunk = 65535 / (K + (pseudo ? 1 : 0));
+        for (int l0 = 0; l0 < L; l0 += chunk) {
+            const int nl = std::min(chunk, L - l0);
+            sse_train_gram(G_rr, ldrr, G_rt, ldrt, gtt, beta, ldb, sel, row_off + (size_t)l0 * K, nsel + (size_t)l0 * K, T, K, nl,
+                           sse + (size_t)l0 * (K + 1) * T, st, t0, t1, col_index, col_off ? col_off + l0 : nullptr,
+                           col_cnt ? col_cnt + l0 : nullptr, pseudo, sel_row_off ? sel_row_off + (size_t)l0 * K : nullptr);
+        }
+        return;
+    }
+    dim3 grid((unsigned)ceil_div(t1 - t0, 128), (unsigned)gy);
     ProfScope ps(PROF_RESID_VOTE, st, 0.0);
     sse_train_gram_kernel<<<grid, 128, 0, st>>>(G_rr, ldrr, G_rt, ldrt, gtt, beta, ldb, sel, row_off, nsel, T, K, sse, t0, t1,
-                                                col_index, col_off, col_cnt);
+                                                col_index, col_off, col_cnt, pseudo ? 1 : 0, sel_row_off);
     SCRC_CUDA(cudaGetLastError());
     SCRC_LAUNCHED();
 }

@@ -47,16 +47,20 @@ void resid_vote(const ResidVoteArgs& a, int mode, int num_sms, cudaStream_t s);
 void reduce_sse(const double* partial, int T, int K, int L, int CR, double* sse, cudaStream_t s, int t0 = 0, int t1 = -1,
                 const int* skip_cnt = nullptr);
 
-// Training SSE of every (fit, module, target) from the Gram matrices instead of the n1 cells:
+// SSE of every (fit, module, target) from the Gram matrices of a data split instead of its cells (used for the
+// training split AND the test split: pass that split's X'X, X'y and y'y):
 //   ||y_t - X_sel b||^2 = y_t'y_t - 2 b'(X_sel'y_t) + b'(X_sel'X_sel) b
 // with y'y = gtt[t], X'y = G_rt[sel, t], X'X = G_rr[sel, sel]  (same quantity as
 // colSums(residuals_train_nnls^2), R/scregclust.R:1590-1602, in O(s^2) instead of O(n1 s) per pair).
-// Modules without a model get gtt[t] exactly.  Output layout = sse[l][j][t] with K+1 module slots.
+// Modules without a model get gtt[t] exactly.  Output layout = sse[l][j][t] with K+1 module slots; with `pseudo`
+// slot K of every fit is filled with gtt[t] (the "no model" sum of squares, denominator of R2).  sel_row_off
+// (optional, [L*K]): rows of `sel` when they differ from the rows of `beta` (importance step: the s + 1 leave-one-out
+// problems of a module share one regulator list).
 void sse_train_gram(const double* G_rr, int64_t ldrr, const double* G_rt, int64_t ldrt, const double* gtt,
                     const double* beta, int64_t ldb, const int* sel /* per stacked row: regulator or -1 */,
                     const int* row_off, const int* nsel, int T, int K, int L, double* sse, cudaStream_t s, int t0 = 0,
                     int t1 = -1, const int* col_index = nullptr, const int* col_off = nullptr,
-                    const int* col_cnt = nullptr);
+                    const int* col_cnt = nullptr, bool pseudo = false, const int* sel_row_off = nullptr);
 
 // resid_var = SSE_train / (n1 - s_j); two_var = 2 var; inv_two_var = RN(1 / two_var); half_log = 0.5 log(2 pi var)
 // (R/scregclust.R:1635-1638, allocation.cpp:59-62).  nsel: device [L*K].

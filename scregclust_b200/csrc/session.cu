@@ -177,6 +177,12 @@ void Ctx::finish() {
         tick("eigen-decomposition");
         gtt.alloc(T);
         col_sumsq(Z1t.data(), Z1t.ld, n1, T, gtt.p, st);
+        // the same for the test split: SSE_test = y'y - 2 b'X'y + b'X'X b needs no pass over the n2 cells either
+        gram(Z2r, Z2r, G2_rr, true, dev);
+        gram(Z2r, Z2t, G2_rt, false, dev);
+        gtt2.alloc(T);
+        col_sumsq(Z2t.data(), Z2t.ld, n2, T, gtt2.p, st);
+        tick("test-split gram");
 
         // Initial fit (scregclust.R:1049-1101): OLS when n1 >= P, ridge with the df search otherwise.
         DMat tmp;
@@ -223,6 +229,7 @@ void Ctx::finish() {
         G_rr.alloc(P, P); G_rt.alloc(P, T);
         eig.P = (int)P; eig.V.alloc(P, P); eig.Vt.alloc(P, P); eig.lam.alloc(P);
         gtt.alloc(T); beta_init.alloc(P, T); res_sds.alloc(T); bas.alloc(P, T);
+        G2_rr.alloc(P, P); G2_rt.alloc(P, T); gtt2.alloc(T);
     }
     if (world() > 1) {
         comm->group_begin();
@@ -232,6 +239,9 @@ void Ctx::finish() {
         comm->broadcast_bytes(eig.Vt.data(), eig.Vt.bytes(), 0, st);
         comm->broadcast_bytes(eig.lam.p, (size_t)P * 8, 0, st);
         comm->broadcast_bytes(gtt.p, (size_t)T * 8, 0, st);
+        comm->broadcast_bytes(G2_rr.data(), G2_rr.bytes(), 0, st);
+        comm->broadcast_bytes(G2_rt.data(), G2_rt.bytes(), 0, st);
+        comm->broadcast_bytes(gtt2.p, (size_t)T * 8, 0, st);
         comm->broadcast_bytes(beta_init.data(), beta_init.bytes(), 0, st);
         comm->broadcast_bytes(res_sds.p, (size_t)T * 8, 0, st);
         comm->broadcast_bytes(bas.data(), bas.bytes(), 0, st);
@@ -730,7 +740,6 @@ void Ctx::fit_cycle(int F, const double* lambda, const int* k_in, const scrc_opt
     pt.mark(phase_s, 4);
     // ---------------- Step 2a/2b: residuals, SSE, variances, votes ----------------
     const int CRte = resid_vote_pick_cr((int)n2, (int)T, F, dev.num_sms);
-    partial.ensure(resid_vote_partial_elems((int)T, K, F, CRte));
     const size_t fkt = (size_t)F * K * T, fk1t = (size_t)F * (K + 1) * T, ft = (size_t)F * T;
     sse_train.ensure(fk1t); sse_test.ensure(fk1t); var.ensure(fkt); two_var.ensure(fkt); inv_two_var.ensure(fkt); half_log.ensure(fkt);
     r2.ensure(fkt); best_r2.ensure(ft); best_idx.ensure(ft); k_new.ensure(ft);
@@ -747,22 +756,30 @@ void Ctx::fit_cycle(int F, const double* lambda, const int* k_in, const scrc_opt
     ResidVoteArgs ra;
     ra.beta = nnls.beta.data(); ra.ldb = nnls.beta.ld; ra.rows_total = rows_total;
     ra.T = (int)T; ra.K = K; ra.L = F; ra.row_off = row_off_d.p; ra.kpad = kpad_d.p; ra.nsel = nsel_d.p;
-    ra.two_var = two_var.p; ra.inv_two_var = inv_two_var.p; ra.half_log = half_log.p; ra.partial = partial.p; ra.votes = votes.p;
+    ra.two_var = two_var.p; ra.inv_two_var = inv_two_var.p; ra.half_log = half_log.p; ra.partial = nullptr; ra.votes = votes.p;
     ra.t_begin = t0; ra.t_end = t1;
     if (use_quick) { ra.col_index = nnls.cols.p; ra.col_off = q_off.p; ra.col_cnt = q_cnt.p; }
-    // train split: SSE from the Gram matrices (no pass over the n1 cells), then the variances
+    // Both splits: sums of squared residuals from the split's Gram matrices (no pass over the cells) -- the training
+    // ones give the variances (scregclust.R:1635-1638), the test ones R2 (scregclust.R:1628-1632); slot K of the
+    // test table is the "no model" sum of squares (scregclust.R:1505-1515), the denominator of R2.
     sse_train_gram(G_rr.data(), G_rr.ld, G_rt.data(), G_rt.ld, gtt.p, nnls.beta.data(), nnls.beta.ld, row_src.p,
                    row_off_d.p, nsel_d.p, (int)T, K, F, sse_train.p, st, t0, t1, ra.col_index, ra.col_off, ra.col_cnt);
     make_resid_var(sse_train.p, nsel_d.p, (int)n1, (int)T, K, F, var.p, two_var.p, inv_two_var.p, half_log.p, st, t0, t1);
-    // test split
-    ZselT.reshape(rows_alloc, n2);
-    if (rows_total == 0) SCRC_CUDA(cudaMemsetAsync(ZselT.data(), 0, ZselT.bytes(), st));
-    gather_transpose(Z2r.data(), Z2r.ld, (int)n2, row_src.p, rows_total, ZselT.data(), ZselT.ld, st);
-    ra.ZselT = ZselT.data(); ra.ldzs = ZselT.ld; ra.Z = Z2t.data(); ra.ldz = Z2t.ld; ra.ncells = (int)n2; ra.CR = CRte;
+    sse_train_gram(G2_rr.data(), G2_rr.ld, G2_rt.data(), G2_rt.ld, gtt2.p, nnls.beta.data(), nnls.beta.ld, row_src.p,
+                   row_off_d.p, nsel_d.p, (int)T, K, F, sse_test.p, st, t0, t1, ra.col_index, ra.col_off, ra.col_cnt,
+                   /*pseudo=*/true);
+    // per-cell votes (test split): the only pass over cells of a cycle; skipped in a last cycle
+    if (vote) {
+        ZselT.reshape(rows_alloc, n2);
+        if (rows_total == 0) SCRC_CUDA(cudaMemsetAsync(ZselT.data(), 0, ZselT.bytes(), st));
+        gather_transpose(Z2r.data(), Z2r.ld, (int)n2, row_src.p, rows_total, ZselT.data(), ZselT.ld, st);
+        ra.ZselT = ZselT.data(); ra.ldzs = ZselT.ld; ra.Z = Z2t.data(); ra.ldz = Z2t.ld; ra.ncells = (int)n2; ra.CR = CRte;
+    }
     if (!use_prior) {
-        if (vote) SCRC_CUDA(cudaMemsetAsync(votes.p, 0, fkt * 4, st));
-        resid_vote(ra, vote ? 1 : 0, dev.num_sms, st);
-        reduce_sse(partial.p, (int)T, K, F, CRte, sse_test.p, st, t0, t1);
+        if (vote) {
+            SCRC_CUDA(cudaMemsetAsync(votes.p, 0, fkt * 4, st));
+            resid_vote(ra, 1, dev.num_sms, st);
+        }
         finish_alloc(sse_test.p, vote ? votes.p : nullptr, (int)T, K, F, r2.p, best_r2.p, best_idx.p, k_new.p, st, t0, t1);
     } else {
         // Network prior (allocation.cpp:39-56,74-77): the sweep is sequential in update_order because every
@@ -784,7 +801,6 @@ void Ctx::fit_cycle(int F, const double* lambda, const int* k_in, const scrc_opt
         for (int f = 0; f < F; ++f) {
             r1.row_off = row_off_d.p + (size_t)f * K; r1.kpad = kpad_d.p + (size_t)f * K;
             r1.nsel = nsel_d.p + (size_t)f * K;
-            r1.partial = partial.p + (size_t)f * CRte * 2 * (K + 1) * T;
             resid_vote(r1, 2, dev.num_sms, st);
             for (int64_t t = 0; t < T; ++t) k0[t] = k_in[(int64_t)f * T + t] - 1;     // allocation.cpp:23
             SCRC_CUDA(cudaMemcpyAsync(d_k.p, k0.data(), T * 4, cudaMemcpyHostToDevice, st));
@@ -795,7 +811,6 @@ void Ctx::fit_cycle(int F, const double* lambda, const int* k_in, const scrc_opt
             SCRC_CUDA(cudaStreamSynchronize(st));   // k0 is reused by the next fit
             check_cancel();                          // allocation.cpp:96 polls per gene; here per fit
         }
-        reduce_sse(partial.p, (int)T, K, F, CRte, sse_test.p, st);
         // r2 / best_r2 from the SSEs; k_new (0-based from the sweep) is shifted to 1-based below
         finish_alloc(sse_test.p, nullptr, (int)T, K, F, r2.p, best_r2.p, best_idx.p, nullptr, st);
         add_one_kernel<<<(unsigned)ceil_div((int64_t)F * T, 256), 256, 0, st>>>(k_new.p, (int64_t)F * T);   // allocation.cpp:99
@@ -1057,31 +1072,24 @@ void Ctx::importance(int F, const int* k_final, const unsigned char* models, con
     nnls_solve(nb, opt.tol_nnls, opt.max_optim_iter, imp_scale.p, 1, dev.num_sms, st);   // scregclust.R:1865-1873
 
     pt.mark(phase_s, 9);
-    // test residuals: SSE per (problem, target of the module)                          scregclust.R:1875-1878
+    // test-split SSE per (problem, target of the module) (scregclust.R:1875-1878), from the test split's Gram
+    // matrices: the s + 1 problems of a module share its regulator list (rows imp_arow of imp_row_src), their
+    // coefficient blocks (rows imp_brow of nb.beta) carry an exact zero row for the regulator left out
+    std::vector<int> h_ns(nprob);
+    for (const Group& g : groups) for (int r = 0; r <= g.s; ++r) h_ns[g.first_prob + r] = g.s;
     imp_row_src.ensure(rows_a); imp_arow.ensure(nprob); imp_brow.ensure(nprob); imp_kpad.ensure(nprob);
     imp_coff.ensure(nprob); imp_ccnt.ensure(nprob);
     SCRC_CUDA(cudaMemcpyAsync(imp_row_src.p, h_row_src.data(), rows_a * 4, cudaMemcpyHostToDevice, st));
     SCRC_CUDA(cudaMemcpyAsync(imp_arow.p, h_arow.data(), nprob * 4, cudaMemcpyHostToDevice, st));
     SCRC_CUDA(cudaMemcpyAsync(imp_brow.p, h_brow.data(), nprob * 4, cudaMemcpyHostToDevice, st));
-    SCRC_CUDA(cudaMemcpyAsync(imp_kpad.p, h_kpad.data(), nprob * 4, cudaMemcpyHostToDevice, st));
+    SCRC_CUDA(cudaMemcpyAsync(imp_kpad.p, h_ns.data(), nprob * 4, cudaMemcpyHostToDevice, st));
     SCRC_CUDA(cudaMemcpyAsync(imp_coff.p, h_coff.data(), nprob * 4, cudaMemcpyHostToDevice, st));
     SCRC_CUDA(cudaMemcpyAsync(imp_ccnt.p, h_ccnt.data(), nprob * 4, cudaMemcpyHostToDevice, st));
-    imp_Zs.reshape(rows_a, n2);
-    gather_transpose(Z2r.data(), Z2r.ld, (int)n2, imp_row_src.p, rows_a, imp_Zs.data(), imp_Zs.ld, st);
-    const int CR = resid_vote_pick_cr((int)n2, Tmax, nprob, dev.num_sms);
-    imp_part.ensure(resid_vote_partial_elems(Tmax, 1, nprob, CR));
     imp_sse.ensure((size_t)nprob * 2 * Tmax);
     if (W > 1) SCRC_CUDA(cudaMemsetAsync(imp_sse.p, 0, (size_t)nprob * 2 * Tmax * 8, st));
-    ResidVoteArgs ra;
-    ra.ZselT = imp_Zs.data(); ra.ldzs = imp_Zs.ld; ra.beta = nb.beta.data(); ra.ldb = nb.beta.ld; ra.rows_total = rows_b;
-    ra.Z = Z2t.data(); ra.ldz = Z2t.ld; ra.ncells = (int)n2; ra.T = Tmax; ra.K = 1; ra.L = nprob;
-    ra.row_off = imp_arow.p; ra.kpad = imp_kpad.p; ra.two_var = nullptr; ra.half_log = nullptr;
-    ra.partial = imp_part.p; ra.votes = nullptr; ra.CR = CR;
-    ra.row_off_b = imp_brow.p; ra.col_index = nb.cols.p; ra.col_off = imp_coff.p; ra.col_cnt = imp_ccnt.p;
-    // the A operand (rows_a rows) and the B operand (rows_b rows) need tensor maps of their own extent
-    ra.rows_total_a = rows_a;
-    resid_vote(ra, 0, dev.num_sms, st);
-    reduce_sse(imp_part.p, Tmax, 1, nprob, CR, imp_sse.p, st, 0, -1, W > 1 ? imp_ccnt.p : nullptr);
+    sse_train_gram(G2_rr.data(), G2_rr.ld, G2_rt.data(), G2_rt.ld, gtt2.p, nb.beta.data(), nb.beta.ld, imp_row_src.p,
+                   imp_brow.p, imp_kpad.p, Tmax, 1, nprob, imp_sse.p, st, 0, Tmax, nb.cols.p, imp_coff.p, imp_ccnt.p,
+                   /*pseudo=*/false, /*sel_row_off=*/imp_arow.p);
     if (W > 1) comm->allreduce_sum_f64(imp_sse.p, (size_t)nprob * 2 * Tmax, st);
     if (z2t_css.n == 0) { z2t_css.alloc(T); col_centered_ss(Z2t.data(), Z2t.ld, n2, T, z2t_css.p, st); }
     std::vector<double>& h_sse = imp_h_sse;

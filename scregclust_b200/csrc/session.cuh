@@ -56,6 +56,8 @@ struct Ctx {
     DevBuf<double> sds_t;        // z1_target_sds
     DevBuf<double> inv_sds_t;    // 1 / z1_target_sds
     DMat G_rr, G_rt;             // Z1r'Z1r, Z1r'Z1t
+    DMat G2_rr, G2_rt;           // Z2r'Z2r, Z2r'Z2t: the test-split sums of squares come from these (alloc.cuh: sse_train_gram)
+    DevBuf<double> gtt2;         // colSums(z2_target_centered^2)
     EigBasis eig;                // of G_rr / n1
     DMat beta_init;              // P x T
     DevBuf<double> res_sds;      // T
