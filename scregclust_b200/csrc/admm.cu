@@ -558,7 +558,6 @@ int admm_solve(AdmmBatch& b, const EigBasis& eig, const AdmmOpts& o, bool cold, 
     };
     int it = 1;
     int sweeps = 0;
-    int active_cols = b.C;   // refreshed whenever the host polls the device counters
     bool need_rhs = true;   // the first sweep and every sweep after a possible rho change build the rhs explicitly
     while (true) {
         if (need_rhs) {
@@ -599,7 +598,6 @@ int admm_solve(AdmmBatch& b, const EigBasis& eig, const AdmmOpts& o, bool cold, 
             SCRC_CUDA(cudaMemcpyAsync(h_scratch, d.n_active, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream));
             SCRC_CUDA(cudaStreamSynchronize(stream));
             if (h_scratch[0] == 0) break;
-            active_cols = h_scratch[1];
             // cooperative cancellation (optim.cpp:307 polls the interrupt flag every iteration)
             if (cancel && cancel->load(std::memory_order_relaxed)) { b.aborted = true; break; }
         }

@@ -18,7 +18,6 @@ struct RvParams {
     const double* two_var;
     const double* inv_two_var;
     const double* half_log;
-    double* partial;
     int* votes;
     int CR, tiles_n, ctiles;
     const int* row_off_b;
@@ -39,7 +38,7 @@ __device__ __forceinline__ void consumer_bar() {   // the 8 consumer warps only
 // MODE 1: per-cell votes; MODE 2: squared residuals written out (only used for the sequential network-prior sweep,
 // which needs every gene's K x n2 slab).  The test-split sums of squares no longer come from this pass: like the
 // training ones they are evaluated from the split's Gram matrices (sse_train_gram), O(s^2) per (module, target).
-template <int MODE, bool PIPE>
+template <int MODE>
 __global__ void __launch_bounds__(GEMM_THREADS, 2) resid_vote_kernel(const __grid_constant__ RvParams p) {
     constexpr bool VOTE = (MODE == 1);
     constexpr int MT = RV_BM / (GEMM_WARPS_M * 8);   // 4
@@ -147,10 +146,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) resid_vote_kernel(const __gri
                         best[i][jj][e] = -INFINITY;
                         bidx[i][jj][e] = 0;
                     }
-            // Software pipeline over the modules: the DMMA mainloop of module j + 1 is issued BEFORE the FP64 epilogue
-            // of module j, so the tensor pipe works on the next prediction while this warp scores the previous one
-            // (the epilogue no longer waits at the end of its own accumulator chains).  Stages are consumed in the
-            // producer's order (module by module).
+            // (Issuing the mainloop of module j + 1 ahead of the epilogue of module j was tried and measured: no gain
+            // -- 101.5 vs 99.8 ms at config 3, 749 vs 737 ms at config 4 -- the second accumulator set costs spills.)
             auto mainloop = [&](int j, double (&acc)[MT][NT][2]) {
 #pragma unroll
                 for (int i = 0; i < MT; ++i)
@@ -233,26 +230,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) resid_vote_kernel(const __gri
                 }
             };
             {
-                double accA[MT][NT][2], accB[MT][NT][2];
+                double accA[MT][NT][2];
                 double iv[NT][2], nhl[NT][2];
-                if (!PIPE) {
-                    for (int j = 0; j < p.K; ++j) {
-                        load_consts(j, iv, nhl);
-                        mainloop(j, accA);
-                        epilogue(j, accA, iv, nhl);
-                    }
-                } else {
-                mainloop(0, accA);
-                for (int j = 0; j < p.K; j += 2) {
+                for (int j = 0; j < p.K; ++j) {
                     load_consts(j, iv, nhl);
-                    if (j + 1 < p.K) mainloop(j + 1, accB);
+                    mainloop(j, accA);
                     epilogue(j, accA, iv, nhl);
-                    if (j + 1 < p.K) {
-                        load_consts(j + 1, iv, nhl);
-                        if (j + 2 < p.K) mainloop(j + 2, accA);
-                        epilogue(j + 1, accB, iv, nhl);
-                    }
-                }
                 }
             }
             if (VOTE) {
@@ -297,10 +280,6 @@ int resid_vote_pick_cr(int ncells, int T, int L, int num_sms) {
     const int ctiles = (int)ceil_div(ncells, RV_BM);
     return std::max(1, (int)ceil_div(ctiles, 16));   // 16 cell tiles (1024 cells) per CTA
 }
-size_t resid_vote_partial_elems(int T, int K, int L, int CR) {
-    return (size_t)L * CR * 2 * (K + 1) * T;
-}
-
 void resid_vote(const ResidVoteArgs& a, int mode, int num_sms, cudaStream_t st) {
     if (a.K + 1 > RV_MAX_K + 1) throw Error(-60, "resid_vote: at most 64 modules are supported");
     RvParams p;
@@ -310,7 +289,7 @@ void resid_vote(const ResidVoteArgs& a, int mode, int num_sms, cudaStream_t st) 
     p.tb = make_tmap_f64(a.beta, std::max<int64_t>(a.rows_total, 16), a.T, a.ldb, RV_BN);
     p.Z = a.Z; p.ldz = a.ldz; p.ncells = a.ncells; p.T = a.T; p.K = a.K; p.L = a.L;
     p.row_off = a.row_off; p.kpad = a.kpad; p.nsel = a.nsel; p.two_var = a.two_var; p.inv_two_var = a.inv_two_var; p.half_log = a.half_log;
-    p.partial = a.partial; p.votes = a.votes; p.CR = a.CR;
+    p.votes = a.votes; p.CR = a.CR;
     p.row_off_b = a.row_off_b; p.col_index = a.col_index; p.col_off = a.col_off; p.col_cnt = a.col_cnt;
     p.sq_out = a.sq_out;
     if (mode == 1 && !a.inv_two_var) throw Error(-63, "resid_vote: vote mode needs the reciprocal table");
@@ -324,10 +303,8 @@ void resid_vote(const ResidVoteArgs& a, int mode, int num_sms, cudaStream_t st) 
                      (mode == 1 ? 2 * a.K * RV_BN * 8 + RV_BN * a.K * 4 : 0) + 2 * a.K * 4;
     if (mode != 1 && mode != 2) throw Error(-65, "resid_vote: mode must be 1 (votes) or 2 (store)");
     static SmemAttr attr[3];
-    static const bool pipe = getenv("SCRC_VOTE_PIPELINE") != nullptr;   // module software pipeline (experiment switch)
-    if (mode == 1 && pipe) attr[0].ensure(resid_vote_kernel<1, true>, smem);
-    else if (mode == 1) attr[1].ensure(resid_vote_kernel<1, false>, smem);
-    else attr[2].ensure(resid_vote_kernel<2, false>, smem);
+    if (mode == 1) attr[1].ensure(resid_vote_kernel<1>, smem);
+    else attr[2].ensure(resid_vote_kernel<2>, smem);
     const int64_t nwork = (int64_t)a.L * a.CR * p.tiles_n;
     if (nwork > 0x7fffffffLL) throw Error(-61, "resid_vote: too many work items");
     const int grid = (int)nwork;
@@ -338,37 +315,14 @@ void resid_vote(const ResidVoteArgs& a, int mode, int num_sms, cudaStream_t st) 
         const double Ts = (double)(p.t_end - p.t_begin);
         const double bytes = 8.0 * (double)a.L * a.ncells * Ts + 8.0 * (double)a.rows_total * (a.ncells * (double)p.tiles_n + Ts * p.ctiles);
         ProfScope ps(PROF_RESID_VOTE, st, bytes);
-        if (mode == 1 && pipe) resid_vote_kernel<1, true><<<grid, GEMM_THREADS, smem, st>>>(p);
-        else if (mode == 1) resid_vote_kernel<1, false><<<grid, GEMM_THREADS, smem, st>>>(p);
-        else resid_vote_kernel<2, false><<<grid, GEMM_THREADS, smem, st>>>(p);
+        if (mode == 1) resid_vote_kernel<1><<<grid, GEMM_THREADS, smem, st>>>(p);
+        else resid_vote_kernel<2><<<grid, GEMM_THREADS, smem, st>>>(p);
     }
     SCRC_CUDA(cudaGetLastError());
     SCRC_LAUNCHED();
 }
 
-// ---------------------------------------------------------------- reductions / finishing kernels
-__global__ void reduce_sse_kernel(const double* __restrict__ partial, int T, int K1, int L, int CR, double* sse, int t0,
-                                  int Ts, const int* __restrict__ skip_cnt) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // over L*K1*Ts
-    if (i >= (int64_t)L * K1 * Ts) return;
-    const int t = t0 + (int)(i % Ts);
-    const int j = (int)((i / Ts) % K1);
-    const int l = (int)(i / ((int64_t)Ts * K1));
-    if (skip_cnt && skip_cnt[l] == 0) return;      // fit not computed on this rank: leave its entries alone
-    double s = 0.0;
-    for (int c = 0; c < CR * 2; ++c) s += partial[(((int64_t)l * CR * 2 + c) * K1 + j) * T + t];
-    sse[((int64_t)l * K1 + j) * T + t] = s;
-}
-void reduce_sse(const double* partial, int T, int K, int L, int CR, double* sse, cudaStream_t st, int t0, int t1,
-                const int* skip_cnt) {
-    if (t1 < 0) t1 = T;
-    const int64_t n = (int64_t)L * (K + 1) * (t1 - t0);
-    if (n == 0) return;
-    reduce_sse_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(partial, T, K + 1, L, CR, sse, t0, t1 - t0, skip_cnt);
-    SCRC_CUDA(cudaGetLastError());
-    SCRC_LAUNCHED();
-}
-
+// ---------------------------------------------------------------- Gram-form sums of squares / finishing kernels
 // One CTA per (fit*module, 128-target chunk); the module's Gram block lives in shared memory.
 constexpr int SSG_MAX_S = 72;   // 72^2 doubles = 41 KB of static shared memory
 __global__ void __launch_bounds__(128) sse_train_gram_kernel(const double* __restrict__ G_rr, int64_t ldrr,

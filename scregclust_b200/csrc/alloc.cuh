@@ -25,7 +25,6 @@ struct ResidVoteArgs {
     const double* two_var;               // device [L][K][T]   (vote mode)
     const double* inv_two_var = nullptr; // device [L][K][T]   (vote mode): RN(1 / two_var)
     const double* half_log;              // device [L][K][T]   (vote mode)
-    double* partial;                     // device [L][CR][2][K+1][T]
     int* votes;                          // device [L][T][K]   (vote mode, pre-zeroed)
     int CR;                              // cell ranges per (penalty, target tile)
     // optional generalisations (used by the leave-one-regulator-out post-processing):
@@ -38,14 +37,8 @@ struct ResidVoteArgs {
     int t_begin = 0, t_end = -1;         // target slice [t_begin, t_end) handled by this launch (-1: T)
 };
 int resid_vote_pick_cr(int ncells, int T, int L, int num_sms);
-size_t resid_vote_partial_elems(int T, int K, int L, int CR);
-// mode 0: SSE only, 1: SSE + votes, 2: SSE + squared residuals of one fit written to sq_out
+// mode 1: per-cell votes, 2: squared residuals of one fit written to sq_out (network-prior sweep)
 void resid_vote(const ResidVoteArgs& a, int mode, int num_sms, cudaStream_t s);
-
-// sse[l][j][t] (j = 0..K, the last one is the "no model" pseudo module) = fixed-order sum of partials
-// skip_cnt (optional, device [L]): fits with a zero entry are left untouched
-void reduce_sse(const double* partial, int T, int K, int L, int CR, double* sse, cudaStream_t s, int t0 = 0, int t1 = -1,
-                const int* skip_cnt = nullptr);
 
 // SSE of every (fit, module, target) from the Gram matrices of a data split instead of its cells (used for the
 // training split AND the test split: pass that split's X'X, X'y and y'y):

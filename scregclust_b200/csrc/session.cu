@@ -756,7 +756,7 @@ void Ctx::fit_cycle(int F, const double* lambda, const int* k_in, const scrc_opt
     ResidVoteArgs ra;
     ra.beta = nnls.beta.data(); ra.ldb = nnls.beta.ld; ra.rows_total = rows_total;
     ra.T = (int)T; ra.K = K; ra.L = F; ra.row_off = row_off_d.p; ra.kpad = kpad_d.p; ra.nsel = nsel_d.p;
-    ra.two_var = two_var.p; ra.inv_two_var = inv_two_var.p; ra.half_log = half_log.p; ra.partial = nullptr; ra.votes = votes.p;
+    ra.two_var = two_var.p; ra.inv_two_var = inv_two_var.p; ra.half_log = half_log.p; ra.votes = votes.p;
     ra.t_begin = t0; ra.t_end = t1;
     if (use_quick) { ra.col_index = nnls.cols.p; ra.col_off = q_off.p; ra.col_cnt = q_cnt.p; }
     // Both splits: sums of squared residuals from the split's Gram matrices (no pass over the cells) -- the training

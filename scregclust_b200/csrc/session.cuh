@@ -73,7 +73,7 @@ struct Ctx {
     int* h_fk = nullptr;          // pinned: [FK admm iterations | abort flag | FK selected counts]
     size_t h_fk_cap = 0;
     DMat ZselT;
-    DevBuf<double> partial, sse_train, sse_test, var, two_var, inv_two_var, half_log, r2, best_r2;
+    DevBuf<double> sse_train, sse_test, var, two_var, inv_two_var, half_log, r2, best_r2;
     DevBuf<int> votes, best_idx, k_new;
     DevBuf<unsigned char> models_d;
     DevBuf<double> weights_d, signs_d;
@@ -108,9 +108,8 @@ struct Ctx {
     // scratch of the post-processing and of the coefficient packing, kept across calls (cudaMalloc / cudaFree
     // synchronise the device and cost more than the kernels they serve)
     NnlsBatch imp_nb;
-    DevBuf<double> imp_scale, imp_part, imp_sse;
+    DevBuf<double> imp_scale, imp_sse;
     DevBuf<int> imp_row_src, imp_arow, imp_brow, imp_kpad, imp_coff, imp_ccnt;
-    DMat imp_Zs;
     std::vector<double> imp_h_sse, h_sds;
     DevBuf<int> pack_src, pack_s, pack_a;
     DevBuf<long long> pack_base;
