@@ -273,9 +273,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) resid_vote_kernel(const __gri
 }
 
 int resid_vote_pick_cr(int ncells, int T, int L, int num_sms) {
-    // The split of the cells into ranges fixes the association order of the SSE sums, so it must
-    // depend on the number of cells only -- not on how many fits share the launch -- or a fit's
-    // result would change with the batch it is computed in (and with the number of GPUs).
+    // Cell ranges per (fit, target tile).  The kernel only adds integer votes, so the split does not affect any
+    // result; 1024 cells per CTA amortise the per-CTA staging of the score constants.
     (void)T; (void)L; (void)num_sms;
     const int ctiles = (int)ceil_div(ncells, RV_BM);
     return std::max(1, (int)ceil_div(ctiles, 16));   // 16 cell tiles (1024 cells) per CTA
