@@ -475,6 +475,7 @@ def main():
         line["roofline_secondary"] = sec
         os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
         totals = grid_totals(res, n_modules)
+        line["work_counters"] = totals
         r_med = res[i_med]
         first = {"lambda": float(pens[i_med]), "admm_iterations": [int(v) for v in r_med.admm_iterations[0]],
                  "selected": [np.flatnonzero(r_med.models_history[0][:, j]).tolist() for j in range(n_modules)]}
@@ -484,6 +485,9 @@ def main():
                 tab[f"{args.workload}/seed{args.seed}"] = {"totals": totals, "first_cycle": first,
                                                            "cycles_per_penalty": [int(r.n_cycles_run) for r in res]}
                 json.dump(tab, open(CYCLES_TABLE, "w"), indent=1, sort_keys=True)
+                side = os.path.join(ROOT, "gpurun_out")          # travels back from the GPU box
+                if os.path.isdir(side):
+                    json.dump(tab, open(os.path.join(side, "bench_cycles.json"), "w"), indent=1, sort_keys=True)
             except Exception:
                 pass
             if not args.no_cpu_baseline:
