@@ -140,17 +140,30 @@ void Ctx::create(int device, const double* z1r, const double* z2r, const double*
     AllocScope as(dev.stream);
     begin(n1_, n2_, P_, T_, K_);
     cudaStream_t st = dev.stream;
-    // the regulators of the first split go first: the Gram matrix and its eigenbasis only need them
-    Z1r.upload(z1r, n1, st); Z1t.upload(z1t, n1, st); Z2r.upload(z2r, n2, st); Z2t.upload(z2t, n2, st);
+    // The regulators of the first split go first, on the compute stream: X'X and its eigen-decomposition (the
+    // longest, latency-bound part of the precompute) only need them and run while the other three matrices are
+    // still arriving on a second stream (pinned host buffers; pageable ones simply serialise).
+    cudaStream_t cp = nullptr;
+    cudaEvent_t ev_alloc = nullptr, ev_copy = nullptr;
+    SCRC_CUDA(cudaStreamCreateWithFlags(&cp, cudaStreamNonBlocking));
+    SCRC_CUDA(cudaEventCreateWithFlags(&ev_alloc, cudaEventDisableTiming));
+    SCRC_CUDA(cudaEventCreateWithFlags(&ev_copy, cudaEventDisableTiming));
+    struct Guard { cudaStream_t s; cudaEvent_t a, b; ~Guard() { cudaEventDestroy(a); cudaEventDestroy(b); cudaStreamDestroy(s); } } guard{cp, ev_alloc, ev_copy};
+    SCRC_CUDA(cudaEventRecord(ev_alloc, st));          // the buffers were allocated in stream order on `st`
+    SCRC_CUDA(cudaStreamWaitEvent(cp, ev_alloc, 0));
+    Z1r.upload(z1r, n1, st);
     SCRC_CUDA(cudaMemcpyAsync(sds_t.p, sds, T * 8, cudaMemcpyDefault, st));
-    finish();
+    Z1t.upload(z1t, n1, cp); Z2r.upload(z2r, n2, cp); Z2t.upload(z2t, n2, cp);
+    SCRC_CUDA(cudaEventRecord(ev_copy, cp));
+    finish(ev_copy);
+    SCRC_CUDA(cudaStreamSynchronize(cp));
 }
 
 // Everything after the four scaled matrices and z1_target_sds are resident.  In a multi-GPU job rank 0
 // computes the precompute once and broadcasts it (0.25 GB at config 3, < 1 ms over NVLink): the
 // eigen-decomposition is latency-bound and gains nothing from being repeated, and every rank then works
 // from bit-identical Gram matrices and eigenvectors by construction.
-void Ctx::finish() {
+void Ctx::finish(cudaEvent_t inputs_ready) {
     cudaStream_t st = dev.stream;
     const bool dbg = getenv("SCRC_DEBUG_TIMING") != nullptr;
     const bool root = rank() == 0;
@@ -171,10 +184,11 @@ void Ctx::finish() {
     if (root) {
         // Gram matrices (optim.cpp:17-27,99,414,421) -- computed once, the reference redoes them per call
         gram(Z1r, Z1r, G_rr, true, dev);
-        gram(Z1r, Z1t, G_rt, false, dev);
-        tick("gram");
         build_eig(G_rr, 1.0 / (double)n1, eig, dev);   // eigenbasis of X'X with X = Z1r / sqrt(n1)
-        tick("eigen-decomposition");
+        tick("X'X + eigen-decomposition");
+        if (inputs_ready) SCRC_CUDA(cudaStreamWaitEvent(st, inputs_ready, 0));   // targets and test split have arrived
+        gram(Z1r, Z1t, G_rt, false, dev);
+        tick("X'Y");
         gtt.alloc(T);
         col_sumsq(Z1t.data(), Z1t.ld, n1, T, gtt.p, st);
         // the same for the test split: SSE_test = y'y - 2 b'X'y + b'X'X b needs no pass over the n2 cells either
@@ -230,6 +244,7 @@ void Ctx::finish() {
         eig.P = (int)P; eig.V.alloc(P, P); eig.Vt.alloc(P, P); eig.lam.alloc(P);
         gtt.alloc(T); beta_init.alloc(P, T); res_sds.alloc(T); bas.alloc(P, T);
         G2_rr.alloc(P, P); G2_rt.alloc(P, T); gtt2.alloc(T);
+        if (inputs_ready) SCRC_CUDA(cudaStreamWaitEvent(st, inputs_ready, 0));
     }
     if (world() > 1) {
         comm->group_begin();

@@ -89,7 +89,7 @@ struct Ctx {
                     const int* split_indices, const int* stratification, int center, int K,
                     unsigned char* keep_gene, int64_t* dims_out);
     void begin(int64_t n1, int64_t n2, int64_t P, int64_t T, int K);   // dimensions + input buffers
-    void finish();                                                      // Gram, eigenbasis, initial fit
+    void finish(cudaEvent_t inputs_ready = nullptr);                    // Gram, eigenbasis, initial fit
     void fit_cycle(int F, const double* lambda, const int* k_in, const scrc_options& opt, bool skip_alloc,
                    scrc_cycle_out* out, const scrc_prior* prior = nullptr, const scrc_quick* quick = nullptr);
     // quick mode (scregclust.R:1435-1496): |cross_corr1| (lazy), per-fit target subsets of the last cycle

@@ -164,9 +164,9 @@ def scregclust(expression, genesymbols, is_regulator, penalization, n_modules, i
         _abort("quick_mode only available when allocate_per_obs is TRUE.")               # :809-817
     if quick_mode and not (0 <= float(quick_mode_percent) < 1):
         _abort("quick_mode_percent needs to be numeric in [0, 1).")                      # :819-831
-    if quick_mode or not allocate_per_obs:
-        # the session path implements allocate_per_obs = TRUE, quick_mode = FALSE (DESIGN.md sections 7-8)
-        raise NotImplementedError("quick_mode = TRUE and allocate_per_obs = FALSE are not built in this library")
+    if not allocate_per_obs:
+        # the aggregate branch is unreachable through the reference's public API
+        raise NotImplementedError("allocate_per_obs = FALSE is not built in this library")
     rng = np.random.default_rng(seed)
     p, n = ex.shape
     genesymbols = np.asarray(genesymbols)
@@ -197,7 +197,8 @@ def scregclust(expression, genesymbols, is_regulator, penalization, n_modules, i
             max_optim_iter=int(max_optim_iter), tol_coop_rel=tol_coop_rel, tol_coop_abs=tol_coop_abs, tol_nnls=tol_nnls,
             return_coeffs=True, compute_predictive_r2=bool(compute_predictive_r2),
             prior_indicator=prior_indicator if use_prior else None, prior_baseline=prior_baseline,
-            prior_weight=float(prior_weight) if use_prior else 0.0, update_orders=update_orders)
+            prior_weight=float(prior_weight) if use_prior else 0.0, update_orders=update_orders,
+            quick_mode=bool(quick_mode), quick_mode_percent=float(quick_mode_percent))
     finally:
         ses.close()
 

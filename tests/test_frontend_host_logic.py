@@ -174,8 +174,6 @@ def test_unsupported_modes_fail_loudly():
     args = dict(expression=expression, genesymbols=genesymbols, is_regulator=is_regulator, penalization=0.1,
                 n_modules=2, split_indices=split, session_factory=OracleExpressionSession)
     with pytest.raises(NotImplementedError):
-        scregclust(quick_mode=True, **args)
-    with pytest.raises(NotImplementedError):
         scregclust(allocate_per_obs=False, **args)
     with pytest.raises(ScregclustError, match="quick_mode only available"):
         scregclust(quick_mode=True, allocate_per_obs=False, **args)

@@ -160,6 +160,24 @@ def test_allocate_into_modules(api, rng, K, n2, T, weight):
     assert np.array_equal(got_arr, orc.alloc_array(z2 * z2, K))
 
 
+def test_allocate_into_modules_rejects_indices_that_would_leave_the_arrays(api, rng):
+    """The reference documents these as assumptions (allocation.cpp:4-6); the ABI checks them because the sequential
+    prior sweep indexes device memory with them."""
+    from scregclust_b200._capi import ScrcError
+    K, n2, T = 3, 20, 6
+    arr = np.asfortranarray(rng.random((K, n2, T))); var = np.asfortranarray(rng.random((T, K)) + 0.5)
+    k = rng.integers(1, K + 1, T).astype(np.int32)
+    prior = [[(t + 1) % T] for t in range(T)]
+    good = np.arange(T, dtype=np.int32)
+    api.allocate_into_modules(arr, var, prior, k, good, 1e-6, 0.5)
+    for bad_k, bad_order, bad_prior in [(np.where(np.arange(T) == 2, K + 1, k).astype(np.int32), good, prior),
+                                        (k, np.array([0, 1, 1, 3, 4, 5], np.int32), prior),
+                                        (k, good, [[T + 3]] + prior[1:])]:
+        with pytest.raises(ScrcError) as e:
+            api.allocate_into_modules(arr, var, bad_prior, bad_k, bad_order, 1e-6, 0.5)
+        assert e.value.code == -20
+
+
 def test_plain_c_client_runs_on_the_device(tmp_path):
     """tests/c/abi_smoke.c --gpu: coop_lasso and coef_nnls through the C ABI from a C program."""
     import subprocess
