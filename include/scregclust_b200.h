@@ -95,6 +95,19 @@ int scrc_coef_ols(const double* y, const double* x, int64_t n, int64_t p, int64_
 /* coef_ridge(y, x, lambda): R/utils.R:49-57. */
 int scrc_coef_ridge(const double* y, const double* x, int64_t n, int64_t p, int64_t m, double lambda,
                     double* beta_out);
+/* kmeanspp(x, n_cluster, n_init_clusterings, n_max_iter): R/utils.R:351-375 -- k-means++ seeding (kmeanspp_init,
+ * R/utils.R:275-322) followed by stats::kmeans (Hartigan-Wong) per initialisation; the clustering with the smallest
+ * tot.withinss is returned.  x: n x p column-major (host or device pointer).  R's RNG stays with the caller:
+ *   first_centers[i]            the value of sample(n, size = 1L) of initialisation i (1-based)
+ *   uniforms[i * (K-1) + r]     the unif_rand() consumed by the r-th sample.int(prob = ps) of initialisation i
+ * drawn in R as  for (i in seq_len(n_init)) { first[i] <- sample(n, 1L); u[i, ] <- runif(K - 1L) }  -- the same
+ * stream the reference consumes.  cluster_out: n, 1-based; tot_withinss_out / ifault_out: per initialisation (may be
+ * NULL; ifault as in stats::kmeans: 0 ok, 2 did not converge in n_max_iter, 4 Quick-TRANSfer steps exceeded; an empty
+ * cluster is an error, as in R).  Distances are sequential sums in R's order; see DESIGN.md for what is pinned. */
+int scrc_kmeanspp(const double* x, int64_t n, int64_t p, int n_cluster, int n_init_clusterings, int n_max_iter,
+                  const int* first_centers, const double* uniforms, int* cluster_out, double* tot_withinss_out,
+                  int* ifault_out);
+
 /* crossprod(x, y) = x'y on the FP64 tensor pipe (compute_xtx, src/optim.cpp:17-27, when y == x). */
 int scrc_crossprod(const double* x, const double* y, int64_t n, int64_t px, int64_t py, double* out);
 
@@ -169,6 +182,10 @@ int scrc_ctx_get_inputs(scrc_ctx* ctx, double* z1_reg, double* z2_reg, double* z
 int scrc_ctx_get_init(scrc_ctx* ctx, double* res_sds, double* init_df, double* beta_init);
 /* cross_corr1 = fast_cor(z1_target_centered, z1_reg_scaled), T x P (R/scregclust.R:1116). */
 int scrc_ctx_cross_corr(scrc_ctx* ctx, double* out);
+/* k_start_cl <- kmeanspp(cross_corr1, n_modules, n_initializations, 100L) (R/scregclust.R:1131-1136) on the
+ * session's own cross_corr1, which never leaves the device; arguments as scrc_kmeanspp. */
+int scrc_ctx_kmeanspp(scrc_ctx* ctx, int n_init_clusterings, int n_max_iter, const int* first_centers,
+                      const double* uniforms, int* cluster_out, double* tot_withinss_out, int* ifault_out);
 /* G_rr (P x P) and G_rt (P x T), any may be NULL. */
 int scrc_ctx_get_gram(scrc_ctx* ctx, double* g_rr, double* g_rt);
 

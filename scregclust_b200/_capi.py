@@ -111,6 +111,9 @@ SIGNATURES = {
     "scrc_fast_cor": (C.c_int, [c_double_p, c_double_p, C.c_int64, C.c_int64, C.c_int64, c_double_p]),
     "scrc_coef_ols": (C.c_int, [c_double_p, c_double_p, C.c_int64, C.c_int64, C.c_int64, c_double_p]),
     "scrc_coef_ridge": (C.c_int, [c_double_p, c_double_p, C.c_int64, C.c_int64, C.c_int64, C.c_double, c_double_p]),
+    "scrc_kmeanspp": (C.c_int, [c_double_p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, c_int_p, c_double_p, c_int_p,
+                                c_double_p, c_int_p]),
+    "scrc_ctx_kmeanspp": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_int_p, c_double_p, c_int_p, c_double_p, c_int_p]),
     "scrc_crossprod": (C.c_int, [c_double_p, c_double_p, C.c_int64, C.c_int64, C.c_int64, c_double_p]),
     "scrc_bench_gemm": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int, c_double_p]),
     "scrc_profile_enable": (C.c_int, [C.c_int]),

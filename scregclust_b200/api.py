@@ -125,6 +125,24 @@ def coef_ridge(y, x, lambda_):
     return out
 
 
+def kmeanspp(x, n_cluster, first_centers, uniforms, n_max_iter=10, return_details=False):
+    """``kmeanspp(x, n_cluster, n_init_clusterings, n_max_iter)`` of R/utils.R:351-375 -> cluster labels (1-based).
+
+    R's RNG stays with the caller: ``first_centers[i]`` is ``sample(n, 1L)`` (1-based) and ``uniforms[i, :]`` the
+    ``n_cluster - 1`` ``unif_rand()`` draws of initialisation ``i``; the number of initialisations is their length."""
+    lib = _capi.load()
+    x = f64(np.atleast_2d(x))
+    n, p = x.shape
+    fc = np.ascontiguousarray(first_centers, dtype=np.int32)
+    u = np.ascontiguousarray(uniforms, dtype=np.float64).reshape(fc.size, max(int(n_cluster) - 1, 0))
+    cl = np.zeros(n, dtype=np.int32)
+    tot = np.zeros(fc.size)
+    fault = np.zeros(fc.size, dtype=np.int32)
+    check(lib.scrc_kmeanspp(dptr(x), n, p, int(n_cluster), int(fc.size), int(n_max_iter), iptr(fc), dptr(u), iptr(cl),
+                            dptr(tot), iptr(fault)))
+    return (cl, tot, fault) if return_details else cl
+
+
 def crossprod(x, y=None):
     """R's ``crossprod(x, y)`` / ``compute_xtx`` (src/optim.cpp:17-27) on the FP64 tensor pipe."""
     lib = _capi.load()

@@ -285,6 +285,24 @@ int scrc_ctx_get_gram(scrc_ctx* ctx, double* g_rr, double* g_rt) {
         SCRC_CUDA(cudaStreamSynchronize(c.dev.stream));
     });
 }
+namespace {
+// cross_corr1 = fast_cor(z1_target_centered, z1_reg_scaled) on device copies (R/scregclust.R:1116), T x P
+void session_cross_corr(Ctx& c, DMat& C) {
+    cudaStream_t st = c.dev.stream;
+    DMat X(c.n1, c.T), Y(c.n1, c.P);
+    C.alloc(c.T, c.P);
+    SCRC_CUDA(cudaMemcpyAsync(X.data(), c.Z1t.data(), c.Z1t.bytes(), cudaMemcpyDeviceToDevice, st));
+    SCRC_CUDA(cudaMemcpyAsync(Y.data(), c.Z1r.data(), c.Z1r.bytes(), cudaMemcpyDeviceToDevice, st));
+    DevBuf<double> xss(c.T), yss(c.P);
+    col_center_ss(X.data(), X.ld, c.n1, c.T, xss.p, st);
+    col_center_ss(Y.data(), Y.ld, c.n1, c.P, yss.p, st);
+    DenseArgs a{X.data(), X.ld, Y.data(), Y.ld, C.data(), C.ld, (int)c.T, (int)c.P, (int)c.n1};
+    a.rvec = xss.p; a.cvec = yss.p;
+    gemm_tn_dense(EPI_COR, a, c.dev.num_sms, st);
+    SCRC_CUDA(cudaStreamSynchronize(st));           // X, Y, xss, yss are released on return
+}
+}  // namespace
+
 int scrc_ctx_cross_corr(scrc_ctx* ctx, double* out) {
     if (!ctx || !out) return fail(SCRC_ERR_ARG, "null pointer");
     return guarded([&] {
@@ -292,18 +310,41 @@ int scrc_ctx_cross_corr(scrc_ctx* ctx, double* out) {
         SCRC_CUDA(cudaSetDevice(c.dev.id));
         cudaStream_t st = c.dev.stream;
         AllocScope as(st);
-        // fast_cor(z1_target_centered, z1_reg_scaled) on device copies (R/scregclust.R:1116)
-        DMat X(c.n1, c.T), Y(c.n1, c.P), C(c.T, c.P);
-        SCRC_CUDA(cudaMemcpyAsync(X.data(), c.Z1t.data(), c.Z1t.bytes(), cudaMemcpyDeviceToDevice, st));
-        SCRC_CUDA(cudaMemcpyAsync(Y.data(), c.Z1r.data(), c.Z1r.bytes(), cudaMemcpyDeviceToDevice, st));
-        DevBuf<double> xss(c.T), yss(c.P);
-        col_center_ss(X.data(), X.ld, c.n1, c.T, xss.p, st);
-        col_center_ss(Y.data(), Y.ld, c.n1, c.P, yss.p, st);
-        DenseArgs a{X.data(), X.ld, Y.data(), Y.ld, C.data(), C.ld, (int)c.T, (int)c.P, (int)c.n1};
-        a.rvec = xss.p; a.cvec = yss.p;
-        gemm_tn_dense(EPI_COR, a, c.dev.num_sms, st);
+        DMat C;
+        session_cross_corr(c, C);
         C.download(out, c.T, st);
         SCRC_CUDA(cudaStreamSynchronize(st));
+    });
+}
+
+int scrc_kmeanspp(const double* x, int64_t n, int64_t p, int n_cluster, int n_init_clusterings, int n_max_iter,
+                  const int* first_centers, const double* uniforms, int* cluster_out, double* tot_withinss_out,
+                  int* ifault_out) {
+    if (!x || !first_centers || !uniforms || !cluster_out || n <= 0 || p <= 0)
+        return fail(SCRC_ERR_ARG, "scrc_kmeanspp: null pointer or non-positive dimension");
+    return guarded([&] {
+        Device& dev = dropin_device();
+        cudaStream_t st = dev.stream;
+        AllocScope as(st);
+        DMat X(n, p);
+        X.upload(x, n, st);
+        kmeanspp_device(st, X.data(), X.ld, n, p, n_cluster, n_init_clusterings, n_max_iter, first_centers, uniforms,
+                        cluster_out, tot_withinss_out, ifault_out);
+    });
+}
+
+int scrc_ctx_kmeanspp(scrc_ctx* ctx, int n_init_clusterings, int n_max_iter, const int* first_centers,
+                      const double* uniforms, int* cluster_out, double* tot_withinss_out, int* ifault_out) {
+    if (!ctx || !first_centers || !uniforms || !cluster_out) return fail(SCRC_ERR_ARG, "scrc_ctx_kmeanspp: null pointer");
+    return guarded([&] {
+        Ctx& c = ctx->impl;
+        SCRC_CUDA(cudaSetDevice(c.dev.id));
+        cudaStream_t st = c.dev.stream;
+        AllocScope as(st);
+        DMat C;
+        session_cross_corr(c, C);                   // the matrix R clusters (R/scregclust.R:1131-1136), never leaves the device
+        kmeanspp_device(st, C.data(), C.ld, c.T, c.P, c.K, n_init_clusterings, n_max_iter, first_centers, uniforms,
+                        cluster_out, tot_withinss_out, ifault_out);
     });
 }
 

@@ -131,6 +131,11 @@ struct Ctx {
 void validate_prior_inputs(const char* who, const int* k, int64_t T, int K, const int* prior_off, const int* prior_idx,
                            const int* order);
 
+// kmeanspp() of R/utils.R:351-375 on a device-resident n x p matrix (kmeans.cu); the caller owns R's RNG draws
+void kmeanspp_device(cudaStream_t st, const double* x_dev, int64_t ldx, int64_t n, int64_t p, int K, int n_init,
+                     int n_max_iter, const int* first_centers, const double* uniforms, int* cluster_out,
+                     double* tot_withinss_out, int* ifault_out);
+
 // drop-in helpers (session.cu)
 void dropin_coop_lasso(Device& dev, const double* y, int64_t n, int64_t m, const double* x, int64_t p, double lambda,
                        const double* weights, const double* beta0, const AdmmOpts& o, double* beta_out, int* iters);

@@ -203,6 +203,17 @@ class Session:
         check(self._lib.scrc_ctx_get_gram(self._h, dptr(g_rr), dptr(g_rt)))
         return g_rr, g_rt
 
+    def kmeanspp(self, first_centers, uniforms, n_max_iter=100, return_details=False):
+        """``k_start_cl <- kmeanspp(cross_corr1, n_modules, n_initializations, 100L)`` (R/scregclust.R:1131-1136) on the
+        session's own cross_corr1 (it never leaves the device).  ``first_centers`` / ``uniforms``: R's draws, see
+        :func:`scregclust_b200.api.kmeanspp`."""
+        fc = np.ascontiguousarray(first_centers, dtype=np.int32)
+        u = np.ascontiguousarray(uniforms, dtype=np.float64).reshape(fc.size, self.K - 1)
+        cl = np.zeros(self.T, dtype=np.int32); tot = np.zeros(fc.size); fault = np.zeros(fc.size, dtype=np.int32)
+        check(self._lib.scrc_ctx_kmeanspp(self._h, int(fc.size), int(n_max_iter), iptr(fc), dptr(u), iptr(cl), dptr(tot),
+                                          iptr(fault)))
+        return (cl, tot, fault) if return_details else cl
+
     def cross_corr(self):
         out = np.zeros((self.T, self.P), order="F")
         check(self._lib.scrc_ctx_cross_corr(self._h, dptr(out)))
