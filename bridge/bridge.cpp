@@ -129,6 +129,23 @@ Rcpp::NumericMatrix scrc_fast_cor_(Rcpp::NumericMatrix x, Rcpp::NumericMatrix y)
   return out;
 }
 
+// kmeanspp(x, n_cluster, n_init_clusterings, n_max_iter) of R/utils.R:351-375 on the device.  The R caller draws
+// first_centers[i] <- sample(n, 1L) and uniforms[, i] <- runif(n_cluster - 1L) per initialisation (bridge/scregclust_b200.R),
+// which consumes R's RNG stream exactly as kmeanspp_init() does.  uniforms: (n_cluster - 1) x n_init.
+// [[Rcpp::export]]
+Rcpp::IntegerVector scrc_kmeanspp_(Rcpp::NumericMatrix x, int n_cluster, Rcpp::IntegerVector first_centers,
+                                   Rcpp::NumericMatrix uniforms, int n_max_iter) {
+  Rcpp::IntegerVector cluster(x.nrow());
+  std::vector<int> ifault(first_centers.size());
+  check(scrc_kmeanspp(x.begin(), x.nrow(), x.ncol(), n_cluster, (int)first_centers.size(), n_max_iter,
+                      first_centers.begin(), uniforms.begin(), cluster.begin(), nullptr, ifault.data()));
+  for (size_t i = 0; i < ifault.size(); ++i) {      // the warnings of stats::kmeans
+    if (ifault[i] == 2) Rcpp::Rcout << "Warning: did not converge in " << n_max_iter << " iterations" << std::endl;
+    if (ifault[i] == 4) Rcpp::Rcout << "Warning: Quick-TRANSfer stage steps exceeded maximum" << std::endl;
+  }
+  return cluster;
+}
+
 static void poll_interrupt(void*) { R_CheckUserInterrupt(); }
 
 // Runs `work` on a worker thread while the R thread polls for a user interrupt every 50 ms; a pending interrupt sets

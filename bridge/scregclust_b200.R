@@ -13,6 +13,20 @@ coef_ols   <- function(y, x)         scrc_coef_ols_(y, x)             # R/utils.
 coef_ridge <- function(y, x, lambda) scrc_coef_ridge_(y, x, lambda)   # R/utils.R:49-57
 fast_cor   <- function(x, y)         scrc_fast_cor_(x, y)             # R/utils.R:533-541
 
+# kmeanspp() of R/utils.R:351-375 with the distances, the seeding bookkeeping and the Hartigan-Wong runs on the device.
+# The draws below consume R's RNG stream exactly as kmeanspp_init() does (one sample(n, 1L), then one unif_rand() per
+# sample.int(prob =) call), so a seeded R session gives the same initial centres with either implementation.
+kmeanspp <- function(x, n_cluster, n_init_clusterings = 10L, n_max_iter = 10L) {
+  n <- nrow(x)
+  first <- integer(n_init_clusterings)
+  u <- matrix(0, n_cluster - 1L, n_init_clusterings)
+  for (i in seq_len(n_init_clusterings)) {
+    first[i] <- sample(n, size = 1L)
+    u[, i] <- runif(n_cluster - 1L)
+  }
+  scrc_kmeanspp_(x, as.integer(n_cluster), first, u, as.integer(n_max_iter))
+}
+
 scrc_grid_fit_r <- function(z1_reg_scaled, z2_reg_scaled, z1_target_centered, z2_target_centered, z1_target_sds,
                             penalization, n_modules, k_start_cl, n_cycles = 50L, noise_threshold = 0.025,
                             min_module_size = 0L, max_optim_iter = 10000L, tol_coop_rel = 1e-8, tol_coop_abs = 1e-12,
