@@ -122,6 +122,19 @@ def test_forced_last_cycle_after_n_cycles(case):
     assert all(g.n_cycles_run <= 3 for g in got)
 
 
+def test_zero_cycles_refits_the_initial_configuration(case):
+    """n_cycles = 0: cycle 1 is already the forced last cycle (R/scregclust.R:1269-1284) -- one re-fit of k_start, no allocation."""
+    from scregclust_b200.driver import scregclust_fit
+    w, kw, _ = case
+    ref = orc.scregclust_fit(w.z1_reg, w.z2_reg, w.z1_target, w.z2_target, w.z1_target_sds, w.penalization,
+                             w.n_modules, w.k_init, n_cycles=0, **kw)
+    ses = OracleSession(w)
+    got = scregclust_fit(penalization=w.penalization, n_modules=w.n_modules, initial_target_modules=w.k_init,
+                         session=ses, n_cycles=0, **kw)
+    _same(got, ref)
+    assert ses.calls == [(len(w.penalization), True)] and all(not g.converged and g.n_cycles_run == 1 for g in got)
+
+
 def test_quick_mode_bookkeeping_of_the_loop(case):
     """quick mode (R/scregclust.R:1435-1496): no subset in cycle 1, afterwards R's `idx` (the latest allocation) goes
     with every call -- also with the final re-fit -- and the trajectory equals the oracle's quick-mode run."""
