@@ -160,20 +160,22 @@ def cpu_sample(w, budget_s, lam, totals, gpu_first_cycle=None):
             spot["sets_equal"] &= bool(np.array_equal(gpu_first_cycle["models"][:, j - 1], c["models"][:, j - 1]))
     sec_per_iter = t1 / max(its, 1)
     sec_per_model = t2 / max(done2, 1)
-    # ---- array reset + allocation on a gene subset (the full K x n2 x T array is 8 GB at config 3)
+    # ---- array reset, the per-module strided writes and the allocation on a gene subset (the full K x n2 x T array is
+    # 8 GB at config 3): exactly the operations of one cycle of oracle/twin_cycle.full_fit
     g = int(max(8, min(T, 2.5e8 // (K * n2 * 8))))
     z2sq = np.asfortranarray(w.z2_target[:, :g] ** 2)
     arr = np.empty((K, n2, g), order="F")
+    nonempty = int(sum(1 for j in range(1, K + 1) if np.any(k == j)))
     t0 = time.perf_counter()
     ref_cpu.fill_array(arr, z2sq)                             # reset_array (src/utils.cpp:43-63)
-    arr[0, :, :] = z2sq * 0.9                                 # one strided module write (scregclust.R:1599)
+    for j in range(nonempty):
+        arr[j, :, :] = z2sq * 0.9                             # sq_residuals_test[j, , ] <- ... (scregclust.R:1599)
     t_fill = time.perf_counter() - t0
     rv = np.asfortranarray(np.ones((g, K)))
     t0 = time.perf_counter()
     ref_cpu.allocate_into_modules(arr, rv, None, None, np.ones(g, dtype=np.int32), np.arange(g, dtype=np.int32), 1e-6, 0.0)
     t_alloc = time.perf_counter() - t0
-    nonempty = int(sum(1 for j in range(1, K + 1) if np.any(k == j)))
-    sec_per_gene_cycle = (t_fill * (1 + (nonempty - 1) * 0.5) + t_alloc) / g
+    sec_per_gene_cycle = (t_fill + t_alloc) / g
     # ---- post-processing: leave-one-regulator-out NNLS importance (R/scregclust.R:1823-1912) on one module
     t_imp, imp_mods = 0.0, 0
     for j, c in sample.items():
