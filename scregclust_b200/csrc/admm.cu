@@ -34,7 +34,8 @@ struct AdmmDev {
     int force_small;       // batch too small for large tiles: always 64 x 64
     double small_cost;     // time of a 64 x 64 tile relative to a large one (measured, see admm_solve)
 };
-constexpr int TILE_HDR = 4;   // tiles[0] = live 64-col tiles, [1] = live 128-col tiles, [2] = tile shape of the next sweep
+constexpr int TILE_HDR = 4;   // tiles[0] = live 64-col tiles, [1] = live 128-col tiles, [2] = 128-col tiles given to the large-tile kernel,
+                              // [3] = position in the 64-col list where the 64 x 64 kernel starts
 
 void AdmmBatch::resize(int P_, int C_, int nprob_) {
     P = P_; C = C_; nprob = nprob_;
@@ -104,14 +105,42 @@ __device__ void admm_tile_lists(const AdmmDev& d) {
         if (threadIdx.x == 0) d.tiles[pass] = s_run;
         __syncthreads();
     }
-    // Tile shape of the next sweep, from the exact live-tile counts: whole waves of large tiles against whole waves
-    // of 64 x 64 tiles (4-5 x as many CTAs, each cheaper but less efficient).  Both shapes give the same bits: the
+    // Tile shapes of the next sweep, from the exact live-tile lists.  The large-tile kernel takes a PREFIX of the
+    // 128-column list sized to whole waves of the device (tiles[2] entries), the 64 x 64 kernel takes the live
+    // 64-column tiles to the right of that prefix (from list position tiles[3]): the last, partly filled wave of
+    // large tiles is replaced by waves of tiles a fifth of the size.  Candidates = every whole number of large waves
+    // near the total (and none at all); cost in units of one large tile.  Every split gives the same bits: the
     // accumulation order along k does not depend on the tile.
-    if (threadIdx.x == 0) {
-        const long long tb = (long long)((d.P + d.bm_big - 1) / d.bm_big) * d.tiles[1];
-        const long long ts = (long long)((d.P + 63) / 64) * d.tiles[0];
-        const double wb = (double)((tb + d.nsm - 1) / d.nsm), ws = (double)((ts + d.nsm - 1) / d.nsm) * d.small_cost;
-        d.tiles[2] = (d.force_small || ws < wb) ? 1 : 0;
+    if (threadIdx.x < 32) {
+        const int t64 = d.tiles[0], t128 = d.tiles[1];
+        const int* l64 = d.tiles + TILE_HDR;
+        const int* l128 = l64 + d.n64;
+        const long long rb = (d.P + d.bm_big - 1) / d.bm_big, rs = (d.P + 63) / 64;
+        const long long wb = (rb * t128 + d.nsm - 1) / d.nsm;            // waves if every tile were large
+        // lane 0: no large tiles; lanes 1..31: wb - 30 + lane whole waves of large tiles (clamped)
+        long long w = (lane == 0) ? 0 : wb - 31 + lane;
+        if (w < 0) w = 0;
+        long long nb = d.force_small ? 0 : (w * d.nsm) / rb;
+        if (nb > t128) nb = t128;
+        int start = t64;                                                  // first 64-column tile right of the prefix
+        if (nb < t128) {
+            const int bound = l128[nb] * 2;
+            int lo = 0, hi = t64;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (l64[mid] < bound) lo = mid + 1; else hi = mid; }
+            start = lo;
+        }
+        const double cost = (double)((rb * nb + d.nsm - 1) / d.nsm) +
+                            (double)((rs * (t64 - start) + d.nsm - 1) / d.nsm) * d.small_cost;
+        // arg-min over the warp; ties go to the candidate with more large tiles
+        double bc = cost; long long bn = nb; int bs = start;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double oc = __shfl_xor_sync(0xffffffffu, bc, o);
+            const long long on = __shfl_xor_sync(0xffffffffu, bn, o);
+            const int os = __shfl_xor_sync(0xffffffffu, bs, o);
+            if (oc < bc || (oc == bc && on > bn)) { bc = oc; bn = on; bs = os; }
+        }
+        if (lane == 0) { d.tiles[2] = (int)bn; d.tiles[3] = bs; }
     }
 }
 __global__ void __launch_bounds__(1024) admm_tiles_kernel(AdmmDev d) { admm_tile_lists(d); }
@@ -154,15 +183,16 @@ struct AdmmGemmPolicy {
         const int* active;
         const double* rho;
         const double* lam;
-        const int* tile_count;   // live column tiles of this tile width ...
-        const int* tile_list;    // ... and their indices (admm_tile_lists)
-        const int* shape;        // tile shape chosen on the device for this sweep (0 large, 1 small)
+        const int* hdr;          // tile header written by admm_tile_lists (counts and the split between the shapes)
+        const int* tile_list;    // live column tiles of this tile width
     };
     __device__ static int tiles_m(const Params& p) { return (p.P + BM - 1) / BM; }
-    // both shapes are launched every sweep; the one that was not chosen finds no tiles and exits
-    __device__ static int num_tiles(const Params& p) { return (*p.shape == (BN == 64 ? 1 : 0)) ? tiles_m(p) * (*p.tile_count) : 0; }
+    // both shapes are launched every sweep: the large one walks the first hdr[2] entries of the 128-column list,
+    // the 64 x 64 one the 64-column list from position hdr[3]; either may find nothing to do and exits
+    __device__ static int first(const Params& p) { return BN == 64 ? p.hdr[3] : 0; }
+    __device__ static int num_tiles(const Params& p) { return tiles_m(p) * (BN == 64 ? p.hdr[0] - p.hdr[3] : p.hdr[2]); }
     __device__ static bool tile(const Params& p, int t, TileInfo& ti) {
-        const int tm = t % tiles_m(p), tn = p.tile_list[t / tiles_m(p)];
+        const int tm = t % tiles_m(p), tn = p.tile_list[first(p) + t / tiles_m(p)];
         ti.ta = &p.ta; ti.tb = &p.tb;
         ti.m0 = tm * BM; ti.n0 = tn * BN; ti.k0 = 0; ti.k1 = p.P;
         return true;
@@ -198,9 +228,8 @@ static void launch_admm_gemm(const AdmmDev& d, const DMat& A, const double* Bm, 
     p.out = out; p.ld = d.ld; p.P = d.P; p.C = d.C;
     p.col_prob = d.col_prob; p.active = d.active; p.rho = d.rho; p.lam = lam;
     static_assert(BN == 64 || BN == 128, "tile lists exist for 64- and 128-column tiles");
-    p.tile_count = d.tiles + (BN == 64 ? 0 : 1);
+    p.hdr = d.tiles;
     p.tile_list = d.tiles + TILE_HDR + (BN == 64 ? 0 : d.n64);
-    p.shape = d.tiles + 2;
     constexpr int smem = GemmSmem<BM, BN, STAGES>::TOTAL;
     static SmemAttr attr;
     attr.ensure(gemm_tn_kernel<Pol>, smem);

@@ -273,11 +273,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) resid_vote_kernel(const __gri
 }
 
 int resid_vote_pick_cr(int ncells, int T, int L, int num_sms) {
-    // Cell ranges per (fit, target tile).  The kernel only adds integer votes, so the split does not affect any
-    // result; 1024 cells per CTA amortise the per-CTA staging of the score constants.
-    (void)T; (void)L; (void)num_sms;
-    const int ctiles = (int)ceil_div(ncells, RV_BM);
-    return std::max(1, (int)ceil_div(ctiles, 16));   // 16 cell tiles (1024 cells) per CTA
+    // Cell ranges per (fit, target tile); T = width of the target slice the launch covers.  The kernel only adds
+    // integer votes, so the split does not affect any result.  16 cell tiles (1024 cells) per CTA amortise the
+    // per-CTA staging of the score constants; launches with few fits or a narrow slice (late cycles, one rank of
+    // several) split finer -- down to 4 cell tiles per CTA -- so that the grid keeps about 6 waves of 2 CTAs per SM.
+    const int64_t ctiles = ceil_div(ncells, RV_BM), tiles_n = std::max<int64_t>(1, ceil_div(T, RV_BN));
+    int per = 16;
+    while (per > 4 && (int64_t)L * tiles_n * ceil_div(ctiles, per) < (int64_t)12 * num_sms) per >>= 1;
+    return std::max(1, (int)ceil_div(ctiles, per));
 }
 void resid_vote(const ResidVoteArgs& a, int mode, int num_sms, cudaStream_t st) {
     if (a.K + 1 > RV_MAX_K + 1) throw Error(-60, "resid_vote: at most 64 modules are supported");

@@ -754,7 +754,7 @@ void Ctx::fit_cycle(int F, const double* lambda, const int* k_in, const scrc_opt
 
     pt.mark(phase_s, 4);
     // ---------------- Step 2a/2b: residuals, SSE, variances, votes ----------------
-    const int CRte = resid_vote_pick_cr((int)n2, (int)T, F, dev.num_sms);
+    const int CRte = resid_vote_pick_cr((int)n2, t1 - t0, F, dev.num_sms);
     const size_t fkt = (size_t)F * K * T, fk1t = (size_t)F * (K + 1) * T, ft = (size_t)F * T;
     sse_train.ensure(fk1t); sse_test.ensure(fk1t); var.ensure(fkt); two_var.ensure(fkt); inv_two_var.ensure(fkt); half_log.ensure(fkt);
     r2.ensure(fkt); best_r2.ensure(ft); best_idx.ensure(ft); k_new.ensure(ft);

@@ -105,8 +105,10 @@ def test_nnls_against_scipy(rng):
     assert np.all(grad[beta == 0] > -1e-7)                    # complementary slackness
 
 
-def test_nnls_unconverged_columns_are_zero(rng):
-    x = rng.standard_normal((100, 6)); y = rng.standard_normal((100, 4))
+def test_nnls_unconverged_columns_are_zero():
+    rng = np.random.default_rng(7)          # own stream: every column must need more than two outer iterations
+    x = rng.standard_normal((100, 6))
+    y = x @ (rng.random((6, 4)) + 0.5) + 0.1 * rng.standard_normal((100, 4))
     beta, its = orc.coef_nnls(x, y, eps=1e-300, max_iter=2)
     assert np.all(its == 2) and np.all(beta == 0)             # optim.cpp:423,502
 
