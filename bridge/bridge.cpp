@@ -174,7 +174,8 @@ Rcpp::List scrc_grid(Rcpp::NumericMatrix z1_reg, Rcpp::NumericMatrix z2_reg, Rcp
                      Rcpp::NumericMatrix z2_target, Rcpp::NumericVector z1_target_sds, Rcpp::NumericVector penalization,
                      int n_modules, Rcpp::IntegerVector initial_target_modules, int n_cycles, double noise_threshold,
                      int min_module_size, int max_optim_iter, double tol_coop_rel, double tol_coop_abs, double tol_nnls,
-                     bool compute_predictive_r2, bool quick_mode, double quick_mode_percent, Rcpp::List prior_indicator,
+                     bool compute_predictive_r2, bool quick_mode, double quick_mode_percent, bool allocate_per_obs,
+                     Rcpp::List prior_indicator,
                      double prior_baseline, double prior_weight, Rcpp::IntegerMatrix update_orders /* T x (L * cycles) or 0 x 0 */,
                      Rcpp::IntegerVector devices) {
   const int64_t n1 = z1_reg.nrow(), n2 = z2_reg.nrow(), P = z1_reg.ncol(), T = z1_target.ncol();
@@ -187,6 +188,7 @@ Rcpp::List scrc_grid(Rcpp::NumericMatrix z1_reg, Rcpp::NumericMatrix z2_reg, Rcp
   gp.opt.tol_nnls = tol_nnls;
   gp.compute_predictive_r2 = compute_predictive_r2; gp.keep_coeffs = 1;
   gp.quick_mode = quick_mode; gp.quick_mode_percent = quick_mode_percent;
+  gp.allocate_per_obs = allocate_per_obs;            // FALSE: the aggregate branch of R/scregclust.R:1678-1728
   std::vector<int> off, idx;
   if (prior_weight != 0.0 && prior_indicator.size() == T) {
     prior_csr(prior_indicator, T, off, idx);

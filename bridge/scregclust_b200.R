@@ -31,7 +31,7 @@ scrc_grid_fit_r <- function(z1_reg_scaled, z2_reg_scaled, z1_target_centered, z2
                             penalization, n_modules, k_start_cl, n_cycles = 50L, noise_threshold = 0.025,
                             min_module_size = 0L, max_optim_iter = 10000L, tol_coop_rel = 1e-8, tol_coop_abs = 1e-12,
                             tol_nnls = 1e-4, compute_predictive_r2 = TRUE, quick_mode = FALSE, quick_mode_percent = 0.1,
-                            prior_indicator_list = list(), prior_baseline = 1e-6, prior_weight = 0,
+                            allocate_per_obs = TRUE, prior_indicator_list = list(), prior_baseline = 1e-6, prior_weight = 0,
                             devices = 0L) {
   n_target <- ncol(z1_target_centered)
   update_orders <- matrix(0L, 0L, 0L)
@@ -45,7 +45,8 @@ scrc_grid_fit_r <- function(z1_reg_scaled, z2_reg_scaled, z1_target_centered, z2
     z1_reg_scaled, z2_reg_scaled, z1_target_centered, z2_target_centered, z1_target_sds,
     as.double(penalization), as.integer(n_modules), as.integer(k_start_cl), as.integer(n_cycles),
     noise_threshold, as.integer(min_module_size), as.integer(max_optim_iter), tol_coop_rel, tol_coop_abs, tol_nnls,
-    compute_predictive_r2, quick_mode, quick_mode_percent, prior_indicator_list, prior_baseline, prior_weight,
+    compute_predictive_r2, quick_mode, quick_mode_percent, allocate_per_obs, prior_indicator_list, prior_baseline,
+    prior_weight,
     update_orders, as.integer(devices)
   )
 }

@@ -237,13 +237,20 @@ int scrc_importance_ex(scrc_ctx* ctx, int F, const int* k_final, const unsigned 
  * prior_off / prior_idx: CSR form of `prior_indicator` over the T target genes (0-based neighbours);
  * update_order: F x T, the 0-based permutation R draws with sample() for each fit and cycle
  * (R/scregclust.R:1666) -- the caller owns the RNG, so the result matches a serial R run only if it
- * replays R's draws.  With prior_weight == 0 this is identical to scrc_fit_cycle. */
+ * replays R's draws.  With prior_weight == 0 this is identical to scrc_fit_cycle.
+ * aggregate != 0 selects the `allocate_per_obs = FALSE` branch of Step 2b instead (R/scregclust.R:1678-1728): genes
+ * are reassigned from the per-module test sums of squares and residual variances of the cycle (no pass over the
+ * cells), mixed with the prior as written there; prior_off / update_order may then be NULL (no prior: the result
+ * does not depend on the order).  update_order is 0-based here too (R draws 1-based gene indices at :1702).
+ * The reference's argument checks make this branch unreachable in v0.2.2 (:807-817); it is provided for
+ * completeness and reproduces the source as written. */
 typedef struct scrc_prior {
     const int* prior_off;      /* T + 1 */
     const int* prior_idx;      /* prior_off[T] entries */
     double baseline;           /* prior_baseline (1e-6) */
     double weight;             /* prior_weight   (0.5)  */
     const int* update_order;   /* F x T */
+    int aggregate;             /* 0: per-cell votes (allocate_per_obs = TRUE); 1: aggregate branch */
 } scrc_prior;
 int scrc_fit_cycle_prior(scrc_ctx* ctx, int F, const double* lambda, const int* k_in, const scrc_options* opt,
                          const scrc_prior* prior, scrc_cycle_out* out);
@@ -336,6 +343,7 @@ typedef struct scrc_grid_params {
     void* update_order_user;
     int quick_mode;                         /* R/scregclust.R:201: 0 */
     double quick_mode_percent;              /* 0.1 */
+    int allocate_per_obs;                   /* R/scregclust.R:199: 1; 0 = aggregate branch (see scrc_prior.aggregate) */
     /* Optional interrupt flag owned by the caller (NULL: none): polled before every device call of the loop; once
      * it reads non-zero the fit stops with SCRC_ERR_INTERRUPTED on every rank (same mechanism as
      * scrc_ctx_request_cancel).  The bridge sets it from the R thread while the fit runs on a worker thread. */

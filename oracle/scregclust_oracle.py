@@ -476,6 +476,57 @@ def allocate_into_modules(resid_array, resid_var, prior_indicator, k_, update_or
     return (out, votes_all) if return_votes else out
 
 
+def allocate_aggregate(k_, sum_squares_test, resid_var, n2, prior_indicator, update_order,
+                       prior_baseline, prior_weight, ambiguity=None):
+    """Aggregate reallocation, the ``allocate_per_obs = FALSE`` branch of Step 2b (R/scregclust.R:1678-1728).
+
+    ``sum_squares_test`` / ``resid_var`` are T x K, ``k_`` 1-based (-1 noise), ``update_order`` 0-based here (R draws
+    1-based gene indices, ``sample(length(idx), length(idx))``), ``prior_indicator`` 0-based as everywhere.
+    Restated as written, including what looks unintended: the scores are built from
+    ``n2 log(2 pi s2) + SS / s2`` (minus twice a log-likelihood) but normalised like log-probabilities, mixed with
+    the prior's log-probabilities and minimised (``which.min``), and ``module_totals`` is computed once from the
+    incoming configuration and never updated while genes move.  The branch cannot be reached through the
+    public API of v0.2.2 (the argument check at R/scregclust.R:807-817 rejects ``allocate_per_obs = FALSE``).
+    ``ambiguity`` (optional int array of length T, filled in place): 1 where the two smallest scores of a gene agree to
+    ``AMBIGUITY_REL`` relative -- ``log`` / ``exp`` differ in the last place between math libraries.
+    """
+    idx = np.asarray(k_, dtype=np.int64).copy()
+    n_genes, n_modules = resid_var.shape
+    module_totals = np.array([np.sum(idx == i) for i in range(1, n_modules + 1)], dtype=np.float64)   # :1682
+    with np.errstate(all="ignore"):
+        mll = float(n2) * np.log((2.0 * math.pi) * resid_var) + sum_squares_test / resid_var          # :1685-1688
+        d = mll - np.max(mll, axis=1)[:, None]                                                        # :1691-1694
+        rs = np.zeros(n_genes, dtype=np.longdouble)            # rowSums accumulates in long double, column by column
+        for j in range(n_modules):
+            rs = rs + np.exp(d[:, j])
+        mlp = d - np.log(rs.astype(np.float64))[:, None]                                               # :1695-1698
+    for gene in update_order:
+        prior_frac = np.zeros(n_modules)
+        pri = prior_indicator[gene] if len(prior_indicator) > 0 else ()
+        for i in pri:                                                                                  # :1706-1714
+            if 1 <= idx[i] <= n_modules:
+                prior_frac[idx[i] - 1] += 1.0
+        nz = module_totals > 0
+        prior_frac[nz] = prior_frac[nz] / module_totals[nz]                                            # :1716-1718
+        prior_frac = prior_frac + prior_baseline
+        tot = np.longdouble(0.0)                               # sum() accumulates in long double
+        for v in prior_frac:
+            tot = tot + v
+        with np.errstate(all="ignore"):
+            prior_log_prob = np.log(prior_frac) - math.log(float(tot))                                 # :1720
+            total = (1.0 - prior_weight) * mlp[gene] + prior_weight * prior_log_prob                   # :1722-1725
+        ok = ~np.isnan(total)
+        if not ok.any():
+            raise ValueError("which.min of an all-NaN score vector (R: replacement has length zero)")
+        cand = np.where(ok, total, np.inf)
+        best = int(np.argmin(cand))                            # which.min: first minimum, NaN skipped
+        if ambiguity is not None and n_modules > 1:
+            two = np.partition(cand, 1)[:2]
+            ambiguity[gene] = int((two[1] - two[0]) <= AMBIGUITY_REL * max(1.0, abs(two[0])))
+        idx[gene] = best + 1                                                                           # :1727
+    return idx.astype(np.int32)
+
+
 # --------------------------------------------------------------------------- #
 # R/utils.R:13-57, 533-541, 631-656
 # --------------------------------------------------------------------------- #
@@ -635,7 +686,8 @@ class FitResult:
     best_r2_idx: list = field(default_factory=list)        # T (1-based)
     admm_iterations: list = field(default_factory=list)    # per cycle: length-K int (0 = skipped)
     nnls_iterations: list = field(default_factory=list)    # per cycle: K x T int (0 = skipped)
-    votes: list = field(default_factory=list)              # per cycle: T x K int
+    votes: list = field(default_factory=list)              # per cycle: T x K int (None in the aggregate branch)
+    allocations: list = field(default_factory=list)        # per cycle: T int, Step 2b's result before the noise / size rules
     ambiguity: list = field(default_factory=list)          # per cycle: T int (rounding-tied cells)
     models_history: list = field(default_factory=list)
     resid_var_history: list = field(default_factory=list)  # per cycle T x K
@@ -693,9 +745,10 @@ def scregclust_fit(z1_reg_scaled, z2_reg_scaled, z1_target_centered, z2_target_c
                    max_optim_iter=10000, tol_coop_rel=1e-8, tol_coop_abs=1e-12,
                    tol_nnls=1e-4, update_orders=None, compute_predictive_r2=False,
                    materialize_array=True, pre=None, keep_history=False, quick_mode=False,
-                   quick_mode_percent=0.1, quick_first_cycle_idx=None):
+                   quick_mode_percent=0.1, quick_first_cycle_idx=None, allocate_per_obs=True):
     """The alternating loop of ``scregclust()`` (R/scregclust.R:1222-1803) for
-    ``allocate_per_obs = TRUE``, ``quick_mode = FALSE``.
+    ``allocate_per_obs = TRUE`` (default) or the aggregate branch (``allocate_per_obs=False``, scregclust.R:1678-1728,
+    unreachable through the reference's argument checks but part of its source).
 
     ``update_orders`` -- optional callable ``(penalty_index, cycle) -> permutation``
     standing in for R's ``sample()`` (scregclust.R:1666); default = identity, which
@@ -728,6 +781,10 @@ def scregclust_fit(z1_reg_scaled, z2_reg_scaled, z1_target_centered, z2_target_c
     ss_train0 = np.sum(z1t * z1t, axis=0)
     ss_test0 = np.sum(z2sq, axis=0)
 
+    if not allocate_per_obs:
+        if quick_mode:
+            raise ValueError("quick_mode only available when allocate_per_obs is TRUE.")          # scregclust.R:807-817
+        materialize_array = False                                                                 # scregclust.R:1177,1521
     sq_arr = alloc_array(z2sq, n_modules) if materialize_array else None
     abs_corr = np.abs(fast_cor(z1t, z1r)) if quick_mode else None          # scregclust.R:1116-1122
     results = []
@@ -822,7 +879,11 @@ def scregclust_fit(z1_reg_scaled, z2_reg_scaled, z1_target_centered, z2_target_c
                 key = (tuple(reg_cl), tuple(signs[reg_cl, j]))
                 if key not in seen:
                     seen.add(key); distinct[j] = True
-            if materialize_array:
+            if not allocate_per_obs:
+                idx = allocate_aggregate(k, ss_test, resid_var, n2, prior_indicator, order, prior_baseline,
+                                         prior_weight, ambiguity=amb)
+                votes = None
+            elif materialize_array:
                 idx, votes = allocate_into_modules(sq_arr, resid_var, prior_indicator, k, order,
                                                    prior_baseline, prior_weight, return_votes=True,
                                                    ambiguity=amb, distinct=distinct)
@@ -832,6 +893,7 @@ def scregclust_fit(z1_reg_scaled, z2_reg_scaled, z1_target_centered, z2_target_c
                                                  prior_weight, amb, distinct)
             fr.votes.append(votes)
             fr.ambiguity.append(amb)
+            fr.allocations.append(np.asarray(idx, dtype=np.int32).copy())
             idx = idx.copy()
             idx[best_r2[cycle] < noise_threshold] = -1
             module_size = np.array([np.sum(idx == i) for i in range(1, n_modules + 1)])

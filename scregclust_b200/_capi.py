@@ -42,7 +42,7 @@ class CycleOut(C.Structure):
 
 class Prior(C.Structure):
     _fields_ = [("prior_off", c_int_p), ("prior_idx", c_int_p), ("baseline", C.c_double), ("weight", C.c_double),
-                ("update_order", c_int_p)]
+                ("update_order", c_int_p), ("aggregate", C.c_int)]
 
 
 class Quick(C.Structure):
@@ -59,7 +59,7 @@ class GridParams(C.Structure):
                 ("keep_diagnostics", C.c_int), ("prior_off", c_int_p), ("prior_idx", c_int_p),
                 ("prior_baseline", C.c_double), ("prior_weight", C.c_double), ("update_order", UPDATE_ORDER_FN),
                 ("update_order_user", C.c_void_p), ("quick_mode", C.c_int), ("quick_mode_percent", C.c_double),
-                ("cancel", C.POINTER(C.c_int))]
+                ("allocate_per_obs", C.c_int), ("cancel", C.POINTER(C.c_int))]
 
 
 class GridInfo(C.Structure):

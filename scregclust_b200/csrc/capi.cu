@@ -52,7 +52,7 @@ extern "C" {
 
 void scrc_set_last_error_(const char* msg) { g_err = msg ? msg : ""; }
 
-int scrc_version(void) { return 200; }
+int scrc_version(void) { return 201; }
 const char* scrc_last_error(void) { return g_err.c_str(); }
 unsigned long long scrc_launch_count(void) { return scrc::g_launch_count.load(); }
 int scrc_set_device(int device) {

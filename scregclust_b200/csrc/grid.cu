@@ -136,6 +136,9 @@ static void grid_loop(GridBackend& be, const scrc_grid_params& gp, scrc_grid_res
     if (gp.quick_mode && gp.prior_weight != 0.0 && gp.prior_off)
         throw Error(SCRC_ERR_UNSUPPORTED, "scrc_grid_fit: quick mode together with a network prior is not supported");
     const bool use_prior = gp.prior_weight != 0.0 && gp.prior_off != nullptr;
+    const bool aggregate = gp.allocate_per_obs == 0;
+    if (aggregate && gp.quick_mode)                                                       // R/scregclust.R:807-817
+        throw Error(SCRC_ERR_ARG, "quick_mode only available when allocate_per_obs is TRUE.");
     const bool diag = gp.keep_diagnostics != 0;
     res.pens.clear();
     res.pens.resize(L);
@@ -198,13 +201,16 @@ static void grid_loop(GridBackend& be, const scrc_grid_params& gp, scrc_grid_res
                 pr.prior_off = gp.prior_off; pr.prior_idx = gp.prior_idx; pr.baseline = gp.prior_baseline;
                 pr.weight = gp.prior_weight; pr.update_order = orders.data();
             }
+            if (aggregate) {   // allocate_per_obs = FALSE: the prior (if any) enters through the same structure
+                pr.aggregate = 1; pr.baseline = gp.prior_baseline; pr.weight = gp.prior_weight;
+            }
             sweeps = 0;
             if (gp.cancel && *gp.cancel) be.request_cancel();
             const double tc0 = wall_now();
             // quick mode from cycle two on (R/scregclust.R:1444); in a fit cycle R's `idx` is the configuration itself
             scrc_quick qk{ks.data(), gp.quick_mode_percent};
             const bool quick_now = gp.quick_mode && st[run[0]].cycle != 1;
-            be.fit_cycle(F, lam.data(), ks.data(), gp.opt, false, hint.data(), use_prior ? &pr : nullptr,
+            be.fit_cycle(F, lam.data(), ks.data(), gp.opt, false, hint.data(), (use_prior || aggregate) ? &pr : nullptr,
                          quick_now ? &qk : nullptr, &co);
             t_cycle += wall_now() - tc0;
             res.info.admm_sweeps += sweeps; res.info.device_calls += 1;
@@ -407,7 +413,7 @@ void scrc_grid_default_params(scrc_grid_params* p) {
     scrc_default_options(&p->opt);
     p->compute_predictive_r2 = 1; p->keep_coeffs = 1; p->keep_diagnostics = 0;
     p->prior_baseline = 1e-6; p->prior_weight = 0.0;
-    p->quick_mode = 0; p->quick_mode_percent = 0.1;
+    p->quick_mode = 0; p->quick_mode_percent = 0.1; p->allocate_per_obs = 1;
 }
 
 int scrc_grid_fit(scrc_ctx* ctx, const scrc_grid_params* p, scrc_grid_result** out) {

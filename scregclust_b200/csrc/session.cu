@@ -494,16 +494,23 @@ void validate_prior_inputs(const char* who, const int* k, int64_t T, int K, cons
 // spread over the ranks, Step 2 is then replicated on every rank.
 void Ctx::fit_cycle(int F, const double* lambda, const int* k_in, const scrc_options& opt, bool skip_alloc,
                     scrc_cycle_out* out, const scrc_prior* prior, const scrc_quick* quick) {
-    const bool use_prior = prior && prior->weight != 0.0 && !skip_alloc;
+    // aggregate: the allocate_per_obs = FALSE branch of Step 2b (R/scregclust.R:1678-1728); use_prior: the per-cell vote
+    // with a network prior (sequential sweep over a materialised residual array)
+    const bool aggregate = prior && prior->aggregate != 0 && !skip_alloc;
+    const bool agg_prior = aggregate && prior->weight != 0.0 && prior->prior_off != nullptr;
+    const bool use_prior = prior && prior->weight != 0.0 && !skip_alloc && !aggregate;
     const bool use_quick = quick && quick->idx_latest;
     if (use_quick && use_prior) throw Error(SCRC_ERR_UNSUPPORTED, "quick mode together with a network prior is not supported");
+    if (use_quick && aggregate) throw Error(SCRC_ERR_ARG, "quick_mode only available when allocate_per_obs is TRUE.");
+    if (agg_prior && !prior->update_order)
+        throw Error(SCRC_ERR_ARG, "scrc_fit_cycle_prior: update_order is required for the aggregate branch with a prior");
     if (use_quick && !(quick->percent >= 0.0 && quick->percent < 1.0))
         throw Error(SCRC_ERR_ARG, "quick_mode_percent needs to be numeric in [0, 1).");
     if (use_prior && (!prior->update_order || !prior->prior_off))
         throw Error(SCRC_ERR_ARG, "scrc_fit_cycle_prior: prior_off and update_order are required when prior_weight != 0");
     if (F <= 0) throw Error(SCRC_ERR_ARG, "scrc_fit_cycle: F must be positive");
     if ((int64_t)F * K > 65535) throw Error(SCRC_ERR_UNSUPPORTED, "scrc_fit_cycle: more than 65535 (fit, module) pairs in one call");
-    if (use_prior)
+    if (use_prior || agg_prior)
         for (int f = 0; f < F; ++f)
             validate_prior_inputs("scrc_fit_cycle_prior", k_in + (int64_t)f * T, T, K, f == 0 ? prior->prior_off : nullptr,
                                   prior->prior_idx, prior->update_order + (int64_t)f * T);
@@ -736,7 +743,7 @@ void Ctx::fit_cycle(int F, const double* lambda, const int* k_in, const scrc_opt
 
     // target slice of this rank (whole range with a prior: the sweep is sequential)
     int64_t ts0 = 0, ts1 = T;
-    const bool sliced = (W > 1) && !use_prior;
+    const bool sliced = (W > 1) && !use_prior && !aggregate;   // (the aggregate sweep is tiny: replicated like the prior sweep)
     if (sliced) shard_slice(T, RV_BN, R, W, &ts0, &ts1);
     const int t0 = (int)ts0, t1 = (int)ts1;
     const bool want_nnls_it = out && out->nnls_iterations;
@@ -784,13 +791,31 @@ void Ctx::fit_cycle(int F, const double* lambda, const int* k_in, const scrc_opt
                    row_off_d.p, nsel_d.p, (int)T, K, F, sse_test.p, st, t0, t1, ra.col_index, ra.col_off, ra.col_cnt,
                    /*pseudo=*/true);
     // per-cell votes (test split): the only pass over cells of a cycle; skipped in a last cycle
-    if (vote) {
+    const bool cell_votes = vote && !aggregate;
+    if (cell_votes) {
         ZselT.reshape(rows_alloc, n2);
         if (rows_total == 0) SCRC_CUDA(cudaMemsetAsync(ZselT.data(), 0, ZselT.bytes(), st));
         gather_transpose(Z2r.data(), Z2r.ld, (int)n2, row_src.p, rows_total, ZselT.data(), ZselT.ld, st);
         ra.ZselT = ZselT.data(); ra.ldzs = ZselT.ld; ra.Z = Z2t.data(); ra.ldz = Z2t.ld; ra.ncells = (int)n2; ra.CR = CRte;
     }
-    if (!use_prior) {
+    if (aggregate) {
+        // allocate_per_obs = FALSE (R/scregclust.R:1678-1728): reassignment from the T x K test sums of squares and
+        // residual variances of this cycle; no pass over the cells, no votes
+        finish_alloc(sse_test.p, nullptr, (int)T, K, F, r2.p, best_r2.p, best_idx.p, nullptr, st);
+        DevBuf<int> d_kin((size_t)ft), d_off(agg_prior ? T + 1 : 1), d_idx(1), d_order(agg_prior ? (size_t)ft : 1);
+        DevBuf<double> d_mlp(fkt);
+        SCRC_CUDA(cudaMemcpyAsync(d_kin.p, k_in, ft * 4, cudaMemcpyHostToDevice, st));
+        if (agg_prior) {
+            const int nidx = prior->prior_off[T];
+            d_idx.ensure((size_t)std::max(nidx, 1));
+            SCRC_CUDA(cudaMemcpyAsync(d_off.p, prior->prior_off, (T + 1) * 4, cudaMemcpyHostToDevice, st));
+            if (nidx > 0) SCRC_CUDA(cudaMemcpyAsync(d_idx.p, prior->prior_idx, (size_t)nidx * 4, cudaMemcpyHostToDevice, st));
+            SCRC_CUDA(cudaMemcpyAsync(d_order.p, prior->update_order, ft * 4, cudaMemcpyHostToDevice, st));
+        }
+        alloc_aggregate_device(sse_test.p, var.p, K, T, F, (double)n2, d_kin.p, agg_prior ? d_off.p : nullptr, d_idx.p,
+                               agg_prior ? d_order.p : nullptr, prior->baseline, prior->weight, d_mlp.p, k_new.p, st);
+        SCRC_CUDA(cudaStreamSynchronize(st));   // the staging buffers above are released with this scope
+    } else if (!use_prior) {
         if (vote) {
             SCRC_CUDA(cudaMemsetAsync(votes.p, 0, fkt * 4, st));
             resid_vote(ra, 1, dev.num_sms, st);
@@ -871,7 +896,8 @@ void Ctx::fit_cycle(int F, const double* lambda, const int* k_in, const scrc_opt
         auto d2h = [&](void* dst, const void* src, size_t bytes) {
             if (dst && bytes) SCRC_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));
         };
-        if (vote) { d2h(out->k_new, o_kn, ft * 4); d2h(out->votes, o_votes, fkt * 4); }
+        if (vote) { d2h(out->k_new, o_kn, ft * 4); if (cell_votes) d2h(out->votes, o_votes, fkt * 4); }
+        if (aggregate && out->votes) std::memset(out->votes, 0, fkt * 4);   // the aggregate branch casts no votes
         d2h(out->models, models_d.p, FK * P);
         d2h(out->weights, weights_d.p, FK * P * 8);
         d2h(out->signs, signs_d.p, FK * P * 8);
@@ -1382,6 +1408,100 @@ void alloc_sequential_device(const double* d_arr, int K, int64_t n2, int64_t T, 
                              double baseline, double weight, int* d_votes, cudaStream_t st) {
     alloc_sequential_kernel<<<1, 1024, 0, st>>>(d_arr, K, n2, T, d_resid_var, d_prior_off, d_prior_idx, d_k, d_order,
                                                 baseline, weight, d_votes);
+    SCRC_CUDA(cudaGetLastError());
+    SCRC_LAUNCHED();
+}
+
+// ---------------------------------------------------------------- aggregate reallocation (allocate_per_obs = FALSE)
+// R/scregclust.R:1678-1728, restated as written: scores n2 log(2 pi s2) + SS / s2 normalised like log-probabilities
+// (:1685-1698), mixed with the log prior fractions (:1706-1725) and minimised (which.min, :1727); module_totals
+// comes from the incoming configuration and is not updated while genes move (:1682).  One CTA per fit.
+// rowSums() / sum() accumulate in long double in R; a compensated double sum stands in for it here.
+__device__ __forceinline__ void acc2(double& hi, double& lo, double v) {
+    const double t = hi + v;
+    const double bp = t - hi;
+    lo += (hi - (t - bp)) + (v - bp);
+    hi = t;
+}
+__global__ void __launch_bounds__(256) alloc_aggregate_kernel(const double* __restrict__ sse_test, const double* __restrict__ var,
+                                                              int K, int64_t T, double n2, const int* __restrict__ k_in,
+                                                              const int* __restrict__ prior_off, const int* __restrict__ prior_idx,
+                                                              const int* __restrict__ order, double baseline, double w,
+                                                              double* __restrict__ mlp, int* __restrict__ k_out) {
+    __shared__ double s_tot[RV_MAX_K];
+    const int f = blockIdx.x;
+    const double* ss = sse_test + (int64_t)f * (K + 1) * T;
+    const double* vr = var + (int64_t)f * K * T;
+    const int* kin = k_in + (int64_t)f * T;
+    int* idx = k_out + (int64_t)f * T;
+    double* lp = mlp + (int64_t)f * K * T;            // [t][j]
+    for (int j = threadIdx.x; j < K; j += blockDim.x) s_tot[j] = 0.0;
+    __syncthreads();
+    if (threadIdx.x == 0)
+        for (int64_t t = 0; t < T; ++t) if (kin[t] >= 1 && kin[t] <= K) s_tot[kin[t] - 1] += 1.0;      // :1682
+    auto mll = [&](int64_t t, int j) {
+        const double v = vr[(int64_t)j * T + t];
+        return n2 * log((2.0 * M_PI) * v) + ss[(int64_t)j * T + t] / v;                                // :1685-1688
+    };
+    for (int64_t t = threadIdx.x; t < T; t += blockDim.x) {
+        idx[t] = kin[t];                                                                                // idx <- k (:1681)
+        double mx = -INFINITY;
+        for (int j = 0; j < K; ++j) { const double m = mll(t, j); if (m > mx) mx = m; }   // (a NaN score leaves the gene where it is)
+        double hi = 0.0, lo = 0.0;
+        for (int j = 0; j < K; ++j) acc2(hi, lo, exp(mll(t, j) - mx));
+        const double lrs = log(hi + lo);
+        for (int j = 0; j < K; ++j) lp[t * K + j] = (mll(t, j) - mx) - lrs;                             // :1691-1698
+    }
+    __syncthreads();
+    auto pick = [&](int64_t g, const double* plp) {
+        int bi = -1; double best = 0.0;
+        for (int j = 0; j < K; ++j) {
+            const double tot = (1.0 - w) * lp[g * K + j] + w * plp[j];                                  // :1722-1725
+            if (tot == tot && (bi < 0 || tot < best)) { best = tot; bi = j; }                           // which.min
+        }
+        if (bi >= 0) idx[g] = bi + 1;
+    };
+    if (!prior_off) {
+        // no prior entries: every gene sees the same prior fractions, so the order does not matter
+        __shared__ double s_plp[RV_MAX_K];
+        if (threadIdx.x == 0) {
+            double hi = 0.0, lo = 0.0;
+            for (int j = 0; j < K; ++j) acc2(hi, lo, 0.0 / (s_tot[j] > 0.0 ? s_tot[j] : 1.0) + baseline);
+            const double ls = log(hi + lo);
+            for (int j = 0; j < K; ++j) s_plp[j] = log(0.0 + baseline) - ls;
+        }
+        __syncthreads();
+        for (int64_t t = threadIdx.x; t < T; t += blockDim.x) pick(t, s_plp);
+        return;
+    }
+    if (threadIdx.x != 0) return;
+    const int* ord = order + (int64_t)f * T;
+    double frac[RV_MAX_K], plp[RV_MAX_K];
+    for (int64_t oi = 0; oi < T; ++oi) {
+        const int64_t g = ord[oi];
+        for (int j = 0; j < K; ++j) frac[j] = 0.0;
+        for (int e = prior_off[g]; e < prior_off[g + 1]; ++e) {                                         // :1706-1714
+            const int m = idx[prior_idx[e]];
+            if (m >= 1 && m <= K) frac[m - 1] += 1.0;
+        }
+        double hi = 0.0, lo = 0.0;
+        for (int j = 0; j < K; ++j) {
+            if (s_tot[j] > 0.0) frac[j] /= s_tot[j];                                                    // :1716-1718
+            frac[j] += baseline;
+            acc2(hi, lo, frac[j]);
+        }
+        const double ls = log(hi + lo);
+        for (int j = 0; j < K; ++j) plp[j] = log(frac[j]) - ls;                                         // :1720
+        pick(g, plp);
+    }
+}
+
+void alloc_aggregate_device(const double* d_sse_test, const double* d_var, int K, int64_t T, int F, double n2,
+                            const int* d_k_in, const int* d_prior_off, const int* d_prior_idx, const int* d_order,
+                            double baseline, double weight, double* d_mlp, int* d_k_out, cudaStream_t st) {
+    if (K > RV_MAX_K) throw Error(SCRC_ERR_UNSUPPORTED, "aggregate allocation: at most 64 modules are supported");
+    alloc_aggregate_kernel<<<F, 256, 0, st>>>(d_sse_test, d_var, K, T, n2, d_k_in, d_prior_off, d_prior_idx, d_order,
+                                              baseline, weight, d_mlp, d_k_out);
     SCRC_CUDA(cudaGetLastError());
     SCRC_LAUNCHED();
 }

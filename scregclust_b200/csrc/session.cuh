@@ -146,6 +146,9 @@ void dropin_ols(Device& dev, const double* y, const double* x, int64_t n, int64_
                 bool ridge, double* beta_out);
 void dropin_crossprod(Device& dev, const double* x, const double* y, int64_t n, int64_t px, int64_t py, double* out);
 // Sequential Gauss-Seidel allocation sweep on a device-resident array (allocation.cpp:33-97).
+void alloc_aggregate_device(const double* d_sse_test, const double* d_var, int K, int64_t T, int F, double n2,
+                            const int* d_k_in, const int* d_prior_off, const int* d_prior_idx, const int* d_order,
+                            double baseline, double weight, double* d_mlp, int* d_k_out, cudaStream_t st);
 void alloc_sequential_device(const double* d_arr, int K, int64_t n2, int64_t T, const double* d_resid_var,
                              const int* d_prior_off, const int* d_prior_idx, int* d_k /* 0-based, -2 noise, in/out */,
                              const int* d_order, double baseline, double weight, int* d_votes, cudaStream_t st);

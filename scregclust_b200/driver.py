@@ -221,8 +221,11 @@ class Session:
 
     # ------------------------------------------------------------------ one batched cycle
     def fit_cycle(self, lambdas, ks, options=None, skip_allocation=False, want_votes=False, want_nnls_iters=False,
-                  prior=None, light=False, quick=None):
+                  prior=None, light=False, quick=None, aggregate=False):
         """Step 1 + 2a (+ 2b) for ``F`` (lambda, k) pairs; returns a dict of arrays in R's layouts.
+
+        ``aggregate``: Step 2b by the ``allocate_per_obs = FALSE`` branch (R/scregclust.R:1678-1728) -- from the cycle's
+        test sums of squares and variances, no votes; ``prior`` is optional then.
 
         ``quick``: optional ``(idx_latest[F, T], quick_mode_percent)`` -- quick mode (R/scregclust.R:1435-1496).
 
@@ -259,13 +262,18 @@ class Session:
         out.admm_iterations = iptr(res["admm_iterations"]); out.nnls_iterations = iptr(res["nnls_iterations"])
         out.n_selected = iptr(res["n_selected"])
         out.admm_sweeps = C.pointer(sweeps)
+        if aggregate and quick is not None:
+            raise ValueError("quick_mode only available when allocate_per_obs is TRUE.")
         if prior is not None and not skip_allocation and float(prior[2]) != 0.0:
             from .api import _csr
             off, idx = _csr(prior[0], T)
             if off is None:
                 off = np.zeros(T + 1, dtype=np.int32); idx = np.zeros(1, dtype=np.int32)
             orders = np.ascontiguousarray(prior[3], dtype=np.int32).reshape(F, T)
-            pr = Prior(iptr(off), iptr(idx), float(prior[1]), float(prior[2]), iptr(orders))
+            pr = Prior(iptr(off), iptr(idx), float(prior[1]), float(prior[2]), iptr(orders), 1 if aggregate else 0)
+            check(self._lib.scrc_fit_cycle_prior(self._h, F, dptr(lam), iptr(k), C.byref(opt), C.byref(pr), C.byref(out)))
+        elif aggregate and not skip_allocation:
+            pr = Prior(None, None, float(prior[1]) if prior is not None else 1e-6, 0.0, None, 1)
             check(self._lib.scrc_fit_cycle_prior(self._h, F, dptr(lam), iptr(k), C.byref(opt), C.byref(pr), C.byref(out)))
         elif quick is not None:
             idx = np.ascontiguousarray(quick[0], dtype=np.int32).reshape(F, self.T)
@@ -381,13 +389,16 @@ class _PyBackend:
                 ks = np.ctypeslib.as_array(k_in, shape=(F, T)).copy()
                 o = out.contents
                 pr = None
+                kw = {}
                 if prior:
                     pc = prior.contents
-                    off = np.ctypeslib.as_array(pc.prior_off, shape=(T + 1,)).copy()
-                    idx = np.ctypeslib.as_array(pc.prior_idx, shape=(max(int(off[T]), 1),)).copy()
-                    orders = np.ctypeslib.as_array(pc.update_order, shape=(F, T)).copy()
-                    pr = (_csr_lists(off, idx, T), pc.baseline, pc.weight, orders)
-                kw = {}
+                    if pc.prior_off and pc.update_order:
+                        off = np.ctypeslib.as_array(pc.prior_off, shape=(T + 1,)).copy()
+                        idx = np.ctypeslib.as_array(pc.prior_idx, shape=(max(int(off[T]), 1),)).copy()
+                        orders = np.ctypeslib.as_array(pc.update_order, shape=(F, T)).copy()
+                        pr = (_csr_lists(off, idx, T), pc.baseline, pc.weight, orders)
+                    if pc.aggregate:
+                        kw["aggregate"] = True
                 if quick:
                     kw["quick"] = (np.ctypeslib.as_array(quick.contents.idx_latest, shape=(F, T)).copy(), quick.contents.percent)
                 if getattr(ses, "accepts_hint", False) and hint:
@@ -520,7 +531,7 @@ def scregclust_fit(z1_reg_scaled=None, z2_reg_scaled=None, z1_target_centered=No
                    tol_coop_rel=1e-8, tol_coop_abs=1e-12, tol_nnls=1e-4, device=0, session=None,
                    keep_diagnostics=False, return_coeffs=True, compute_predictive_r2=False, prior_indicator=None,
                    prior_baseline=1e-6, prior_weight=0.0, update_orders=None, comm=None, quick_mode=False,
-                   quick_mode_percent=0.1):
+                   quick_mode_percent=0.1, allocate_per_obs=True):
     """The alternating loop of ``scregclust()`` (R/scregclust.R:1222-1912) for all penalization values,
     one ``scrc_grid_fit`` call.  Returns one :class:`FitResult` per penalization value, in order.
 
@@ -529,7 +540,8 @@ def scregclust_fit(z1_reg_scaled=None, z2_reg_scaled=None, z1_target_centered=No
     :class:`Session` is accepted and then driven through ``scrc_grid_fit_custom`` (the CPU tests pass an
     oracle-backed one).  Network prior (R/scregclust.R:584-615): ``prior_indicator`` is a list of T lists of
     0-based neighbour targets, ``update_orders(penalty_index, cycle)`` returns the permutation R's
-    ``sample()`` would draw (R/scregclust.R:1666; identity when omitted).
+    ``sample()`` would draw (R/scregclust.R:1666; identity when omitted).  ``allocate_per_obs=False`` selects the
+    aggregate branch of Step 2b (R/scregclust.R:1678-1728; unreachable through the reference's own argument checks).
 
     Multi-GPU: with ``comm`` (or a session created with one) the call is collective -- every rank calls
     it with the same arguments and every rank gets the complete result.
@@ -555,6 +567,7 @@ def scregclust_fit(z1_reg_scaled=None, z2_reg_scaled=None, z1_target_centered=No
         gp.keep_diagnostics = 1 if keep_diagnostics else 0
         gp.quick_mode = 1 if quick_mode else 0
         gp.quick_mode_percent = float(quick_mode_percent)
+        gp.allocate_per_obs = 1 if allocate_per_obs else 0
         keep = []
         if prior_indicator is not None and len(prior_indicator) > 0 and float(prior_weight) != 0.0:
             from .api import _csr

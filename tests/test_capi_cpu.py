@@ -34,7 +34,7 @@ def test_header_symbols_exported(lib):
 
 def test_version_and_defaults(lib):
     from scregclust_b200 import _capi
-    assert lib.scrc_version() == 200
+    assert lib.scrc_version() == 201
     o = _capi.Options()
     lib.scrc_default_options(C.byref(o))
     # R/scregclust.R:193-196 and src/optim.cpp:67-69

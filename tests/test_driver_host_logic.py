@@ -25,19 +25,22 @@ class OracleSession:
         self.quick_calls = []    # idx_latest handed to each call (None: no quick-mode subset)
         self._last = None
 
-    def _one(self, lam, k, n_cycles, quick=None):
+    def _one(self, lam, k, n_cycles, quick=None, aggregate=False):
         w = self.w
         kw = {}
         if quick is not None:
             kw = dict(quick_mode=True, quick_mode_percent=quick[1], quick_first_cycle_idx=quick[0])
+        if aggregate:
+            kw["allocate_per_obs"] = False
         return orc.scregclust_fit(w.z1_reg, w.z2_reg, w.z1_target, w.z2_target, w.z1_target_sds, [lam], self.K, k,
                                   n_cycles=n_cycles, pre=self.pre, keep_history=True, materialize_array=False, **kw)[0]
 
     def fit_cycle(self, lambdas, ks, options=None, skip_allocation=False, want_votes=False, want_nnls_iters=False,
-                  prior=None, light=False, quick=None):
+                  prior=None, light=False, quick=None, aggregate=False):
         F, K, T, P = len(lambdas), self.K, self.T, self.P
         ks = np.asarray(ks).reshape(F, T)
         self.calls.append((F, bool(skip_allocation)))
+        self.aggregate_calls = getattr(self, "aggregate_calls", 0) + (1 if aggregate else 0)
         self.quick_calls.append(None if quick is None else np.asarray(quick[0]).copy())
         res = {"k_new": np.zeros((F, T), np.int32), "models": np.zeros((F, K, P), np.uint8),
                "best_r2": np.zeros((F, T)), "admm_iterations": np.zeros((F, K), np.int32),
@@ -56,9 +59,9 @@ class OracleSession:
                 res["n_selected"][f] = r.models[0].sum(axis=0)
                 self._last.append(r.coeffs[0])
             else:
-                r = self._one(lambdas[f], ks[f], 1, None if quick is None else (quick[0][f], quick[1]))
+                r = self._one(lambdas[f], ks[f], 1, None if quick is None else (quick[0][f], quick[1]), aggregate)
                 res["models"][f] = r.models_history[0].T
-                res["k_new"][f] = np.argmax(r.votes[0], axis=1) + 1
+                res["k_new"][f] = r.allocations[0] if aggregate else np.argmax(r.votes[0], axis=1) + 1
                 res["best_r2"][f] = r.r2_history[0].max(axis=1)
                 res["admm_iterations"][f] = r.admm_iterations[0]
                 res["n_selected"][f] = r.models_history[0].sum(axis=0)
@@ -133,6 +136,25 @@ def test_zero_cycles_refits_the_initial_configuration(case):
                          session=ses, n_cycles=0, **kw)
     _same(got, ref)
     assert ses.calls == [(len(w.penalization), True)] and all(not g.converged and g.n_cycles_run == 1 for g in got)
+
+
+def test_aggregate_branch_through_the_loop(case):
+    """allocate_per_obs = FALSE (R/scregclust.R:1678-1728): the loop hands the flag to every fit cycle (not to the final
+    re-fit) and reproduces the oracle's trajectory; quick mode is refused with the reference's message."""
+    from scregclust_b200.driver import scregclust_fit
+    from scregclust_b200._capi import ScrcError
+    w, kw, per_obs = case
+    ref = orc.scregclust_fit(w.z1_reg, w.z2_reg, w.z1_target, w.z2_target, w.z1_target_sds, w.penalization,
+                             w.n_modules, w.k_init, allocate_per_obs=False, **kw)
+    ses = OracleSession(w)
+    got = scregclust_fit(penalization=w.penalization, n_modules=w.n_modules, initial_target_modules=w.k_init,
+                         session=ses, allocate_per_obs=False, **kw)
+    _same(got, ref)
+    assert ses.aggregate_calls == sum(1 for c in ses.calls if not c[1])
+    assert any(not np.array_equal(a.k_final[0], b.k_final[0]) for a, b in zip(ref, per_obs))   # it is a different rule
+    with pytest.raises(ScrcError, match="quick_mode only available when allocate_per_obs is TRUE"):
+        scregclust_fit(penalization=w.penalization, n_modules=w.n_modules, initial_target_modules=w.k_init,
+                       session=OracleSession(w), allocate_per_obs=False, quick_mode=True, **kw)
 
 
 def test_quick_mode_bookkeeping_of_the_loop(case):

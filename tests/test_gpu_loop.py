@@ -530,3 +530,51 @@ def test_loop_matches_golden_trajectory():
         assert rel_err(r.r2[0], g[f"r2_{i}"]) < 1e-8
         assert rel_err(r.sigmas[0], g[f"sigmas_{i}"]) < 1e-8
         assert np.allclose(r.importance[0], g[f"importance_{i}"], rtol=1e-8, atol=1e-9, equal_nan=True)
+
+
+@pytest.mark.parametrize("name,seed,with_prior", [("tiny", 3, False), ("tiny", 3, True), ("small", 1, True)])
+def test_aggregate_branch_cycle_and_loop(name, seed, with_prior):
+    """Next-row f2, second half: the allocate_per_obs = FALSE branch of Step 2b (R/scregclust.R:1678-1728) on the device --
+    reassignment from the cycle's test sums of squares and variances, with and without a network prior -- against
+    the oracle: the first cycle gene by gene (genes whose two best scores agree to 1e-12 may differ: log / exp are
+    library functions), then the whole loop."""
+    from scregclust_b200.driver import Session, scregclust_fit
+    w = make_workload(name, seed=seed)
+    T = w.z1_target.shape[1]
+    prng = np.random.default_rng(5)
+    prior = [sorted(prng.choice(T, size=3, replace=False).tolist()) for _ in range(T)] if with_prior else None
+    def update_orders(li, cycle):
+        return np.random.default_rng(77 * li + cycle).permutation(T).astype(np.int32)
+    kw = dict(min_module_size=2)
+    if with_prior:
+        kw.update(prior_indicator=prior, prior_baseline=1e-6, prior_weight=0.5, update_orders=update_orders)
+    ref = orc.scregclust_fit(w.z1_reg, w.z2_reg, w.z1_target, w.z2_target, w.z1_target_sds, w.penalization,
+                             w.n_modules, w.k_init, allocate_per_obs=False, keep_history=True, **kw)
+    # ---- one cycle from the initial configuration
+    L = len(w.penalization)
+    with Session(w.z1_reg, w.z2_reg, w.z1_target, w.z2_target, w.z1_target_sds, w.n_modules) as ses:
+        pr = None
+        if with_prior:
+            pr = (prior, 1e-6, 0.5, np.stack([update_orders(li, 1) for li in range(L)]))
+        res = ses.fit_cycle(w.penalization, np.stack([w.k_init] * L), prior=pr, aggregate=True, want_votes=True)
+    for f, r in enumerate(ref):
+        diff = np.flatnonzero(res["k_new"][f] != r.allocations[0])
+        assert np.all(r.ambiguity[0][diff] == 1), (f, diff[:8])
+        if not with_prior:
+            assert diff.size == 0
+        assert not res["votes"][f].any()                           # the branch casts no votes
+        assert np.max(np.abs(res["r2_test"][f].T - r.r2_history[0])) < 1e-8
+    # ---- the loop
+    got = scregclust_fit(w.z1_reg, w.z2_reg, w.z1_target, w.z2_target, w.z1_target_sds, w.penalization,
+                         w.n_modules, w.k_init, allocate_per_obs=False, **kw)
+    same = 0
+    for g, r in zip(got, ref):
+        c, genes = _first_divergence(g, r)
+        if c is not None:
+            assert np.all(r.ambiguity[c - 1][genes] == 1), (g.penalization, c, genes[:8])
+            continue
+        same += 1
+        assert g.n_cycles_run == r.n_cycles_run and g.converged == r.converged
+        assert np.array_equal(g.k_final[0], r.k_final[0])
+        assert np.max(np.abs(g.r2[0] - r.r2[0])) < 1e-8
+    assert same >= max(1, len(ref) - 1)

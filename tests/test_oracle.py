@@ -359,3 +359,32 @@ def test_coop_lasso_single_column_is_the_weighted_lasso(rng):
     assert it < 100000
     assert np.max(np.abs(beta[:, 0] - ref)) < 1e-7 * max(1.0, np.max(np.abs(ref)))
     assert np.array_equal(np.abs(beta[:, 0]) > 1e-6, np.abs(ref) > 1e-6) and 0 < np.sum(np.abs(ref) > 1e-6) < p
+
+
+def test_aggregate_allocation_branch():
+    """R/scregclust.R:1678-1728 (allocate_per_obs = FALSE).  Without a prior the normalisation is monotone per gene, so the
+    result is the arg-min of n2 log(2 pi s2) + SS / s2; with a prior the sweep depends on the order, module totals
+    stay those of the incoming configuration, and noise genes (-1) are reassigned like any other gene."""
+    rng = np.random.default_rng(11)
+    T, K, n2 = 60, 5, 200
+    ss = rng.random((T, K)) * 80 + 20; rv = rng.random((T, K)) * 0.5 + 0.1
+    k = rng.integers(1, K + 1, T).astype(np.int32); k[:5] = -1
+    plain = orc.allocate_aggregate(k, ss, rv, n2, (), np.arange(T), 1e-6, 0.0)
+    assert np.array_equal(plain, np.argmin(n2 * np.log(2 * np.pi * rv) + ss / rv, axis=1) + 1)
+    assert np.array_equal(plain, orc.allocate_aggregate(k, ss, rv, n2, (), np.arange(T)[::-1], 1e-6, 0.0))
+    # exact tie -> which.min takes the first module
+    ss2 = ss.copy(); rv2 = rv.copy(); ss2[:, 3] = ss2[:, 1]; rv2[:, 3] = rv2[:, 1]
+    tied = orc.allocate_aggregate(k, ss2, rv2, n2, (), np.arange(T), 1e-6, 0.0)
+    assert not np.any(tied == 4)
+    # hand-worked prior step: one gene, two modules with equal model scores, all neighbours in module 2 ->
+    # the prior's log-probability is larger for module 2, and which.min therefore picks module 1
+    ss3 = np.full((3, 2), 10.0); rv3 = np.full((3, 2), 1.0)
+    out = orc.allocate_aggregate(np.array([1, 2, 2]), ss3, rv3, 50, [[1, 2], [], []], np.array([0]), 1e-6, 0.5)
+    assert out.tolist() == [1, 2, 2]
+    out = orc.allocate_aggregate(np.array([2, 1, 1]), ss3, rv3, 50, [[1, 2], [], []], np.array([0]), 1e-6, 0.5)
+    assert out.tolist() == [2, 1, 1]
+    # order dependence through the neighbours' current modules
+    prior = [sorted(rng.choice(T, size=3, replace=False).tolist()) for _ in range(T)]
+    a = orc.allocate_aggregate(k, ss, rv, n2, prior, np.arange(T), 1e-6, 0.9)
+    b = orc.allocate_aggregate(k, ss, rv, n2, prior, np.arange(T)[::-1], 1e-6, 0.9)
+    assert np.all((a >= 1) & (a <= K)) and not np.array_equal(a, b)
