@@ -56,12 +56,22 @@ def main():
     ap.add_argument("--max-doubles", type=float, default=6e8)
     ap.add_argument("--lam", type=float, default=0.1)
     ap.add_argument("--out", default="gpurun_out/microbench.json")
+    ap.add_argument("--ns", default="", help="comma-separated cell counts (default 1000,10000,50000,200000)")
+    ap.add_argument("--Ps", default="", help="comma-separated regulator counts (default 256..4096)")
+    ap.add_argument("--batches", default="", help="comma-separated module counts (default 1,4,16,64)")
+    ap.add_argument("--no-fast-cor", action="store_true")
     a = ap.parse_args()
     Ps = [256, 512, 1024, 2048, 4096]
     ns = [1000, 10000, 50000, 200000]
     batches = [1, 4, 16, 64]
     if a.quick:
         Ps, ns, batches = [256, 1024], [1000, 10000], [1, 16]
+    if a.ns:
+        ns = [int(v) for v in a.ns.split(",")]
+    if a.Ps:
+        Ps = [int(v) for v in a.Ps.split(",")]
+    if a.batches:
+        batches = [int(v) for v in a.batches.split(",")]
     m, n2 = 128, 256
     lib = _capi.load()
     rows = []
@@ -100,14 +110,15 @@ def main():
                        "admm_problem_iters_per_s": round(piters / max(admm_ms, 1e-9) * 1e3, 1),
                        "sweeps_per_s": round(sweeps / max(admm_ms, 1e-9) * 1e3, 1),
                        "gemm_admm_tflops": round(pr["gemm_admm"][1] / max(pr["gemm_admm"][0], 1e-9) / 1e9, 2),
-                       "selected_per_module_mean": float(res["n_selected"].mean())}
+                       "selected_per_module_mean": float(res["n_selected"].mean()),
+                       "class_ms": {c: round(v[0], 3) for c, v in pr.items()}}
                 rows.append(row)
                 print(json.dumps(row), flush=True)
                 ses.close()
                 del zr, zt, z1r, z2r, z1t, z2t
     # fast_cor(n, px = 4096, py = P) through the drop-in entry point (host buffers, copies included)
     px = 4096 if not a.quick else 512
-    for P in Ps:
+    for P in ([] if a.no_fast_cor else Ps):
         for n in ns:
             if n * (px + P) > a.max_doubles:
                 rows.append({"kind": "fast_cor", "n": n, "px": px, "py": P, "skipped": "host matrices too large"})
