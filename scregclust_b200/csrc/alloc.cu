@@ -327,6 +327,8 @@ void resid_vote(const ResidVoteArgs& a, int mode, int num_sms, cudaStream_t st) 
 // ---------------------------------------------------------------- Gram-form sums of squares / finishing kernels
 // One CTA per (fit*module, 128-target chunk); the module's Gram block lives in shared memory.
 constexpr int SSG_MAX_S = 72;   // 72^2 doubles = 41 KB of static shared memory
+constexpr int SSG_TILE = 64;    // larger selections: 64 x 32 tiles of the Gram block
+constexpr int SSG_TILE_C = 32;
 __global__ void __launch_bounds__(128) sse_train_gram_kernel(const double* __restrict__ G_rr, int64_t ldrr,
                                                              const double* __restrict__ G_rt, int64_t ldrt,
                                                              const double* __restrict__ gtt,
@@ -338,7 +340,7 @@ __global__ void __launch_bounds__(128) sse_train_gram_kernel(const double* __res
                                                              const int* __restrict__ col_cnt, int pseudo,
                                                              const int* __restrict__ sel_row_off) {
     __shared__ double s_g[SSG_MAX_S * SSG_MAX_S];
-    __shared__ int s_sel[SSG_MAX_S];
+    __shared__ int s_sel[SSG_TILE + SSG_TILE_C > SSG_MAX_S ? SSG_TILE + SSG_TILE_C : SSG_MAX_S];
     // pseudo: one extra slot per fit (j == K) that holds y'y, the "no model" sum of squares (scregclust.R:1505-1515)
     const int KK = K + (pseudo ? 1 : 0);
     const int l = blockIdx.y / KK, j = blockIdx.y % KK;
@@ -347,34 +349,65 @@ __global__ void __launch_bounds__(128) sse_train_gram_kernel(const double* __res
     const int ro = j < K ? row_off[fk] : 0;
     const int so = j < K ? (sel_row_off ? sel_row_off[fk] : ro) : 0;   // rows of `sel` (may differ from the rows of beta)
     const int t = t0 + blockIdx.x * 128 + threadIdx.x;
-    const bool in_smem = s <= SSG_MAX_S;
-    if (in_smem) {
+    // quick mode: column t of this fit is target col_index[col_off[l] + t] (per-fit target subsets)
+    const bool valid = t < t1 && !(col_cnt && t >= col_cnt[l]);
+    const int tg = valid ? (col_index ? col_index[col_off[l] + t] : t) : 0;
+    const double* b = beta + ro + (int64_t)(valid ? t : t0) * ldb;
+    double cross = 0.0, quad = 0.0;
+    if (s <= SSG_MAX_S) {
+        // the module's whole Gram block in shared memory
         for (int a = threadIdx.x; a < s; a += 128) s_sel[a] = sel[so + a];
         __syncthreads();
         for (int e = threadIdx.x; e < s * s; e += 128) s_g[e] = G_rr[s_sel[e % s] + (int64_t)s_sel[e / s] * ldrr];
         __syncthreads();
-    }
-    if (t >= t1) return;
-    // quick mode: column t of this fit is target col_index[col_off[l] + t] (per-fit target subsets)
-    if (col_cnt && t >= col_cnt[l]) return;
-    const int tg = col_index ? col_index[col_off[l] + t] : t;
-    double acc = gtt[tg];
-    if (s > 0) {
-        const double* b = beta + ro + (int64_t)t * ldb;
-        double cross = 0.0, quad = 0.0;
-        for (int a = 0; a < s; ++a) {
-            const double ba = b[a];
-            const int ia = in_smem ? s_sel[a] : sel[so + a];
-            cross += ba * G_rt[ia + (int64_t)tg * ldrt];
-            double row = 0.0;
-            for (int c = 0; c < s; ++c) {
-                const double g = in_smem ? s_g[a + c * s] : G_rr[ia + (int64_t)sel[so + c] * ldrr];
-                row += g * b[c];
+        if (valid)
+            for (int a = 0; a < s; ++a) {
+                const double ba = b[a];
+                cross += ba * G_rt[s_sel[a] + (int64_t)tg * ldrt];
+                double row = 0.0;
+                for (int c = 0; c < s; ++c) row += s_g[a + c * s] * b[c];
+                quad += ba * row;
             }
-            quad += ba * row;
+    } else {
+        // large selections (weak penalization, or the ridge-initialised n1 < P regime: hundreds of regulators per
+        // module): the Gram block goes through shared memory in 64 x 32 tiles (zero padded); a thread keeps the 32
+        // coefficients of its target that the column tile needs in registers, so the inner product runs on one
+        // broadcast shared-memory operand per FMA
+        int* s_sa = s_sel;
+        int* s_sc = s_sel + SSG_TILE;
+        for (int c0 = 0; c0 < s; c0 += SSG_TILE_C) {
+            const int nc = min(SSG_TILE_C, s - c0);
+            double bc[SSG_TILE_C];
+#pragma unroll
+            for (int c = 0; c < SSG_TILE_C; ++c) bc[c] = (valid && c < nc) ? b[c0 + c] : 0.0;
+            for (int a0 = 0; a0 < s; a0 += SSG_TILE) {
+                const int na = min(SSG_TILE, s - a0);
+                __syncthreads();                                   // the previous tile has been consumed
+                if (threadIdx.x < SSG_TILE) s_sa[threadIdx.x] = threadIdx.x < na ? sel[so + a0 + threadIdx.x] : -1;
+                else if (threadIdx.x - SSG_TILE < SSG_TILE_C)
+                    s_sc[threadIdx.x - SSG_TILE] = (int)threadIdx.x - SSG_TILE < nc ? sel[so + c0 + threadIdx.x - SSG_TILE] : -1;
+                __syncthreads();
+                for (int e = threadIdx.x; e < SSG_TILE * SSG_TILE_C; e += 128) {
+                    const int ia = s_sa[e % SSG_TILE], ic = s_sc[e / SSG_TILE];
+                    s_g[e] = (ia >= 0 && ic >= 0) ? G_rr[ia + (int64_t)ic * ldrr] : 0.0;
+                }
+                __syncthreads();
+                if (valid) {
+                    for (int a = 0; a < na; ++a) {
+                        double row = 0.0;
+#pragma unroll
+                        for (int c = 0; c < SSG_TILE_C; ++c) row += s_g[a + c * SSG_TILE] * bc[c];
+                        const double ba = b[a0 + a];
+                        quad += ba * row;
+                        if (c0 == 0) cross += ba * G_rt[s_sa[a] + (int64_t)tg * ldrt];
+                    }
+                }
+            }
         }
-        acc = (acc - 2.0 * cross) + quad;
     }
+    if (!valid) return;
+    double acc = gtt[tg];
+    if (s > 0) acc = (acc - 2.0 * cross) + quad;
     sse[((int64_t)l * (K + 1) + j) * T + t] = acc;
 }
 void sse_train_gram(const double* G_rr, int64_t ldrr, const double* G_rt, int64_t ldrt, const double* gtt,

@@ -287,6 +287,7 @@ class Session:
         self.d2h_bytes += sum(v.nbytes for v in res.values() if v is not None)
         self.admm_sweeps += int(sweeps.value)
         self.admm_problem_iterations += int(res["admm_iterations"].sum())
+        self._last_nsel = res["n_selected"]                 # coeffs_fit() unpacks the last cycle's coefficients with it
         return res
 
     def importance(self, k_final, models, signs, options=None, want_r2_removed=False):

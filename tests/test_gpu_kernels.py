@@ -201,3 +201,29 @@ def test_kernels_match_golden_fixtures(api):
     k = api.allocate_into_modules(np.asfortranarray(g["alloc_arr"]), np.asfortranarray(g["alloc_var"]), [],
                                   g["alloc_k"], g["alloc_order"], 1e-6, 0.0)
     assert np.array_equal(k, g["alloc_out"])
+
+
+@pytest.mark.gpu
+def test_gram_form_sse_with_large_selections():
+    """Weak penalization (or the ridge-initialised n1 < P regime, R/scregclust.R:1089-1100) keeps hundreds of regulators
+    per module: the Gram-form sums of squares then run through the tiled path (64 x 64 blocks of the Gram matrix).
+    Checked against the explicit residuals of the coefficients the same cycle returns: resid_var = ||z1 - X1 b||^2 /
+    (n1 - s), r2_test = 1 - ||z2 - X2 b||^2 / ||z2||^2 (R/scregclust.R:1590-1638)."""
+    from scregclust_b200.driver import Session
+    from scregclust_b200.synthetic import make_workload
+    w = make_workload(seed=4, shape=(800, 96, 220, 3), penalization=[0.002, 0.01])
+    n1 = w.z1_reg.shape[0]
+    L = len(w.penalization)
+    with Session(w.z1_reg, w.z2_reg, w.z1_target, w.z2_target, w.z1_target_sds, w.n_modules) as ses:
+        res = ses.fit_cycle(w.penalization, np.stack([w.k_init] * L), skip_allocation=True)
+        assert res["n_selected"].max() > 72                      # the tiled path is the one exercised
+        ss2 = (w.z2_target ** 2).sum(axis=0)
+        for f in range(L):
+            cos, sels = ses.coeffs_fit(f)
+            for j, (b, sel) in enumerate(zip(cos, sels)):
+                if b is None:
+                    continue
+                sse1 = ((w.z1_target - w.z1_reg[:, sel] @ b) ** 2).sum(axis=0)
+                sse2 = ((w.z2_target - w.z2_reg[:, sel] @ b) ** 2).sum(axis=0)
+                assert np.allclose(res["resid_var"][f, j], sse1 / (n1 - sel.size), rtol=1e-8, atol=0)
+                assert np.allclose(res["r2_test"][f, j], 1.0 - sse2 / ss2, rtol=0, atol=1e-8)
