@@ -466,7 +466,7 @@ def main():
                 sec.append({"kernel": "admm_rhs_kernel / admm_update_kernel / admm_finalize_kernel (ADMM elementwise sweep)",
                             "bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
                             "share_of_step": el["ms_per_step"] / ms_prof,
-                            "bytes_note": "algorithmic bytes per active column: 56 P on plain sweeps, 136 P on rho-adaptation "
+                            "bytes_note": "algorithmic bytes per active column: 56 P on plain sweeps, 120 P on rho-adaptation "
                                           "sweeps (DESIGN.md section 4; counted per sweep on the device)",
                             "peak_source": "MEASURED_PEAKS.json hbm_gbs (copy-measured)"})
             rv = prof["resid_vote"]

@@ -157,7 +157,8 @@ __global__ void admm_init_prob_kernel(AdmmDev d, double rho0, double alpha0) {
 }
 
 // ------------------------------------------------------------------ rhs = xty + rho*zeta + mult   (optim.cpp:143)
-__global__ void __launch_bounds__(256) admm_rhs_kernel(AdmmDev d) {
+__global__ void __launch_bounds__(256) admm_rhs_kernel(AdmmDev d, const double* __restrict__ zeta,
+                                                       const double* __restrict__ mult) {
     const int c = blockIdx.x;
     const int p = d.col_prob[c];
     if (!d.active[p]) return;
@@ -165,7 +166,7 @@ __global__ void __launch_bounds__(256) admm_rhs_kernel(AdmmDev d) {
     const int64_t base = (int64_t)c * d.ld;
     for (int i = threadIdx.x; i < d.P; i += blockDim.x) {
         const int64_t idx = base + i;
-        d.R[idx] = (d.xty[idx] + rho * d.zeta[idx]) + d.mult[idx];
+        d.R[idx] = (d.xty[idx] + rho * zeta[idx]) + mult[idx];
     }
 }
 
@@ -200,6 +201,9 @@ struct AdmmGemmPolicy {
     template <int MT, int NT>
     __device__ static void epilogue(const Params& p, const TileInfo& ti, double (&acc)[MT][NT][2],
                                     int warp_m, int warp_n, int lane) {
+        // (Measured and dropped: one real division per (row, problem) plus the exact quotient correction per element
+        // instead of a division per element -- the cache of the last divisor serialises the col_prob / active / rho
+        // loads of the epilogue; 33.4 -> 32.3 TFLOP/s over a config-3 grid.)
         for_each_acc<MT, NT>(acc, warp_m, warp_n, lane, [&](int rr, int cc, double v0, double v1) {
             const int row = ti.m0 + rr;
             if (row >= p.P) return;
@@ -256,10 +260,20 @@ constexpr int UPD_CACHE = 4096;   // doubles per cached array (R * cached column
 constexpr int UPD_BOXC = 64;      // columns per TMA box
 
 struct UpdMaps { CUtensorMap b, z, m; };   // beta, zeta, mult viewed as (P x C) with an (R x 64) box
+// zeta and mult live in two buffers each (the matrices called zeta / zeta_old, mult / mult_old).  A rho-adaptation
+// sweep must leave "the snapshot" equal to the values it just produced (optim.cpp:282-285), so instead of storing
+// them twice it writes them ONCE, over the previous snapshot, and that buffer becomes both the current state and
+// the snapshot; the first sweep after it writes the other buffer, later plain sweeps update in place.
+struct UpdPtrs {
+    const double *z_in, *m_in;    // current zeta / mult (the buffers the TMA maps z, m point at)
+    double *z_out, *m_out;        // where this sweep's zeta / mult go
+    const double *z_snap, *m_snap;   // zeta_old / mult_old as of the last rho-adaptation sweep (UPDATE_ITER only)
+};
 
 template <int R, bool UPDATE_ITER, bool FUSE_RHS>
 __global__ void __launch_bounds__(ADMM_UPD_WARPS * 32) admm_update_kernel(AdmmDev d, const int* __restrict__ prob_ids,
-                                                                          const __grid_constant__ UpdMaps maps) {
+                                                                          const __grid_constant__ UpdMaps maps,
+                                                                          const UpdPtrs ptr) {
     constexpr int CPW = 32 / R;
     constexpr int CS = UPD_CACHE / R;
     constexpr int STEP = ADMM_UPD_WARPS * CPW;
@@ -333,7 +347,7 @@ __global__ void __launch_bounds__(ADMM_UPD_WARPS * 32) admm_update_kernel(AdmmDe
         double b = 0.0, z = 0.0, mu = 0.0;
         if (rv) {
             const int64_t idx = base + (int64_t)lc * d.ld;
-            b = d.beta[idx]; z = d.zeta[idx]; mu = d.mult[idx];
+            b = d.beta[idx]; z = ptr.z_in[idx]; mu = ptr.m_in[idx];
         }
         norm_term(b, z, mu);
     }
@@ -365,10 +379,10 @@ __global__ void __launch_bounds__(ADMM_UPD_WARPS * 32) admm_update_kernel(AdmmDe
             if (lc < m) {
                 const int64_t idx = base + (int64_t)lc * d.ld;
                 if (lc < CS) { if (rv) { b[u] = sb[lc * R + row_l]; z[u] = sz[lc * R + row_l]; mu[u] = smu[lc * R + row_l]; } }
-                else if (rv) { b[u] = d.beta[idx]; z[u] = d.zeta[idx]; mu[u] = d.mult[idx]; }
+                else if (rv) { b[u] = d.beta[idx]; z[u] = ptr.z_in[idx]; mu[u] = ptr.m_in[idx]; }
                 if (rv) {
                     if (FUSE_RHS) xt[u] = d.xty[idx];
-                    if (UPDATE_ITER) { bo[u] = d.beta_old[idx]; zo[u] = d.zeta_old[idx]; mo[u] = d.mult_old[idx]; mho[u] = d.mult_hat_old[idx]; }
+                    if (UPDATE_ITER) { bo[u] = d.beta_old[idx]; zo[u] = ptr.z_snap[idx]; mo[u] = ptr.m_snap[idx]; mho[u] = d.mult_hat_old[idx]; }
                 }
             }
         }
@@ -403,11 +417,10 @@ __global__ void __launch_bounds__(ADMM_UPD_WARPS * 32) admm_update_kernel(AdmmDe
                 const double dg = zo[u] - z[u];
                 s[5] += dmh * dmh; s[6] += dh * dh; s[7] += dh * dmh;
                 s[8] += dm * dm; s[9] += dg * dg; s[10] += dg * dm;
-                d.beta_old[idx] = b[u]; d.zeta_old[idx] = zn;           // optim.cpp:282-285
-                d.mult_old[idx] = mn; d.mult_hat_old[idx] = mh;
+                d.beta_old[idx] = b[u]; d.mult_hat_old[idx] = mh;       // optim.cpp:282-285 (zeta_old, mult_old: see UpdPtrs)
             }
-            d.zeta[idx] = zn;                                           // optim.cpp:292
-            d.mult[idx] = mn;
+            ptr.z_out[idx] = zn;                                        // optim.cpp:292
+            ptr.m_out[idx] = mn;
             if (FUSE_RHS) d.R[idx] = (xt[u] + rho * zn) + mn;           // optim.cpp:143 of the next sweep
         }
     }
@@ -561,29 +574,44 @@ int admm_solve(AdmmBatch& b, const EigBasis& eig, const AdmmOpts& o, bool cold, 
         SCRC_SET_UPD(32, 0) SCRC_SET_UPD(16, 4) SCRC_SET_UPD(8, 8)
 #undef SCRC_SET_UPD
     }
-    UpdMaps umaps[3];
+    // zeta / mult buffer pairs (UpdPtrs): index 0 = the matrices named zeta / mult, 1 = zeta_old / mult_old
+    double* zbuf[2] = {d.zeta, d.zeta_old};
+    double* mbuf[2] = {d.mult, d.mult_old};
+    UpdMaps umaps[3][2];
     for (int c = 0; c < 3; ++c) {
         if (ids[c].empty()) continue;
         const int R = 32 >> c;
-        umaps[c].b = make_tmap_f64_plain(d.beta, b.P, b.C, d.ld, R, UPD_BOXC);
-        umaps[c].z = make_tmap_f64_plain(d.zeta, b.P, b.C, d.ld, R, UPD_BOXC);
-        umaps[c].m = make_tmap_f64_plain(d.mult, b.P, b.C, d.ld, R, UPD_BOXC);
+        for (int w = 0; w < 2; ++w) {
+            umaps[c][w].b = make_tmap_f64_plain(d.beta, b.P, b.C, d.ld, R, UPD_BOXC);
+            umaps[c][w].z = make_tmap_f64_plain(zbuf[w], b.P, b.C, d.ld, R, UPD_BOXC);
+            umaps[c][w].m = make_tmap_f64_plain(mbuf[w], b.P, b.C, d.ld, R, UPD_BOXC);
+        }
     }
+    // cur: buffer holding the current zeta / mult; snap: buffer holding the snapshot of the last rho-adaptation sweep.
+    // At the start both matrices of a pair hold the initial value (zeros, or the warm start), so cur == snap == 0.
+    int cur = 0, snap = 0;
     auto launch_update = [&](bool upd, bool fuse) {
+        // rho-adaptation sweep: write over the snapshot (every element is read by its own thread first); the first
+        // sweep after one: write the other buffer; otherwise in place
+        const int outb = upd ? snap : (cur == snap ? 1 - cur : cur);
+        UpdPtrs ptr{zbuf[cur], mbuf[cur], zbuf[outb], mbuf[outb], zbuf[snap], mbuf[snap]};
         for (int c = 0; c < 3; ++c) {
             if (ids[c].empty()) continue;
             const int R = 32 >> c;
             const dim3 grid((unsigned)ceil_div(b.P, R), (unsigned)ids[c].size());
             const int* lst = b.class_ids.p + off[c];
+            const UpdMaps& um = umaps[c][cur];
 #define SCRC_UPD(R_) \
-            if (upd && fuse) admm_update_kernel<R_, true, true><<<grid, ADMM_UPD_WARPS * 32, upd_smem, stream>>>(d, lst, umaps[c]); \
-            else if (upd) admm_update_kernel<R_, true, false><<<grid, ADMM_UPD_WARPS * 32, upd_smem, stream>>>(d, lst, umaps[c]); \
-            else if (fuse) admm_update_kernel<R_, false, true><<<grid, ADMM_UPD_WARPS * 32, upd_smem, stream>>>(d, lst, umaps[c]); \
-            else admm_update_kernel<R_, false, false><<<grid, ADMM_UPD_WARPS * 32, upd_smem, stream>>>(d, lst, umaps[c]);
+            if (upd && fuse) admm_update_kernel<R_, true, true><<<grid, ADMM_UPD_WARPS * 32, upd_smem, stream>>>(d, lst, um, ptr); \
+            else if (upd) admm_update_kernel<R_, true, false><<<grid, ADMM_UPD_WARPS * 32, upd_smem, stream>>>(d, lst, um, ptr); \
+            else if (fuse) admm_update_kernel<R_, false, true><<<grid, ADMM_UPD_WARPS * 32, upd_smem, stream>>>(d, lst, um, ptr); \
+            else admm_update_kernel<R_, false, false><<<grid, ADMM_UPD_WARPS * 32, upd_smem, stream>>>(d, lst, um, ptr);
             if (R == 32) { SCRC_UPD(32) } else if (R == 16) { SCRC_UPD(16) } else { SCRC_UPD(8) }
 #undef SCRC_UPD
             SCRC_LAUNCHED();
         }
+        cur = outb;
+        if (upd) snap = outb;
     };
     int it = 1;
     int sweeps = 0;
@@ -591,7 +619,7 @@ int admm_solve(AdmmBatch& b, const EigBasis& eig, const AdmmOpts& o, bool cold, 
     while (true) {
         if (need_rhs) {
             ProfScope ps(PROF_ADMM_ELEM, stream);
-            admm_rhs_kernel<<<b.C, 256, 0, stream>>>(d);
+            admm_rhs_kernel<<<b.C, 256, 0, stream>>>(d, zbuf[cur], mbuf[cur]);
             SCRC_LAUNCHED();
         }
         // Tail of the solve: once the surviving problems fill less than about half of the SMs with
@@ -641,9 +669,9 @@ int admm_solve(AdmmBatch& b, const EigBasis& eig, const AdmmOpts& o, bool cold, 
         g_prof.add_work(PROF_GEMM_ADMM, 4.0 * (double)b.P * (double)b.P * (double)ci[0]);
         // elementwise sweep, algorithmic bytes per active column: plain sweeps read beta, zeta,
         // mult, X'y and write zeta, mult, rhs = 7 x 8 = 56 P; rho-adaptation sweeps read beta, zeta, mult + 4 snapshots
-        // and write zeta, mult + 4 snapshots (104 P), and the rhs needs its own pass once rho is known (3 reads +
-        // 1 write, 32 P) = 136 P
-        g_prof.add_work(PROF_ADMM_ELEM, (56.0 * (double)(ci[0] - ci[1]) + 136.0 * (double)ci[1]) * (double)b.P);
+        // and write zeta, mult (which double as their snapshots) + the beta and mult_hat snapshots (88 P), and the rhs
+        // needs its own pass once rho is known (3 reads + 1 write, 32 P) = 120 P
+        g_prof.add_work(PROF_ADMM_ELEM, (56.0 * (double)(ci[0] - ci[1]) + 120.0 * (double)ci[1]) * (double)b.P);
     }
     return sweeps;
 }

@@ -13,7 +13,9 @@ cudaEvent_t Profiler::get_event() {
 void Profiler::begin(int cls, cudaStream_t s) {
     Rec r{cls, get_event(), get_event()};
     SCRC_CUDA(cudaEventRecord(r.e0, s));
-    if (pending.size() >= 4096) collect();
+    // collect() blocks the host until the stream has drained, which stalls the launch pipeline of whatever phase it
+    // lands in (100+ ms seen inside session creation): only as a safety valve, far above what a profiled pass records
+    if (pending.size() >= (1u << 20)) collect();
     pending.push_back(r);
     launches[cls] += 1;
 }
