@@ -85,6 +85,10 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def mark(self):
+        """Start of the timed region: samples taken before it (warm-up) are not reported."""
+        self.lines = []
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -396,9 +400,12 @@ def main():
     dgemm_tf = 3 * 2.0 * 8192 ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12
     del a, b
 
+    # nvidia-smi takes a few hundred milliseconds to attach to the device, during which it holds up the launches of
+    # the process it watches: start it before the warm-up steps so that none of that lands in a timed step
+    sampler = ClockSampler(local_rank); sampler.start()
     for _ in range(max(args.warmup, 0)):
         run_step(True)
-    sampler = ClockSampler(local_rank); sampler.start()
+    sampler.mark()
     # pass 1 -- `value`: K steps, nothing but the library's own launches on the stream
     launches0 = api.launch_count()
     ms_dev, ms_wall, (res, stats, checksum) = timed(True, args.steps)
