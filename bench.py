@@ -56,6 +56,8 @@ def parse():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU-baseline sample work")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-threads", type=int, default=0,
+                    help="threads of the CPU legs (0 = all host cores; 1 = what stock R + reference BLAS give outside Eigen's GEMMs)")
     return ap.parse_args()
 
 
@@ -117,7 +119,7 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------
 # CPU arm: reference-faithful C++ twin on a bounded sample
 # --------------------------------------------------------------------------------------------
-def cpu_sample(w, budget_s, lam, totals, gpu_first_cycle=None):
+def cpu_sample(w, budget_s, lam, totals, gpu_first_cycle=None, n_threads=0):
     """Times the first cycle (Step 1 + 2a + 2b) of one penalization value with the cost structure of the
     reference (oracle/ref_cpu.cpp through oracle/twin_cycle.py) on as many modules / genes as fit the
     budget, and extrapolates to the whole grid on the work counters of the GPU run:
@@ -134,7 +136,7 @@ def cpu_sample(w, budget_s, lam, totals, gpu_first_cycle=None):
     from oracle import ref_cpu, twin_cycle
     from oracle import scregclust_oracle as orc
 
-    threads = ref_cpu.set_threads(os.cpu_count() or 1)
+    threads = ref_cpu.set_threads(n_threads if n_threads > 0 else (os.cpu_count() or 1))
     n1, P = w.z1_reg.shape
     n2, T = w.z2_target.shape
     K = w.n_modules
@@ -298,7 +300,7 @@ def main():
             gfc = {"admm_iterations": np.array(first["admm_iterations"]), "models": md}
         vals, desc, threads, details = [], "", 1, {}
         for _ in range(max(1, min(args.steps, 2))):            # each step = one bounded sample
-            v, desc, threads, details = cpu_sample(w, args.cpu_budget, float(pens[i_med]), totals, gfc)
+            v, desc, threads, details = cpu_sample(w, args.cpu_budget, float(pens[i_med]), totals, gfc, args.cpu_threads)
             vals.append(v)
         v = float(np.mean(vals))
         line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "s", "n_gpus": args.gpus,
@@ -510,7 +512,7 @@ def main():
             if not args.no_cpu_baseline:
                 try:
                     gfc = {"admm_iterations": r_med.admm_iterations[0], "models": r_med.models_history[0]}
-                    v, desc, threads, details = cpu_sample(w, args.cpu_budget, float(pens[i_med]), totals, gfc)
+                    v, desc, threads, details = cpu_sample(w, args.cpu_budget, float(pens[i_med]), totals, gfc, args.cpu_threads)
                     line["parity_spot"] = details.pop("parity_spot", None)
                     line["cpu_baseline"] = {"value": v, "unit": "s", "cores": threads, "kind": "port", "sample": desc, **details}
                 except Exception as exc:   # the checker library is optional for the GPU arm
