@@ -52,7 +52,31 @@ def kernel_fixture():
                         alloc_arr=arr, alloc_var=var, alloc_k=k, alloc_order=order, alloc_out=kout)
 
 
+def aggregate_fixture():
+    """allocate_per_obs = FALSE (R/scregclust.R:1678-1728): one reassignment with a prior, one without, and the loop."""
+    rng = np.random.default_rng(9)
+    T, K, n2 = 50, 4, 120
+    ss = rng.random((T, K)) * 60 + 30; rv = rng.random((T, K)) * 0.6 + 0.2
+    k = rng.integers(1, K + 1, T).astype(np.int32); k[:4] = -1
+    prior = [sorted(rng.choice(T, size=3, replace=False).tolist()) for _ in range(T)]
+    order = rng.permutation(T).astype(np.int32)
+    plain = orc.allocate_aggregate(k, ss, rv, n2, (), np.arange(T), 1e-6, 0.0)
+    withp = orc.allocate_aggregate(k, ss, rv, n2, prior, order, 1e-6, 0.5)
+    w = make_workload("tiny", seed=3)
+    res = orc.scregclust_fit(w.z1_reg, w.z2_reg, w.z1_target, w.z2_target, w.z1_target_sds, w.penalization,
+                             w.n_modules, w.k_init, allocate_per_obs=False, min_module_size=2)
+    out = dict(ss=ss, rv=rv, k=k, n2=n2, prior=np.array(prior, dtype=np.int32), order=order, out_plain=plain,
+               out_prior=withp)
+    for i, r in enumerate(res):
+        out[f"k_history_{i}"] = np.stack(r.k_history)
+    np.savez_compressed(os.path.join(HERE, "aggregate_seed9.npz"), **out)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "aggregate":     # added in round 2; leaves the older files untouched
+        aggregate_fixture()
+        sys.exit(0)
     loop_fixture()
     kernel_fixture()
+    aggregate_fixture()
     print("golden fixtures written to", HERE)

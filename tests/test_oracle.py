@@ -388,3 +388,18 @@ def test_aggregate_allocation_branch():
     a = orc.allocate_aggregate(k, ss, rv, n2, prior, np.arange(T), 1e-6, 0.9)
     b = orc.allocate_aggregate(k, ss, rv, n2, prior, np.arange(T)[::-1], 1e-6, 0.9)
     assert np.all((a >= 1) & (a <= K)) and not np.array_equal(a, b)
+
+
+def test_aggregate_golden_vectors():
+    """tests/golden/aggregate_seed9.npz (tests/golden/make_golden.py aggregate): the aggregate branch, gene by gene and through the loop."""
+    g = np.load(os.path.join(GOLD, "aggregate_seed9.npz"))
+    prior = [list(r) for r in g["prior"]]
+    T = g["k"].size
+    assert np.array_equal(orc.allocate_aggregate(g["k"], g["ss"], g["rv"], int(g["n2"]), (), np.arange(T), 1e-6, 0.0), g["out_plain"])
+    assert np.array_equal(orc.allocate_aggregate(g["k"], g["ss"], g["rv"], int(g["n2"]), prior, g["order"], 1e-6, 0.5), g["out_prior"])
+    assert not np.array_equal(g["out_plain"], g["out_prior"])
+    w = make_workload("tiny", seed=3)
+    res = orc.scregclust_fit(w.z1_reg, w.z2_reg, w.z1_target, w.z2_target, w.z1_target_sds, w.penalization,
+                             w.n_modules, w.k_init, allocate_per_obs=False, min_module_size=2)
+    for i, r in enumerate(res):
+        assert np.array_equal(np.stack(r.k_history), g[f"k_history_{i}"])
