@@ -416,7 +416,8 @@ def main():
     # kernel times for the roofline figures.  The events cost a few microseconds per group, which matters for the
     # launch-bound small workloads, so this pass has its own clock (`profiled_pass`) and `value` does not carry it.
     _capi.check(lib.scrc_profile_reset()); _capi.check(lib.scrc_profile_enable(1))
-    ms_prof, _, _ = timed(True, args.steps)
+    prof_steps = max(1, min(args.steps, 3))      # enough launches for the per-class averages; keeps long runs short
+    ms_prof, _, _ = timed(True, prof_steps)
     pm = (C.c_double * 6)(); pw = (C.c_double * 6)(); pl = (C.c_ulonglong * 6)()
     _capi.check(lib.scrc_profile_get(pm, pw, pl)); _capi.check(lib.scrc_profile_enable(0))
     clocks = sampler.stop()
@@ -425,7 +426,7 @@ def main():
 
     if rank == 0:
         names = ["gemm_dense", "gemm_admm", "admm_elementwise", "nnls", "resid_vote", "other"]
-        prof = {n: {"ms_per_step": pm[i] / args.steps, "work_per_step": pw[i] / args.steps, "timed_groups": int(pl[i])}
+        prof = {n: {"ms_per_step": pm[i] / prof_steps, "work_per_step": pw[i] / prof_steps, "timed_groups": int(pl[i])}
                 for i, n in enumerate(names)}
         adm = prof["gemm_admm"]
         achieved = adm["work_per_step"] / (adm["ms_per_step"] * 1e-3) / 1e12 if adm["ms_per_step"] > 0 else 0.0
@@ -458,12 +459,12 @@ def main():
                          "traffic_note": (f"ncu dram bytes of a launch with every column active; algorithmic "
                                           f"{traffic['algorithmic_bytes_per_launch']} B for that launch") if traffic else None,
                          "share_of_step": adm["ms_per_step"] / ms_prof if ms_prof > 0 else None,
-                         "launches_per_step": adm["timed_groups"] / max(args.steps, 1),
+                         "launches_per_step": adm["timed_groups"] / prof_steps,
                          "peak_source": "cuBLAS DGEMM 8192^3 (torch.matmul float64) measured in this run; "
                                         "MEASURED_PEAKS.json has no FP64 figure"},
             "kernel_classes_rank0": prof, "kernel_share_of_step": kernel_ms / ms_prof if ms_prof > 0 else None,
-            "profiled_pass": {"ms_per_step": ms_prof, "steps": args.steps,
-                              "note": "the K steps repeated with CUDA events around every kernel group; kernel_classes_rank0, "
+            "profiled_pass": {"ms_per_step": ms_prof, "steps": prof_steps,
+                              "note": "min(K, 3) steps repeated with CUDA events around every kernel group; kernel_classes_rank0, "
                                       "roofline.achieved and the shares are measured in this pass and relate to its own time"},
             "clocks": clocks, "host_wall_ms_per_step": ms_wall, "assignment_checksum": checksum,
         }
