@@ -468,14 +468,15 @@ def _unpack_grid(lib, handle, K, P, T, keep_diag, return_coeffs, compute_r2):
         check(lib.scrc_grid_result_penalty(handle, i, C.byref(pi)))
         fr = FitResult(penalization=pi.penalization, converged=bool(pi.converged), n_cycles_run=pi.n_cycles_run,
                        final_cycle_length=pi.final_cycle_length)
-        hist = np.zeros((pi.n_history, T), dtype=np.int32)
+        # (every buffer below is filled completely by its accessor: np.empty, and transposed views instead of copies)
+        hist = np.empty((pi.n_history, T), dtype=np.int32)
         check(lib.scrc_grid_result_history(handle, i, iptr(hist)))
         fr.k_history = [hist[h].copy() for h in range(pi.n_history)]
         n_fit_records = pi.n_records - pi.final_cycle_length
-        ai = np.zeros((pi.n_records, K), dtype=np.int32)
-        md = np.zeros((pi.n_records, K, P), dtype=np.uint8)
+        ai = np.empty((pi.n_records, K), dtype=np.int32)
+        md = np.empty((pi.n_records, K, P), dtype=np.uint8)
         check(lib.scrc_grid_result_records(handle, i, iptr(ai), None, md.ctypes.data_as(_capi.c_ubyte_p)))
-        mdb = md.astype(bool).transpose(0, 2, 1)             # views: P x K per record
+        mdb = md.view(bool).transpose(0, 2, 1)               # views: P x K per record (the bytes are 0 / 1)
         fr.admm_iterations = [ai[rec] for rec in range(pi.n_records)]
         fr.models_history = [mdb[rec] for rec in range(pi.n_records)]
         if keep_diag:
@@ -487,17 +488,17 @@ def _unpack_grid(lib, handle, K, P, T, keep_diag, return_coeffs, compute_r2):
                 if vt is not None:
                     fr.votes.append(vt)
         for m in range(pi.final_cycle_length):
-            kf = np.zeros(T, dtype=np.int32); md = np.zeros((K, P), dtype=np.uint8)
-            wt = np.zeros((K, P)); sg = np.zeros((K, P)); r2 = np.zeros((K, T)); rv = np.zeros((K, T))
-            br = np.zeros(T); bi = np.zeros(T, dtype=np.int32); ns = np.zeros(K, dtype=np.int32)
-            r2m = np.zeros(K) if compute_r2 else None
-            imp = np.zeros((K, P)) if compute_r2 else None
+            kf = np.empty(T, dtype=np.int32); md = np.empty((K, P), dtype=np.uint8)
+            wt = np.empty((K, P)); sg = np.empty((K, P)); r2 = np.empty((K, T)); rv = np.empty((K, T))
+            br = np.empty(T); bi = np.empty(T, dtype=np.int32); ns = np.empty(K, dtype=np.int32)
+            r2m = np.empty(K) if compute_r2 else None
+            imp = np.empty((K, P)) if compute_r2 else None
             gf = _capi.GridFinal(iptr(kf), md.ctypes.data_as(_capi.c_ubyte_p), dptr(wt), dptr(sg), dptr(r2), dptr(rv),
                                  dptr(br), iptr(bi), iptr(ns), dptr(r2m), dptr(imp))
             check(lib.scrc_grid_result_final(handle, i, m, C.byref(gf)))
             d2h += sum(a.nbytes for a in (kf, md, wt, sg, r2, rv, br, bi, ns))
-            fr.k_final.append(kf); fr.models.append(md.T.astype(bool)); fr.signs.append(sg.T.copy())
-            fr.weights.append(wt.T.copy()); fr.sigmas.append(np.sqrt(rv.T)); fr.r2.append(r2.T.copy())
+            fr.k_final.append(kf); fr.models.append(md.view(bool).T); fr.signs.append(sg.T)
+            fr.weights.append(wt.T); fr.sigmas.append(np.sqrt(rv).T); fr.r2.append(r2.T)
             fr.best_r2.append(br); fr.best_r2_idx.append(bi)
             if return_coeffs:
                 tot = int(ns.sum())
@@ -510,7 +511,7 @@ def _unpack_grid(lib, handle, K, P, T, keep_diag, return_coeffs, compute_r2):
                     o += s_ * T
                 fr.coeffs.append(cos)
             if compute_r2:
-                fr.r2_module.append(r2m); fr.importance.append(imp.T.copy())
+                fr.r2_module.append(r2m); fr.importance.append(imp.T)
                 n = int(lib.scrc_grid_result_r2_removed_size(handle, i, m))
                 buf = np.zeros(max(n, 1))
                 check(lib.scrc_grid_result_r2_removed(handle, i, m, dptr(buf)))
