@@ -108,3 +108,31 @@ def test_plain_c_client_links_and_reports_errors(lib, tmp_path):
     exe = build_c_client(tmp_path)
     out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0 and "C ABI smoke: ok" in out.stdout, out.stdout + out.stderr
+
+
+def test_struct_layouts_match_the_ctypes_mirrors(tmp_path):
+    """tests/c/abi_layout.c prints sizeof / offsetof(last member) of every struct of the public header as a C compiler sees
+    them; the ctypes mirrors of scregclust_b200/_capi.py must agree (a member added on one side only shifts the rest)."""
+    import ctypes as C
+    import shutil
+    import subprocess
+    from scregclust_b200 import _capi
+    if shutil.which("gcc") is None:
+        pytest.skip("no C compiler")
+    exe = str(tmp_path / "abi_layout")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "c", "abi_layout.c"), "-o", exe], check=True)
+    out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
+    mirrors = {"scrc_options": (_capi.Options, "eps_corr"), "scrc_cycle_out": (_capi.CycleOut, "admm_sweeps"),
+               "scrc_prior": (_capi.Prior, "aggregate"), "scrc_quick": (_capi.Quick, "percent"),
+               "scrc_grid_params": (_capi.GridParams, "cancel"), "scrc_grid_info": (_capi.GridInfo, "device_calls"),
+               "scrc_grid_penalty_info": (_capi.GridPenaltyInfo, "n_records"),
+               "scrc_grid_final": (_capi.GridFinal, "importance"), "scrc_grid_backend": (_capi.GridBackend, "coeffs_fit")}
+    seen = set()
+    for line in out.splitlines():
+        name, size, last = line.split()
+        cls, member = mirrors[name]
+        assert C.sizeof(cls) == int(size), name
+        assert getattr(cls, member).offset == int(last), (name, member)
+        seen.add(name)
+    assert seen == set(mirrors)
